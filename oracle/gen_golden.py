@@ -1,0 +1,337 @@
+"""Generate tests/golden/*.pt from the REAL reference (imported read-only from /root/reference).
+
+Run in the build container only:   python oracle/gen_golden.py
+The reference cannot travel to the GPU box, so the vectors it produces are committed as fixtures;
+this script is committed so they can be regenerated / audited.  Nothing at test / bench / smoke time
+reads /root/reference.
+
+Each fixture ``<name>.pt`` is a dict:
+    cfg         : dict describing how the model was built (consumed by tests/_cfg.py::build_model)
+    state_dict  : the reference module's state_dict (random init under a seed, or upstream pretrained)
+    cases       : list of dicts {name, training, inputs{...}, eps (latent only), loc, scale, loss_per_task,
+                                 loss, q_loc, q_scale, grad_proj{param_name: [9] fp64 = 8 random projections + L2 norm}
+                                 (train cases only; z = q_loc + q_scale * eps is not stored)}
+All tensors fp32 (masks bool).
+"""
+import os
+import random
+import sys
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = "/root/reference"
+sys.path.insert(0, REF)
+import npf  # noqa: E402
+from npf import (  # noqa: E402
+    CNP, LNP, AttnCNP, ConvCNP, ConvLNP, GridConvCNP, GridConvLNP, CNPFLoss, ELBOLossLNPF, NLLLossLNPF,
+)
+from npf.architectures import CNN, MLP, ResConvBlock, SetConv, discard_ith_arg, merge_flat_input  # noqa: E402
+import torch.distributions.normal as _tdn  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+PRE = os.path.join(REF, "results", "pretrained")
+
+torch.set_num_threads(8)
+
+
+def seed_all(s):
+    random.seed(s)
+    np.random.seed(s)
+    torch.manual_seed(s)
+
+
+# ---- record the eps drawn by Normal.rsample so the latent models can be replayed exactly ----------
+_EPS_LOG = []
+_orig_std_normal = _tdn._standard_normal
+
+
+def _recording_standard_normal(shape, dtype, device):
+    e = _orig_std_normal(shape, dtype, device)
+    _EPS_LOG.append(e.detach().clone())
+    return e
+
+
+_tdn._standard_normal = _recording_standard_normal
+
+R_DIM = 128
+
+
+# ---- the configurations (cfg dict is the portable description; build() turns it into the reference) ----
+def build(cfg):
+    fam = cfg["family"]
+    kw = {}
+    if cfg.get("notebook"):
+        if fam in ("CNP", "AttnCNP", "LNP"):
+            kw["XEncoder"] = partial(MLP, n_hidden_layers=1, hidden_size=R_DIM)
+            kw["Decoder"] = merge_flat_input(partial(MLP, n_hidden_layers=4, hidden_size=R_DIM), is_sum_merge=True)
+            kw["r_dim"] = R_DIM
+            kw["XYEncoder"] = merge_flat_input(
+                partial(MLP, n_hidden_layers=2, hidden_size=cfg["xy_hidden"]), is_sum_merge=True)
+        elif fam in ("ConvCNP", "GridConvCNP"):
+            kw["r_dim"] = R_DIM
+            kw["Decoder"] = discard_ith_arg(partial(MLP, n_hidden_layers=4, hidden_size=R_DIM), i=0)
+        elif fam in ("ConvLNP", "GridConvLNP"):
+            kw["r_dim"] = R_DIM
+            kw["Decoder"] = discard_ith_arg(torch.nn.Linear, i=0)
+            kw["is_q_zCct"] = False
+    if "cnn" in cfg:
+        c = cfg["cnn"]
+        Conv = nn.Conv1d if c["dim"] == 1 else nn.Conv2d
+        Norm = {None: nn.Identity, "bn": nn.BatchNorm1d if c["dim"] == 1 else nn.BatchNorm2d}[c.get("norm")]
+        kw["CNN"] = partial(CNN, ConvBlock=ResConvBlock, Conv=Conv, Normalization=Norm, n_blocks=c["n_blocks"],
+                            kernel_size=c["kernel_size"], is_chan_last=True, n_conv_layers=c["n_conv_layers"])
+    for k in ("density_induced", "attention", "n_z_samples_train", "n_z_samples_test", "is_global", "encoded_path",
+              "is_q_zCct"):
+        if k in cfg:
+            kw[k] = cfg[k]
+    if fam in ("ConvCNP", "ConvLNP") and cfg.get("notebook"):
+        kw["Interpolator"] = SetConv
+    cls = dict(CNP=CNP, LNP=LNP, AttnCNP=AttnCNP, ConvCNP=ConvCNP, ConvLNP=ConvLNP, GridConvCNP=GridConvCNP,
+               GridConvLNP=GridConvLNP)[fam]
+    seed_all(cfg.get("init_seed", 0))
+    model = cls(cfg["x_dim"], cfg["y_dim"], **kw)
+    if cfg.get("pretrained"):
+        sd = torch.load(os.path.join(PRE, cfg["pretrained"], "run_0", "params.pt"), map_location="cpu")
+        print("   load pretrained:", model.load_state_dict(sd))
+    return model
+
+
+def gp_like(B, N, y_dim, seed):
+    """Smooth-ish synthetic functions on sorted x in [-1,1] (values do not matter for parity)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, N, 1, generator=g) * 2 - 1
+    ph = torch.rand(B, 1, y_dim, generator=g) * 6.28
+    fr = 2 + 5 * torch.rand(B, 1, y_dim, generator=g)
+    y = torch.sin(fr * x + ph) + 0.1 * torch.randn(B, N, y_dim, generator=g)
+    return x, y
+
+
+def offgrid_inputs(B, C, T, y_dim, seed, x_scale=1.0, dup=False):
+    x, y = gp_like(B, C + T, y_dim, seed)
+    x = x * x_scale
+    Xc, Yc, Xt, Yt = x[:, :C], y[:, :C], x[:, C:], y[:, C:]
+    if dup and C >= 2:
+        Xc = Xc.clone(); Xc[:, 1] = Xc[:, 0]
+        Xt = Xt.clone(); Xt[:, 0] = Xc[:, 0]
+    return dict(X_cntxt=Xc.contiguous(), Y_cntxt=Yc.contiguous(), X_trgt=Xt.contiguous(), Y_trgt=Yt.contiguous())
+
+
+def grid_inputs(B, H, W, y_dim, frac, seed):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, H, W, y_dim, generator=g)
+    n = int(frac * H * W)
+    mask = torch.zeros(B, H * W, dtype=torch.bool)
+    for b in range(B):
+        mask[b, torch.randperm(H * W, generator=g)[:n]] = True
+    mask = mask.view(B, H, W, 1)
+    return dict(X_cntxt=mask, Y_cntxt=img, X_trgt=torch.ones(B, H, W, 1, dtype=torch.bool), Y_trgt=img.clone())
+
+
+N_PROJ = 8
+
+
+def grad_projection(g):
+    """Compact pin of a gradient tensor: 8 fixed random projections <g, v_i> + its L2 norm (fp64 accumulate).
+    v_i = randn(shape) under Generator seed 1000+i -- reproduced by tests/_util.py::grad_projection."""
+    out = []
+    g64 = g.double().reshape(-1)
+    for i in range(N_PROJ):
+        v = torch.randn(g64.numel(), generator=torch.Generator().manual_seed(1000 + i), dtype=torch.float64)
+        out.append(torch.dot(g64, v))
+    out.append(g64.norm())
+    return torch.stack(out)
+
+
+def run_case(model, cfg, name, training, inputs, loss_name, with_grads, extrap=None, seed=0):
+    model.train(training)
+    if extrap is not None:
+        model.set_extrapolation(extrap)
+    crit = dict(cnpf=CNPFLoss, nll=NLLLossLNPF, elbo=ELBOLossLNPF)[loss_name](reduction=None)
+    crit.train(training)
+    model.zero_grad()
+    _EPS_LOG.clear()
+    seed_all(seed)
+    bn_before = {k: v.clone() for k, v in model.state_dict().items() if "running_" in k or "num_batches" in k}
+    out = model(inputs["X_cntxt"], inputs["Y_cntxt"], inputs["X_trgt"], inputs["Y_trgt"])
+    p, z, q_c, q_ct = out
+    per_task = crit(out, inputs["Y_trgt"])
+    loss = per_task.mean(0)
+    case = dict(name=name, training=training, inputs=inputs, loss_name=loss_name,
+                loc=p.base_dist.loc.detach().clone(), scale=p.base_dist.scale.detach().clone(),
+                loss_per_task=per_task.detach().clone(), loss=loss.detach().clone())
+    if extrap is not None:
+        case["extrap"] = list(extrap)
+        case["X_induced"] = model.X_induced.detach().clone()
+    if z is not None:
+        case["q_loc"] = q_c.base_dist.loc.detach().clone()
+        case["q_scale"] = q_c.base_dist.scale.detach().clone()
+        assert len(_EPS_LOG) == 1
+        case["eps"] = _EPS_LOG[0]
+        if q_ct is not None:
+            case["q_ct_loc"] = q_ct.base_dist.loc.detach().clone()
+            case["q_ct_scale"] = q_ct.base_dist.scale.detach().clone()
+    if with_grads:
+        loss.backward()
+        case["grad_proj"] = {k: grad_projection(p_.grad.detach()) for k, p_ in model.named_parameters()
+                             if p_.grad is not None}
+    if training and bn_before:
+        # restore BN running stats so every case starts from the fixture's state_dict; keep the updated ones
+        case["bn_after"] = {k: v.detach().clone() for k, v in model.state_dict().items() if k in bn_before}
+        model.load_state_dict({**model.state_dict(), **bn_before})
+    if extrap is not None:
+        model.set_extrapolation((-1, 1))
+    print(f"   case {name:28s} train={training} loss={loss.item():.6f}")
+    return case
+
+
+def dump(name, cfg, model, cases):
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    n_params = sum(p.numel() for p in model.parameters())
+    torch.save(dict(cfg=cfg, state_dict=sd, cases=cases, n_params=n_params), os.path.join(OUT, name + ".pt"))
+    print(f"== {name}: {n_params} params, {len(cases)} cases")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---------------- CNP ----------------
+    cfg = dict(family="CNP", x_dim=1, y_dim=1)
+    m = build(cfg)
+    dump("cnp_default", cfg, m, [
+        run_case(m, cfg, "train_b16_c32_t64", True, offgrid_inputs(16, 32, 64, 1, 1), "cnpf", True),
+        run_case(m, cfg, "eval_c0", False, offgrid_inputs(3, 0, 9, 1, 2), "cnpf", False),
+        run_case(m, cfg, "train_c1_t1", True, offgrid_inputs(2, 1, 1, 1, 3), "cnpf", True),
+    ])
+    cfg = dict(family="CNP", x_dim=1, y_dim=1, notebook=True, xy_hidden=256, pretrained="RBF_Kernel/CNP")
+    m = build(cfg)
+    dump("cnp_notebook_pretrained", cfg, m, [
+        run_case(m, cfg, "train_b4_c20_t30", True, offgrid_inputs(4, 20, 30, 1, 4), "cnpf", True),
+        run_case(m, cfg, "eval_b4", False, offgrid_inputs(4, 10, 40, 1, 5), "cnpf", False),
+    ])
+    cfg = dict(family="CNP", x_dim=2, y_dim=3, init_seed=3)
+    m = build(cfg)
+    dump("cnp_x2_y3", cfg, m, [
+        run_case(m, cfg, "train_b3_c12_t17", True, _xy2(3, 12, 17, 3, 6), "cnpf", True),
+    ])
+
+    # ---------------- AttnCNP ----------------
+    cfg = dict(family="AttnCNP", x_dim=1, y_dim=1)  # scaledot default
+    m = build(cfg)
+    dump("attncnp_scaledot", cfg, m, [
+        run_case(m, cfg, "train_b4_c19_t23", True, offgrid_inputs(4, 19, 23, 1, 7), "cnpf", True),
+        run_case(m, cfg, "eval_c0", False, offgrid_inputs(2, 0, 5, 1, 8), "cnpf", False),
+    ])
+    cfg = dict(family="AttnCNP", x_dim=1, y_dim=1, notebook=True, xy_hidden=128, attention="transformer",
+               pretrained="RBF_Kernel/AttnCNP")
+    m = build(cfg)
+    dump("attncnp_transformer_pretrained", cfg, m, [
+        run_case(m, cfg, "train_b4_c33_t70", True, offgrid_inputs(4, 33, 70, 1, 9), "cnpf", True),
+        run_case(m, cfg, "eval_b2_c130_t150", False, offgrid_inputs(2, 130, 150, 1, 10), "cnpf", False),
+        run_case(m, cfg, "train_c1_t1", True, offgrid_inputs(2, 1, 1, 1, 11), "cnpf", True),
+    ])
+    cfg = dict(family="AttnCNP", x_dim=1, y_dim=2, attention="multihead", init_seed=5)
+    m = build(cfg)
+    dump("attncnp_multihead_y2", cfg, m, [
+        run_case(m, cfg, "train_b3_c16_t40", True, offgrid_inputs(3, 16, 40, 2, 12), "cnpf", True),
+    ])
+
+    # ---------------- ConvCNP (off-grid 1-D) ----------------
+    cfg = dict(family="ConvCNP", x_dim=1, y_dim=1)
+    m = build(cfg)
+    dump("convcnp_default", cfg, m, [
+        run_case(m, cfg, "train_b3_c9_t13", True, offgrid_inputs(3, 9, 13, 1, 13), "cnpf", True),
+        run_case(m, cfg, "train_b2_c128_t128", True, offgrid_inputs(2, 128, 128, 1, 14), "cnpf", True),
+        run_case(m, cfg, "eval_c0", False, offgrid_inputs(2, 0, 7, 1, 15), "cnpf", False),
+        run_case(m, cfg, "train_c1_t1", True, offgrid_inputs(2, 1, 1, 1, 16), "cnpf", True),
+        run_case(m, cfg, "train_dup_x", True, offgrid_inputs(2, 6, 5, 1, 17, dup=True), "cnpf", True),
+        run_case(m, cfg, "eval_extrap", False, offgrid_inputs(2, 10, 12, 1, 18, x_scale=2.0), "cnpf", False,
+                 extrap=(-2, 2)),
+    ])
+    cfg = dict(family="ConvCNP", x_dim=1, y_dim=2, init_seed=7)
+    m = build(cfg)
+    dump("convcnp_default_y2", cfg, m, [
+        run_case(m, cfg, "train_b2_c11_t9", True, offgrid_inputs(2, 11, 9, 2, 19), "cnpf", True),
+    ])
+    cfg = dict(family="ConvCNP", x_dim=1, y_dim=1, notebook=True, density_induced=64, pretrained="RBF_Kernel/ConvCNP",
+               cnn=dict(dim=1, norm="bn", n_blocks=5, kernel_size=19, n_conv_layers=2))
+    m = build(cfg)
+    dump("convcnp_notebook_pretrained", cfg, m, [
+        run_case(m, cfg, "eval_b4_c30_t50", False, offgrid_inputs(4, 30, 50, 1, 20), "cnpf", False),
+        run_case(m, cfg, "train_b4_c25_t40", True, offgrid_inputs(4, 25, 40, 1, 21), "cnpf", True),
+    ])
+
+    # ---------------- GridConvCNP (on-grid 2-D) ----------------
+    for y in (1, 3):
+        cfg = dict(family="GridConvCNP", x_dim=1, y_dim=y, init_seed=y)
+        m = build(cfg)
+        dump(f"gridconvcnp_default_y{y}", cfg, m, [
+            run_case(m, cfg, "train_b2_32x32", True, grid_inputs(2, 32, 32, y, 0.3, 22 + y), "cnpf", True),
+            run_case(m, cfg, "eval_b1_20x28_sparse", False, grid_inputs(1, 20, 28, y, 0.02, 30 + y), "cnpf", False),
+        ])
+    cfg = dict(family="GridConvCNP", x_dim=1, y_dim=3, notebook=True, pretrained="celeba32/ConvCNP",
+               cnn=dict(dim=2, norm="bn", n_blocks=5, kernel_size=9, n_conv_layers=2))
+    m = build(cfg)
+    dump("gridconvcnp_notebook_pretrained", cfg, m, [
+        run_case(m, cfg, "eval_b2_32x32", False, grid_inputs(2, 32, 32, 3, 0.2, 40), "cnpf", False),
+        run_case(m, cfg, "train_b2_32x32", True, grid_inputs(2, 32, 32, 3, 0.3, 41), "cnpf", True),
+    ])
+
+    # ---------------- latent models ----------------
+    cfg = dict(family="GridConvLNP", x_dim=1, y_dim=3, n_z_samples_train=4, n_z_samples_test=3, init_seed=9)
+    m = build(cfg)
+    dump("gridconvlnp_default_y3", cfg, m, [
+        run_case(m, cfg, "train_b1_16x16_nz4", True, grid_inputs(1, 16, 16, 3, 0.3, 42), "nll", True),
+        run_case(m, cfg, "eval_b1_12x20_nz3", False, grid_inputs(1, 12, 20, 3, 0.3, 43), "nll", False),
+    ])
+    cfg = dict(family="GridConvLNP", x_dim=1, y_dim=3, notebook=True, n_z_samples_train=16, n_z_samples_test=32,
+               is_global=True, pretrained="celeba32/ConvLNP",
+               cnn=dict(dim=2, norm="bn", n_blocks=4, kernel_size=9, n_conv_layers=2))
+    m = build(cfg)
+    m.n_z_samples_test = 3
+    cfg["n_z_samples_test"] = 3
+    dump("gridconvlnp_notebook_pretrained", cfg, m, [
+        run_case(m, cfg, "eval_b1_24x24_nz3", False, grid_inputs(1, 24, 24, 3, 0.25, 44), "nll", False),
+    ])
+    cfg = dict(family="ConvLNP", x_dim=1, y_dim=1, n_z_samples_train=3, n_z_samples_test=2, init_seed=11)
+    m = build(cfg)
+    dump("convlnp_default", cfg, m, [
+        run_case(m, cfg, "train_b2_c10_t14_nz3", True, offgrid_inputs(2, 10, 14, 1, 45), "nll", True),
+        run_case(m, cfg, "eval_b1_nz2", False, offgrid_inputs(1, 6, 9, 1, 46), "nll", False),
+    ])
+    cfg = dict(family="ConvLNP", x_dim=1, y_dim=1, notebook=True, density_induced=64, n_z_samples_train=16,
+               n_z_samples_test=32, is_global=True, pretrained="RBF_Kernel/ConvLNP",
+               cnn=dict(dim=1, norm="bn", n_blocks=4, kernel_size=19, n_conv_layers=2))
+    m = build(cfg)
+    m.n_z_samples_test = 4
+    cfg["n_z_samples_test"] = 4
+    dump("convlnp_notebook_pretrained", cfg, m, [
+        run_case(m, cfg, "eval_b2_c20_t30_nz4", False, offgrid_inputs(2, 20, 30, 1, 47), "nll", False),
+    ])
+    cfg = dict(family="LNP", x_dim=1, y_dim=1, notebook=True, xy_hidden=128, n_z_samples_train=5, n_z_samples_test=4,
+               init_seed=13)  # NB: bare LNP(1,1) raises KeyError upstream (no default XYEncoder), so pass one
+    m = build(cfg)
+    dump("lnp_default", cfg, m, [
+        run_case(m, cfg, "train_b3_c8_t12_nz5", True, offgrid_inputs(3, 8, 12, 1, 48), "nll", True),
+    ])
+    cfg = dict(family="LNP", x_dim=1, y_dim=1, notebook=True, xy_hidden=128, n_z_samples_train=3, n_z_samples_test=4, init_seed=14,
+               is_q_zCct=True, encoded_path="both")
+    m = build(cfg)
+    dump("lnp_both_elbo", cfg, m, [
+        run_case(m, cfg, "train_b3_c8_t12_nz3_elbo", True, offgrid_inputs(3, 8, 12, 1, 49), "elbo", True),
+    ])
+
+
+def _xy2(B, C, T, y_dim, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, C + T, 2, generator=g) * 2 - 1
+    y = torch.sin(3 * x.sum(-1, keepdim=True)) + 0.1 * torch.randn(B, C + T, y_dim, generator=g)
+    return dict(X_cntxt=x[:, :C].contiguous(), Y_cntxt=y[:, :C].contiguous(), X_trgt=x[:, C:].contiguous(),
+                Y_trgt=y[:, C:].contiguous())
+
+
+if __name__ == "__main__":
+    main()
+    os.system(f"du -sh {OUT}")
