@@ -1,0 +1,232 @@
+/*
+ * npf_b200.h -- C ABI of libnpf_b200.so: the B200 (sm_100a) kernels behind the Neural-Process hot path.
+ *
+ * The reference (YannDubs/Neural-Process-Family) has no FFI: its operator boundary is the Python
+ * sub-module factory protocol (tier 2).  Each entry point below replaces the ATen
+ * op sequence of one reference function (cited as upstream file:line) and is what a binding of that
+ * function would call (see INTEGRATION.md for the ctypes stubs).
+ *
+ * Conventions (all entry points):
+ *   - C linkage, POD arguments only, no torch types.
+ *   - every pointer is a CALLER-OWNED DEVICE pointer to contiguous fp32 unless stated otherwise;
+ *     leading dimensions (ld*) are in elements.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  No allocation, no
+ *     synchronisation and no global mutable state inside => re-entrant per stream.
+ *   - returns 0 on success, a negative NPF_E* code otherwise; npf_last_error() gives the text
+ *     (thread-local).  Kernel launch errors are reported via cudaGetLastError() after the launch.
+ *   - "accumulate" outputs (weight / bias / theta gradients) are ADDED to: zero them first.
+ *   - fp32 storage everywhere.  `precision` selects the arithmetic of GEMM-shaped inner products:
+ *       NPF_PREC_FP32  : fp32 FFMA                                   (parity bar 1e-4 rel)
+ *       NPF_PREC_BF16  : bf16 tensor-core operands, fp32 accumulate   (parity bar 1e-2 rel)
+ *       NPF_PREC_BF16X3: 3-term split-bf16 tensor-core, fp32 accumulate (parity bar 1e-4 rel)
+ */
+#ifndef NPF_B200_H
+#define NPF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPF_ABI_VERSION 1
+
+/* error codes */
+#define NPF_OK 0
+#define NPF_EINVAL (-1)   /* bad argument (shape, alignment, null pointer)        */
+#define NPF_ECUDA (-2)    /* CUDA runtime / launch error                          */
+#define NPF_ENOTSUP (-3)  /* valid request this build does not implement          */
+
+/* precision of GEMM-shaped inner products */
+#define NPF_PREC_FP32 0
+#define NPF_PREC_BF16 1
+#define NPF_PREC_BF16X3 2
+
+/* flags */
+#define NPF_RELU_OUT 1   /* apply relu to the output                               */
+#define NPF_RELU_IN 2    /* apply relu to the (first / activation) input on load   */
+#define NPF_ACCUM 4      /* add to the output instead of overwriting it            */
+
+typedef void* npf_stream_t;
+
+#if defined(__GNUC__)
+#define NPF_API __attribute__((visibility("default")))
+#else
+#define NPF_API
+#endif
+
+NPF_API int npf_abi_version(void);
+NPF_API const char* npf_last_error(void);
+/* number of kernels launched by this library in the calling process so far (monotonic; for bench.py) */
+NPF_API unsigned long long npf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear layers  (nn.Linear inside MLP.forward, npf/architectures/mlp.py:95-109; SetConv resizer
+ * npf/architectures/setcnn.py:268; 1x1 "pointwise" convs of ResConvBlock, npf/architectures/cnn.py:214;
+ * Q/K/V projections npf/architectures/attention.py:472-474)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Y[M,N] = act_out( act_in(X)[M,K] . W[N,K]^T  (+ u[M] (x) w2[N])  + b[N] )
+ * b, u/w2 optional (NULL).  u (x) w2 is the rank-1 "density column" of SetConv's Linear(in+1 -> out). */
+NPF_API int npf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy,
+                   int M, int K, int N, int flags, const float* u, const float* w2, int ldw2, int precision,
+                   npf_stream_t stream);
+
+/* dX[M,K] = (dY[M,N] . W[N,K]) (.) (mask_src[M,K] > 0)      mask_src optional; NPF_ACCUM honoured.
+ * Chains of Linear->ReLU pass the PRE-activation gradient between layers: mask_src is the layer's own
+ * (post-relu) input. */
+NPF_API int npf_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int M, int K,
+                        int N, const float* mask_src, int ldm, int flags, int precision, npf_stream_t stream);
+
+/* dW[N,K] += dY[M,N]^T . act_in(X)[M,K] ;  db[N] += sum_m dY[m,:] ;  dw2[N*ldw2] += sum_m dY[m,:] u[m]
+ * db, u/dw2 optional. */
+NPF_API int npf_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db,
+                          int M, int K, int N, int flags, const float* u, float* dw2, int ldw2, int precision,
+                          npf_stream_t stream);
+
+/* dZ = dH (.) (H > 0)   (stand-alone ReLU backward, n elements) */
+NPF_API int npf_relu_bwd(const float* dH, const float* H, float* dZ, long n, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SetConv with the exponential-quadratic RBF  (SetConv.forward npf/architectures/setcnn.py:234-268,
+ * ExpRBF.forward :126-142).  x_dim == 1 (asserted upstream, :226).
+ *   sigma = 1e-5 + softplus(theta);  a_qk = -((x_q - x_k)/sigma)^2
+ *   feat[b,q,:] = sum_k softmax_k(a_qk) values[b,k,:]      dens[b,q] = sum_k exp(a_qk)
+ * keys [B,K] with batch stride key_bs (0 => one key set shared by all tasks, e.g. the induced grid);
+ * queries [B,Q] with batch stride qry_bs (0 => shared).  If keys_regular != 0 the keys are an
+ * increasing, uniformly spaced grid and the kernel only visits the run-time sigma-window of keys whose
+ * softmax weight is not below 2^-60 of the largest one (exact in fp32); otherwise all keys are visited.
+ * mstat[B,Q,2] receives (max logit, sum_k exp(a - max)) per query (saved for backward).
+ * ------------------------------------------------------------------------------------------------ */
+NPF_API int npf_setconv_fwd(const float* keys, long key_bs, const float* queries, long qry_bs, const float* values,
+                    const float* theta, float* feat, float* dens, float* mstat, int B, int K, int Q, int Cin,
+                    int keys_regular, npf_stream_t stream);
+
+/* Given dfeat[B,Q,Cin], ddens[B,Q]:  dvalues[B,K,Cin] (overwritten; may be NULL) and dtheta[1] (+=). */
+NPF_API int npf_setconv_bwd(const float* keys, long key_bs, const float* queries, long qry_bs, const float* values,
+                    const float* theta, const float* feat, const float* dens, const float* mstat,
+                    const float* dfeat, const float* ddens, float* dvalues, float* dtheta, int B, int K, int Q,
+                    int Cin, int keys_regular, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise convolution, channel-last, zero padding k/2  (depthwise half of make_depth_sep_conv,
+ * npf/utils/helpers.py:354-403, and conv2_depthwise of ResConvBlock.forward npf/architectures/cnn.py:204-215;
+ * the CNN wrapper's channel permutes :363-370 disappear because we stay channel-last).
+ *   Y[b,h,w,c] = sum_{i,j} Wt[c,i,j] * act(X)[b,h+i-kh/2,w+j-kw/2,c] + bias[c] (+ res[b,h,w,c])
+ *   act(x) = relu(pre_scale[c]*x + pre_shift[c])  if NPF_RELU_IN (pre_scale/shift optional = folded
+ *   BatchNorm affine of norm1/norm2), identity otherwise.   1-D signals: H = 1, kh = 1.
+ * ------------------------------------------------------------------------------------------------ */
+NPF_API int npf_dwconv_fwd(const float* X, const float* Wt, const float* bias, const float* res, float* Y, int B, int H,
+                   int Wd, int C, int kh, int kw, int flags, const float* pre_scale, const float* pre_shift,
+                   npf_stream_t stream);
+
+/* dX (overwritten, or += with NPF_ACCUM; NULL to skip), dWt[C,kh,kw] (+=), dbias[C] (+=).
+ * dX excludes the residual branch (its gradient is dY itself; the caller adds it).  If pre_scale is
+ * given, dX is the gradient w.r.t. X through the affine (i.e. multiplied by pre_scale[c]), and
+ * dpre_scale[C]/dpre_shift[C] (+=, optional) receive the affine's gradients. */
+NPF_API int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, float* dX, float* dWt, float* dbias, int B,
+                   int H, int Wd, int C, int kh, int kw, int flags, const float* pre_scale,
+                   const float* pre_shift, float* dpre_scale, float* dpre_shift, npf_stream_t stream);
+
+/* per-channel batch statistics of a channel-last tensor X[M,C]: sum[C] += sum_m x, sumsq[C] += sum_m x^2
+ * (train-mode BatchNorm of the notebook CNN configs; SURVEY.md 8e: these two vectors are what a
+ * multi-GPU run all-reduces). */
+NPF_API int npf_channel_stats(const float* X, float* sum, float* sumsq, long M, int C, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * On-grid context encoding  (GridConvCNP.cntxt_to_induced npf/neuralproc/gridconvnp.py:136-162 with the
+ * abs-weight depthwise conv of npf/utils/helpers.py:316-331)
+ *   sig = conv_|w|(Y * M), den = conv_|w|(M);   feat[b,h,w,:] = [sig / max(den, 1e-5) (y) ; den (y)]
+ * img [B,H,W,y] fp32, mask [B,H,W,mc] uint8 (mc = 1 or y), Wt [y,k,k] (raw weights; abs applied here).
+ * ------------------------------------------------------------------------------------------------ */
+NPF_API int npf_gridconv_in_fwd(const float* img, const uint8_t* mask, int mc, const float* Wt, float* feat, int B, int H,
+                        int Wd, int y, int k, npf_stream_t stream);
+/* dWt[y,k,k] += gradient through sig, den and abs(), given dfeat[B,H,W,2y] */
+NPF_API int npf_gridconv_in_bwd(const float* img, const uint8_t* mask, int mc, const float* Wt, const float* feat,
+                        const float* dfeat, float* dWt, int B, int H, int Wd, int y, int k, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sum-merge, pooling, normalisation glue
+ * ------------------------------------------------------------------------------------------------ */
+/* MergeFlatInputs sum-merge (npf/architectures/encoders.py:175-183) with the broadcasts of
+ * CNP.trgt_dependent_representation (npf/neuralproc/np.py:103-110):
+ *   out[z,b,t,:] = relu(x1[b,t,:] + x2[z,b,(x2_has_t ? t : 0),:])         x1 [B,T,C], x2 [Z,B,(T|1),C] */
+NPF_API int npf_merge_relu_fwd(const float* x1, const float* x2, float* out, int Z, int B, int T, int C, int x2_has_t,
+                       npf_stream_t stream);
+/* dx1[B,T,C] (overwritten; NULL to skip) = sum_z dpre, dx2 (overwritten) = (sum_t) dpre, dpre = dout (.) (out>0) */
+NPF_API int npf_merge_relu_bwd(const float* dout, const float* out, float* dx1, float* dx2, int Z, int B, int T, int C,
+                       int x2_has_t, npf_stream_t stream);
+
+/* mean over the middle axis: R[b,:] = mean_n X[b,n,:]  (CNP.encode_globally npf/neuralproc/np.py:95) */
+NPF_API int npf_mean_pool_fwd(const float* X, float* R, int B, int N, int C, npf_stream_t stream);
+/* dX[b,n,:] = dR[b,:] / N */
+NPF_API int npf_mean_pool_bwd(const float* dR, float* dX, int B, int N, int C, npf_stream_t stream);
+
+/* Y = LayerNorm(A + Bm) * gamma + beta over the last dim C, eps = 1e-5
+ * (TransformerAttender.forward npf/architectures/attention.py:585-586).  rstat[M,2] = (mean, rstd). */
+NPF_API int npf_add_layernorm_fwd(const float* A, const float* Bm, const float* gamma, const float* beta, float* Y,
+                          float* rstat, long M, int C, npf_stream_t stream);
+/* dS[M,C] = gradient w.r.t. the sum (A + Bm); dgamma[C], dbeta[C] (+=) */
+NPF_API int npf_add_layernorm_bwd(const float* dY, const float* A, const float* Bm, const float* gamma,
+                          const float* rstat, float* dS, float* dgamma, float* dbeta, long M, int C,
+                          npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-head scaled-dot cross-attention of targets over context
+ * (BaseAttender.forward / DotAttender.score npf/architectures/attention.py:129-156, 204-220; head split
+ * of MultiheadAttender :507-527: head h owns channels [h*D, (h+1)*D) -- no permute is materialised).
+ *   O[b,t,h,:] = sum_c softmax_c(Q[b,t,h,:].K[b,c,h,:] * scale) V[b,c,h,:]
+ * Q [B,Tq,H*D], K [B,Tk,H*D], V [B,Tk,H*Dv], O [B,Tq,H*Dv], LSE [B,H,Tq] (log-sum-exp, saved).
+ * The [Tq,Tk] logits are never written to memory.
+ * ------------------------------------------------------------------------------------------------ */
+NPF_API int npf_xattn_fwd(const float* Q, const float* K, const float* V, float* O, float* LSE, int B, int Tq, int Tk,
+                  int H, int D, int Dv, float scale, int precision, npf_stream_t stream);
+NPF_API int npf_xattn_bwd(const float* Q, const float* K, const float* V, const float* O, const float* LSE,
+                  const float* dO, float* dQ, float* dK, float* dV, int B, int Tq, int Tk, int H, int D, int Dv,
+                  float scale, int precision, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Predictive head and losses
+ * ------------------------------------------------------------------------------------------------ */
+/* NeuralProcessFamily.decode tail (npf/neuralproc/base.py:350-353, scale transform :116):
+ *   loc = suff[:, :y];  scale = min_scale + (1 - min_scale) * softplus(suff[:, y:])        suff [M,2y] */
+NPF_API int npf_gauss_head_fwd(const float* suff, float* loc, float* scale, long M, int y, float min_scale,
+                       npf_stream_t stream);
+NPF_API int npf_gauss_head_bwd(const float* suff, const float* dloc, const float* dscale, float* dsuff, long M, int y,
+                       float min_scale, npf_stream_t stream);
+
+/* sum_log_prob (npf/losses.py:18-24) of Independent(Normal(loc, scale)):
+ *   slp[z,b] = sum_{t,j} -log(scale) - 0.5 log(2 pi) - 0.5 ((Y - loc)/scale)^2
+ * loc/scale [Z,B,T*y] (T*y = n), Y [B,T*y] broadcast over z. */
+NPF_API int npf_gauss_nll_fwd(const float* loc, const float* scale, const float* Y, float* slp, int Z, int B, long n,
+                      npf_stream_t stream);
+/* dloc, dscale given g[z,b] = dLoss/dslp[z,b] */
+NPF_API int npf_gauss_nll_bwd(const float* loc, const float* scale, const float* Y, const float* g, float* dloc,
+                      float* dscale, int Z, int B, long n, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent path (LatentNeuralProcessFamily.infer_latent_dist / latent_path npf/neuralproc/base.py:495-547,
+ * scale transform :432; global latent of ConvLNP.add_global_latent npf/neuralproc/convnp.py:322-335)
+ * ------------------------------------------------------------------------------------------------ */
+/*   q_loc = suff[:, :zd];  q_scale = 0.1 + 0.9 sigmoid(suff[:, zd:]);  z[s,m,:] = q_loc + q_scale * eps[s,m,:]
+ * suff [M,2zd], eps/z [S,M,zd].  q_loc/q_scale [M,zd] are also written (they parameterise q(z|C)). */
+NPF_API int npf_latent_sample_fwd(const float* suff, const float* eps, float* q_loc, float* q_scale, float* z, int S,
+                          long M, int zd, npf_stream_t stream);
+/* dsuff[M,2zd] (overwritten) from dz[S,M,zd] plus optional direct grads dq_loc/dq_scale [M,zd] (e.g. KL) */
+NPF_API int npf_latent_sample_bwd(const float* suff, const float* eps, const float* dz, const float* dq_loc,
+                          const float* dq_scale, float* dsuff, int S, long M, int zd, npf_stream_t stream);
+/* out[n,p,:] = [ zin[n,p,:C/2] ; mean_p zin[n,p,C/2:] ]       zin/out [N,P,C] */
+NPF_API int npf_global_latent_fwd(const float* zin, float* out, int N, int P, int C, npf_stream_t stream);
+NPF_API int npf_global_latent_bwd(const float* dout, float* dzin, int N, int P, int C, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Input validation without a host sync  (NeuralProcessFamily._validate_inputs npf/neuralproc/base.py:241-247,
+ * isin_range npf/utils/helpers.py:55-57): flag[0] |= 1 if any x outside [lo, hi]  (flag is device int32)
+ * ------------------------------------------------------------------------------------------------ */
+NPF_API int npf_range_check(const float* X, long n, float lo, float hi, int* flag, npf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPF_B200_H */

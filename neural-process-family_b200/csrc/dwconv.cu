@@ -1,0 +1,424 @@
+// Channel-last depthwise convolution (1-D and 2-D) for the ResConvBlock stack
+// (upstream npf/architectures/cnn.py:204-215 conv2_depthwise / conv1.depthwise; npf/utils/helpers.py:354-403).
+//
+//   Y[b,h,w,c] = sum_{i,j} Wt[c,i,j] * act(X)[b,h+i-kh/2,w+j-kw/2,c] + bias[c] (+ res[b,h,w,c])
+//   act(x) = relu(scale[c]*x + shift[c])  (NPF_RELU_IN; scale/shift = folded BatchNorm affine, optional)
+//
+// One CTA stages a (TH+kh-1) x (TW+KW-1) x CT halo tile of act(X) and the CT channels' filters in shared memory;
+// a thread owns 4 channels x 8 consecutive outputs along w and slides over the input row in registers, so each
+// staged float4 is read once per filter row instead of once per tap.  The same kernel with flipped filters and a
+// relu-mask epilogue is the data gradient; the filter gradient kernel uses the mirrored register scheme.
+// KW is a compile-time (padded) filter width in {9, 11, 19}; narrower filters are centred and zero-padded.
+#include "common.cuh"
+
+namespace npf {
+
+struct DwParams {
+    const float* X;      // input (fwd: activations; bwd-data: dY)
+    const float* Wt;     // [C, kh, kw]
+    const float* bias;   // [C] or null
+    const float* res;    // residual added to the output, or null
+    float* Y;
+    const float* Xorig;  // bwd-data only: forward input, for the relu/affine mask
+    const float* scale;  // per-channel pre-activation affine (null = identity)
+    const float* shift;
+    float* dscale;       // bwd-data only (optional): gradients of the affine
+    float* dshift;
+    int H, Wd, C, kh, kw;
+    int TH, TW, CT;
+    int tiles_w;
+    int relu_in;  // apply act() while staging X
+    int flip;     // use spatially flipped filters (data gradient)
+    int mask;     // epilogue: multiply by act'(Xorig)
+    int accum;
+};
+
+__device__ __forceinline__ float4 f4_fma(const float4 a, const float4 b, const float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int CT = p.CT, CQ = CT >> 2;
+    const int rows = p.TH + p.kh - 1, cols = p.TW + KW - 1;
+    float4* Xs = reinterpret_cast<float4*>(smem);                 // [rows][cols][CQ]
+    float4* Ws = Xs + (size_t)rows * cols * CQ;                   // [kh][KW][CQ]
+
+    const int tile = blockIdx.x;
+    const int h0 = (tile / p.tiles_w) * p.TH, w0 = (tile % p.tiles_w) * p.TW;
+    const int c0 = blockIdx.y * CT;
+    const int b = blockIdx.z;
+    const int ph = p.kh / 2, pw = KW / 2, joff = (KW - p.kw) / 2;
+    const int nthr = blockDim.x * blockDim.y * blockDim.z;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const long img = (long)b * p.H * p.Wd;
+
+    // stage filters (centred in the padded width, optionally flipped)
+    for (int idx = tid; idx < p.kh * KW * CT; idx += nthr) {
+        const int c = idx % CT, j = (idx / CT) % KW, i = idx / (CT * KW);
+        float v = 0.f;
+        const int jr = j - joff;
+        if (jr >= 0 && jr < p.kw && c0 + c < p.C) {
+            const int ii = p.flip ? p.kh - 1 - i : i, jj = p.flip ? p.kw - 1 - jr : jr;
+            v = __ldg(p.Wt + ((long)(c0 + c) * p.kh + ii) * p.kw + jj);
+        }
+        reinterpret_cast<float*>(Ws)[((size_t)i * KW + j) * CT + c] = v;
+    }
+    // stage the halo tile of act(X); zero outside the image (padding applies to the activated signal)
+    for (int idx = tid; idx < rows * cols * CQ; idx += nthr) {
+        const int q = idx % CQ, col = (idx / CQ) % cols, r = idx / (CQ * cols);
+        const int gh = h0 + r - ph, gw = w0 + col - pw, c = c0 + 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.Wd && c < p.C) {
+            v = __ldg(reinterpret_cast<const float4*>(p.X + (img + (long)gh * p.Wd + gw) * p.C + c));
+            if (p.relu_in) {
+                if (p.scale) {
+                    const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+                    v = make_float4(fmaf(s.x, v.x, t.x), fmaf(s.y, v.y, t.y), fmaf(s.z, v.z, t.z), fmaf(s.w, v.w, t.w));
+                }
+                v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+            }
+        }
+        Xs[idx] = v;
+    }
+    __syncthreads();
+
+    const int q = threadIdx.x, s = threadIdx.y, r = threadIdx.z;
+    float4 acc[8];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) acc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int i = 0; i < p.kh; ++i) {
+        float4 wr[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) wr[j] = Ws[((size_t)i * KW + j) * CQ + q];
+        const float4* xrow = Xs + ((size_t)(r + i) * cols + s * 8) * CQ + q;
+#pragma unroll
+        for (int xc = 0; xc < KW + 7; ++xc) {
+            const float4 xv = xrow[(size_t)xc * CQ];
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+                const int j = xc - pp;
+                if (j >= 0 && j < KW) acc[pp] = f4_fma(wr[j], xv, acc[pp]);
+            }
+        }
+    }
+
+    const int c = c0 + 4 * q;
+    const int gh = h0 + r;
+    float4 ds = make_float4(0.f, 0.f, 0.f, 0.f), dt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < p.C && gh < p.H) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.mask && p.scale) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+            sh = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+        }
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            const int gw = w0 + s * 8 + pp;
+            if (gw >= p.Wd) continue;
+            const long off = (img + (long)gh * p.Wd + gw) * p.C + c;
+            float4 v = make_float4(acc[pp].x + bv.x, acc[pp].y + bv.y, acc[pp].z + bv.z, acc[pp].w + bv.w);
+            if (p.mask) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(p.Xorig + off));
+                const float4 pre = make_float4(fmaf(sc.x, x.x, sh.x), fmaf(sc.y, x.y, sh.y), fmaf(sc.z, x.z, sh.z), fmaf(sc.w, x.w, sh.w));
+                v.x = pre.x > 0.f ? v.x : 0.f; v.y = pre.y > 0.f ? v.y : 0.f;
+                v.z = pre.z > 0.f ? v.z : 0.f; v.w = pre.w > 0.f ? v.w : 0.f;
+                if (p.dscale) {
+                    dt.x += v.x; dt.y += v.y; dt.z += v.z; dt.w += v.w;
+                    ds = f4_fma(v, x, ds);
+                }
+                v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+            }
+            if (p.res) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + off));
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+            }
+            float4* out = reinterpret_cast<float4*>(p.Y + off);
+            if (p.accum) {
+                const float4 o = *out;
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *out = v;
+        }
+    }
+    if (p.mask && p.dscale) {
+        // block-reduce the affine gradients over (s, r) through shared memory (reuse the tile space), then atomics
+        __syncthreads();
+        float* red = smem;  // [2][CT]
+        for (int idx = tid; idx < 2 * CT; idx += nthr) red[idx] = 0.f;
+        __syncthreads();
+        if (c < p.C) {
+            atomicAdd(red + 4 * q + 0, ds.x); atomicAdd(red + 4 * q + 1, ds.y);
+            atomicAdd(red + 4 * q + 2, ds.z); atomicAdd(red + 4 * q + 3, ds.w);
+            atomicAdd(red + CT + 4 * q + 0, dt.x); atomicAdd(red + CT + 4 * q + 1, dt.y);
+            atomicAdd(red + CT + 4 * q + 2, dt.z); atomicAdd(red + CT + 4 * q + 3, dt.w);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < CT; idx += nthr) {
+            if (c0 + idx < p.C) {
+                atomicAdd(p.dscale + c0 + idx, red[idx]);
+                atomicAdd(p.dshift + c0 + idx, red[CT + idx]);
+            }
+        }
+    }
+}
+
+// Filter gradient: dWt[c,i,j] += sum_{b,h,w} dY[b,h,w,c] * act(X)[b,h+i-kh/2,w+j-kw/2,c]
+// block = (CT/4 channel quads, kh filter rows, NS strip lanes)
+template <int KW>
+__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(DwParams p, const float* __restrict__ dY, float* __restrict__ dWt) {
+    extern __shared__ __align__(16) float smem[];
+    const int CT = p.CT, CQ = CT >> 2;
+    const int rows = p.TH + p.kh - 1, cols = p.TW + KW - 1;
+    float4* Xs = reinterpret_cast<float4*>(smem);                  // [rows][cols][CQ]
+    float4* Gs = Xs + (size_t)rows * cols * CQ;                    // [TH][TW][CQ]
+    float* dWs = reinterpret_cast<float*>(Gs + (size_t)p.TH * p.TW * CQ);  // [kh][KW][CT]
+
+    const int tile = blockIdx.x;
+    const int h0 = (tile / p.tiles_w) * p.TH, w0 = (tile % p.tiles_w) * p.TW;
+    const int c0 = blockIdx.y * CT;
+    const int b = blockIdx.z;
+    const int ph = p.kh / 2, pw = KW / 2, joff = (KW - p.kw) / 2;
+    const int nthr = blockDim.x * blockDim.y * blockDim.z;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const long img = (long)b * p.H * p.Wd;
+
+    for (int idx = tid; idx < p.kh * KW * CT; idx += nthr) dWs[idx] = 0.f;
+    for (int idx = tid; idx < rows * cols * CQ; idx += nthr) {
+        const int q = idx % CQ, col = (idx / CQ) % cols, r = idx / (CQ * cols);
+        const int gh = h0 + r - ph, gw = w0 + col - pw, c = c0 + 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.Wd && c < p.C) {
+            v = __ldg(reinterpret_cast<const float4*>(p.X + (img + (long)gh * p.Wd + gw) * p.C + c));
+            if (p.relu_in) {
+                if (p.scale) {
+                    const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+                    v = make_float4(fmaf(s.x, v.x, t.x), fmaf(s.y, v.y, t.y), fmaf(s.z, v.z, t.z), fmaf(s.w, v.w, t.w));
+                }
+                v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+            }
+        }
+        Xs[idx] = v;
+    }
+    for (int idx = tid; idx < p.TH * p.TW * CQ; idx += nthr) {
+        const int q = idx % CQ, col = (idx / CQ) % p.TW, r = idx / (CQ * p.TW);
+        const int gh = h0 + r, gw = w0 + col, c = c0 + 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gh < p.H && gw < p.Wd && c < p.C)
+            v = __ldg(reinterpret_cast<const float4*>(dY + (img + (long)gh * p.Wd + gw) * p.C + c));
+        Gs[idx] = v;
+    }
+    __syncthreads();
+
+    const int q = threadIdx.x, i = threadIdx.y, ls = threadIdx.z, NS = blockDim.z;
+    float4 acc[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nstrips = p.TW >> 3;
+    for (int r = 0; r < p.TH; ++r) {
+        for (int st = ls; st < nstrips; st += NS) {
+            float4 dy[8];
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) dy[pp] = Gs[((size_t)r * p.TW + st * 8 + pp) * CQ + q];
+            const float4* xrow = Xs + ((size_t)(r + i) * cols + st * 8) * CQ + q;
+#pragma unroll
+            for (int xc = 0; xc < KW + 7; ++xc) {
+                const float4 xv = xrow[(size_t)xc * CQ];
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                    const int pp = xc - j;
+                    if (pp >= 0 && pp < 8) acc[j] = f4_fma(dy[pp], xv, acc[j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        float* d = dWs + ((size_t)i * KW + j) * CT + 4 * q;
+        atomicAdd(d + 0, acc[j].x); atomicAdd(d + 1, acc[j].y); atomicAdd(d + 2, acc[j].z); atomicAdd(d + 3, acc[j].w);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < p.kh * KW * CT; idx += nthr) {
+        const int c = idx % CT, j = (idx / CT) % KW, ii = idx / (CT * KW);
+        const int jr = j - joff;
+        if (jr >= 0 && jr < p.kw && c0 + c < p.C)
+            atomicAdd(dWt + ((long)(c0 + c) * p.kh + ii) * p.kw + jr, dWs[idx]);
+    }
+}
+
+// sum[c] += sum_m X[m,c] ; sumsq[c] += sum_m X[m,c]^2   (also used for the conv bias gradient with sumsq == null)
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ X, float* sum, float* sumsq, long M, int C,
+                                                            long rows_per_block) {
+    __shared__ float s1[8][33], s2[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + tx;
+    const long m0 = (long)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
+    float a = 0.f, b = 0.f;
+    if (c < C)
+        for (long m = m0 + ty; m < m1; m += 8) {
+            const float v = __ldg(X + m * C + c);
+            a += v;
+            b = fmaf(v, v, b);
+        }
+    s1[ty][tx] = a; s2[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { a += s1[i][tx]; b += s2[i][tx]; }
+        atomicAdd(sum + c, a);
+        if (sumsq) atomicAdd(sumsq + c, b);
+    }
+}
+
+static int pick_kw(int kw) { return kw <= 9 ? 9 : (kw <= 11 ? 11 : (kw <= 19 ? 19 : -1)); }
+
+static void pick_tiles(DwParams& p, dim3& block) {
+    if (p.H == 1) { p.TH = 1; p.TW = 64; p.CT = p.C >= 128 ? 128 : ((p.C + 3) / 4) * 4; }
+    else          { p.TH = 8; p.TW = 16; p.CT = p.C >= 32 ? 32 : ((p.C + 3) / 4) * 4; }
+    block = dim3(p.CT / 4, p.TW / 8, p.TH);
+    p.tiles_w = (int)cdiv(p.Wd, p.TW);
+}
+
+template <int KW>
+static int launch_dw(DwParams& p, int B, cudaStream_t st) {
+    dim3 block;
+    pick_tiles(p, block);
+    const size_t smem = ((size_t)(p.TH + p.kh - 1) * (p.TW + KW - 1) * p.CT + (size_t)p.kh * KW * p.CT) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dwconv_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) { set_error("dwconv: tile needs %zu B of shared memory", smem); return NPF_ENOTSUP; }
+    dim3 grid((unsigned)(p.tiles_w * cdiv(p.H, p.TH)), (unsigned)cdiv(p.C, p.CT), (unsigned)B);
+    dwconv_kernel<KW><<<grid, block, smem, st>>>(p);
+    count_launch();
+    return check_launch("dwconv_kernel");
+}
+
+template <int KW>
+static int launch_dw_wgrad(DwParams& p, const float* dY, float* dWt, int B, cudaStream_t st) {
+    dim3 block;
+    pick_tiles(p, block);
+    int ns = 256 / ((p.CT / 4) * p.kh);
+    if (ns < 1) ns = 1;
+    if (ns > p.TW / 8) ns = p.TW / 8;
+    block = dim3(p.CT / 4, p.kh, ns);
+    if (block.x * block.y * block.z > 256) { set_error("dwconv wgrad: kh=%d too large", p.kh); return NPF_ENOTSUP; }
+    const size_t smem = ((size_t)(p.TH + p.kh - 1) * (p.TW + KW - 1) * p.CT + (size_t)p.TH * p.TW * p.CT +
+                         (size_t)p.kh * KW * p.CT) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dwconv_wgrad_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) { set_error("dwconv wgrad: tile needs %zu B of shared memory", smem); return NPF_ENOTSUP; }
+    dim3 grid((unsigned)(p.tiles_w * cdiv(p.H, p.TH)), (unsigned)cdiv(p.C, p.CT), (unsigned)B);
+    dwconv_wgrad_kernel<KW><<<grid, block, smem, st>>>(p, dY, dWt);
+    count_launch();
+    return check_launch("dwconv_wgrad_kernel");
+}
+
+static int launch_stats(const float* X, float* sum, float* sumsq, long M, int C, cudaStream_t st) {
+    long rows_per_block = cdiv(M, 2L * kNumSMs);
+    if (rows_per_block < 64) rows_per_block = 64;
+    dim3 grid((unsigned)cdiv(M, rows_per_block), (unsigned)cdiv(C, 32));
+    channel_stats_kernel<<<grid, 256, 0, st>>>(X, sum, sumsq, M, C, rows_per_block);
+    count_launch();
+    return check_launch("channel_stats_kernel");
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace npf
+
+using namespace npf;
+
+
+extern "C" int npf_dwconv_fwd(const float* X, const float* Wt, const float* bias, const float* res, float* Y, int B,
+                              int H, int Wd, int C, int kh, int kw, int flags, const float* pre_scale,
+                              const float* pre_shift, npf_stream_t stream) {
+    NPF_REQUIRE(X && Wt && Y, "npf_dwconv_fwd: null pointer");
+    NPF_REQUIRE(B >= 0 && H >= 1 && Wd >= 1 && C >= 4 && C % 4 == 0, "npf_dwconv_fwd: bad shape (C must be a multiple of 4)");
+    NPF_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), "npf_dwconv_fwd: kernel sizes must be odd");
+    NPF_REQUIRE(H > 1 || kh == 1, "npf_dwconv_fwd: 1-D signals use H = 1, kh = 1");
+    NPF_REQUIRE((pre_scale == nullptr) == (pre_shift == nullptr), "npf_dwconv_fwd: scale and shift go together");
+    NPF_REQUIRE(aligned16(X) && aligned16(Y) && (!res || aligned16(res)) && (!bias || aligned16(bias)) &&
+                    (!pre_scale || (aligned16(pre_scale) && aligned16(pre_shift))),
+                "npf_dwconv_fwd: pointers must be 16-byte aligned");
+    NPF_REQUIRE(B <= 65535, "npf_dwconv_fwd: batch > 65535");
+    if (B == 0) return NPF_OK;
+    DwParams p{};
+    p.X = X; p.Wt = Wt; p.bias = bias; p.res = res; p.Y = Y;
+    p.scale = pre_scale; p.shift = pre_shift;
+    p.H = H; p.Wd = Wd; p.C = C; p.kh = kh; p.kw = kw;
+    p.relu_in = (flags & NPF_RELU_IN) ? 1 : 0;
+    p.accum = (flags & NPF_ACCUM) ? 1 : 0;
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    switch (pick_kw(kw)) {
+        case 9: rc = launch_dw<9>(p, B, st); break;
+        case 11: rc = launch_dw<11>(p, B, st); break;
+        case 19: rc = launch_dw<19>(p, B, st); break;
+        default: set_error("npf_dwconv_fwd: kernel width %d > 19", kw); return NPF_ENOTSUP;
+    }
+    return rc;
+}
+
+extern "C" int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, float* dX, float* dWt, float* dbias,
+                              int B, int H, int Wd, int C, int kh, int kw, int flags, const float* pre_scale,
+                              const float* pre_shift, float* dpre_scale, float* dpre_shift, npf_stream_t stream) {
+    NPF_REQUIRE(dY && X && Wt, "npf_dwconv_bwd: null pointer");
+    NPF_REQUIRE(B >= 0 && H >= 1 && Wd >= 1 && C >= 4 && C % 4 == 0, "npf_dwconv_bwd: bad shape");
+    NPF_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), "npf_dwconv_bwd: kernel sizes must be odd");
+    NPF_REQUIRE((pre_scale == nullptr) == (pre_shift == nullptr), "npf_dwconv_bwd: scale and shift go together");
+    NPF_REQUIRE((dpre_scale == nullptr) == (dpre_shift == nullptr), "npf_dwconv_bwd: dscale and dshift go together");
+    NPF_REQUIRE(!dpre_scale || (pre_scale && dX), "npf_dwconv_bwd: affine gradients need the affine and dX");
+    NPF_REQUIRE(aligned16(dY) && aligned16(X) && (!dX || aligned16(dX)), "npf_dwconv_bwd: pointers must be 16-byte aligned");
+    NPF_REQUIRE(B <= 65535, "npf_dwconv_bwd: batch > 65535");
+    if (B == 0) return NPF_OK;
+    cudaStream_t st = as_stream(stream);
+    const int relu_in = (flags & NPF_RELU_IN) ? 1 : 0;
+    int rc = NPF_OK;
+    const int kwsel = pick_kw(kw);
+    if (kwsel < 0) { set_error("npf_dwconv_bwd: kernel width %d > 19", kw); return NPF_ENOTSUP; }
+    if (dX) {
+        DwParams p{};
+        p.X = dY; p.Wt = Wt; p.Y = dX; p.Xorig = X;
+        p.scale = pre_scale; p.shift = pre_shift; p.dscale = dpre_scale; p.dshift = dpre_shift;
+        p.H = H; p.Wd = Wd; p.C = C; p.kh = kh; p.kw = kw;
+        p.relu_in = 0; p.flip = 1; p.mask = relu_in; p.accum = (flags & NPF_ACCUM) ? 1 : 0;
+        switch (kwsel) {
+            case 9: rc = launch_dw<9>(p, B, st); break;
+            case 11: rc = launch_dw<11>(p, B, st); break;
+            default: rc = launch_dw<19>(p, B, st); break;
+        }
+        if (rc != NPF_OK) return rc;
+    }
+    if (dWt) {
+        DwParams p{};
+        p.X = X; p.scale = pre_scale; p.shift = pre_shift;
+        p.H = H; p.Wd = Wd; p.C = C; p.kh = kh; p.kw = kw; p.relu_in = relu_in;
+        switch (kwsel) {
+            case 9: rc = launch_dw_wgrad<9>(p, dY, dWt, B, st); break;
+            case 11: rc = launch_dw_wgrad<11>(p, dY, dWt, B, st); break;
+            default: rc = launch_dw_wgrad<19>(p, dY, dWt, B, st); break;
+        }
+        if (rc != NPF_OK) return rc;
+    }
+    if (dbias) rc = launch_stats(dY, dbias, nullptr, (long)B * H * Wd, C, st);
+    return rc;
+}
+
+extern "C" int npf_channel_stats(const float* X, float* sum, float* sumsq, long M, int C, npf_stream_t stream) {
+    NPF_REQUIRE(X && sum, "npf_channel_stats: null pointer");
+    NPF_REQUIRE(M >= 0 && C >= 1, "npf_channel_stats: bad shape");
+    if (M == 0) return NPF_OK;
+    return launch_stats(X, sum, sumsq, M, C, as_stream(stream));
+}
