@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- tasks/sec of one meta-batch forward + loss + backward (the BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--precision P]
+
+Default workload = BASELINE.json configs[1]: ConvCNP(1,1) default constructor (I=384 induced points, 3 ResConvBlocks
+k=11), meta-batch 256 tasks PER GPU, 128 context / 128 target points, fp32 storage, synthetic data (random-init
+weights under seed 0, X ~ U(-1,1), Y ~ N(0,1)).  Weak scaling: every rank processes its own 256 tasks; for N > 1 the
+flat gradient is all-reduced (NCCL) inside the timed region.  One JSON line on stdout (rank 0).
+
+`--impl reference` times the reference algorithm's CPU path (the oracle port, torch CPU ops on all host threads) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "neural-process-family_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (family, ctor kwargs, B per GPU, C, T, loss, description)
+    "convcnp1d_b256_c128_t128": dict(family="ConvCNP", B=256, C=128, T=128, loss="cnpf",
+                                     desc="BASELINE configs[1]: ConvCNP 1D default ctor, batch 256, 128 ctx / 128 tgt"),
+    "cnp_b16_c32_t64": dict(family="CNP", B=16, C=32, T=64, loss="cnpf", desc="BASELINE configs[0]: CNP toy"),
+    "attncnp_b64_c512_t512": dict(family="AttnCNP", B=64, C=512, T=512, loss="cnpf",
+                                  desc="BASELINE configs[2]: AttnCNP transformer attention 512 ctx / 512 tgt"),
+    "gridconvcnp_b128_32x32": dict(family="GridConvCNP", B=128, C=0, T=0, loss="cnpf",
+                                   desc="BASELINE configs[3]: GridConvCNP 32x32x3, 128 images per GPU"),
+    "gridconvlnp_b64_32x32_nz16": dict(family="GridConvLNP", B=64, C=0, T=0, loss="nll",
+                                       desc="BASELINE configs[4]: GridConvLNP 32x32x3, 16 z samples, 64 images per GPU"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def make_model(family):
+    import npf_b200
+    from functools import partial
+    from npf_b200.architectures import MLP, merge_flat_input
+    torch.manual_seed(0)
+    if family == "ConvCNP":
+        return npf_b200.ConvCNP(1, 1)
+    if family == "CNP":
+        return npf_b200.CNP(1, 1)
+    if family == "AttnCNP":
+        return npf_b200.AttnCNP(1, 1, attention="transformer", XYEncoder=merge_flat_input(
+            partial(MLP, n_hidden_layers=2, hidden_size=128), is_sum_merge=True))
+    if family == "GridConvCNP":
+        return npf_b200.GridConvCNP(1, 3)
+    if family == "GridConvLNP":
+        return npf_b200.GridConvLNP(1, 3, n_z_samples_train=16, is_q_zCct=False)
+    raise ValueError(family)
+
+
+def make_inputs(wl, B, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    if wl["family"].startswith("Grid"):
+        img = torch.rand(B, 32, 32, 3, generator=g)
+        mask = torch.zeros(B, 1024, dtype=torch.bool)
+        for b in range(B):
+            mask[b, torch.randperm(1024, generator=g)[:307]] = True
+        t = dict(X_cntxt=mask.view(B, 32, 32, 1), Y_cntxt=img, X_trgt=torch.ones(B, 32, 32, 1, dtype=torch.bool),
+                 Y_trgt=img.clone())
+    else:
+        C, T = wl["C"], wl["T"]
+        t = dict(X_cntxt=torch.rand(B, C, 1, generator=g) * 2 - 1, Y_cntxt=torch.randn(B, C, 1, generator=g),
+                 X_trgt=torch.rand(B, T, 1, generator=g) * 2 - 1, Y_trgt=torch.randn(B, T, 1, generator=g))
+    if pin:
+        t = {k: v.pin_memory() for k, v in t.items()}
+    return {k: v.to(device) for k, v in t.items()} if device != "cpu" else t
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        mhz = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        return dict(sm_mhz=mhz[len(mhz) // 2] if mhz else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    samples=len(mhz))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_timing(wl, steps, warmup, budget_s=25.0):
+    """The reference algorithm on host cores: oracle port (torch CPU, all threads), fwd + loss + bwd, bounded sample."""
+    from oracle import npf_oracle as O
+    import _util
+    torch.set_num_threads(os.cpu_count() or 1)
+    fam = wl["family"]
+    model = make_model(fam)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    Bc = {"ConvCNP": 8, "CNP": wl["B"], "AttnCNP": 4, "GridConvCNP": 8, "GridConvLNP": 2}[fam]
+    inp = make_inputs(wl, Bc, seed=1)
+    cfg = dict(family=fam, attention="transformer")
+    eps = None
+    if fam == "GridConvLNP":
+        eps = torch.randn(16, Bc, 32, 32, 128)
+    case = dict(inputs=inp, training=True, loss_name=wl["loss"], eps=eps)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        sdd = {k: v for k, v in sd.items()}
+        Xc, Yc, Xt, Yt = inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"]
+        if fam == "ConvCNP":
+            loc, scale = O.convcnp_forward(sdd, Xc, Yc, Xt)
+        elif fam == "CNP":
+            loc, scale = O.cnp_forward(sdd, Xc, Yc, Xt)
+        elif fam == "AttnCNP":
+            loc, scale = O.attncnp_forward(sdd, Xc, Yc, Xt, attention="transformer")
+        elif fam == "GridConvCNP":
+            loc, scale = O.gridconvcnp_forward(sdd, Xc, Yc)
+        else:
+            loc, scale, *_ = O.gridconvlnp_forward(sdd, Xc, Yc, eps)
+        loss = O.cnpf_loss(loc, scale, Yt) if wl["loss"] == "cnpf" else O.nll_lnpf_loss(loc, scale, Yt)
+        loss.backward()
+
+    t0 = time.perf_counter()
+    step()
+    one = time.perf_counter() - t0
+    w = max(1, min(warmup, int(3.0 / max(one, 1e-3))))
+    for _ in range(w - 1):
+        step()
+    k = max(1, min(steps, int(budget_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    dt = (time.perf_counter() - t0) / k
+    return dict(value=Bc / dt, unit="tasks/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{k} steps of {Bc} tasks ({fam}, same C/T as the GPU workload) in {dt * k:.1f}s; oracle/npf_oracle.py "
+                       f"(torch CPU restatement of the reference op sequence)"), dt * 1e3, k, w
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="convcnp1d_b256_c128_t128", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-times", action="store_true", help="print the per-kernel CUDA-event breakdown to stderr")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = dict(workload=args.workload, description=wl["desc"], tasks_per_gpu=wl["B"], global_batch=wl["B"] * max(world, 1),
+               n_cntxt=wl["C"], n_trgt=wl["T"], parallelism=f"dp{max(world, 1)} (tasks sharded, flat-gradient all-reduce)",
+               l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, ms, k, w = cpu_reference_timing(wl, args.steps, args.warmup)
+        line = dict(impl="reference", metric="tasks/sec (meta-batch fwd+bwd)", value=cb["value"], unit="tasks/s",
+                    n_gpus=args.gpus, steps=k, warmup=w, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic", config=cfg, cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit="tasks/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    import npf_b200
+    from npf_b200 import ops
+    from npf_b200.parallel import FlatGradients
+    from _cfg import loss_for
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    npf_b200.set_precision(args.precision)
+    model = make_model(wl["family"]).to(dev).train()
+    crit = loss_for(wl["loss"], reduction="mean").train()
+    flat = FlatGradients(model, process_group=None if world == 1 else dist.group.WORLD)
+    B = wl["B"]
+    n_sets = 4
+    dev_inputs = [make_inputs(wl, B, seed=100 * rank + i, device=dev) for i in range(n_sets)]
+    host_inputs = [make_inputs(wl, B, seed=100 * rank + i, pin=True) for i in range(n_sets)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+    def step(inp):
+        flat.zero_()
+        out = model(inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"])
+        loss = crit(out, inp["Y_trgt"])
+        loss.backward()
+        flat.all_reduce_mean()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(dev_inputs[i % n_sets])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM, CUDA events around every step, L2 flushed between steps ------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n0 = ops.launch_count()
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        evs[i][0].record()
+        step(dev_inputs[i % n_sets])
+        evs[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = ops.launch_count() - n0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end through the public API from pinned host buffers --------------------------------
+    for i in range(3):
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host_inputs[i % n_sets].items()}
+        float(step(inp).item())
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host_inputs[i % n_sets].items()}
+        float(step(inp).item())  # device -> host read of the step's loss
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    h2d = sum(v.numel() * v.element_size() for v in host_inputs[0].values())
+
+    # ---- per-kernel CUDA-event breakdown (separate instrumented steps; events on the launching stream) --------------
+    from npf_b200 import _cabi
+    _cabi.enable_timing(True)
+    for i in range(min(args.steps, 10)):
+        flush.fill_(0.0)
+        step(dev_inputs[i % n_sets])
+    torch.cuda.synchronize()
+    ktimes = _cabi.collect_timing()  # name -> (total_ms, calls)
+    _cabi.enable_timing(False)
+    n_prof = min(args.steps, 10)
+
+    tot = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(tot[0]), float(tot[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    tasks = B * world * args.steps
+    value = tasks / (dev_ms * 1e-3)
+    peaks = measured_peaks()
+    roof = roofline(wl, ktimes, n_prof, B, peaks)
+    line = dict(metric="tasks/sec (meta-batch fwd+bwd)", value=value, unit="tasks/s", n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype={"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (fp32-equivalent)"}[args.precision],
+                data="synthetic", config=cfg, clocks=clocks,
+                e2e=dict(value=tasks / (e2e_ms * 1e-3), unit="tasks/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+                gpu_launches=launches, wall_ms_per_step=t_wall * 1e3 / args.steps, roofline=roof,
+                kernel_ms_per_step={k: round(v[0] / n_prof, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])})
+    if not args.no_cpu_baseline:
+        cb, _, _, _ = cpu_reference_timing(wl, 10, 2)
+        line["cpu_baseline"] = cb
+    if args.kernel_times:
+        for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
+            print(f"  {k:28s} {v[0] / n_prof:9.4f} ms/step  {v[1] // n_prof:4d} calls/step", file=sys.stderr)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def roofline(wl, ktimes, n_prof, B, peaks):
+    """Roofline of the dominant kernel group from the live CUDA-event breakdown.  Algorithmic bytes / flops per task are
+    SURVEY.md section 8(d)'s figures (stated in DESIGN.md)."""
+    if not ktimes:
+        return None
+    name = max(ktimes, key=lambda k: ktimes[k][0])
+    total_ms, calls = ktimes[name]
+    ms_per_launch = total_ms / max(calls, 1)
+    r = 128
+    out = dict(kernel=name, launches_per_step=calls // n_prof, avg_launch_ms=ms_per_launch,
+               share_of_step=total_ms / sum(v[0] for v in ktimes.values()), peak_source=peaks["source"], traffic=None)
+    if name.startswith("npf_linear"):
+        # dominant 128x128 layers: 2*M*K*N flops per launch; M = rows per launch varies, so use the step total
+        flops_step = gemm_flops_per_step(wl, B)
+        ach = flops_step / (total_ms / n_prof * 1e-3) / 1e12
+        out.update(bound="tensor", achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"],
+                   note="all npf_linear_* launches of one step: algorithmic GEMM flops / their summed CUDA-event time; "
+                        "fp32 FFMA path vs the measured bf16 tensor peak")
+    elif name.startswith("npf_setconv"):
+        I = 384
+        bytes_task = 4 * (I * r + wl["T"] * 1 + wl["T"] * r)
+        ach = bytes_task * B / (ms_per_launch * 1e-3) / 1e9
+        out.update(bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                   note="algorithmic bytes 4*(I*r + T*x + T*r) per task (induced->target direction)")
+    else:
+        out.update(bound="hbm", achieved=None, peak=peaks["hbm_gbs"], unit="GB/s", frac=None)
+    return out
+
+
+def gemm_flops_per_step(wl, B):
+    r, fam = 128, wl["family"]
+    if fam == "ConvCNP":
+        I, T = 384, wl["T"]
+        fwd = 3 * 2 * I * r * r + 2 * I * 2 * r + 2 * T * (r + 1) * r + 4 * 2 * T * r * r + 2 * T * r * 2
+        return 3 * fwd * B
+    return 0
+
+
+if __name__ == "__main__":
+    main()

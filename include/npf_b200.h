@@ -129,10 +129,15 @@ NPF_API int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, flo
                    int H, int Wd, int C, int kh, int kw, int flags, const float* pre_scale,
                    const float* pre_shift, float* dpre_scale, float* dpre_shift, npf_stream_t stream);
 
-/* per-channel batch statistics of a channel-last tensor X[M,C]: sum[C] += sum_m x, sumsq[C] += sum_m x^2
- * (train-mode BatchNorm of the notebook CNN configs; SURVEY.md 8e: these two vectors are what a
- * multi-GPU run all-reduces). */
-NPF_API int npf_channel_stats(const float* X, float* sum, float* sumsq, long M, int C, npf_stream_t stream);
+/* per-channel batch statistics of a channel-last tensor X[M,C] (train-mode BatchNorm of the notebook CNN
+ * configs, two-pass like ATen: first the mean, then the centred second moment):
+ *   sum[C] += sum_m (x - center[c]) ;  sumsq[C] += sum_m (x - center[c])^2      center optional (NULL = 0)
+ * these vectors are what a multi-GPU run would all-reduce for synchronised BatchNorm. */
+NPF_API int npf_channel_stats(const float* X, const float* center, float* sum, float* sumsq, long M, int C,
+                      npf_stream_t stream);
+/* Y[m,c] (+)= a[c] * X[m,c] + b[c]   (BatchNorm backward through the batch statistics) */
+NPF_API int npf_channel_affine(const float* X, const float* a, const float* b, float* Y, long M, int C, int accumulate,
+                       npf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * On-grid context encoding  (GridConvCNP.cntxt_to_induced npf/neuralproc/gridconvnp.py:136-162 with the

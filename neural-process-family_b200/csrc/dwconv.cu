@@ -253,25 +253,27 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(DwParams p, const flo
 }
 
 // sum[c] += sum_m X[m,c] ; sumsq[c] += sum_m X[m,c]^2   (also used for the conv bias gradient with sumsq == null)
-__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ X, float* sum, float* sumsq, long M, int C,
-                                                            long rows_per_block) {
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ X, const float* __restrict__ center, float* sum,
+                                                            float* sumsq, long M, int C, long rows_per_block) {
     __shared__ float s1[8][33], s2[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.y * 32 + tx;
     const long m0 = (long)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
     float a = 0.f, b = 0.f;
-    if (c < C)
+    if (c < C) {
+        const float ctr = center ? __ldg(center + c) : 0.f;
         for (long m = m0 + ty; m < m1; m += 8) {
-            const float v = __ldg(X + m * C + c);
+            const float v = __ldg(X + m * C + c) - ctr;
             a += v;
             b = fmaf(v, v, b);
         }
+    }
     s1[ty][tx] = a; s2[ty][tx] = b;
     __syncthreads();
     if (ty == 0 && c < C) {
 #pragma unroll
         for (int i = 1; i < 8; ++i) { a += s1[i][tx]; b += s2[i][tx]; }
-        atomicAdd(sum + c, a);
+        if (sum) atomicAdd(sum + c, a);
         if (sumsq) atomicAdd(sumsq + c, b);
     }
 }
@@ -325,11 +327,21 @@ static int launch_dw_wgrad(DwParams& p, const float* dY, float* dWt, int B, cuda
     return check_launch("dwconv_wgrad_kernel");
 }
 
-static int launch_stats(const float* X, float* sum, float* sumsq, long M, int C, cudaStream_t st) {
+// Y[m,c] (+)= a[c] * X[m,c] + b[c]
+__global__ void channel_affine_kernel(const float* __restrict__ X, const float* __restrict__ a, const float* __restrict__ b,
+                                      float* __restrict__ Y, long n, int C, int accumulate) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const float v = fmaf(__ldg(a + c), __ldg(X + i), __ldg(b + c));
+        Y[i] = accumulate ? Y[i] + v : v;
+    }
+}
+
+static int launch_stats(const float* X, const float* center, float* sum, float* sumsq, long M, int C, cudaStream_t st) {
     long rows_per_block = cdiv(M, 2L * kNumSMs);
     if (rows_per_block < 64) rows_per_block = 64;
     dim3 grid((unsigned)cdiv(M, rows_per_block), (unsigned)cdiv(C, 32));
-    channel_stats_kernel<<<grid, 256, 0, st>>>(X, sum, sumsq, M, C, rows_per_block);
+    channel_stats_kernel<<<grid, 256, 0, st>>>(X, center, sum, sumsq, M, C, rows_per_block);
     count_launch();
     return check_launch("channel_stats_kernel");
 }
@@ -412,13 +424,27 @@ extern "C" int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, 
         }
         if (rc != NPF_OK) return rc;
     }
-    if (dbias) rc = launch_stats(dY, dbias, nullptr, (long)B * H * Wd, C, st);
+    if (dbias) rc = launch_stats(dY, nullptr, dbias, nullptr, (long)B * H * Wd, C, st);
     return rc;
 }
 
-extern "C" int npf_channel_stats(const float* X, float* sum, float* sumsq, long M, int C, npf_stream_t stream) {
-    NPF_REQUIRE(X && sum, "npf_channel_stats: null pointer");
+extern "C" int npf_channel_stats(const float* X, const float* center, float* sum, float* sumsq, long M, int C,
+                                 npf_stream_t stream) {
+    NPF_REQUIRE(X && (sum || sumsq), "npf_channel_stats: null pointer");
     NPF_REQUIRE(M >= 0 && C >= 1, "npf_channel_stats: bad shape");
     if (M == 0) return NPF_OK;
-    return launch_stats(X, sum, sumsq, M, C, as_stream(stream));
+    return launch_stats(X, center, sum, sumsq, M, C, as_stream(stream));
+}
+
+extern "C" int npf_channel_affine(const float* X, const float* a, const float* b, float* Y, long M, int C, int accumulate,
+                                  npf_stream_t stream) {
+    NPF_REQUIRE(X && a && b && Y, "npf_channel_affine: null pointer");
+    NPF_REQUIRE(M >= 0 && C >= 1, "npf_channel_affine: bad shape");
+    const long n = M * C;
+    if (n == 0) return NPF_OK;
+    long blocks = cdiv(n, 256);
+    if (blocks > 16L * kNumSMs) blocks = 16L * kNumSMs;
+    channel_affine_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(X, a, b, Y, n, C, accumulate);
+    count_launch();
+    return check_launch("channel_affine_kernel");
 }

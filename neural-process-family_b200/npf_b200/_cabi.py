@@ -1,0 +1,130 @@
+"""ctypes binding of libnpf_b200.so (the C ABI declared in include/npf_b200.h).
+
+The library is loaded lazily on the first kernel call so that module construction, ``state_dict``
+handling and the other host-side logic can be exercised on a machine without a GPU.  There is NO
+fallback: if the shared library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_long, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnpf_b200.so")
+
+# error codes / flags (mirror include/npf_b200.h)
+NPF_OK, NPF_EINVAL, NPF_ECUDA, NPF_ENOTSUP = 0, -1, -2, -3
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+RELU_OUT, RELU_IN, ACCUM = 1, 2, 4
+
+P, I, L, F = c_void_p, c_int, c_long, c_float
+
+# name -> argtypes; every entry returns int except the three bookkeeping calls
+SIGNATURES = {
+    "npf_linear_fwd": [P, I, P, I, P, P, I, I, I, I, I, P, P, I, I, P],
+    "npf_linear_bwd_data": [P, I, P, I, P, I, I, I, I, P, I, I, I, P],
+    "npf_linear_bwd_weight": [P, I, P, I, P, I, P, I, I, I, I, P, P, I, I, P],
+    "npf_relu_bwd": [P, P, P, L, P],
+    "npf_setconv_fwd": [P, L, P, L, P, P, P, P, P, I, I, I, I, I, P],
+    "npf_setconv_bwd": [P, L, P, L, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
+    "npf_dwconv_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P],
+    "npf_dwconv_bwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
+    "npf_channel_stats": [P, P, P, P, L, I, P],
+    "npf_channel_affine": [P, P, P, P, L, I, I, P],
+    "npf_gridconv_in_fwd": [P, P, I, P, P, I, I, I, I, I, P],
+    "npf_gridconv_in_bwd": [P, P, I, P, P, P, P, I, I, I, I, I, P],
+    "npf_merge_relu_fwd": [P, P, P, I, I, I, I, I, P],
+    "npf_merge_relu_bwd": [P, P, P, P, I, I, I, I, I, P],
+    "npf_mean_pool_fwd": [P, P, I, I, I, P],
+    "npf_mean_pool_bwd": [P, P, I, I, I, P],
+    "npf_add_layernorm_fwd": [P, P, P, P, P, P, L, I, P],
+    "npf_add_layernorm_bwd": [P, P, P, P, P, P, P, P, L, I, P],
+    "npf_xattn_fwd": [P, P, P, P, P, I, I, I, I, I, I, F, I, P],
+    "npf_xattn_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, P],
+    "npf_gauss_head_fwd": [P, P, P, L, I, F, P],
+    "npf_gauss_head_bwd": [P, P, P, P, L, I, F, P],
+    "npf_gauss_nll_fwd": [P, P, P, P, I, I, L, P],
+    "npf_gauss_nll_bwd": [P, P, P, P, P, P, I, I, L, P],
+    "npf_latent_sample_fwd": [P, P, P, P, P, I, L, I, P],
+    "npf_latent_sample_bwd": [P, P, P, P, P, P, I, L, I, P],
+    "npf_global_latent_fwd": [P, P, I, I, I, P],
+    "npf_global_latent_bwd": [P, P, I, I, I, P],
+    "npf_range_check": [P, L, F, F, P, P],
+}
+BOOKKEEPING = {
+    "npf_abi_version": (c_int, []),
+    "npf_last_error": (c_char_p, []),
+    "npf_launch_count": (c_ulonglong, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises RuntimeError if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"npf_b200: CUDA extension not built ({LIB_PATH} missing). Run `python __graft_entry__.py build` "
+            "(or `make -C neural-process-family_b200/csrc`). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    for name, (restype, argtypes) in BOOKKEEPING.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    if lib.npf_abi_version() != 1:
+        raise RuntimeError(f"npf_b200: ABI version mismatch ({lib.npf_abi_version()} != 1)")
+    _lib = lib
+    return lib
+
+
+_timing = None  # name -> list of (start_event, end_event) when enabled
+
+
+def enable_timing(on):
+    """Per-entry-point CUDA-event timing on the launching stream (bench.py's kernel breakdown / roofline)."""
+    global _timing
+    _timing = {} if on else None
+
+
+def collect_timing():
+    """name -> (total_ms, n_calls); synchronises.  Clears the log."""
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in (_timing or {}).items():
+        out[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+    if _timing is not None:
+        _timing.clear()
+    return out
+
+
+def call(name, *args):
+    """Invoke an entry point; raise on a non-zero return code (ValueError for NPF_EINVAL)."""
+    lib = load()
+    if _timing is not None:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        _timing.setdefault(name, []).append((a, b))
+    else:
+        rc = getattr(lib, name)(*args)
+    if rc != NPF_OK:
+        msg = lib.npf_last_error().decode("utf-8", "replace")
+        if rc == NPF_EINVAL:
+            raise ValueError(f"{name}: {msg}")
+        if rc == NPF_ENOTSUP:
+            raise NotImplementedError(f"{name}: {msg}")
+        raise RuntimeError(f"{name} failed (rc={rc}): {msg}")
+
+
+def launch_count():
+    return int(load().npf_launch_count())

@@ -1,0 +1,5 @@
+from .attention import *
+from .cnn import *
+from .encoders import *
+from .mlp import *
+from .setcnn import *

@@ -1,0 +1,582 @@
+"""torch.autograd.Functions over the C ABI of libnpf_b200.so.
+
+PyTorch is used for device memory (torch.empty / zeros from the caching allocator), the current CUDA stream
+and autograd bookkeeping; every arithmetic op on the hot path is a kernel of the library.  All tensors are
+fp32, contiguous, on a CUDA device.  No CPU fallback: calling an op with CPU tensors raises.
+"""
+import torch
+
+from . import _cabi
+from ._cabi import ACCUM, RELU_IN, RELU_OUT, call
+
+__all__ = [
+    "set_precision", "get_precision", "linear", "mlp_chain", "setconv", "dwconv", "channel_moments",
+    "merge_relu", "mean_pool", "add_layernorm", "xattn", "gauss_head", "gauss_sum_log_prob", "latent_sample",
+    "global_latent", "gridconv_in", "range_flag", "launch_count",
+]
+
+_PRECISION = {"fp32": _cabi.PREC_FP32, "bf16": _cabi.PREC_BF16, "bf16x3": _cabi.PREC_BF16X3}
+_precision = _cabi.PREC_FP32
+
+
+def set_precision(name):
+    """'fp32' (FFMA, 1e-4 parity), 'bf16' (tensor cores, 1e-2 parity) or 'bf16x3' (split-bf16 tensor cores)."""
+    global _precision
+    _precision = _PRECISION[name]
+
+
+def get_precision():
+    return {v: k for k, v in _PRECISION.items()}[_precision]
+
+
+def launch_count():
+    return _cabi.launch_count()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("npf_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if t.dtype != torch.float32 and t.dtype != torch.uint8 and t.dtype != torch.bool and t.dtype != torch.int32:
+            raise TypeError(f"npf_b200 kernels take fp32 tensors, got {t.dtype}")
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ======================================================================================================
+# Linear / MLP chain
+# ======================================================================================================
+def _lin_fwd(x2, W, b, N, K, flags=0, ldw=None, u=None, w2_ptr=None, ldw2=0):
+    M = x2.shape[0]
+    y = torch.empty(M, N, device=x2.device, dtype=torch.float32)
+    call("npf_linear_fwd", _p(x2), x2.stride(0) if M else K, _p(W) if not isinstance(W, int) else W, ldw or K, _p(b),
+         _p(y), N, M, K, N, flags, _p(u), w2_ptr, ldw2, _precision, _stream())
+    return y
+
+
+def _lin_bwd_data(dz, W_ptr, ldw, M, K, N, mask=None, out=None, accumulate=False):
+    dx = out if out is not None else torch.empty(M, K, device=dz.device, dtype=torch.float32)
+    call("npf_linear_bwd_data", _p(dz), N, W_ptr, ldw, _p(dx), K, M, K, N, _p(mask), K if mask is not None else 0,
+         ACCUM if accumulate else 0, _precision, _stream())
+    return dx
+
+
+def _lin_bwd_weight(dz, x2, dW_ptr, lddw, db, M, K, N, flags=0, u=None, dw2_ptr=None, ldw2=0):
+    call("npf_linear_bwd_weight", _p(dz), N, _p(x2), K, dW_ptr, lddw, _p(db), M, K, N, flags, _p(u), dw2_ptr, ldw2,
+         _precision, _stream())
+
+
+class _MLPChain(torch.autograd.Function):
+    """y = L_n(relu(L_{n-1}(... relu(L_1(x))))) with every L_i an nn.Linear (bias optional); optionally a final
+    relu.  Saves the post-relu activations; the backward passes the pre-activation gradient from layer to layer
+    with the relu mask fused into the data-gradient GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, final_relu, has_bias, *params):
+        _chk(x, *params)
+        n_layers = len(params) // 2 if has_bias else len(params)
+        Ws = params[:n_layers]
+        bs = params[n_layers:] if has_bias else (None,) * n_layers
+        lead = x.shape[:-1]
+        h = _c(x).reshape(-1, x.shape[-1])
+        acts = [h]
+        for i, (W, b) in enumerate(zip(Ws, bs)):
+            last = i == n_layers - 1
+            flags = RELU_OUT if (not last or final_relu) else 0
+            h = _lin_fwd(h, _c(W), None if b is None else _c(b), W.shape[0], W.shape[1], flags)
+            acts.append(h)
+        ctx.save_for_backward(*acts, *Ws)
+        ctx.n_layers, ctx.final_relu, ctx.has_bias = n_layers, final_relu, has_bias
+        ctx.x_shape = x.shape
+        return h.reshape(*lead, Ws[-1].shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        n = ctx.n_layers
+        saved = ctx.saved_tensors
+        acts, Ws = saved[: n + 1], saved[n + 1:]
+        M = acts[0].shape[0]
+        dz = _c(dy).reshape(M, -1)
+        if ctx.final_relu:
+            dzm = torch.empty_like(dz)
+            call("npf_relu_bwd", _p(dz), _p(acts[n]), _p(dzm), dz.numel(), _stream())
+            dz = dzm
+        dWs, dbs = [None] * n, [None] * n
+        dx = None
+        for i in range(n - 1, -1, -1):
+            W = _c(Ws[i])
+            N, K = W.shape
+            dW = torch.zeros_like(W)
+            db = torch.zeros(N, device=W.device, dtype=torch.float32) if ctx.has_bias else None
+            if M > 0:
+                _lin_bwd_weight(dz, acts[i], _p(dW), K, db, M, K, N)
+            dWs[i], dbs[i] = dW, db
+            if i > 0:
+                dz = _lin_bwd_data(dz, _p(W), K, M, K, N, mask=acts[i])
+            elif ctx.needs_input_grad[0]:
+                dx = _lin_bwd_data(dz, _p(W), K, M, K, N).reshape(ctx.x_shape)
+        grads = tuple(dWs) + (tuple(dbs) if ctx.has_bias else ())
+        return (dx, None, None) + grads
+
+
+def mlp_chain(x, weights, biases, final_relu=False):
+    """weights: list of [out,in] tensors; biases: list of [out] tensors or None (all or none)."""
+    has_bias = biases is not None and biases[0] is not None
+    params = tuple(weights) + (tuple(biases) if has_bias else ())
+    return _MLPChain.apply(x, final_relu, has_bias, *params)
+
+
+def linear(x, weight, bias=None, relu=False):
+    return mlp_chain(x, [weight], None if bias is None else [bias], final_relu=relu)
+
+
+# ======================================================================================================
+# SetConv
+# ======================================================================================================
+class _SetConv(torch.autograd.Function):
+    """out = Linear([ sum_k softmax_k(a) v_k ; sum_k exp(a) ]) with the exp-quadratic RBF.  The density column of the
+    Linear is applied as a rank-1 epilogue term, so the [.., C+1] concatenation never exists."""
+
+    @staticmethod
+    def forward(ctx, keys, queries, values, theta, W, b, keys_regular):
+        _chk(keys, queries, values, theta, W, b)
+        B, K, C = values.shape
+        Q = queries.shape[-1]  # queries: [B,Q] per task or [Q] shared; keys likewise
+        keys, queries, values = _c(keys), _c(queries), _c(values)
+        key_bs = 0 if keys.dim() == 1 else K
+        qry_bs = 0 if queries.dim() == 1 else Q
+        dev = values.device
+        feat = torch.empty(B, Q, C, device=dev, dtype=torch.float32)
+        dens = torch.empty(B, Q, device=dev, dtype=torch.float32)
+        mstat = torch.empty(B, Q, 2, device=dev, dtype=torch.float32)
+        call("npf_setconv_fwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat), _p(dens),
+             _p(mstat), B, K, Q, C, int(keys_regular), _stream())
+        W = _c(W)
+        N = W.shape[0]
+        out = torch.empty(B, Q, N, device=dev, dtype=torch.float32)
+        if B * Q > 0:
+            call("npf_linear_fwd", _p(feat), C, _p(W), C + 1, _p(b), _p(out), N, B * Q, C, N, 0, _p(dens),
+                 W.data_ptr() + 4 * C, C + 1, _precision, _stream())
+        ctx.save_for_backward(keys, queries, values, theta, W, feat, dens, mstat)
+        ctx.dims = (B, K, Q, C, N, key_bs, qry_bs, int(keys_regular))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        keys, queries, values, theta, W, feat, dens, mstat = ctx.saved_tensors
+        B, K, Q, C, N, key_bs, qry_bs, regular = ctx.dims
+        dev = values.device
+        dout = _c(dout).reshape(B * Q, N)
+        M = B * Q
+        dW = torch.zeros_like(W)
+        db = torch.zeros(N, device=dev, dtype=torch.float32)
+        dtheta = torch.zeros_like(theta)
+        dvalues = None
+        if M > 0:
+            _lin_bwd_weight(dout, feat, _p(dW), C + 1, db, M, C, N, u=dens, dw2_ptr=dW.data_ptr() + 4 * C, ldw2=C + 1)
+            dfeat = _lin_bwd_data(dout, _p(W), C + 1, M, C, N)
+            ddens = _lin_bwd_data(dout, W.data_ptr() + 4 * C, C + 1, M, 1, N)
+            if ctx.needs_input_grad[2]:
+                dvalues = torch.empty_like(values)
+            call("npf_setconv_bwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat), _p(dens),
+                 _p(mstat), _p(dfeat), _p(ddens), _p(dvalues), _p(dtheta), B, K, Q, C, regular, _stream())
+        elif ctx.needs_input_grad[2]:
+            dvalues = torch.zeros_like(values)
+        return None, None, dvalues, dtheta, dW, db, None
+
+
+def setconv(keys, queries, values, theta, weight, bias, keys_regular=False):
+    """keys [B,K,1] or shared [K]; queries [B,Q,1] or shared [Q]; values [B,K,C]; weight [N, C+1]; -> [B,Q,N]."""
+    if keys.dim() == 3:
+        keys = keys.squeeze(-1)
+    if queries.dim() == 3:
+        queries = queries.squeeze(-1)
+    return _SetConv.apply(keys, queries, values, theta, weight, bias, keys_regular)
+
+
+# ======================================================================================================
+# Depthwise conv (+ folded pre-activation affine) and batch statistics
+# ======================================================================================================
+class _DWConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Wt, bias, res, relu_in, scale, shift):
+        _chk(x, Wt, bias, res, scale, shift)
+        x = _c(x)
+        B, C = x.shape[0], x.shape[-1]
+        if x.dim() == 3:
+            H, Wd = 1, x.shape[1]
+            kh, kw = 1, Wt.shape[-1]
+        else:
+            H, Wd = x.shape[1], x.shape[2]
+            kh, kw = Wt.shape[-2], Wt.shape[-1]
+        Wt = _c(Wt)
+        y = torch.empty_like(x)
+        res_c = None if res is None else _c(res)
+        call("npf_dwconv_fwd", _p(x), _p(Wt), _p(bias), _p(res_c), _p(y), B, H, Wd, C, kh, kw,
+             RELU_IN if relu_in else 0, _p(scale), _p(shift), _stream())
+        ctx.save_for_backward(x, Wt, scale, shift)
+        ctx.cfg = (B, H, Wd, C, kh, kw, relu_in, bias is not None, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wt, scale, shift = ctx.saved_tensors
+        B, H, Wd, C, kh, kw, relu_in, has_bias, has_res = ctx.cfg
+        dy = _c(dy)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dW = torch.zeros_like(Wt)
+        db = torch.zeros(C, device=x.device, dtype=torch.float32) if has_bias else None
+        need_aff = scale is not None and (ctx.needs_input_grad[5] or ctx.needs_input_grad[6])
+        dscale = torch.zeros_like(scale) if need_aff else None
+        dshift = torch.zeros_like(shift) if need_aff else None
+        if need_aff and dx is None:
+            dx = torch.empty_like(x)
+        call("npf_dwconv_bwd", _p(dy), _p(x), _p(Wt), _p(dx), _p(dW), _p(db), B, H, Wd, C, kh, kw,
+             RELU_IN if relu_in else 0, _p(scale), _p(shift), _p(dscale), _p(dshift), _stream())
+        return (dx if ctx.needs_input_grad[0] else None, dW, db, dy if has_res else None, None, dscale, dshift)
+
+
+def dwconv(x, weight, bias=None, res=None, relu_in=False, scale=None, shift=None):
+    """Channel-last depthwise conv.  x [B,L,C] (1-D) or [B,H,W,C] (2-D); weight [C,1,k] / [C,1,k,k]."""
+    return _DWConv.apply(x, weight, bias, res, relu_in, scale, shift)
+
+
+class _ChannelMoments(torch.autograd.Function):
+    """mean[c], biased var[c] of a channel-last tensor (two passes, like ATen's batch_norm statistics)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _chk(x)
+        x = _c(x)
+        C = x.shape[-1]
+        M = x.numel() // C
+        s = torch.zeros(C, device=x.device, dtype=torch.float32)
+        call("npf_channel_stats", _p(x), None, _p(s), None, M, C, _stream())
+        mean = s / M
+        q = torch.zeros(C, device=x.device, dtype=torch.float32)
+        call("npf_channel_stats", _p(x), _p(mean), None, _p(q), M, C, _stream())
+        var = q / M
+        ctx.save_for_backward(x, mean)
+        ctx.M = M
+        return mean, var
+
+    @staticmethod
+    def backward(ctx, dmean, dvar):
+        x, mean = ctx.saved_tensors
+        M = ctx.M
+        a = (2.0 / M) * dvar
+        b = dmean / M - a * mean
+        dx = torch.empty_like(x)
+        call("npf_channel_affine", _p(x), _p(_c(a)), _p(_c(b)), _p(dx), M, x.shape[-1], 0, _stream())
+        return dx
+
+
+def channel_moments(x):
+    return _ChannelMoments.apply(x)
+
+
+# ======================================================================================================
+# sum-merge / pooling / layernorm
+# ======================================================================================================
+class _MergeRelu(torch.autograd.Function):
+    """out[z,b,t,:] = relu(x1[b,t,:] + x2[z,b,(t|0),:])"""
+
+    @staticmethod
+    def forward(ctx, x1, x2, x2_has_t):
+        _chk(x1, x2)
+        x1, x2 = _c(x1), _c(x2)
+        B, T, C = x1.shape
+        Z = x2.shape[0]
+        out = torch.empty(Z, B, T, C, device=x1.device, dtype=torch.float32)
+        call("npf_merge_relu_fwd", _p(x1), _p(x2), _p(out), Z, B, T, C, int(x2_has_t), _stream())
+        ctx.save_for_backward(out)
+        ctx.cfg = (Z, B, T, C, int(x2_has_t), x2.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        Z, B, T, C, has_t, x2_shape = ctx.cfg
+        dout = _c(dout)
+        dx1 = torch.empty(B, T, C, device=out.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        dx2 = torch.empty(x2_shape, device=out.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        call("npf_merge_relu_bwd", _p(dout), _p(out), _p(dx1), _p(dx2), Z, B, T, C, has_t, _stream())
+        return dx1, dx2, None
+
+
+def merge_relu(x1, x2):
+    """x1 [B,T,C]; x2 [B,T,C] | [Z,B,T,C] | [Z,B,1,C]  ->  [B,T,C] (if x2 is 3-D) else [Z,B,T,C]."""
+    squeeze = x2.dim() == 3
+    if squeeze:
+        x2 = x2.unsqueeze(0)
+    has_t = x2.shape[2] == x1.shape[1] and not (x2.shape[2] == 1 and x1.shape[1] != 1)
+    out = _MergeRelu.apply(x1, x2, has_t)
+    return out.squeeze(0) if squeeze else out
+
+
+class _MeanPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _chk(x)
+        x = _c(x)
+        B, N, C = x.shape
+        r = torch.empty(B, 1, C, device=x.device, dtype=torch.float32)
+        call("npf_mean_pool_fwd", _p(x), _p(r), B, N, C, _stream())
+        ctx.cfg = (B, N, C)
+        return r
+
+    @staticmethod
+    def backward(ctx, dr):
+        B, N, C = ctx.cfg
+        dx = torch.empty(B, N, C, device=dr.device, dtype=torch.float32)
+        call("npf_mean_pool_bwd", _p(_c(dr)), _p(dx), B, N, C, _stream())
+        return dx
+
+
+def mean_pool(x):
+    """[B,N,C] -> [B,1,C] mean over the set axis."""
+    return _MeanPool.apply(x)
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta):
+        _chk(a, b, gamma, beta)
+        a, b = _c(a), _c(b)
+        C = a.shape[-1]
+        M = a.numel() // C
+        y = torch.empty_like(a)
+        rstat = torch.empty(M, 2, device=a.device, dtype=torch.float32)
+        call("npf_add_layernorm_fwd", _p(a), _p(b), _p(gamma), _p(beta), _p(y), _p(rstat), M, C, _stream())
+        ctx.save_for_backward(a, b, gamma, rstat)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b, gamma, rstat = ctx.saved_tensors
+        C = a.shape[-1]
+        M = a.numel() // C
+        ds = torch.empty_like(a)
+        dg = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        call("npf_add_layernorm_bwd", _p(_c(dy)), _p(a), _p(b), _p(gamma), _p(rstat), _p(ds), _p(dg), _p(dbeta), M, C,
+             _stream())
+        return ds, ds, dg, dbeta
+
+
+def add_layernorm(a, b, gamma, beta):
+    """LayerNorm(a + b) over the last dim (eps 1e-5, affine)."""
+    return _AddLayerNorm.apply(a, b, gamma, beta)
+
+
+# ======================================================================================================
+# attention
+# ======================================================================================================
+class _XAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, n_heads, scale):
+        _chk(q, k, v)
+        q, k, v = _c(q), _c(k), _c(v)
+        B, Tq, E = q.shape
+        Tk = k.shape[1]
+        Ev = v.shape[2]
+        D, Dv = E // n_heads, Ev // n_heads
+        o = torch.empty(B, Tq, Ev, device=q.device, dtype=torch.float32)
+        lse = torch.empty(B, n_heads, Tq, device=q.device, dtype=torch.float32)
+        call("npf_xattn_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, Tq, Tk, n_heads, D, Dv, float(scale), _precision,
+             _stream())
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.cfg = (B, Tq, Tk, n_heads, D, Dv, float(scale))
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        B, Tq, Tk, H, D, Dv, scale = ctx.cfg
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        call("npf_xattn_bwd", _p(q), _p(k), _p(v), _p(o), _p(lse), _p(_c(do)), _p(dq), _p(dk), _p(dv), B, Tq, Tk, H, D, Dv,
+             scale, _precision, _stream())
+        return dq, dk, dv, None, None
+
+
+def xattn(q, k, v, n_heads, scale):
+    """softmax(q k^T * scale) v per head; head h = channels [h*D, (h+1)*D).  q [B,Tq,E], k [B,Tk,E], v [B,Tk,Ev]."""
+    return _XAttn.apply(q, k, v, n_heads, scale)
+
+
+# ======================================================================================================
+# predictive head / log-likelihood
+# ======================================================================================================
+class _GaussHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, suff, min_scale):
+        _chk(suff)
+        suff = _c(suff)
+        y = suff.shape[-1] // 2
+        M = suff.numel() // (2 * y)
+        loc = torch.empty(*suff.shape[:-1], y, device=suff.device, dtype=torch.float32)
+        scale = torch.empty_like(loc)
+        call("npf_gauss_head_fwd", _p(suff), _p(loc), _p(scale), M, y, float(min_scale), _stream())
+        ctx.save_for_backward(suff)
+        ctx.cfg = (M, y, float(min_scale))
+        return loc, scale
+
+    @staticmethod
+    def backward(ctx, dloc, dscale):
+        (suff,) = ctx.saved_tensors
+        M, y, min_scale = ctx.cfg
+        dsuff = torch.empty_like(suff)
+        call("npf_gauss_head_bwd", _p(suff), _p(None if dloc is None else _c(dloc)), _p(None if dscale is None else _c(dscale)),
+             _p(dsuff), M, y, min_scale, _stream())
+        return dsuff, None
+
+
+def gauss_head(suff, min_scale=0.01):
+    """suff [..., 2y] -> loc [..., y], scale = min_scale + (1 - min_scale) softplus(.) [..., y]."""
+    return _GaussHead.apply(suff, min_scale)
+
+
+class _GaussSLP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loc, scale, Y):
+        _chk(loc, scale, Y)
+        loc, scale, Y = _c(loc), _c(scale), _c(Y)
+        Z, B = loc.shape[0], loc.shape[1]
+        n = loc.numel() // max(Z * B, 1) if Z * B > 0 else 0
+        slp = torch.empty(Z, B, device=loc.device, dtype=torch.float32)
+        call("npf_gauss_nll_fwd", _p(loc), _p(scale), _p(Y), _p(slp), Z, B, n, _stream())
+        ctx.save_for_backward(loc, scale, Y)
+        ctx.cfg = (Z, B, n)
+        return slp
+
+    @staticmethod
+    def backward(ctx, g):
+        loc, scale, Y = ctx.saved_tensors
+        Z, B, n = ctx.cfg
+        dloc, dscale = torch.empty_like(loc), torch.empty_like(scale)
+        call("npf_gauss_nll_bwd", _p(loc), _p(scale), _p(Y), _p(_c(g)), _p(dloc), _p(dscale), Z, B, n, _stream())
+        return dloc, dscale, None
+
+
+def gauss_sum_log_prob(loc, scale, Y):
+    """sum over targets and y of log N(Y; loc, scale):  loc/scale [Z,B,*,y], Y [B,*,y] -> [Z,B]."""
+    return _GaussSLP.apply(loc, scale, Y)
+
+
+# ======================================================================================================
+# latent path
+# ======================================================================================================
+class _LatentSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, suff, eps):
+        _chk(suff, eps)
+        suff, eps = _c(suff), _c(eps)
+        zd = suff.shape[-1] // 2
+        M = suff.numel() // (2 * zd)
+        S = eps.shape[0]
+        q_loc = torch.empty(*suff.shape[:-1], zd, device=suff.device, dtype=torch.float32)
+        q_scale = torch.empty_like(q_loc)
+        z = torch.empty_like(eps)
+        call("npf_latent_sample_fwd", _p(suff), _p(eps), _p(q_loc), _p(q_scale), _p(z), S, M, zd, _stream())
+        ctx.save_for_backward(suff, eps)
+        ctx.cfg = (S, M, zd)
+        return q_loc, q_scale, z
+
+    @staticmethod
+    def backward(ctx, dq_loc, dq_scale, dz):
+        suff, eps = ctx.saved_tensors
+        S, M, zd = ctx.cfg
+        dsuff = torch.empty_like(suff)
+        call("npf_latent_sample_bwd", _p(suff), _p(eps), _p(None if dz is None else _c(dz)),
+             _p(None if dq_loc is None else _c(dq_loc)), _p(None if dq_scale is None else _c(dq_scale)), _p(dsuff), S, M,
+             zd, _stream())
+        return dsuff, None
+
+
+def latent_sample(suff, eps):
+    """suff [*lat, 2z], eps [S, *lat, z] -> (q_loc, q_scale [*lat, z], z [S, *lat, z]); q_scale = 0.1 + 0.9 sigmoid."""
+    return _LatentSample.apply(suff, eps)
+
+
+class _GlobalLatent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        _chk(z)
+        z = _c(z)
+        N, C = z.shape[0], z.shape[-1]
+        P = z.numel() // (N * C)
+        out = torch.empty_like(z)
+        call("npf_global_latent_fwd", _p(z), _p(out), N, P, C, _stream())
+        ctx.cfg = (N, P, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, P, C = ctx.cfg
+        dout = _c(dout)
+        dz = torch.empty_like(dout)
+        call("npf_global_latent_bwd", _p(dout), _p(dz), N, P, C, _stream())
+        return dz
+
+
+def global_latent(z):
+    """[N, *spatial, C]: second half of the channels replaced by its mean over all spatial positions."""
+    return _GlobalLatent.apply(z)
+
+
+# ======================================================================================================
+# on-grid context encoding
+# ======================================================================================================
+class _GridConvIn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, mask_u8, Wt):
+        _chk(img, mask_u8, Wt)
+        img, mask_u8, Wt = _c(img), _c(mask_u8), _c(Wt)
+        B, H, Wd, y = img.shape
+        k = Wt.shape[-1]
+        feat = torch.empty(B, H, Wd, 2 * y, device=img.device, dtype=torch.float32)
+        call("npf_gridconv_in_fwd", _p(img), _p(mask_u8), mask_u8.shape[-1], _p(Wt), _p(feat), B, H, Wd, y, k, _stream())
+        ctx.save_for_backward(img, mask_u8, Wt, feat)
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        img, mask_u8, Wt, feat = ctx.saved_tensors
+        B, H, Wd, y = img.shape
+        k = Wt.shape[-1]
+        dW = torch.zeros_like(Wt)
+        call("npf_gridconv_in_bwd", _p(img), _p(mask_u8), mask_u8.shape[-1], _p(Wt), _p(feat), _p(_c(dfeat)), _p(dW), B, H,
+             Wd, y, k, _stream())
+        return None, None, dW
+
+
+def gridconv_in(img, mask, weight):
+    """img [B,H,W,y] fp32, mask [B,H,W,1|y] bool/uint8, weight [y,1,k,k] (abs applied inside) -> [B,H,W,2y]."""
+    if mask.dtype != torch.uint8:
+        mask = mask.to(torch.uint8)
+    return _GridConvIn.apply(img, mask, weight)
+
+
+# ======================================================================================================
+# input validation
+# ======================================================================================================
+def range_flag(flag, *tensors, lo=-1.0, hi=1.0):
+    """OR into the device int32 ``flag`` whether any element of the tensors lies outside [lo, hi] (no sync)."""
+    for t in tensors:
+        if t.numel() == 0:
+            continue
+        _chk(t)
+        t = _c(t)
+        call("npf_range_check", _p(t), t.numel(), float(lo), float(hi), _p(flag), _stream())

@@ -1,0 +1,62 @@
+"""Data parallelism over tasks: every rank owns a contiguous shard of the meta-batch and a replica of the parameters;
+the only exchange is ONE all-reduce of a flat fp32 gradient buffer per step.
+
+``FlatGradients`` allocates one contiguous buffer and makes every ``p.grad`` a view into it, so the backward kernels'
+results land in the bucket directly and the collective is a single NCCL call (0.5-2 MB: latency-bound on NVLink 5 /
+NVSwitch).  Works with any ``torch.distributed`` backend (``gloo`` on CPU for the host-logic tests)."""
+import torch
+import torch.distributed as dist
+
+__all__ = ["FlatGradients", "shard_tasks"]
+
+
+class FlatGradients:
+    def __init__(self, module, process_group=None):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.group = process_group
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._attach()
+
+    def _attach(self):
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        """Zero the bucket (one memset) and re-attach the views if an optimizer dropped them."""
+        self.flat.zero_()
+        if any(p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or
+               p.grad.data_ptr() >= self.flat.data_ptr() + 4 * max(self.flat.numel(), 1) for p in self.params[:1]):
+            self._attach()
+
+    @property
+    def world_size(self):
+        if self.group is None and not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
+    def all_reduce_mean(self):
+        """grad <- mean over ranks of the per-rank (local-batch-mean) gradients: equals the gradient of the global
+        batch mean for equal shards.  No-op on a single rank."""
+        w = self.world_size
+        if w == 1:
+            return self.flat
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.mul_(1.0 / w)
+        return self.flat
+
+
+def shard_tasks(batch, rank, world_size):
+    """Contiguous split of the task axis: rank g gets tasks [g*B/G, (g+1)*B/G).  ``batch`` is a dict of tensors whose
+    first axis is the task axis; B must be divisible by the world size."""
+    out = {}
+    for k, v in batch.items():
+        B = v.shape[0]
+        if B % world_size:
+            raise ValueError(f"meta-batch {B} is not divisible by world size {world_size}")
+        s = B // world_size
+        out[k] = v[rank * s: (rank + 1) * s]
+    return out

@@ -1,0 +1,110 @@
+"""CPU-only (-m "not gpu") checks of the host side: the C-ABI library loads and exports exactly what include/npf_b200.h
+declares, the module trees keep the reference's state_dict keys / parameter counts, constructor error behaviour."""
+import ctypes
+import os
+import re
+from functools import partial
+
+import pytest
+import torch
+import torch.nn as nn
+
+from _cfg import build_model
+from _util import ROOT, fixture_names, load_fixture
+
+import npf_b200
+from npf_b200 import _cabi
+from npf_b200.architectures import CNN, MLP, ResConvBlock, SetConv, get_attender, merge_flat_input
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "npf_b200.h")).read()
+    return set(re.findall(r"NPF_API\s+[\w\s\*]+?\b(npf_\w+)\s*\(", src))
+
+
+def test_cabi_exports_every_declared_symbol():
+    declared = _header_symbols()
+    assert len(declared) >= 30
+    assert os.path.exists(_cabi.LIB_PATH), "libnpf_b200.so not built (run `python __graft_entry__.py build`)"
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in npf_b200.h but not exported"
+    bound = set(_cabi.SIGNATURES) | set(_cabi.BOOKKEEPING)
+    assert bound == declared, f"ctypes table and header disagree: {bound ^ declared}"
+    lib.npf_abi_version.restype = ctypes.c_int
+    assert lib.npf_abi_version() == 1
+
+
+def test_cabi_argument_validation_without_gpu():
+    """Entry points validate their arguments before touching CUDA: callable on a CPU box."""
+    lib = _cabi.load()
+    rc = lib.npf_linear_fwd(None, 1, None, 1, None, None, 1, 4, 4, 4, 0, None, None, 0, 0, None)
+    assert rc == _cabi.NPF_EINVAL
+    assert b"null pointer" in lib.npf_last_error()
+    with pytest.raises(ValueError):
+        _cabi.call("npf_mean_pool_fwd", 1, 1, 2, 0, 8, None)  # N == 0
+
+
+@pytest.mark.parametrize("name", fixture_names())
+def test_state_dict_keys_and_param_counts(name):
+    fx = load_fixture(name)
+    model = build_model(fx["cfg"])
+    missing_unexpected = model.load_state_dict(fx["state_dict"], strict=True)
+    assert not missing_unexpected.missing_keys and not missing_unexpected.unexpected_keys
+    assert sum(p.numel() for p in model.parameters()) == fx["n_params"]
+    assert list(model.state_dict().keys()) == list(fx["state_dict"].keys())  # same order as the reference
+
+
+def test_notebook_param_counts():
+    """Exact structural check against the counts printed by the upstream notebooks."""
+    R = 128
+    counts = {
+        "cnp_notebook_pretrained": 252098, "attncnp_transformer_pretrained": 252738,
+        "convcnp_notebook_pretrained": 276612, "gridconvcnp_notebook_pretrained": 340721,
+        "convlnp_notebook_pretrained": 376068, "gridconvlnp_notebook_pretrained": 487793,
+        "cnp_default": 169922, "attncnp_scaledot": 169922, "convcnp_default": 137476, "gridconvcnp_default_y1": 163195,
+    }
+    for name, n in counts.items():
+        model = build_model(load_fixture(name)["cfg"])
+        assert sum(p.numel() for p in model.parameters()) == n, name
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(ValueError):
+        npf_b200.CNP(1, 1, encoded_path="nonsense")
+    with pytest.raises(ValueError):
+        get_attender("not-an-attention", 128, 128, 128)
+    with pytest.raises(AssertionError):
+        SetConv(2, 1, 128)  # x_dim != 1, as upstream setcnn.py:226
+    with pytest.raises(AssertionError):
+        get_attender("multihead", 100, 100, 100, n_heads=8)  # head divisibility, upstream attention.py:442
+    with pytest.raises(AssertionError):
+        npf_b200.CNPFLoss()((None, None, object(), None), torch.zeros(1))  # q_zCc must be None, upstream losses.py:116
+    with pytest.raises(NotImplementedError):
+        MLP(4, 4, activation=nn.Tanh())
+
+
+def test_model_attributes_and_extrapolation_grid():
+    m = npf_b200.ConvCNP(1, 1)
+    assert (m.x_dim, m.y_dim, m.r_dim, m.n_induced, m.density_induced) == (1, 1, 128, 384, 128)
+    assert torch.allclose(m.X_induced, torch.linspace(-1.5, 1.5, 384))
+    m.set_extrapolation((-2, 2))
+    assert m.n_induced == int(128 * 5) and abs(float(m.X_induced[0]) + 2.5) < 1e-6
+    lm = npf_b200.GridConvLNP(1, 3, n_z_samples_train=16)
+    assert isinstance(lm, npf_b200.neuralproc.LatentNeuralProcessFamily) and isinstance(lm, npf_b200.GridConvCNP)
+    assert lm.n_z_samples_train == 16 and lm.z_dim == 128
+
+
+def test_no_cpu_fallback():
+    m = npf_b200.CNP(1, 1).eval()
+    with pytest.raises(RuntimeError):
+        m(torch.rand(2, 3, 1), torch.rand(2, 3, 1), torch.rand(2, 4, 1))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "neural-process-family_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
