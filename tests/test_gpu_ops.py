@@ -9,7 +9,8 @@ import torch.nn.functional as F
 from _util import rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-4
+TOL = 1e-4   # forward values
+GTOL = 1e-3  # gradients (fp32 split reductions / atomics; scalar grads such as d(theta) sum ~1e5 cancelling terms)
 
 
 @pytest.fixture(scope="module")
@@ -37,7 +38,7 @@ def _check_grads(cuda_inputs, ref_inputs, out_c, out_r, names, seed=99):
         if r.grad is None:
             continue
         assert c.grad is not None, n
-        assert rel_err(c.grad, r.grad) < TOL, f"grad {n}: {rel_err(c.grad, r.grad)}"
+        assert rel_err(c.grad, r.grad) < GTOL, f"grad {n}: {rel_err(c.grad, r.grad)}"
 
 
 @pytest.mark.parametrize("M,K,N", [(1, 1, 1), (37, 1, 128), (300, 128, 128), (129, 129, 2), (1000, 3, 32), (513, 256, 130)])
