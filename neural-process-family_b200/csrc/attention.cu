@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256) xattn_bwd_dq_kernel(AttnParams p) {
     float* Vs = Ks + KT * ldk;         // [KT][Dv+1]
     float* Qs = Vs + KT * ldvv;        // [8][D]
     float* Gs = Qs + 8 * D;            // [8][Dv]   dO rows
-    float* Ps = Gs + 8 * Dv;           // [8][KT]   dS
+    float* Os = Gs + 8 * Dv;           // [8][Dv]   O rows
+    float* Ps = Os + 8 * Dv;           // [8][KT]   dS
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.y, b = blockIdx.z;
     const int q = blockIdx.x * 8 + warp;
@@ -115,14 +116,16 @@ __global__ void __launch_bounds__(256) xattn_bwd_dq_kernel(AttnParams p) {
     const float* Vb = p.V + (long)b * p.Tk * ldv;
     const long qrow = (long)b * p.Tq + q;
 
-    float di = 0.f;
     for (int d = lane; d < D; d += 32) Qs[warp * D + d] = active ? __ldg(p.Q + qrow * ldq + h * D + d) : 0.f;
     for (int c = lane; c < Dv; c += 32) {
-        const float g = active ? __ldg(p.dO + qrow * ldv + h * Dv + c) : 0.f;
-        Gs[warp * Dv + c] = g;
-        if (active) di = fmaf(g, __ldg(p.O + qrow * ldv + h * Dv + c), di);
+        Gs[warp * Dv + c] = active ? __ldg(p.dO + qrow * ldv + h * Dv + c) : 0.f;
+        Os[warp * Dv + c] = active ? __ldg(p.O + qrow * ldv + h * Dv + c) : 0.f;
     }
-    di = warp_sum(di);
+    __syncwarp();
+    // Di = dO . O accumulated in the SAME order as dP = dO . V below, so that for a single key (O == V) the
+    // softmax gradient P (dP - Di) cancels exactly, as it does in a materialised softmax backward
+    float di = 0.f;
+    for (int c = 0; c < Dv; ++c) di = fmaf(Gs[warp * Dv + c], Os[warp * Dv + c], di);
     const float lse = active ? __ldg(p.LSE + ((long)b * p.H + h) * p.Tq + q) : 0.f;
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -201,17 +204,15 @@ __global__ void __launch_bounds__(256) xattn_bwd_dkv_kernel(AttnParams p) {
         load_tile(Qs, ldq_s, Qb, ldq, q0, p.Tq, D, h * D);
         load_tile(Gs, ldg_s, Gb, ldv, q0, p.Tq, Dv, h * Dv);
         __syncthreads();
-        // per-query row statistics of this tile: lse and Di = dO . O  (8 warps x 8 queries each)
-        for (int r = warp; r < KT; r += 8) {
-            const int q = q0 + r;
+        // per-query row statistics of this tile: lse and Di = dO . O, summed sequentially over channels (same order
+        // as dP = V . dO below; see the dQ kernel)
+        if (threadIdx.x < KT) {
+            const int r = threadIdx.x, q = q0 + r;
             float di = 0.f;
             if (q < p.Tq)
-                for (int c = lane; c < Dv; c += 32) di = fmaf(Gs[r * ldg_s + c], __ldg(Ob + (long)q * ldv + h * Dv + c), di);
-            di = warp_sum(di);
-            if (lane == 0) {
-                Ds[r] = di;
-                Ls[r] = (q < p.Tq) ? __ldg(p.LSE + ((long)b * p.H + h) * p.Tq + q) : 0.f;
-            }
+                for (int c = 0; c < Dv; ++c) di = fmaf(Gs[r * ldg_s + c], __ldg(Ob + (long)q * ldv + h * Dv + c), di);
+            Ds[r] = di;
+            Ls[r] = (q < p.Tq) ? __ldg(p.LSE + ((long)b * p.H + h) * p.Tq + q) : 0.f;
         }
         __syncthreads();
         float s0 = 0.f, s1 = 0.f, g0 = 0.f, g1 = 0.f;
@@ -318,7 +319,7 @@ extern "C" int npf_xattn_bwd(const float* Q, const float* K, const float* V, con
     p.Q = Q; p.K = K; p.V = V; p.O = O; p.LSE = LSE; p.dO = dO; p.dQ = dQ; p.dK = dK; p.dV = dV;
     p.Tq = Tq; p.Tk = Tk; p.H = H; p.D = D; p.Dv = Dv; p.scale = scale;
     {
-        const size_t smem = sizeof(float) * ((size_t)KT * (D + 1) + (size_t)KT * (Dv + 1) + 8 * D + 8 * Dv + 8 * KT);
+        const size_t smem = sizeof(float) * ((size_t)KT * (D + 1) + (size_t)KT * (Dv + 1) + 8 * D + 16 * Dv + 8 * KT);
         int rc = set_smem((const void*)xattn_bwd_dq_kernel, smem);
         if (rc != NPF_OK) return rc;
         dim3 grid((unsigned)cdiv(Tq, 8), (unsigned)H, (unsigned)B);

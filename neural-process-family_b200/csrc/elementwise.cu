@@ -413,14 +413,14 @@ extern "C" int npf_gauss_nll_bwd(const float* loc, const float* scale, const flo
 
 extern "C" int npf_latent_sample_fwd(const float* suff, const float* eps, float* q_loc, float* q_scale, float* z, int S,
                                      long M, int zd, npf_stream_t stream) {
-    NPF_REQUIRE(suff && eps && q_loc && q_scale && z, "npf_latent_sample_fwd: null pointer");
+    NPF_REQUIRE(suff && q_loc && q_scale && (S == 0 || (eps && z)), "npf_latent_sample_fwd: null pointer");
     NPF_REQUIRE(S >= 0 && M >= 0 && zd >= 1, "npf_latent_sample_fwd: bad shape");
     if (M == 0) return NPF_OK;
     LAUNCH_1D(latent_sample_fwd_kernel, M * zd, as_stream(stream), suff, eps, q_loc, q_scale, z, S, M, zd);
 }
 extern "C" int npf_latent_sample_bwd(const float* suff, const float* eps, const float* dz, const float* dq_loc,
                                      const float* dq_scale, float* dsuff, int S, long M, int zd, npf_stream_t stream) {
-    NPF_REQUIRE(suff && eps && dsuff, "npf_latent_sample_bwd: null pointer");
+    NPF_REQUIRE(suff && dsuff && (S == 0 || !dz || eps), "npf_latent_sample_bwd: null pointer");
     NPF_REQUIRE(S >= 0 && M >= 0 && zd >= 1, "npf_latent_sample_bwd: bad shape");
     if (M == 0) return NPF_OK;
     LAUNCH_1D(latent_sample_bwd_kernel, M * zd, as_stream(stream), suff, eps, dz, dq_loc, dq_scale, dsuff, S, M, zd);

@@ -252,6 +252,7 @@ using namespace npf;
 extern "C" int npf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy,
                               int M, int K, int N, int flags, const float* u, const float* w2, int ldw2,
                               int precision, npf_stream_t stream) {
+    if (M == 0) return NPF_OK;
     NPF_REQUIRE(X && W && Y, "npf_linear_fwd: null pointer");
     NPF_REQUIRE(M >= 0 && K >= 1 && N >= 1, "npf_linear_fwd: bad shape M=%d K=%d N=%d", M, K, N);
     NPF_REQUIRE(ldx >= K && ldw >= K && ldy >= N, "npf_linear_fwd: leading dimension too small");
@@ -278,6 +279,7 @@ extern "C" int npf_linear_fwd(const float* X, int ldx, const float* W, int ldw, 
 extern "C" int npf_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int M,
                                    int K, int N, const float* mask_src, int ldm, int flags, int precision,
                                    npf_stream_t stream) {
+    if (M == 0) return NPF_OK;
     NPF_REQUIRE(dY && W && dX, "npf_linear_bwd_data: null pointer");
     NPF_REQUIRE(M >= 0 && K >= 1 && N >= 1, "npf_linear_bwd_data: bad shape");
     NPF_REQUIRE(lddy >= N && ldw >= K && lddx >= K, "npf_linear_bwd_data: leading dimension too small");
@@ -301,6 +303,7 @@ extern "C" int npf_linear_bwd_data(const float* dY, int lddy, const float* W, in
 extern "C" int npf_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw,
                                      float* db, int M, int K, int N, int flags, const float* u, float* dw2, int ldw2,
                                      int precision, npf_stream_t stream) {
+    if (M == 0) return NPF_OK;
     NPF_REQUIRE(dY && X && dW, "npf_linear_bwd_weight: null pointer");
     NPF_REQUIRE(M >= 0 && K >= 1 && N >= 1, "npf_linear_bwd_weight: bad shape");
     NPF_REQUIRE(lddy >= N && ldx >= K && lddw >= K, "npf_linear_bwd_weight: leading dimension too small");

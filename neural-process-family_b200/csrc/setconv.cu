@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(256) setconv_fwd_kernel(const float* __restric
 // ----------------------------------------------------------------------------------------------------------------
 // backward w.r.t. theta: one warp per query, block partials -> one atomic per CTA
 //   dsigma = (-2/sigma) * sum_q [ T_q - G_q*A1_q + ddens_q*A2_q ]
-//   T_q = dF_q . sum_k w_qk a_qk V_k ;  G_q = dF_q . feat_q ;  A1_q = sum_k w_qk a_qk ;  A2_q = sum_k e^{a_qk} a_qk
+//   T_q = dF_q . sum_k w_qk (a_qk - m_q) V_k ;  G_q = dF_q . feat_q ;  A1_q = sum_k w_qk (a_qk - m_q) ;
+//   A2_q = sum_k e^{a_qk} a_qk.   The softmax part is sum_k w_k a_k (g_k - G); because sum_k w_k (g_k - G) = 0 the
+//   logits may be shifted by any constant: shifting by the max logit m_q keeps both products O(1) instead of
+//   O((d/sigma)^2) and removes the catastrophic cancellation (exactly 0 for a single key, like autograd's softmax).
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) setconv_bwd_theta_kernel(const float* __restrict__ keys, long key_bs,
                                                                 const float* __restrict__ queries, long qry_bs,
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(256) setconv_bwd_theta_kernel(const float* __r
             for (int c = 0; c < 4; ++c) df[c] = (c < C) ? __ldg(dF + c) : 0.f;
             for (int k = w.lo + lane; k <= w.hi; k += 32) {
                 const float a = logit(xq, __ldg(kb + k), sigma);
-                const float wa = expf(a - m) * inv_s * a;
+                const float wa = expf(a - m) * inv_s * (a - m);
                 A1 += wa;
                 A2 = fmaf(expf(a), a, A2);
                 float g = 0.f;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(256) setconv_bwd_theta_kernel(const float* __r
                 float wa_mine = 0.f;
                 if (kmine <= w.hi) {
                     const float a = logit(xq, __ldg(kb + kmine), sigma);
-                    wa_mine = expf(a - m) * inv_s * a;
+                    wa_mine = expf(a - m) * inv_s * (a - m);
                     A1 += wa_mine;
                     A2 = fmaf(expf(a), a, A2);
                 }

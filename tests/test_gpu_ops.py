@@ -38,7 +38,9 @@ def _check_grads(cuda_inputs, ref_inputs, out_c, out_r, names, seed=99):
         if r.grad is None:
             continue
         assert c.grad is not None, n
-        assert rel_err(c.grad, r.grad) < GTOL, f"grad {n}: {rel_err(c.grad, r.grad)}"
+        # relative to the largest entry, floored (gradients that are exactly 0 analytically, e.g. dq with one key)
+        err = (c.grad.detach().double().cpu() - r.grad).abs().max().item() / max(r.grad.abs().max().item(), 1e-3)
+        assert err < GTOL, f"grad {n}: {err}"
 
 
 @pytest.mark.parametrize("M,K,N", [(1, 1, 1), (37, 1, 128), (300, 128, 128), (129, 129, 2), (1000, 3, 32), (513, 256, 130)])
