@@ -1,15 +1,470 @@
-// Tensor-core (tcgen05 / TMEM) path for the 128-wide linear layers.  Placeholder until the UMMA kernel
-// lands: every entry reports NPF_ENOTSUP so callers fall back to the fp32 FFMA kernel in gemm.cu.
+// Tensor-core path of the 128-wide linear layers: tcgen05.mma (UMMA) with the accumulator in TMEM.
+//
+//   NPF_PREC_BF16   : operands rounded to bf16, fp32 accumulate                        (1e-2 parity)
+//   NPF_PREC_BF16X3 : x = hi + lo (both bf16); x.w ~ hi.hi + hi.lo + lo.hi, fp32 accumulate (1e-4 parity; 3 MMAs)
+//
+// Activations stay fp32 in HBM (layout contract of the library), so operands are converted on the fly: the CTA's
+// threads load the fp32 tile with coalesced 16-byte loads, apply the prologue (relu), split/round to bf16 and write
+// the UMMA canonical *no-swizzle* layout straight into shared memory (8x8 "core matrices" of 128 contiguous
+// bytes; LBO = stride between core matrices along the reduction dim, SBO = along rows).  One elected thread then
+// issues the K/16 MMAs (x1 or x3), commits to an mbarrier, and all 8 warps drain the 128xN fp32 accumulator from
+// TMEM (tcgen05.ld 32x32b) through the bias / relu / rank-1 / relu-mask epilogue into global memory.
+// The weight matrix is converted and staged ONCE per CTA (persistent over row tiles).
+//
+//   linear_tc_kernel : fwd  Y = act(X) W^T            (A = X rows K-major,  B = W   [N x K] K-major)
+//                      bwd  dX = dY W                 (A = dY rows K-major, B = W^T [K x N], staged transposed)
+//   wgrad_tc_kernel  : dW += dY^T X                   (A = dY, B = X, both MN-major: the reduction runs over rows)
+//
+// Shapes covered: reduction dim <= 128 and output dim <= 256, both multiples of 16.  Anything else reports
+// NPF_ENOTSUP and the caller uses the fp32 FFMA kernel.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace npf {
 
-int linear_fwd_tc(const float*, int, const float*, int, const float*, float*, int, int, int, int, int, const float*,
-                  const float*, int, int, cudaStream_t) { return NPF_ENOTSUP; }
-int linear_bwd_data_tc(const float*, int, const float*, int, float*, int, int, int, int, const float*, int, int, int,
-                       cudaStream_t) { return NPF_ENOTSUP; }
-int linear_bwd_weight_tc(const float*, int, const float*, int, float*, int, int, int, int, int, int, cudaStream_t) {
-    return NPF_ENOTSUP;
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy (tcgen05.commit)
+}
+// bounded spin: a lost arrival traps (error return) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, SWIZZLE_NONE, descriptor version 1 (sm_100):
+//   bits [0,14) start address >> 4, [16,30) leading-dim byte offset >> 4, [32,46) stride-dim byte offset >> 4,
+//   [46,48) version = 1, [61,64) layout type = 0 (no swizzle).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor, kind::f16: c_format f32 (1 @ bit 4), a/b format bf16 (1 @ bits 7, 10), a_major @ 15,
+// b_major @ 16 (1 = MN-major), N >> 3 @ bits [17,23), M >> 4 @ bits [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------------------------------------ K-major staging
+// Tile of R rows x KR reduction elements, element (row, k) at byte
+//     (k/8) * LBO + (row/8) * 128 + (row%8) * 16 + (k%8) * 2,      LBO = R * 16
+// (core matrix = 8 rows x 8 k = 128 contiguous bytes).  Source: fp32 row-major with leading dimension ld.
+// A half-warp writes one core matrix per instruction (conflict-free 8-byte stores).
+template <int NSPLIT>
+__device__ __forceinline__ void stage_kmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, long ld, int row0, int rows_valid,
+                                             int R, int KR, int relu, int vec_ok) {
+    const int tid = threadIdx.x;
+    const int hw = tid >> 4, l16 = tid & 15;
+    const int r = l16 & 7, half = l16 >> 3;
+    const int n_rg = R >> 3, n_kc = KR >> 3;
+    const uint32_t lbo = (uint32_t)R * 16u;
+    for (int cm = hw; cm < n_rg * n_kc; cm += 16) {  // core matrix index: kc fastest so a CTA pass reads whole rows
+        const int kc = cm % n_kc, rg = cm / n_kc;
+        const int row = rg * 8 + r;
+        const int k = kc * 8 + half * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows_valid) {
+            const float* g = src + (long)(row0 + row) * ld + k;
+            if (vec_ok) v = __ldg(reinterpret_cast<const float4*>(g));
+            else { v.x = __ldg(g); v.y = __ldg(g + 1); v.z = __ldg(g + 2); v.w = __ldg(g + 3); }
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        }
+        const uint32_t off = (uint32_t)kc * lbo + (uint32_t)rg * 128u + (uint32_t)r * 16u + (uint32_t)half * 8u;
+        *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        if (NSPLIT == 3) {
+            const float rx = v.x - bf16_round(v.x), ry = v.y - bf16_round(v.y), rz = v.z - bf16_round(v.z), rw = v.w - bf16_round(v.w);
+            *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(rx, ry), pack_bf16(rz, rw));
+        }
+    }
+}
+
+// Transposed staging of the weights for the data gradient: B'(row = k_out, red = n) = W[n, k_out], K-major in n.
+template <int NSPLIT>
+__device__ __forceinline__ void stage_kmajor_transposed(uint8_t* hi, uint8_t* lo, const float* __restrict__ W, long ldw, int R /*rows = K_out*/,
+                                                        int KR /*reduction = N*/) {
+    const uint32_t lbo = (uint32_t)R * 16u;
+    for (int idx = threadIdx.x; idx < R * KR; idx += blockDim.x) {
+        const int row = idx % R, n = idx / R;  // consecutive threads walk k_out: coalesced reads of W[n, :]
+        const float v = __ldg(W + (long)n * ldw + row);
+        const uint32_t off = (uint32_t)(n >> 3) * lbo + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(n & 7) * 2u;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+        if (NSPLIT == 3) *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+struct TcLinParams {
+    const float* A; long lda;       // [M, KR] activations (X or dY)
+    const float* W; long ldw;       // fwd: [NO, KR]; bwd-data: [KR, NO]
+    float* C; long ldc;             // [M, NO]
+    const float* bias;              // [NO] or null
+    const float* u; const float* w2; long ldw2;   // rank-1 epilogue
+    const float* mask; long ldm;    // relu mask source [M, NO]
+    int M, KR, NO;
+    int relu_in, relu_out, transposed_w, a_vec, c_vec;
+    int n_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------ fwd / bwd-data
+template <int NSPLIT>
+__global__ void __launch_bounds__(256, 1) linear_tc_kernel(TcLinParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int KR = p.KR, NO = p.NO;
+    const uint32_t a_bytes = 128u * KR * 2u, b_bytes = (uint32_t)NO * KR * 2u;
+    uint8_t* a_hi = smem_raw;
+    uint8_t* a_lo = a_hi + a_bytes;                               // only touched when NSPLIT == 3
+    uint8_t* b_hi = smem_raw + (NSPLIT == 3 ? 2 : 1) * a_bytes;
+    uint8_t* b_lo = b_hi + b_bytes;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ncols = NO <= 32 ? 32u : (NO <= 64 ? 64u : (NO <= 128 ? 128u : 256u));
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) mbar_init(&mma_bar, 1);
+    // weights: converted and staged once per CTA
+    if (p.transposed_w) stage_kmajor_transposed<NSPLIT>(b_hi, b_lo, p.W, p.ldw, NO, KR);
+    else stage_kmajor<NSPLIT>(b_hi, b_lo, p.W, p.ldw, 0, NO, NO, KR, 0, (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0));
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = make_idesc(128, NO, 0, 0);
+    const uint32_t a_lbo = 128u * 16u, b_lbo = (uint32_t)NO * 16u;
+
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int m0 = tile * 128;
+        const int rows = min(128, p.M - m0);
+        stage_kmajor<NSPLIT>(a_hi, a_lo, p.A, p.lda, m0, rows, 128, KR, p.relu_in, p.a_vec);
+        fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+            uint32_t acc = 0;
+            for (int ks = 0; ks < KR / 16; ++ks) {
+                const uint32_t ao = (uint32_t)ks * 2u * a_lbo, bo = (uint32_t)ks * 2u * b_lbo;
+                umma_bf16(tmem, make_desc(sa_hi + ao, a_lbo, 128), make_desc(sb_hi + bo, b_lbo, 128), idesc, acc);
+                acc = 1;
+                if (NSPLIT == 3) {
+                    umma_bf16(tmem, make_desc(sa_hi + ao, a_lbo, 128), make_desc(sb_lo + bo, b_lbo, 128), idesc, 1);
+                    umma_bf16(tmem, make_desc(sa_lo + ao, a_lbo, 128), make_desc(sb_hi + bo, b_lbo, 128), idesc, 1);
+                }
+            }
+            umma_commit(&mma_bar);   // implies tcgen05.fence::before_thread_sync
+        }
+        mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+
+        // epilogue: warp w drains TMEM lanes 32*(w%4) .. +31 (its rows), column half (w/4)
+        const int lane_base = 32 * (warp & 3);
+        const int row = m0 + lane_base + lane;
+        const int col_half = (NO + 1) / 2;
+        const int c_begin = (warp >> 2) * ((col_half + 31) / 32 * 32);
+        const int c_end = (warp >> 2) ? NO : min(NO, (col_half + 31) / 32 * 32);
+        const float up = (p.u && row < p.M) ? __ldg(p.u + row) : 0.f;
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);   // warp-collective: no divergence before this
+            if (row < p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int c = c0 + j;
+                    if (c < NO) {
+                        float x = v[j];
+                        if (p.bias) x += __ldg(p.bias + c);
+                        if (p.u) x = fmaf(up, __ldg(p.w2 + (long)c * p.ldw2), x);
+                        if (p.relu_out) x = fmaxf(x, 0.f);
+                        if (p.mask) x = (__ldg(p.mask + (long)row * p.ldm + c) > 0.f) ? x : 0.f;
+                        v[j] = x;
+                    }
+                }
+                float* out = p.C + (long)row * p.ldc + c0;
+                if (p.c_vec && c0 + 32 <= NO) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < NO) out[j] = v[j];
+                }
+            }
+        }
+        tc_fence_before();   // TMEM reads done before the next tile's MMA overwrites the accumulator
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[n, k] += sum_m dY[m, n] X[m, k].  MMA shape M = N_out (rows of dW, <= 128 -> padded to 128), N = K_out, K = rows m.
+// Both operands MN-major, no swizzle: element (mn, k) at byte (k/8)*LBO + (mn/8)*128 + (k%8)*16 + (mn%8)*2,
+// LBO = MN*16: a source row m (contiguous in mn) lands as 16-byte chunks -> conflict-free 16-byte stores.
+template <int NSPLIT>
+__device__ __forceinline__ void stage_mnmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, long ld, long row0, int rows_valid,
+                                              int MN /*padded extent in smem*/, int mn_valid, int relu, int vec_ok) {
+    const uint32_t lbo = (uint32_t)MN * 16u;
+    const int n_chunks = MN >> 3;                      // 16-byte chunks per source row
+    for (int c = threadIdx.x; c < 128 * n_chunks; c += blockDim.x) {
+        const int r = c & 7, j = (c >> 3) % n_chunks, kg = (c >> 3) / n_chunks;   // 8 lanes: 8 consecutive rows of one chunk column
+        const int m = kg * 8 + r;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (m < rows_valid && j * 8 < mn_valid) {
+            const float* g = src + (row0 + m) * ld + j * 8;
+            if (vec_ok && j * 8 + 8 <= mn_valid) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g + 4));
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (j * 8 + i < mn_valid) v[i] = __ldg(g + i);
+            }
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+        }
+        const uint32_t off = (uint32_t)kg * lbo + (uint32_t)j * 128u + (uint32_t)r * 16u;
+        *reinterpret_cast<uint4*>(hi + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        if (NSPLIT == 3) {
+            float q[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = v[i] - bf16_round(v[i]);
+            *reinterpret_cast<uint4*>(lo + off) = make_uint4(pack_bf16(q[0], q[1]), pack_bf16(q[2], q[3]), pack_bf16(q[4], q[5]), pack_bf16(q[6], q[7]));
+        }
+    }
+}
+
+struct TcWgParams {
+    const float* dY; long lddy;    // [M, N]
+    const float* X; long ldx;      // [M, K]
+    float* dW; long lddw;          // [N, K], accumulated with atomics
+    long M; int N, K;
+    int relu_in, dy_vec, x_vec;
+    long rows_per_cta;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(TcWgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    const int K = p.K;
+    const uint32_t a_bytes = 128u * 128u * 2u, b_bytes = 128u * (uint32_t)K * 2u;   // [128 m][128 n], [128 m][K]
+    uint8_t* a_hi = smem_raw;
+    uint8_t* a_lo = a_hi + a_bytes;
+    uint8_t* b_hi = smem_raw + (NSPLIT == 3 ? 2 : 1) * a_bytes;
+    uint8_t* b_lo = b_hi + b_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ncols = K <= 32 ? 32u : (K <= 64 ? 64u : (K <= 128 ? 128u : 256u));
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) mbar_init(&mma_bar, 1);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = make_idesc(128, K, 1, 1);
+    const uint32_t a_lbo = 128u * 16u, b_lbo = (uint32_t)K * 16u;
+
+    const long m_begin = (long)blockIdx.x * p.rows_per_cta;
+    const long m_end = min(p.M, m_begin + p.rows_per_cta);
+    uint32_t phase = 0, acc = 0;
+    for (long m0 = m_begin; m0 < m_end; m0 += 128) {
+        const int rows = (int)min((long)128, m_end - m0);
+        if (acc) {           // previous sub-tile's MMAs must have consumed the operand buffers
+            mbar_wait(&mma_bar, phase);
+            phase ^= 1;
+        }
+        stage_mnmajor<NSPLIT>(a_hi, a_lo, p.dY, p.lddy, m0, rows, 128, p.N, 0, p.dy_vec);
+        stage_mnmajor<NSPLIT>(b_hi, b_lo, p.X, p.ldx, m0, rows, K, K, p.relu_in, p.x_vec);
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+            for (int ks = 0; ks < 8; ++ks) {     // 128 rows = 8 k-steps of 16 rows (2 k-groups of 8)
+                const uint32_t ao = (uint32_t)ks * 2u * a_lbo, bo = (uint32_t)ks * 2u * b_lbo;
+                umma_bf16(tmem, make_desc(sa_hi + ao, a_lbo, 128), make_desc(sb_hi + bo, b_lbo, 128), idesc, acc);
+                acc = 1;
+                if (NSPLIT == 3) {
+                    umma_bf16(tmem, make_desc(sa_hi + ao, a_lbo, 128), make_desc(sb_lo + bo, b_lbo, 128), idesc, 1);
+                    umma_bf16(tmem, make_desc(sa_lo + ao, a_lbo, 128), make_desc(sb_hi + bo, b_lbo, 128), idesc, 1);
+                }
+            }
+            umma_commit(&mma_bar);
+        }
+        acc = 1;
+    }
+    if (acc) {
+        mbar_wait(&mma_bar, phase);
+        tc_fence_after();
+        const int lane_base = 32 * (warp & 3);
+        const int n = lane_base + lane;                    // row of dW
+        const int half = (K / 2 + 31) / 32 * 32;
+        const int c_begin = (warp >> 2) * half, c_end = (warp >> 2) ? K : min(K, half);
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+            if (n < p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < K) atomicAdd(p.dW + (long)n * p.lddw + c0 + j, v[j]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool tc_shape_ok(int red, int out) { return red % 16 == 0 && red >= 16 && red <= 128 && out % 16 == 0 && out >= 16 && out <= 256; }
+
+template <int NSPLIT>
+static int launch_lin(TcLinParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (128 + p.NO) * p.KR * 2;
+    static size_t reserved = 0;
+    if (smem > reserved) {
+        if (cudaFuncSetAttribute(linear_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return NPF_ENOTSUP;
+        }
+        reserved = 220 * 1024;
+    }
+    if (smem > 220 * 1024) return NPF_ENOTSUP;
+    p.n_tiles = (int)cdiv(p.M, 128);
+    // CTAs per SM limited by shared memory; stay persistent with one CTA per resident slot
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 3) per_sm = 3;
+    int grid = kNumSMs * per_sm;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    linear_tc_kernel<NSPLIT><<<grid, 256, smem, st>>>(p);
+    count_launch();
+    return check_launch("linear_tc_kernel");
+}
+
+int linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int K,
+                  int N, int flags, const float* u, const float* w2, int ldw2, int precision, cudaStream_t st) {
+    if (!tc_shape_ok(K, N) || (flags & NPF_ACCUM)) return NPF_ENOTSUP;
+    TcLinParams p{};
+    p.A = X; p.lda = ldx; p.W = W; p.ldw = ldw; p.C = Y; p.ldc = ldy; p.bias = b;
+    p.u = u; p.w2 = w2; p.ldw2 = ldw2;
+    p.M = M; p.KR = K; p.NO = N;
+    p.relu_in = (flags & NPF_RELU_IN) ? 1 : 0; p.relu_out = (flags & NPF_RELU_OUT) ? 1 : 0;
+    p.transposed_w = 0;
+    p.a_vec = (ldx % 4 == 0) && aligned16(X);
+    p.c_vec = (ldy % 4 == 0) && aligned16(Y);
+    return precision == NPF_PREC_BF16X3 ? launch_lin<3>(p, st) : launch_lin<1>(p, st);
+}
+
+int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int M, int K, int N,
+                       const float* mask_src, int ldm, int flags, int precision, cudaStream_t st) {
+    if (!tc_shape_ok(N, K) || (flags & NPF_ACCUM)) return NPF_ENOTSUP;
+    TcLinParams p{};
+    p.A = dY; p.lda = lddy; p.W = W; p.ldw = ldw; p.C = dX; p.ldc = lddx;
+    p.mask = mask_src; p.ldm = ldm;
+    p.M = M; p.KR = N; p.NO = K;
+    p.transposed_w = 1;
+    p.a_vec = (lddy % 4 == 0) && aligned16(dY);
+    p.c_vec = (lddx % 4 == 0) && aligned16(dX);
+    return precision == NPF_PREC_BF16X3 ? launch_lin<3>(p, st) : launch_lin<1>(p, st);
+}
+
+template <int NSPLIT>
+static int launch_wg(TcWgParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (128 * 128 + 128 * p.K) * 2;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return NPF_ENOTSUP;
+        }
+        attr = true;
+    }
+    if (smem > 220 * 1024) return NPF_ENOTSUP;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 3) per_sm = 3;
+    long ctas = (long)kNumSMs * per_sm;
+    long rows = cdiv(cdiv(p.M, ctas), 128) * 128;
+    if (rows < 128) rows = 128;
+    p.rows_per_cta = rows;
+    const long grid = cdiv(p.M, rows);
+    wgrad_tc_kernel<NSPLIT><<<(unsigned)grid, 256, smem, st>>>(p);
+    count_launch();
+    return check_launch("wgrad_tc_kernel");
+}
+
+int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int K, int N,
+                         int flags, int precision, cudaStream_t st) {
+    // MMA M dimension = N (rows of dW, padded to 128), MMA N dimension = K, reduction over the M rows
+    if (N > 128 || N < 1 || K % 16 != 0 || K < 16 || K > 256) return NPF_ENOTSUP;
+    if (N % 8 != 0) return NPF_ENOTSUP;
+    TcWgParams p{};
+    p.dY = dY; p.lddy = lddy; p.X = X; p.ldx = ldx; p.dW = dW; p.lddw = lddw;
+    p.M = M; p.N = N; p.K = K;
+    p.relu_in = (flags & NPF_RELU_IN) ? 1 : 0;
+    p.dy_vec = (lddy % 4 == 0) && aligned16(dY);
+    p.x_vec = (ldx % 4 == 0) && aligned16(X);
+    return precision == NPF_PREC_BF16X3 ? launch_wg<3>(p, st) : launch_wg<1>(p, st);
 }
 
 }  // namespace npf

@@ -1,0 +1,63 @@
+"""-m gpu: the tcgen05 / TMEM tensor-core path of the linear layers (NPF_PREC_BF16, NPF_PREC_BF16X3) against fp64
+torch: the 3-term split-bf16 mode must meet the fp32 bar (1e-4), plain bf16 the 1e-2 bar of the north star."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _cfg import build_model, loss_for
+from _util import load_fixture, rel_err
+
+pytestmark = pytest.mark.gpu
+BARS = {"bf16": (1e-2, 3e-2), "bf16x3": (1e-4, 1e-3)}   # (forward, gradient) relative tolerances
+
+
+@pytest.fixture(scope="module")
+def npf():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import npf_b200
+    yield npf_b200
+    npf_b200.set_precision("fp32")
+
+
+def _g(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float64) * scale
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,K,H,N", [(1, 128, 128, 128), (300, 128, 128, 128), (1000, 64, 128, 32), (4099, 128, 256, 16), (130, 128, 128, 2)])
+def test_tc_mlp_chain(npf, prec, M, K, H, N):
+    npf.set_precision(prec)
+    ftol, gtol = BARS[prec]
+    ts = [_g(M, K, seed=1), _g(H, K, seed=2, scale=K ** -0.5), _g(H, seed=3), _g(H, H, seed=4, scale=H ** -0.5), _g(H, seed=5),
+          _g(N, H, seed=6, scale=H ** -0.5), _g(N, seed=7)]
+    r = [t.clone().requires_grad_(True) for t in ts]
+    c = [t.float().cuda().requires_grad_(True) for t in ts]
+    yr = F.linear(torch.relu(F.linear(torch.relu(F.linear(r[0], r[1], r[2])), r[3], r[4])), r[5], r[6])
+    yc = npf.ops.mlp_chain(c[0], [c[1], c[3], c[5]], [c[2], c[4], c[6]])
+    assert rel_err(yc, yr) < ftol, rel_err(yc, yr)
+    go = _g(*yr.shape, seed=9)
+    yr.backward(go)
+    yc.backward(go.float().cuda())
+    for n, a, b in zip("x W1 b1 W2 b2 W3 b3".split(), c, r):
+        err = (a.grad.double().cpu() - b.grad).abs().max().item() / max(b.grad.abs().max().item(), 1e-3)
+        assert err < gtol, f"{prec} grad {n}: {err}"
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_tc_model_parity_convcnp(npf, prec):
+    """Whole ConvCNP (pointwise convs, SetConv resizer with the rank-1 density column, decoder MLP) on tensor cores."""
+    npf.set_precision(prec)
+    ftol, gtol = BARS[prec]
+    fx = load_fixture("convcnp_default")
+    model = build_model(fx["cfg"])
+    model.load_state_dict(fx["state_dict"])
+    model.cuda().train()
+    for case in fx["cases"][:2]:
+        model.zero_grad(set_to_none=True)
+        inp = {k: v.cuda() for k, v in case["inputs"].items()}
+        out = model(inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"])
+        per_task = loss_for("cnpf")(out, inp["Y_trgt"])
+        assert rel_err(out[0].base_dist.loc, case["loc"]) < ftol, (prec, rel_err(out[0].base_dist.loc, case["loc"]))
+        assert rel_err(out[0].base_dist.scale, case["scale"]) < ftol
+        assert rel_err(per_task, case["loss_per_task"]) < ftol
