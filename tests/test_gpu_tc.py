@@ -8,7 +8,7 @@ from _cfg import build_model, loss_for
 from _util import load_fixture, rel_err
 
 pytestmark = pytest.mark.gpu
-BARS = {"bf16": (1e-2, 3e-2), "bf16x3": (1e-4, 1e-3)}   # (forward, gradient) relative tolerances
+BARS = {"bf16": (1e-2, 1e-1), "bf16x3": (1e-4, 1e-3)}   # (forward, gradient) relative tolerances
 
 
 @pytest.fixture(scope="module")
