@@ -101,26 +101,44 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // Tile of R rows x KR reduction elements, element (row, k) at byte
 //     (k/8) * LBO + (row/8) * 128 + (row%8) * 16 + (k%8) * 2,      LBO = R * 16
 // (core matrix = 8 rows x 8 k = 128 contiguous bytes).  Source: fp32 row-major with leading dimension ld.
-// A half-warp writes one core matrix per instruction (conflict-free 8-byte stores).
-template <int NSPLIT>
-__device__ __forceinline__ void stage_kmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, long ld, int row0, int rows_valid,
-                                             int R, int KR, int relu, int vec_ok) {
-    const int tid = threadIdx.x;
-    const int hw = tid >> 4, l16 = tid & 15;
+// A half-warp owns one core matrix per step (conflict-free 8-byte stores; 8 full 32-byte sectors per load).
+// Loads are split from the convert+store so that a whole tile (16 x 16 B per thread = 64 KB per CTA) is in
+// flight at once, and so that the NEXT tile can be prefetched into registers under the current tile's MMA + epilogue.
+constexpr int kPre = 16;   // float4 registers per thread per batch
+
+__device__ __forceinline__ void load_kmajor(float4 (&pre)[kPre], const float* __restrict__ src, long ld, long row0, int rows_valid,
+                                            int R, int KR, int cm_base, int vec_ok) {
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
     const int r = l16 & 7, half = l16 >> 3;
-    const int n_rg = R >> 3, n_kc = KR >> 3;
-    const uint32_t lbo = (uint32_t)R * 16u;
-    for (int cm = hw; cm < n_rg * n_kc; cm += 16) {  // core matrix index: kc fastest so a CTA pass reads whole rows
+    const int n_kc = KR >> 3, n_cm = (R >> 3) * n_kc;
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+        const int cm = cm_base + hw + 16 * i;       // kc fastest: one pass of the CTA reads 8 whole rows
         const int kc = cm % n_kc, rg = cm / n_kc;
-        const int row = rg * 8 + r;
-        const int k = kc * 8 + half * 4;
+        const int row = rg * 8 + r, k = kc * 8 + half * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows_valid) {
-            const float* g = src + (long)(row0 + row) * ld + k;
+        if (cm < n_cm && row < rows_valid) {
+            const float* g = src + (row0 + row) * ld + k;
             if (vec_ok) v = __ldg(reinterpret_cast<const float4*>(g));
             else { v.x = __ldg(g); v.y = __ldg(g + 1); v.z = __ldg(g + 2); v.w = __ldg(g + 3); }
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         }
+        pre[i] = v;
+    }
+}
+
+template <int NSPLIT>
+__device__ __forceinline__ void store_kmajor(const float4 (&pre)[kPre], uint8_t* hi, uint8_t* lo, int R, int KR, int cm_base, int relu) {
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    const int r = l16 & 7, half = l16 >> 3;
+    const int n_kc = KR >> 3, n_cm = (R >> 3) * n_kc;
+    const uint32_t lbo = (uint32_t)R * 16u;
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+        const int cm = cm_base + hw + 16 * i;
+        if (cm >= n_cm) continue;
+        const int kc = cm % n_kc, rg = cm / n_kc;
+        float4 v = pre[i];
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         const uint32_t off = (uint32_t)kc * lbo + (uint32_t)rg * 128u + (uint32_t)r * 16u + (uint32_t)half * 8u;
         *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
         if (NSPLIT == 3) {
@@ -131,17 +149,40 @@ __device__ __forceinline__ void stage_kmajor(uint8_t* hi, uint8_t* lo, const flo
 }
 
 // Transposed staging of the weights for the data gradient: B'(row = k_out, red = n) = W[n, k_out], K-major in n.
+// Batched float4 loads along k_out (coalesced rows of W), four 2-byte scatter stores each (once per CTA).
 template <int NSPLIT>
 __device__ __forceinline__ void stage_kmajor_transposed(uint8_t* hi, uint8_t* lo, const float* __restrict__ W, long ldw, int R /*rows = K_out*/,
-                                                        int KR /*reduction = N*/) {
+                                                        int KR /*reduction = N*/, int vec_ok) {
     const uint32_t lbo = (uint32_t)R * 16u;
-    for (int idx = threadIdx.x; idx < R * KR; idx += blockDim.x) {
-        const int row = idx % R, n = idx / R;  // consecutive threads walk k_out: coalesced reads of W[n, :]
-        const float v = __ldg(W + (long)n * ldw + row);
-        const uint32_t off = (uint32_t)(n >> 3) * lbo + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(n & 7) * 2u;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
-        if (NSPLIT == 3) *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int rq = R >> 2, total = rq * KR;      // float4 count
+    for (int base = 0; base < total; base += 256 * kPre) {
+        float4 pre[kPre];
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+            const int idx = base + threadIdx.x + 256 * i;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < total) {
+                const float* g = W + (long)(idx / rq) * ldw + (idx % rq) * 4;
+                if (vec_ok) v = __ldg(reinterpret_cast<const float4*>(g));
+                else { v.x = __ldg(g); v.y = __ldg(g + 1); v.z = __ldg(g + 2); v.w = __ldg(g + 3); }
+            }
+            pre[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+            const int idx = base + threadIdx.x + 256 * i;
+            if (idx >= total) continue;
+            const int n = idx / rq, row0 = (idx % rq) * 4;
+            const float vv[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int row = row0 + e;
+                const uint32_t off = (uint32_t)(n >> 3) * lbo + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(n & 7) * 2u;
+                const __nv_bfloat16 h = __float2bfloat16_rn(vv[e]);
+                *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+                if (NSPLIT == 3) *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16_rn(vv[e] - __bfloat162float(h));
+            }
+        }
     }
 }
 
@@ -153,16 +194,31 @@ struct TcLinParams {
     const float* u; const float* w2; long ldw2;   // rank-1 epilogue
     const float* mask; long ldm;    // relu mask source [M, NO]
     int M, KR, NO;
-    int relu_in, relu_out, transposed_w, a_vec, c_vec;
+    int relu_in, relu_out, transposed_w, a_vec, w_vec, c_vec;
     int n_tiles;
 };
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ------------------------------------------------------------------------------------------------ fwd / bwd-data
 template <int NSPLIT>
-__global__ void __launch_bounds__(256, 1) linear_tc_kernel(TcLinParams p) {
+__global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcLinParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_bias[256], s_w2[256];
 
     const int KR = p.KR, NO = p.NO;
     const uint32_t a_bytes = 128u * KR * 2u, b_bytes = (uint32_t)NO * KR * 2u;
@@ -175,9 +231,27 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(TcLinParams p) {
     const uint32_t ncols = NO <= 32 ? 32u : (NO <= 64 ? 64u : (NO <= 128 ? 128u : 256u));
     if (warp == 0) tmem_alloc(&tmem_slot, ncols);
     if (tid == 0) mbar_init(&mma_bar, 1);
+    for (int c = tid; c < NO; c += 256) {
+        s_bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+        s_w2[c] = p.w2 ? __ldg(p.w2 + (long)c * p.ldw2) : 0.f;
+    }
+
+    float4 pre[kPre];
+    int tile = blockIdx.x;
+    // first activation tile: in flight while the weights are staged
+    if (tile < p.n_tiles) load_kmajor(pre, p.A, p.lda, (long)tile * 128, min(128, p.M - tile * 128), 128, KR, 0, p.a_vec);
     // weights: converted and staged once per CTA
-    if (p.transposed_w) stage_kmajor_transposed<NSPLIT>(b_hi, b_lo, p.W, p.ldw, NO, KR);
-    else stage_kmajor<NSPLIT>(b_hi, b_lo, p.W, p.ldw, 0, NO, NO, KR, 0, (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0));
+    if (p.transposed_w) {
+        stage_kmajor_transposed<NSPLIT>(b_hi, b_lo, p.W, p.ldw, NO, KR, p.w_vec);
+    } else {
+        const int n_cm = (NO >> 3) * (KR >> 3);
+        for (int base = 0; base < n_cm; base += 16 * kPre) {
+            float4 wpre[kPre];
+            load_kmajor(wpre, p.W, p.ldw, 0, NO, NO, KR, base, p.w_vec);
+            store_kmajor<NSPLIT>(wpre, b_hi, b_lo, NO, KR, base, 0);
+        }
+    }
+    if (tile < p.n_tiles) store_kmajor<NSPLIT>(pre, a_hi, a_lo, 128, KR, 0, p.relu_in);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -187,14 +261,9 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(TcLinParams p) {
     const uint32_t a_lbo = 128u * 16u, b_lbo = (uint32_t)NO * 16u;
 
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (; tile < p.n_tiles; tile += gridDim.x) {
         const int m0 = tile * 128;
-        const int rows = min(128, p.M - m0);
-        stage_kmajor<NSPLIT>(a_hi, a_lo, p.A, p.lda, m0, rows, 128, KR, p.relu_in, p.a_vec);
-        fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
         if (tid == 0) {
-            tc_fence_after();
             const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
             uint32_t acc = 0;
             for (int ks = 0; ks < KR / 16; ++ks) {
@@ -208,6 +277,10 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(TcLinParams p) {
             }
             umma_commit(&mma_bar);   // implies tcgen05.fence::before_thread_sync
         }
+        // prefetch the next tile into registers: in flight under this tile's MMA and epilogue
+        const int next = tile + gridDim.x;
+        if (next < p.n_tiles) load_kmajor(pre, p.A, p.lda, (long)next * 128, min(128, p.M - next * 128), 128, KR, 0, p.a_vec);
+
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc_fence_after();
@@ -215,39 +288,44 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(TcLinParams p) {
         // epilogue: warp w drains TMEM lanes 32*(w%4) .. +31 (its rows), column half (w/4)
         const int lane_base = 32 * (warp & 3);
         const int row = m0 + lane_base + lane;
-        const int col_half = (NO + 1) / 2;
-        const int c_begin = (warp >> 2) * ((col_half + 31) / 32 * 32);
-        const int c_end = (warp >> 2) ? NO : min(NO, (col_half + 31) / 32 * 32);
+        const int split = ((NO + 1) / 2 + 15) / 16 * 16;
+        const int c_begin = (warp >> 2) ? split : 0;
+        const int c_end = (warp >> 2) ? NO : min(NO, split);
         const float up = (p.u && row < p.M) ? __ldg(p.u + row) : 0.f;
-        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);   // warp-collective: no divergence before this
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);   // warp-collective
             if (row < p.M) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c = c0 + j;
-                    if (c < NO) {
-                        float x = v[j];
-                        if (p.bias) x += __ldg(p.bias + c);
-                        if (p.u) x = fmaf(up, __ldg(p.w2 + (long)c * p.ldw2), x);
-                        if (p.relu_out) x = fmaxf(x, 0.f);
-                        if (p.mask) x = (__ldg(p.mask + (long)row * p.ldm + c) > 0.f) ? x : 0.f;
-                        v[j] = x;
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    float x = v[j] + s_bias[c0 + j];
+                    if (p.u) x = fmaf(up, s_w2[c0 + j], x);
+                    if (p.relu_out) x = fmaxf(x, 0.f);
+                    v[j] = x;
+                }
+                if (p.mask) {
+                    const float* mk = p.mask + (long)row * p.ldm + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = (__ldg(mk + j) > 0.f) ? v[j] : 0.f;
                 }
                 float* out = p.C + (long)row * p.ldc + c0;
-                if (p.c_vec && c0 + 32 <= NO) {
+                if (p.c_vec) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < NO) out[j] = v[j];
+                    for (int j = 0; j < 16; ++j) out[j] = v[j];
                 }
             }
         }
-        tc_fence_before();   // TMEM reads done before the next tile's MMA overwrites the accumulator
+        tc_fence_before();   // TMEM reads done (and the MMAs have consumed the A buffer) before it is overwritten
         __syncthreads();
+        if (next < p.n_tiles) {
+            store_kmajor<NSPLIT>(pre, a_hi, a_lo, 128, KR, 0, p.relu_in);
+            fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        }
+        __syncthreads();
+        tc_fence_after();
     }
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
@@ -256,36 +334,57 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(TcLinParams p) {
 // dW[n, k] += sum_m dY[m, n] X[m, k].  MMA shape M = N_out (rows of dW, <= 128 -> padded to 128), N = K_out, K = rows m.
 // Both operands MN-major, no swizzle: element (mn, k) at byte (k/8)*LBO + (mn/8)*128 + (k%8)*16 + (mn%8)*2,
 // LBO = MN*16: a source row m (contiguous in mn) lands as 16-byte chunks -> conflict-free 16-byte stores.
-template <int NSPLIT>
-__device__ __forceinline__ void stage_mnmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, long ld, long row0, int rows_valid,
-                                              int MN /*padded extent in smem*/, int mn_valid, int relu, int vec_ok) {
-    const uint32_t lbo = (uint32_t)MN * 16u;
-    const int n_chunks = MN >> 3;                      // 16-byte chunks per source row
-    for (int c = threadIdx.x; c < 128 * n_chunks; c += blockDim.x) {
-        const int r = c & 7, j = (c >> 3) % n_chunks, kg = (c >> 3) / n_chunks;   // 8 lanes: 8 consecutive rows of one chunk column
+// Sub-tiles of 64 rows (4 k-steps): both operands of a sub-tile are prefetched into registers (batched loads).
+constexpr int kWgRows = 64;
+constexpr int kWgIt = 4;     // 16-byte chunks per thread per batch: 64 rows x 128 columns / 8 / 256 threads
+
+// chunk c of a [64 rows x MN] operand: 8 lanes cover 8 consecutive rows of one 8-wide column chunk
+__device__ __forceinline__ void load_mnmajor(float4 (&pre)[2 * kWgIt], const float* __restrict__ src, long ld, long row0, int rows_valid, int MN,
+                                             int mn_valid, int c_base, int vec_ok) {
+    const int n_chunks = MN >> 3, total = kWgRows * n_chunks;
+#pragma unroll
+    for (int i = 0; i < kWgIt; ++i) {
+        const int c = c_base + threadIdx.x + 256 * i;
+        const int r = c & 7, j = (c >> 3) % n_chunks, kg = (c >> 3) / n_chunks;
         const int m = kg * 8 + r;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (m < rows_valid && j * 8 < mn_valid) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (c < total && m < rows_valid && j * 8 < mn_valid) {
             const float* g = src + (row0 + m) * ld + j * 8;
             if (vec_ok && j * 8 + 8 <= mn_valid) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g + 4));
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                a = __ldg(reinterpret_cast<const float4*>(g));
+                b = __ldg(reinterpret_cast<const float4*>(g + 4));
             } else {
+                float t[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (j * 8 + i < mn_valid) v[i] = __ldg(g + i);
+                for (int e = 0; e < 8; ++e) t[e] = (j * 8 + e < mn_valid) ? __ldg(g + e) : 0.f;
+                a = make_float4(t[0], t[1], t[2], t[3]);
+                b = make_float4(t[4], t[5], t[6], t[7]);
             }
-            if (relu) {
+        }
+        pre[2 * i] = a; pre[2 * i + 1] = b;
+    }
+}
+
+template <int NSPLIT>
+__device__ __forceinline__ void store_mnmajor(const float4 (&pre)[2 * kWgIt], uint8_t* hi, uint8_t* lo, int MN, int c_base, int relu) {
+    const uint32_t lbo = (uint32_t)MN * 16u;
+    const int n_chunks = MN >> 3, total = kWgRows * n_chunks;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
+    for (int i = 0; i < kWgIt; ++i) {
+        const int c = c_base + threadIdx.x + 256 * i;
+        if (c >= total) continue;
+        const int r = c & 7, j = (c >> 3) % n_chunks, kg = (c >> 3) / n_chunks;
+        float v[8] = {pre[2 * i].x, pre[2 * i].y, pre[2 * i].z, pre[2 * i].w, pre[2 * i + 1].x, pre[2 * i + 1].y, pre[2 * i + 1].z, pre[2 * i + 1].w};
+        if (relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
         }
         const uint32_t off = (uint32_t)kg * lbo + (uint32_t)j * 128u + (uint32_t)r * 16u;
         *reinterpret_cast<uint4*>(hi + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         if (NSPLIT == 3) {
             float q[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = v[i] - bf16_round(v[i]);
+            for (int e = 0; e < 8; ++e) q[e] = v[e] - bf16_round(v[e]);
             *reinterpret_cast<uint4*>(lo + off) = make_uint4(pack_bf16(q[0], q[1]), pack_bf16(q[2], q[3]), pack_bf16(q[4], q[5]), pack_bf16(q[6], q[7]));
         }
     }
@@ -301,12 +400,12 @@ struct TcWgParams {
 };
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(TcWgParams p) {
+__global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) wgrad_tc_kernel(TcWgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     const int K = p.K;
-    const uint32_t a_bytes = 128u * 128u * 2u, b_bytes = 128u * (uint32_t)K * 2u;   // [128 m][128 n], [128 m][K]
+    const uint32_t a_bytes = (uint32_t)kWgRows * 128u * 2u, b_bytes = (uint32_t)kWgRows * (uint32_t)K * 2u;
     uint8_t* a_hi = smem_raw;
     uint8_t* a_lo = a_hi + a_bytes;
     uint8_t* b_hi = smem_raw + (NSPLIT == 3 ? 2 : 1) * a_bytes;
@@ -322,24 +421,41 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(TcWgParams p) {
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = make_idesc(128, K, 1, 1);
     const uint32_t a_lbo = 128u * 16u, b_lbo = (uint32_t)K * 16u;
+    const int b_batches = (kWgRows * (K >> 3) + 256 * kWgIt - 1) / (256 * kWgIt);   // 1 for K <= 128, 2 for K = 256
 
     const long m_begin = (long)blockIdx.x * p.rows_per_cta;
     const long m_end = min(p.M, m_begin + p.rows_per_cta);
     uint32_t phase = 0, acc = 0;
-    for (long m0 = m_begin; m0 < m_end; m0 += 128) {
-        const int rows = (int)min((long)128, m_end - m0);
+    float4 pa[2 * kWgIt], pb[2 * kWgIt];
+    if (m_begin < m_end) {
+        const int rows = (int)min((long)kWgRows, m_end - m_begin);
+        load_mnmajor(pa, p.dY, p.lddy, m_begin, rows, 128, p.N, 0, p.dy_vec);
+        load_mnmajor(pb, p.X, p.ldx, m_begin, rows, K, K, 0, p.x_vec);
+    }
+    for (long m0 = m_begin; m0 < m_end; m0 += kWgRows) {
+        const int rows = (int)min((long)kWgRows, m_end - m0);
         if (acc) {           // previous sub-tile's MMAs must have consumed the operand buffers
             mbar_wait(&mma_bar, phase);
             phase ^= 1;
         }
-        stage_mnmajor<NSPLIT>(a_hi, a_lo, p.dY, p.lddy, m0, rows, 128, p.N, 0, p.dy_vec);
-        stage_mnmajor<NSPLIT>(b_hi, b_lo, p.X, p.ldx, m0, rows, K, K, p.relu_in, p.x_vec);
+        store_mnmajor<NSPLIT>(pa, a_hi, a_lo, 128, 0, 0);
+        store_mnmajor<NSPLIT>(pb, b_hi, b_lo, K, 0, p.relu_in);
+        for (int bb = 1; bb < b_batches; ++bb) {       // K = 256: second half of the X sub-tile
+            load_mnmajor(pb, p.X, p.ldx, m0, rows, K, K, bb * 256 * kWgIt, p.x_vec);
+            store_mnmajor<NSPLIT>(pb, b_hi, b_lo, K, bb * 256 * kWgIt, p.relu_in);
+        }
+        const long mn = m0 + kWgRows;
+        if (mn < m_end) {    // prefetch the next sub-tile: in flight under the fence / sync / MMA issue
+            const int rn = (int)min((long)kWgRows, m_end - mn);
+            load_mnmajor(pa, p.dY, p.lddy, mn, rn, 128, p.N, 0, p.dy_vec);
+            load_mnmajor(pb, p.X, p.ldx, mn, rn, K, K, 0, p.x_vec);
+        }
         fence_async_smem();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
             const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
-            for (int ks = 0; ks < 8; ++ks) {     // 128 rows = 8 k-steps of 16 rows (2 k-groups of 8)
+            for (int ks = 0; ks < kWgRows / 16; ++ks) {     // k-steps of 16 rows (2 k-groups of 8)
                 const uint32_t ao = (uint32_t)ks * 2u * a_lbo, bo = (uint32_t)ks * 2u * b_lbo;
                 umma_bf16(tmem, make_desc(sa_hi + ao, a_lbo, 128), make_desc(sb_hi + bo, b_lbo, 128), idesc, acc);
                 acc = 1;
@@ -357,15 +473,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(TcWgParams p) {
         tc_fence_after();
         const int lane_base = 32 * (warp & 3);
         const int n = lane_base + lane;                    // row of dW
-        const int half = (K / 2 + 31) / 32 * 32;
-        const int c_begin = (warp >> 2) * half, c_end = (warp >> 2) ? K : min(K, half);
-        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+        const int split = ((K + 1) / 2 + 15) / 16 * 16;
+        const int c_begin = (warp >> 2) ? split : 0, c_end = (warp >> 2) ? K : min(K, split);
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
             if (n < p.N) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < K) atomicAdd(p.dW + (long)n * p.lddw + c0 + j, v[j]);
+                for (int j = 0; j < 16; ++j) atomicAdd(p.dW + (long)n * p.lddw + c0 + j, v[j]);
             }
         }
         tc_fence_before();
@@ -393,7 +508,7 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
     // CTAs per SM limited by shared memory; stay persistent with one CTA per resident slot
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 3) per_sm = 3;
+    if (per_sm > 2) per_sm = 2;
     int grid = kNumSMs * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
     linear_tc_kernel<NSPLIT><<<grid, 256, smem, st>>>(p);
@@ -411,6 +526,7 @@ int linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float*
     p.relu_in = (flags & NPF_RELU_IN) ? 1 : 0; p.relu_out = (flags & NPF_RELU_OUT) ? 1 : 0;
     p.transposed_w = 0;
     p.a_vec = (ldx % 4 == 0) && aligned16(X);
+    p.w_vec = (ldw % 4 == 0) && aligned16(W);
     p.c_vec = (ldy % 4 == 0) && aligned16(Y);
     return precision == NPF_PREC_BF16X3 ? launch_lin<3>(p, st) : launch_lin<1>(p, st);
 }
@@ -424,13 +540,14 @@ int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float
     p.M = M; p.KR = N; p.NO = K;
     p.transposed_w = 1;
     p.a_vec = (lddy % 4 == 0) && aligned16(dY);
+    p.w_vec = (ldw % 4 == 0) && aligned16(W);
     p.c_vec = (lddx % 4 == 0) && aligned16(dX);
     return precision == NPF_PREC_BF16X3 ? launch_lin<3>(p, st) : launch_lin<1>(p, st);
 }
 
 template <int NSPLIT>
 static int launch_wg(TcWgParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (128 * 128 + 128 * p.K) * 2;
+    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (kWgRows * 128 + kWgRows * p.K) * 2;
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(wgrad_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
@@ -442,10 +559,10 @@ static int launch_wg(TcWgParams& p, cudaStream_t st) {
     if (smem > 220 * 1024) return NPF_ENOTSUP;
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 3) per_sm = 3;
+    if (per_sm > 2) per_sm = 2;
     long ctas = (long)kNumSMs * per_sm;
-    long rows = cdiv(cdiv(p.M, ctas), 128) * 128;
-    if (rows < 128) rows = 128;
+    long rows = cdiv(cdiv(p.M, ctas), kWgRows) * kWgRows;
+    if (rows < kWgRows) rows = kWgRows;
     p.rows_per_cta = rows;
     const long grid = cdiv(p.M, rows);
     wgrad_tc_kernel<NSPLIT><<<(unsigned)grid, 256, smem, st>>>(p);

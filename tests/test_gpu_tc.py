@@ -61,3 +61,25 @@ def test_tc_model_parity_convcnp(npf, prec):
         assert rel_err(out[0].base_dist.loc, case["loc"]) < ftol, (prec, rel_err(out[0].base_dist.loc, case["loc"]))
         assert rel_err(out[0].base_dist.scale, case["scale"]) < ftol
         assert rel_err(per_task, case["loss_per_task"]) < ftol
+
+
+@pytest.mark.parametrize("prec", ["bf16x3"])
+@pytest.mark.parametrize("M,K,N", [(513, 128, 128), (513, 128, 256), (513, 16, 256), (513, 64, 32), (513, 128, 16), (70000, 128, 128),
+                                   (513, 256, 16), (513, 32, 128)])
+def test_tc_single_linear_localised(npf, prec, M, K, N):
+    """One layer at a time (forward, data gradient, weight gradient reported separately) + run-to-run determinism of
+    the forward and of the data gradient (no atomics on those paths)."""
+    npf.set_precision(prec)
+    ftol, gtol = BARS[prec]
+    x, W, b = _g(M, K, seed=1), _g(N, K, seed=2, scale=K ** -0.5), _g(N, seed=3)
+    go = _g(M, N, seed=4)
+    res = []
+    for rep in range(2):
+        xc, Wc, bc = (t.float().cuda().requires_grad_(True) for t in (x, W, b))
+        yc = npf.ops.linear(xc, Wc, bc)
+        yc.backward(go.float().cuda())
+        res.append((yc.detach().clone(), xc.grad.clone(), Wc.grad.clone(), bc.grad.clone()))
+    yr = x @ W.t() + b
+    errs = dict(y=rel_err(res[0][0], yr), dx=rel_err(res[0][1], go @ W), dW=rel_err(res[0][2], go.t() @ x), db=rel_err(res[0][3], go.sum(0)))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), f"non-deterministic: {errs}"
+    assert errs["y"] < ftol and errs["dx"] < gtol and errs["dW"] < gtol and errs["db"] < gtol, errs
