@@ -9,6 +9,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "gemm_thin.cuh"
 
 namespace npf {
 
@@ -245,6 +246,7 @@ int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float
 int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int K, int N,
                          int flags, int precision, cudaStream_t st);
 
+
 }  // namespace npf
 
 using namespace npf;
@@ -259,6 +261,23 @@ extern "C" int npf_linear_fwd(const float* X, int ldx, const float* W, int ldw, 
     NPF_REQUIRE((u == nullptr) == (w2 == nullptr), "npf_linear_fwd: u and w2 must be given together");
     if (M == 0) return NPF_OK;
     cudaStream_t st = as_stream(stream);
+    if (K <= kThinMax) {
+        ThinRedParams t{};
+        t.A = X; t.lda = ldx; t.relu_a = (flags & NPF_RELU_IN) ? 1 : 0;
+        t.B = W; t.sb_o = ldw; t.sb_r = 1; t.bias = b; t.u = u; t.w2 = w2; t.ldw2 = ldw2;
+        t.out = Y; t.ldo = ldy; t.M = M; t.R = K; t.O = N;
+        t.relu_out = (flags & NPF_RELU_OUT) ? 1 : 0; t.accum = (flags & NPF_ACCUM) ? 1 : 0;
+        int rc = thin_red(t, st);
+        if (rc != NPF_ENOTSUP) return rc;
+    } else if (N <= kThinMax && !u) {
+        RowDotParams t{};
+        t.A = X; t.lda = ldx; t.relu_a = (flags & NPF_RELU_IN) ? 1 : 0;
+        t.B = W; t.sb_j = ldw; t.sb_i = 1; t.bias = b;
+        t.out = Y; t.ldo = ldy; t.M = M; t.I = K; t.J = N;
+        t.relu_out = (flags & NPF_RELU_OUT) ? 1 : 0; t.accum = (flags & NPF_ACCUM) ? 1 : 0;
+        int rc = rowdot(t, st);
+        if (rc != NPF_ENOTSUP) return rc;
+    }
     if (precision != NPF_PREC_FP32) {
         int rc = linear_fwd_tc(X, ldx, W, ldw, b, Y, ldy, M, K, N, flags, u, w2, ldw2, precision, st);
         if (rc != NPF_ENOTSUP) return rc;
@@ -285,6 +304,21 @@ extern "C" int npf_linear_bwd_data(const float* dY, int lddy, const float* W, in
     NPF_REQUIRE(lddy >= N && ldw >= K && lddx >= K, "npf_linear_bwd_data: leading dimension too small");
     if (M == 0) return NPF_OK;
     cudaStream_t st = as_stream(stream);
+    if (N <= kThinMax) {
+        ThinRedParams t{};
+        t.A = dY; t.lda = lddy; t.B = W; t.sb_o = 1; t.sb_r = ldw;
+        t.mask = mask_src; t.ldm = ldm;
+        t.out = dX; t.ldo = lddx; t.M = M; t.R = N; t.O = K; t.accum = (flags & NPF_ACCUM) ? 1 : 0;
+        int rc = thin_red(t, st);
+        if (rc != NPF_ENOTSUP) return rc;
+    } else if (K <= kThinMax) {
+        RowDotParams t{};
+        t.A = dY; t.lda = lddy; t.B = W; t.sb_j = 1; t.sb_i = ldw;
+        t.mask = mask_src; t.ldm = ldm;
+        t.out = dX; t.ldo = lddx; t.M = M; t.I = N; t.J = K; t.accum = (flags & NPF_ACCUM) ? 1 : 0;
+        int rc = rowdot(t, st);
+        if (rc != NPF_ENOTSUP) return rc;
+    }
     if (precision != NPF_PREC_FP32) {
         int rc = linear_bwd_data_tc(dY, lddy, W, ldw, dX, lddx, M, K, N, mask_src, ldm, flags, precision, st);
         if (rc != NPF_ENOTSUP) return rc;
@@ -310,8 +344,23 @@ extern "C" int npf_linear_bwd_weight(const float* dY, int lddy, const float* X, 
     NPF_REQUIRE((u == nullptr) == (dw2 == nullptr), "npf_linear_bwd_weight: u and dw2 must be given together");
     if (M == 0) return NPF_OK;
     cudaStream_t st = as_stream(stream);
+    if (K <= kThinMax) {   // one pass over dY: dW, db and the rank-1 column together
+        ThinOuterParams t{};
+        t.S = X; t.lds = ldx; t.relu_s = (flags & NPF_RELU_IN) ? 1 : 0;
+        t.T = dY; t.ldt = lddy;
+        t.out = dW; t.so_j = 1; t.so_c = lddw; t.out_ones = db; t.u = u; t.out_u = dw2; t.so_u = ldw2;
+        t.M = M; t.J = K; t.C = N;
+        return thin_outer(t, st);
+    }
     int rc = NPF_ENOTSUP;
-    if (precision != NPF_PREC_FP32) rc = linear_bwd_weight_tc(dY, lddy, X, ldx, dW, lddw, M, K, N, flags, precision, st);
+    if (N <= kThinMax) {
+        ThinOuterParams t{};
+        t.S = dY; t.lds = lddy; t.T = X; t.ldt = ldx; t.relu_t = (flags & NPF_RELU_IN) ? 1 : 0;
+        t.out = dW; t.so_j = lddw; t.so_c = 1;
+        t.M = M; t.J = N; t.C = K;
+        rc = thin_outer(t, st);
+    }
+    if (rc == NPF_ENOTSUP && precision != NPF_PREC_FP32) rc = linear_bwd_weight_tc(dY, lddy, X, ldx, dW, lddw, M, K, N, flags, precision, st);
     if (rc == NPF_ENOTSUP) {
         GemmParams p{};
         p.A = dY; p.lda = lddy; p.B = X; p.ldb = ldx; p.C = dW; p.ldc = lddw;

@@ -106,23 +106,33 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // flight at once, and so that the NEXT tile can be prefetched into registers under the current tile's MMA + epilogue.
 constexpr int kPre = 16;   // float4 registers per thread per batch
 
+__device__ __forceinline__ int ilog2(int x) { return 31 - __clz(x); }
+
+// All tile extents on this path are powers of two (checked on the host), so the (core-matrix -> row group, k chunk)
+// maps are shifts, and because 16 half-warps step through core matrices 16 at a time the k chunk of a thread is
+// CONSTANT: only the row group advances -> one pointer increment and one smem-offset increment per step.
 __device__ __forceinline__ void load_kmajor(float4 (&pre)[kPre], const float* __restrict__ src, long ld, long row0, int rows_valid,
                                             int R, int KR, int cm_base, int vec_ok) {
     const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
     const int r = l16 & 7, half = l16 >> 3;
-    const int n_kc = KR >> 3, n_cm = (R >> 3) * n_kc;
+    const int n_kc = KR >> 3, lg = ilog2(n_kc);
+    const int cm0 = cm_base + hw;
+    const int kc = cm0 & (n_kc - 1);
+    int rg = cm0 >> lg;
+    const int rg_step = n_kc >= 16 ? 1 : (16 >> lg), n_rg = R >> 3;
+    // n_kc > 16 cannot happen (KR <= 128); n_kc == 16 -> each step is the next row group
+    const float* g = src + (row0 + rg * 8 + r) * ld + kc * 8 + half * 4;
+    const long gstep = (long)rg_step * 8 * ld;
 #pragma unroll
     for (int i = 0; i < kPre; ++i) {
-        const int cm = cm_base + hw + 16 * i;       // kc fastest: one pass of the CTA reads 8 whole rows
-        const int kc = cm % n_kc, rg = cm / n_kc;
-        const int row = rg * 8 + r, k = kc * 8 + half * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cm < n_cm && row < rows_valid) {
-            const float* g = src + (row0 + row) * ld + k;
+        if (rg < n_rg && rg * 8 + r < rows_valid) {
             if (vec_ok) v = __ldg(reinterpret_cast<const float4*>(g));
             else { v.x = __ldg(g); v.y = __ldg(g + 1); v.z = __ldg(g + 2); v.w = __ldg(g + 3); }
         }
         pre[i] = v;
+        rg += rg_step;
+        g += gstep;
     }
 }
 
@@ -130,21 +140,25 @@ template <int NSPLIT>
 __device__ __forceinline__ void store_kmajor(const float4 (&pre)[kPre], uint8_t* hi, uint8_t* lo, int R, int KR, int cm_base, int relu) {
     const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
     const int r = l16 & 7, half = l16 >> 3;
-    const int n_kc = KR >> 3, n_cm = (R >> 3) * n_kc;
-    const uint32_t lbo = (uint32_t)R * 16u;
+    const int n_kc = KR >> 3, lg = ilog2(n_kc);
+    const int cm0 = cm_base + hw;
+    const int kc = cm0 & (n_kc - 1);
+    int rg = cm0 >> lg;
+    const int rg_step = n_kc >= 16 ? 1 : (16 >> lg), n_rg = R >> 3;
+    uint32_t off = (uint32_t)kc * ((uint32_t)R * 16u) + (uint32_t)rg * 128u + (uint32_t)r * 16u + (uint32_t)half * 8u;
 #pragma unroll
     for (int i = 0; i < kPre; ++i) {
-        const int cm = cm_base + hw + 16 * i;
-        if (cm >= n_cm) continue;
-        const int kc = cm % n_kc, rg = cm / n_kc;
-        float4 v = pre[i];
-        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        const uint32_t off = (uint32_t)kc * lbo + (uint32_t)rg * 128u + (uint32_t)r * 16u + (uint32_t)half * 8u;
-        *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-        if (NSPLIT == 3) {
-            const float rx = v.x - bf16_round(v.x), ry = v.y - bf16_round(v.y), rz = v.z - bf16_round(v.z), rw = v.w - bf16_round(v.w);
-            *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(rx, ry), pack_bf16(rz, rw));
+        if (rg < n_rg) {
+            float4 v = pre[i];
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            if (NSPLIT == 3) {
+                const float rx = v.x - bf16_round(v.x), ry = v.y - bf16_round(v.y), rz = v.z - bf16_round(v.z), rw = v.w - bf16_round(v.w);
+                *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(rx, ry), pack_bf16(rz, rw));
+            }
         }
+        rg += rg_step;
+        off += (uint32_t)rg_step * 128u;
     }
 }
 
@@ -154,15 +168,17 @@ template <int NSPLIT>
 __device__ __forceinline__ void stage_kmajor_transposed(uint8_t* hi, uint8_t* lo, const float* __restrict__ W, long ldw, int R /*rows = K_out*/,
                                                         int KR /*reduction = N*/, int vec_ok) {
     const uint32_t lbo = (uint32_t)R * 16u;
-    const int rq = R >> 2, total = rq * KR;      // float4 count
+    const int rq = R >> 2, lgq = ilog2(rq), total = rq * KR;      // float4 count; rq is a power of two <= 64
+    const int row0 = (threadIdx.x & (rq - 1)) * 4;                // constant per thread (256 is a multiple of rq)
     for (int base = 0; base < total; base += 256 * kPre) {
         float4 pre[kPre];
+        const int n0 = (base + threadIdx.x) >> lgq, n_step = 256 >> lgq;
 #pragma unroll
         for (int i = 0; i < kPre; ++i) {
-            const int idx = base + threadIdx.x + 256 * i;
+            const int n = n0 + i * n_step;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < total) {
-                const float* g = W + (long)(idx / rq) * ldw + (idx % rq) * 4;
+            if (n < KR) {
+                const float* g = W + (long)n * ldw + row0;
                 if (vec_ok) v = __ldg(reinterpret_cast<const float4*>(g));
                 else { v.x = __ldg(g); v.y = __ldg(g + 1); v.z = __ldg(g + 2); v.w = __ldg(g + 3); }
             }
@@ -170,14 +186,13 @@ __device__ __forceinline__ void stage_kmajor_transposed(uint8_t* hi, uint8_t* lo
         }
 #pragma unroll
         for (int i = 0; i < kPre; ++i) {
-            const int idx = base + threadIdx.x + 256 * i;
-            if (idx >= total) continue;
-            const int n = idx / rq, row0 = (idx % rq) * 4;
+            const int n = n0 + i * n_step;
+            if (n >= KR) continue;
             const float vv[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+            const uint32_t off0 = (uint32_t)(n >> 3) * lbo + (uint32_t)(row0 >> 3) * 128u + (uint32_t)(row0 & 7) * 16u + (uint32_t)(n & 7) * 2u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int row = row0 + e;
-                const uint32_t off = (uint32_t)(n >> 3) * lbo + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(n & 7) * 2u;
+            for (int e = 0; e < 4; ++e) {      // rows row0 .. row0+3 stay inside one 8-row group (row0 is a multiple of 4)
+                const uint32_t off = off0 + (uint32_t)e * 16u;
                 const __nv_bfloat16 h = __float2bfloat16_rn(vv[e]);
                 *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
                 if (NSPLIT == 3) *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16_rn(vv[e] - __bfloat162float(h));
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcL
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_bias[256], s_w2[256];
+    __shared__ __align__(16) float s_bias[256], s_w2[256];
 
     const int KR = p.KR, NO = p.NO;
     const uint32_t a_bytes = 128u * KR * 2u, b_bytes = (uint32_t)NO * KR * 2u;
@@ -297,11 +312,17 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcL
             tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);   // warp-collective
             if (row < p.M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float x = v[j] + s_bias[c0 + j];
-                    if (p.u) x = fmaf(up, s_w2[c0 + j], x);
-                    if (p.relu_out) x = fmaxf(x, 0.f);
-                    v[j] = x;
+                for (int j4 = 0; j4 < 16; j4 += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + j4]);
+                    const float4 ww = *reinterpret_cast<const float4*>(&s_w2[c0 + j4]);
+                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, wv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x = v[j4 + e] + bv[e];
+                        if (p.u) x = fmaf(up, wv[e], x);
+                        if (p.relu_out) x = fmaxf(x, 0.f);
+                        v[j4 + e] = x;
+                    }
                 }
                 if (p.mask) {
                     const float* mk = p.mask + (long)row * p.ldm + c0;
@@ -338,19 +359,23 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcL
 constexpr int kWgRows = 64;
 constexpr int kWgIt = 4;     // 16-byte chunks per thread per batch: 64 rows x 128 columns / 8 / 256 threads
 
-// chunk c of a [64 rows x MN] operand: 8 lanes cover 8 consecutive rows of one 8-wide column chunk
+// chunk c of a [64 rows x MN] operand: 8 lanes cover 8 consecutive rows of one 8-wide column chunk.  MN/8 is a power
+// of two <= 32 and a thread block advances 32 chunk columns per step, so a thread's column chunk j is constant and only
+// the 8-row group kg advances.
 __device__ __forceinline__ void load_mnmajor(float4 (&pre)[2 * kWgIt], const float* __restrict__ src, long ld, long row0, int rows_valid, int MN,
                                              int mn_valid, int c_base, int vec_ok) {
-    const int n_chunks = MN >> 3, total = kWgRows * n_chunks;
+    const int n_chunks = MN >> 3, lgc = ilog2(n_chunks);
+    const int r = threadIdx.x & 7, q = (c_base >> 3) + (threadIdx.x >> 3);
+    const int j = q & (n_chunks - 1), kg_step = 32 >> lgc;
+    int kg = q >> lgc;
+    const bool col_ok = j * 8 < mn_valid, full = vec_ok && (j * 8 + 8 <= mn_valid);
+    const float* g = src + (row0 + kg * 8 + r) * ld + j * 8;
+    const long gstep = (long)kg_step * 8 * ld;
 #pragma unroll
     for (int i = 0; i < kWgIt; ++i) {
-        const int c = c_base + threadIdx.x + 256 * i;
-        const int r = c & 7, j = (c >> 3) % n_chunks, kg = (c >> 3) / n_chunks;
-        const int m = kg * 8 + r;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (c < total && m < rows_valid && j * 8 < mn_valid) {
-            const float* g = src + (row0 + m) * ld + j * 8;
-            if (vec_ok && j * 8 + 8 <= mn_valid) {
+        if (kg < (kWgRows >> 3) && kg * 8 + r < rows_valid && col_ok) {
+            if (full) {
                 a = __ldg(reinterpret_cast<const float4*>(g));
                 b = __ldg(reinterpret_cast<const float4*>(g + 4));
             } else {
@@ -362,31 +387,37 @@ __device__ __forceinline__ void load_mnmajor(float4 (&pre)[2 * kWgIt], const flo
             }
         }
         pre[2 * i] = a; pre[2 * i + 1] = b;
+        kg += kg_step;
+        g += gstep;
     }
 }
 
 template <int NSPLIT>
 __device__ __forceinline__ void store_mnmajor(const float4 (&pre)[2 * kWgIt], uint8_t* hi, uint8_t* lo, int MN, int c_base, int relu) {
     const uint32_t lbo = (uint32_t)MN * 16u;
-    const int n_chunks = MN >> 3, total = kWgRows * n_chunks;
+    const int n_chunks = MN >> 3, lgc = ilog2(n_chunks);
+    const int r = threadIdx.x & 7, q = (c_base >> 3) + (threadIdx.x >> 3);
+    const int j = q & (n_chunks - 1), kg_step = 32 >> lgc;
+    int kg = q >> lgc;
+    uint32_t off = (uint32_t)kg * lbo + (uint32_t)j * 128u + (uint32_t)r * 16u;
 #pragma unroll
     for (int i = 0; i < kWgIt; ++i) {
-        const int c = c_base + threadIdx.x + 256 * i;
-        if (c >= total) continue;
-        const int r = c & 7, j = (c >> 3) % n_chunks, kg = (c >> 3) / n_chunks;
-        float v[8] = {pre[2 * i].x, pre[2 * i].y, pre[2 * i].z, pre[2 * i].w, pre[2 * i + 1].x, pre[2 * i + 1].y, pre[2 * i + 1].z, pre[2 * i + 1].w};
-        if (relu) {
+        if (kg < (kWgRows >> 3)) {
+            float v[8] = {pre[2 * i].x, pre[2 * i].y, pre[2 * i].z, pre[2 * i].w, pre[2 * i + 1].x, pre[2 * i + 1].y, pre[2 * i + 1].z, pre[2 * i + 1].w};
+            if (relu) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-        }
-        const uint32_t off = (uint32_t)kg * lbo + (uint32_t)j * 128u + (uint32_t)r * 16u;
-        *reinterpret_cast<uint4*>(hi + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        if (NSPLIT == 3) {
-            float q[8];
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            *reinterpret_cast<uint4*>(hi + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            if (NSPLIT == 3) {
+                float qd[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) q[e] = v[e] - bf16_round(v[e]);
-            *reinterpret_cast<uint4*>(lo + off) = make_uint4(pack_bf16(q[0], q[1]), pack_bf16(q[2], q[3]), pack_bf16(q[4], q[5]), pack_bf16(q[6], q[7]));
+                for (int e = 0; e < 8; ++e) qd[e] = v[e] - bf16_round(v[e]);
+                *reinterpret_cast<uint4*>(lo + off) = make_uint4(pack_bf16(qd[0], qd[1]), pack_bf16(qd[2], qd[3]), pack_bf16(qd[4], qd[5]), pack_bf16(qd[6], qd[7]));
+            }
         }
+        kg += kg_step;
+        off += (uint32_t)kg_step * lbo;
     }
 }
 
@@ -479,8 +510,14 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) wgrad_tc_kernel(TcWg
             float v[16];
             tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
             if (n < p.N) {
+                float* d = p.dW + (long)n * p.lddw + c0;
+                if ((p.lddw & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) atomicAdd(p.dW + (long)n * p.lddw + c0 + j, v[j]);
+                    for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(d + j, v[j]);
+                }
             }
         }
         tc_fence_before();
@@ -490,7 +527,8 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) wgrad_tc_kernel(TcWg
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-static bool tc_shape_ok(int red, int out) { return red % 16 == 0 && red >= 16 && red <= 128 && out % 16 == 0 && out >= 16 && out <= 256; }
+static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+static bool tc_shape_ok(int red, int out) { return pow2(red) && red >= 16 && red <= 128 && pow2(out) && out >= 16 && out <= 256; }
 
 template <int NSPLIT>
 static int launch_lin(TcLinParams& p, cudaStream_t st) {
@@ -573,8 +611,7 @@ static int launch_wg(TcWgParams& p, cudaStream_t st) {
 int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int K, int N,
                          int flags, int precision, cudaStream_t st) {
     // MMA M dimension = N (rows of dW, padded to 128), MMA N dimension = K, reduction over the M rows
-    if (N > 128 || N < 1 || K % 16 != 0 || K < 16 || K > 256) return NPF_ENOTSUP;
-    if (N % 8 != 0) return NPF_ENOTSUP;
+    if (N > 128 || N < 8 || N % 8 != 0 || !pow2(K) || K < 16 || K > 256) return NPF_ENOTSUP;
     TcWgParams p{};
     p.dY = dY; p.lddy = lddy; p.X = X; p.ldx = ldx; p.dW = dW; p.lddw = lddw;
     p.M = M; p.N = N; p.K = K;

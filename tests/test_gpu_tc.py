@@ -8,7 +8,15 @@ from _cfg import build_model, loss_for
 from _util import load_fixture, rel_err
 
 pytestmark = pytest.mark.gpu
-BARS = {"bf16": (1e-2, 1e-1), "bf16x3": (1e-4, 1e-3)}   # (forward, gradient) relative tolerances
+BARS = {"bf16": (1e-2, 5e-2), "bf16x3": (1e-4, 1e-3)}   # (forward max-rel, gradient L2-rel) tolerances
+
+
+def l2_rel(a, b):
+    """||a - b||_2 / ||b||_2.  Gradients of ReLU chains are compared in L2: a pre-activation within rounding distance of
+    0 flips its mask and moves ONE sample's gradient row by O(1) -- a max-norm metric then measures how many of the ~1e6
+    units happen to sit within 1e-5 of zero, not the arithmetic."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
 @pytest.fixture(scope="module")
@@ -40,7 +48,7 @@ def test_tc_mlp_chain(npf, prec, M, K, H, N):
     yr.backward(go)
     yc.backward(go.float().cuda())
     for n, a, b in zip("x W1 b1 W2 b2 W3 b3".split(), c, r):
-        err = (a.grad.double().cpu() - b.grad).abs().max().item() / max(b.grad.abs().max().item(), 1e-3)
+        err = l2_rel(a.grad, b.grad)
         assert err < gtol, f"{prec} grad {n}: {err}"
 
 
@@ -48,7 +56,7 @@ def test_tc_mlp_chain(npf, prec, M, K, H, N):
 def test_tc_model_parity_convcnp(npf, prec):
     """Whole ConvCNP (pointwise convs, SetConv resizer with the rank-1 density column, decoder MLP) on tensor cores."""
     npf.set_precision(prec)
-    ftol, gtol = BARS[prec]
+    ftol = {"bf16x3": 1e-4, "bf16": 3e-2}[prec]   # plain bf16 through the 10-GEMM-deep stack: ~2e-2 (DESIGN.md section 4)
     fx = load_fixture("convcnp_default")
     model = build_model(fx["cfg"])
     model.load_state_dict(fx["state_dict"])
