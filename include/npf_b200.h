@@ -47,6 +47,7 @@ extern "C" {
 #define NPF_RELU_OUT 1   /* apply relu to the output                               */
 #define NPF_RELU_IN 2    /* apply relu to the (first / activation) input on load   */
 #define NPF_ACCUM 4      /* add to the output instead of overwriting it            */
+#define NPF_ADD_DY 8     /* npf_dwconv_bwd: dX += dY (gradient of a residual branch that reads the same X) */
 
 typedef void* npf_stream_t;
 
@@ -122,7 +123,8 @@ NPF_API int npf_dwconv_fwd(const float* X, const float* Wt, const float* bias, c
                    npf_stream_t stream);
 
 /* dX (overwritten, or += with NPF_ACCUM; NULL to skip), dWt[C,kh,kw] (+=), dbias[C] (+=).
- * dX excludes the residual branch (its gradient is dY itself; the caller adds it).  If pre_scale is
+ * dX excludes the residual branch unless NPF_ADD_DY is set (then dX = conv^T(dY) * act' + dY, for blocks whose
+ * residual is the conv input itself).  If pre_scale is
  * given, dX is the gradient w.r.t. X through the affine (i.e. multiplied by pre_scale[c]), and
  * dpre_scale[C]/dpre_shift[C] (+=, optional) receive the affine's gradients. */
 NPF_API int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, float* dX, float* dWt, float* dbias, int B,

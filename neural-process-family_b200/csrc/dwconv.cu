@@ -252,6 +252,199 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(DwParams p, const flo
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// 1-D fast path (ConvCNP / ConvLNP): no shared-memory tile.  A thread owns 4 channels x 8 consecutive positions and
+// pulls its KW+7 input float4s straight from global memory in one batch (KW+7 independent 16-byte loads in flight per
+// thread; neighbouring threads' halos hit L1/L2, DRAM sees each element once), then runs the taps out of registers.
+// ----------------------------------------------------------------------------------------------------------------
+struct Dw1Params {
+    const float* X; const float* Wt; const float* bias; const float* res; float* Y;
+    const float* Xorig; const float* scale; const float* shift; const float* addgrad;
+    int L, C, kw;
+    int relu_in, flip, mask, accum;
+    long n_groups;        // B * ceil(L / 8)
+    int groups_per_seq;
+};
+
+__device__ __forceinline__ float4 act4(float4 v, bool affine, const float4 s, const float4 t) {
+    if (affine) v = make_float4(fmaf(s.x, v.x, t.x), fmaf(s.y, v.y, t.y), fmaf(s.z, v.z, t.z), fmaf(s.w, v.w, t.w));
+    return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) dwconv1d_kernel(Dw1Params p) {
+    extern __shared__ __align__(16) float4 Ws4[];   // [KW][CQ]
+    const int CQ = p.C >> 2, G = 256 / CQ;
+    const int q = threadIdx.x % CQ, g = threadIdx.x / CQ;
+    const int pw = KW / 2, joff = (KW - p.kw) / 2;
+    for (int idx = threadIdx.x; idx < KW * p.C; idx += 256) {
+        const int c = idx % p.C, j = idx / p.C, jr = j - joff;
+        float v = 0.f;
+        if (jr >= 0 && jr < p.kw) v = __ldg(p.Wt + (long)c * p.kw + (p.flip ? p.kw - 1 - jr : jr));
+        reinterpret_cast<float*>(Ws4)[(size_t)j * p.C + c] = v;
+    }
+    __syncthreads();
+    const long gid = (long)blockIdx.x * G + g;
+    if (gid >= p.n_groups) return;
+    const long b = gid / p.groups_per_seq;
+    const int l0 = (int)(gid % p.groups_per_seq) * 8;
+    const int c = 4 * q;
+    const float* xb = p.X + (b * p.L) * (long)p.C + c;
+    const bool affine = p.relu_in && p.scale != nullptr;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.scale && (p.relu_in || p.mask)) {
+        sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+        sh = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+    }
+    float4 xin[KW + 7];
+#pragma unroll
+    for (int xc = 0; xc < KW + 7; ++xc) {
+        const int pos = l0 + xc - pw;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pos >= 0 && pos < p.L) v = __ldg(reinterpret_cast<const float4*>(xb + (long)pos * p.C));
+        xin[xc] = v;
+    }
+    if (p.relu_in) {
+#pragma unroll
+        for (int xc = 0; xc < KW + 7; ++xc) {
+            const int pos = l0 + xc - pw;
+            if (pos >= 0 && pos < p.L) xin[xc] = act4(xin[xc], affine, sc, sh);   // padding stays exactly 0
+        }
+    }
+    float4 acc[8];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) acc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        const float4 w = Ws4[j * CQ + q];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) acc[pp] = f4_fma(w, xin[pp + j], acc[pp]);
+    }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+        const int pos = l0 + pp;
+        if (pos >= p.L) continue;
+        const long off = ((b * p.L) + pos) * (long)p.C + c;
+        float4 v = make_float4(acc[pp].x + bv.x, acc[pp].y + bv.y, acc[pp].z + bv.z, acc[pp].w + bv.w);
+        if (p.mask) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(p.Xorig + off));
+            const float4 pre = make_float4(fmaf(sc.x, x.x, sh.x), fmaf(sc.y, x.y, sh.y), fmaf(sc.z, x.z, sh.z), fmaf(sc.w, x.w, sh.w));
+            v.x = pre.x > 0.f ? v.x * sc.x : 0.f; v.y = pre.y > 0.f ? v.y * sc.y : 0.f;
+            v.z = pre.z > 0.f ? v.z * sc.z : 0.f; v.w = pre.w > 0.f ? v.w * sc.w : 0.f;
+        }
+        if (p.res) {
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + off));
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+        }
+        if (p.addgrad) {   // gradient of the residual branch (the block input is also the conv input)
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.addgrad + off));
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+        }
+        float4* out = reinterpret_cast<float4*>(p.Y + off);
+        if (p.accum) { const float4 o = *out; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *out = v;
+    }
+}
+
+// 1-D filter + bias gradient in one pass: dWt[c,j] += sum dY[b,l,c] act(X)[b,l+j-p,c] ; dbias[c] += sum dY[b,l,c].
+// Persistent grid; a thread keeps its KW filter-tap sums for 4 channels in registers over all its position groups.
+template <int KW>
+__global__ void __launch_bounds__(256) dwconv1d_wgrad_kernel(Dw1Params p, const float* __restrict__ dY, float* __restrict__ dWt,
+                                                             float* __restrict__ dbias) {
+    extern __shared__ __align__(16) float4 red4[];   // [G][KW + 1][CQ]
+    const int CQ = p.C >> 2, G = 256 / CQ;
+    const int q = threadIdx.x % CQ, g = threadIdx.x / CQ;
+    const int pw = KW / 2, joff = (KW - p.kw) / 2;
+    const int c = 4 * q;
+    const bool affine = p.relu_in && p.scale != nullptr;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (affine) {
+        sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+        sh = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+    }
+    float4 acc[KW], accb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < KW; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long gid = (long)blockIdx.x * G + g; gid < p.n_groups; gid += (long)gridDim.x * G) {
+        const long b = gid / p.groups_per_seq;
+        const int l0 = (int)(gid % p.groups_per_seq) * 8;
+        const float* xb = p.X + (b * p.L) * (long)p.C + c;
+        const float* gb = dY + (b * p.L) * (long)p.C + c;
+        float4 xin[KW + 7], dy[8];
+#pragma unroll
+        for (int xc = 0; xc < KW + 7; ++xc) {
+            const int pos = l0 + xc - pw;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pos >= 0 && pos < p.L) v = __ldg(reinterpret_cast<const float4*>(xb + (long)pos * p.C));
+            xin[xc] = v;
+        }
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            const int pos = l0 + pp;
+            dy[pp] = (pos < p.L) ? __ldg(reinterpret_cast<const float4*>(gb + (long)pos * p.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (p.relu_in) {
+#pragma unroll
+            for (int xc = 0; xc < KW + 7; ++xc) {
+                const int pos = l0 + xc - pw;
+                if (pos >= 0 && pos < p.L) xin[xc] = act4(xin[xc], affine, sc, sh);
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            accb.x += dy[pp].x; accb.y += dy[pp].y; accb.z += dy[pp].z; accb.w += dy[pp].w;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) acc[j] = f4_fma(dy[pp], xin[pp + j], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KW; ++j) red4[((size_t)g * (KW + 1) + j) * CQ + q] = acc[j];
+    red4[((size_t)g * (KW + 1) + KW) * CQ + q] = accb;
+    __syncthreads();
+    const float* red = reinterpret_cast<const float*>(red4);
+    for (int idx = threadIdx.x; idx < (KW + 1) * p.C; idx += 256) {
+        const int ch = idx % p.C, j = idx / p.C;
+        float s = 0.f;
+        for (int gg = 0; gg < G; ++gg) s += red[((size_t)gg * (KW + 1) + j) * p.C + ch];
+        if (j == KW) { if (dbias) atomicAdd(dbias + ch, s); }
+        else {
+            const int jr = j - joff;
+            if (jr >= 0 && jr < p.kw) atomicAdd(dWt + (long)ch * p.kw + jr, s);
+        }
+    }
+}
+
+static bool dw1_ok(int H, int C) { return H == 1 && C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0; }
+
+template <int KW>
+static int launch_dw1(Dw1Params& p, int B, cudaStream_t st) {
+    const int CQ = p.C / 4, G = 256 / CQ;
+    p.groups_per_seq = (p.L + 7) / 8;
+    p.n_groups = (long)B * p.groups_per_seq;
+    const size_t smem = sizeof(float) * (size_t)KW * p.C;
+    dwconv1d_kernel<KW><<<(unsigned)cdiv(p.n_groups, G), 256, smem, st>>>(p);
+    count_launch();
+    return check_launch("dwconv1d_kernel");
+}
+
+template <int KW>
+static int launch_dw1_wgrad(Dw1Params& p, const float* dY, float* dWt, float* dbias, int B, cudaStream_t st) {
+    const int CQ = p.C / 4, G = 256 / CQ;
+    p.groups_per_seq = (p.L + 7) / 8;
+    p.n_groups = (long)B * p.groups_per_seq;
+    const size_t smem = sizeof(float) * (size_t)G * (KW + 1) * p.C;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(dwconv1d_wgrad_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    if (smem > 200 * 1024) return NPF_ENOTSUP;
+    long grid = cdiv(p.n_groups, G);
+    if (grid > 2L * kNumSMs) grid = 2L * kNumSMs;
+    dwconv1d_wgrad_kernel<KW><<<(unsigned)grid, 256, smem, st>>>(p, dY, dWt, dbias);
+    count_launch();
+    return check_launch("dwconv1d_wgrad_kernel");
+}
+
 // sum[c] += sum_m X[m,c] ; sumsq[c] += sum_m X[m,c]^2   (also used for the conv bias gradient with sumsq == null)
 __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ X, const float* __restrict__ center, float* sum,
                                                             float* sumsq, long M, int C, long rows_per_block) {
@@ -374,6 +567,16 @@ extern "C" int npf_dwconv_fwd(const float* X, const float* Wt, const float* bias
     p.accum = (flags & NPF_ACCUM) ? 1 : 0;
     cudaStream_t st = as_stream(stream);
     int rc;
+    if (dw1_ok(H, C) && pick_kw(kw) > 0) {
+        Dw1Params q{};
+        q.X = X; q.Wt = Wt; q.bias = bias; q.res = res; q.Y = Y; q.scale = pre_scale; q.shift = pre_shift;
+        q.L = Wd; q.C = C; q.kw = kw; q.relu_in = p.relu_in; q.accum = p.accum;
+        switch (pick_kw(kw)) {
+            case 9: return launch_dw1<9>(q, B, st);
+            case 11: return launch_dw1<11>(q, B, st);
+            default: return launch_dw1<19>(q, B, st);
+        }
+    }
     switch (pick_kw(kw)) {
         case 9: rc = launch_dw<9>(p, B, st); break;
         case 11: rc = launch_dw<11>(p, B, st); break;
@@ -400,12 +603,42 @@ extern "C" int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, 
     int rc = NPF_OK;
     const int kwsel = pick_kw(kw);
     if (kwsel < 0) { set_error("npf_dwconv_bwd: kernel width %d > 19", kw); return NPF_ENOTSUP; }
-    if (dX) {
+    const bool fast1d = dw1_ok(H, C) && !dpre_scale;
+    if (fast1d) {
+        if (dX) {
+            Dw1Params q{};
+            q.X = dY; q.Wt = Wt; q.Y = dX; q.Xorig = X; q.scale = pre_scale; q.shift = pre_shift;
+            q.addgrad = (flags & NPF_ADD_DY) ? dY : nullptr;
+            q.L = Wd; q.C = C; q.kw = kw; q.flip = 1; q.mask = relu_in; q.accum = (flags & NPF_ACCUM) ? 1 : 0;
+            switch (kwsel) {
+                case 9: rc = launch_dw1<9>(q, B, st); break;
+                case 11: rc = launch_dw1<11>(q, B, st); break;
+                default: rc = launch_dw1<19>(q, B, st); break;
+            }
+            if (rc != NPF_OK) return rc;
+        }
+        if (dWt) {
+            Dw1Params q{};
+            q.X = X; q.scale = pre_scale; q.shift = pre_shift; q.L = Wd; q.C = C; q.kw = kw; q.relu_in = relu_in;
+            switch (kwsel) {
+                case 9: rc = launch_dw1_wgrad<9>(q, dY, dWt, dbias, B, st); break;
+                case 11: rc = launch_dw1_wgrad<11>(q, dY, dWt, dbias, B, st); break;
+                default: rc = launch_dw1_wgrad<19>(q, dY, dWt, dbias, B, st); break;
+            }
+            if (rc != NPF_ENOTSUP) return rc;
+        } else if (dbias) {
+            return launch_stats(dY, nullptr, dbias, nullptr, (long)B * H * Wd, C, st);
+        } else {
+            return rc;
+        }
+    }
+    if (dX && !fast1d) {
         DwParams p{};
         p.X = dY; p.Wt = Wt; p.Y = dX; p.Xorig = X;
         p.scale = pre_scale; p.shift = pre_shift; p.dscale = dpre_scale; p.dshift = dpre_shift;
         p.H = H; p.Wd = Wd; p.C = C; p.kh = kh; p.kw = kw;
         p.relu_in = 0; p.flip = 1; p.mask = relu_in; p.accum = (flags & NPF_ACCUM) ? 1 : 0;
+        p.res = (flags & NPF_ADD_DY) ? dY : nullptr;   // residual-branch gradient added in the epilogue
         switch (kwsel) {
             case 9: rc = launch_dw<9>(p, B, st); break;
             case 11: rc = launch_dw<11>(p, B, st); break;

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnpf_b200.so")
 # error codes / flags (mirror include/npf_b200.h)
 NPF_OK, NPF_EINVAL, NPF_ECUDA, NPF_ENOTSUP = 0, -1, -2, -3
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
-RELU_OUT, RELU_IN, ACCUM = 1, 2, 4
+RELU_OUT, RELU_IN, ACCUM, ADD_DY = 1, 2, 4, 8
 
 P, I, L, F = c_void_p, c_int, c_long, c_float
 

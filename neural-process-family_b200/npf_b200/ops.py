@@ -7,7 +7,7 @@ fp32, contiguous, on a CUDA device.  No CPU fallback: calling an op with CPU ten
 import torch
 
 from . import _cabi
-from ._cabi import ACCUM, RELU_IN, RELU_OUT, call
+from ._cabi import ACCUM, ADD_DY, RELU_IN, RELU_OUT, call
 
 __all__ = [
     "set_precision", "get_precision", "linear", "mlp_chain", "setconv", "dwconv", "channel_moments",
@@ -227,14 +227,17 @@ class _DWConv(torch.autograd.Function):
         call("npf_dwconv_fwd", _p(x), _p(Wt), _p(bias), _p(res_c), _p(y), B, H, Wd, C, kh, kw,
              RELU_IN if relu_in else 0, _p(scale), _p(shift), _stream())
         ctx.save_for_backward(x, Wt, scale, shift)
-        ctx.cfg = (B, H, Wd, C, kh, kw, relu_in, bias is not None, res is not None)
+        # residual == conv input (ResConvBlock with one conv layer): its gradient is folded into the dX kernel
+        res_is_x = res is not None and res_c.data_ptr() == x.data_ptr() and res_c.shape == x.shape
+        ctx.cfg = (B, H, Wd, C, kh, kw, relu_in, bias is not None, res is not None, res_is_x)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, Wt, scale, shift = ctx.saved_tensors
-        B, H, Wd, C, kh, kw, relu_in, has_bias, has_res = ctx.cfg
+        B, H, Wd, C, kh, kw, relu_in, has_bias, has_res, res_is_x = ctx.cfg
         dy = _c(dy)
+        fuse_res = res_is_x and ctx.needs_input_grad[0]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dW = torch.zeros_like(Wt)
         db = torch.zeros(C, device=x.device, dtype=torch.float32) if has_bias else None
@@ -244,8 +247,10 @@ class _DWConv(torch.autograd.Function):
         if need_aff and dx is None:
             dx = torch.empty_like(x)
         call("npf_dwconv_bwd", _p(dy), _p(x), _p(Wt), _p(dx), _p(dW), _p(db), B, H, Wd, C, kh, kw,
-             RELU_IN if relu_in else 0, _p(scale), _p(shift), _p(dscale), _p(dshift), _stream())
-        return (dx if ctx.needs_input_grad[0] else None, dW, db, dy if has_res else None, None, dscale, dshift)
+             (RELU_IN if relu_in else 0) | (ADD_DY if fuse_res else 0), _p(scale), _p(shift), _p(dscale), _p(dshift),
+             _stream())
+        dres = None if (fuse_res or not has_res) else dy
+        return (dx if ctx.needs_input_grad[0] else None, dW, db, dres, None, dscale, dshift)
 
 
 def dwconv(x, weight, bias=None, res=None, relu_in=False, scale=None, shift=None):

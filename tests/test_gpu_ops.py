@@ -281,3 +281,22 @@ def test_range_flag(ops):
 def test_cpu_tensors_raise(ops):
     with pytest.raises(RuntimeError):
         ops.linear(torch.randn(3, 4), torch.randn(5, 4))
+
+
+def test_dwconv_residual_is_input(ops):
+    """ResConvBlock with one conv layer: the residual IS the conv input; its gradient is folded into the dX kernel."""
+    x, W, b = _g(2, 50, 128, seed=1), _g(128, 1, 11, seed=2, scale=0.3), _g(128, seed=3)
+    r = [t.clone().requires_grad_(True) for t in (x, W, b)]
+    c = [_cu(t, True) for t in (x, W, b)]
+    yr = _dw_ref(r[0], r[1], r[2], r[0], True, None, None)
+    yc = ops.dwconv(c[0], c[1], c[2], c[0], True, None, None)
+    assert rel_err(yc, yr) < TOL
+    _check_grads(c, r, yc, yr, ["x", "W", "b"])
+    x2 = _g(1, 5, 6, 32, seed=4)
+    W2 = _g(32, 1, 3, 3, seed=5, scale=0.3)
+    r2 = [t.clone().requires_grad_(True) for t in (x2, W2)]
+    c2 = [_cu(t, True) for t in (x2, W2)]
+    yr2 = _dw_ref(r2[0], r2[1], None, r2[0], True, None, None)
+    yc2 = ops.dwconv(c2[0], c2[1], None, c2[0], True, None, None)
+    assert rel_err(yc2, yr2) < TOL
+    _check_grads(c2, r2, yc2, yr2, ["x", "W"])
