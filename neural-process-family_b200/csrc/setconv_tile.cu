@@ -1,12 +1,315 @@
-// Shared-memory / TMA-staged SetConv for the induced -> target direction (regular key grid).
-// Placeholder: reports NPF_ENOTSUP so callers use the generic kernels in setconv.cu.
+// SetConv fast path for the induced -> target direction (regular key grid, up to 128 channels).
+//
+// The generic kernels (setconv.cu) give every query its own sweep over its sigma-window: with ~20-50 grid rows per
+// window and 128 queries per task every row of V is fetched ~7x (L2-bandwidth bound, ~6x the algorithmic bytes).
+// Here one CTA owns one task and first SORTS its queries by position (rank by counting, in shared memory); a warp
+// then processes 8 position-adjacent queries together over the UNION of their windows, so each V row is loaded once
+// per group (one 16-byte load per lane = the whole 128-channel row per warp) and feeds 8 x 4 FMAs per lane.  The value
+// gradient uses the mirrored scheme: 8 adjacent grid rows against the contiguous run of sorted queries whose windows
+// touch them.  Weights are computed one row (or query) per lane and broadcast with shuffles.
+//
+//   mode 0: feat = sum_k softmax_k(a) V_k, dens, (max logit, sum exp)            (forward)
+//   mode 1: d theta: T - G*A1 + ddens*A2 with max-shifted logits (see setconv.cu)
+//   dV    : dV[k] = sum_q w_qk dF_q                                               (gather, no atomics)
 #include "common.cuh"
 
 namespace npf {
 
-int setconv_tile_fwd(const float*, long, const float*, long, const float*, const float*, float*, float*, float*, int,
-                     int, int, int, cudaStream_t) { return NPF_ENOTSUP; }
-int setconv_tile_bwd(const float*, long, const float*, long, const float*, const float*, const float*, const float*,
-                     const float*, const float*, float*, float*, int, int, int, int, cudaStream_t) { return NPF_ENOTSUP; }
+constexpr float kWindowLogT = 41.6f;
+constexpr int kGroup = 8;        // queries (or rows) per warp pass
+constexpr int kMaxQ = 2048;      // queries per task handled in shared memory
+
+__device__ __forceinline__ float logit_t(float xq, float xk, float sigma) {
+    const float t = fabsf(xk - xq) / sigma;
+    return -(t * t);
+}
+
+// identical policy to key_window() in setconv.cu
+__device__ __forceinline__ void window_t(const float* __restrict__ keys, int K, float xq, float sigma, int& lo_o, int& hi_o) {
+    lo_o = 0; hi_o = K - 1;
+    if (K < 3) return;
+    const float x0 = __ldg(keys), x1 = __ldg(keys + K - 1);
+    const float dx = (x1 - x0) / (float)(K - 1);
+    if (!(dx > 0.f)) return;
+    float pos = (xq - x0) / dx;
+    pos = fminf(fmaxf(pos, 0.f), (float)(K - 1));
+    const int n0 = (int)rintf(pos);
+    const float dn = xq - __ldg(keys + n0);
+    const float D = sqrtf(dn * dn + kWindowLogT * sigma * sigma);
+    float lo = floorf((xq - D - x0) / dx) - 1.f;
+    float hi = ceilf((xq + D - x0) / dx) + 1.f;
+    if (!(lo == lo) || !(hi == hi)) return;
+    lo = fminf(fmaxf(lo, 0.f), (float)(K - 1));
+    hi = fminf(fmaxf(hi, 0.f), (float)(K - 1));
+    lo_o = min((int)lo, n0);
+    hi_o = max((int)hi, n0);
+}
+
+struct TileSmem {
+    float* xs;    // [Q] sorted query positions
+    int* ord;     // [Q] original index of the sorted query
+    int* lo;      // [Q] window (in sorted order)
+    int* hi;
+    float* m;     // [Q] max logit
+    float* invs;  // [Q] 1 / sum exp(a - m)
+};
+
+__device__ __forceinline__ TileSmem carve(float* base, int Q) {
+    TileSmem t;
+    t.xs = base;
+    t.ord = reinterpret_cast<int*>(base + Q);
+    t.lo = t.ord + Q;
+    t.hi = t.lo + Q;
+    t.m = reinterpret_cast<float*>(t.hi + Q);
+    t.invs = t.m + Q;
+    return t;
+}
+
+// sort the task's queries by position (stable: ties by index) via rank counting
+__device__ __forceinline__ void sort_queries(const TileSmem& t, const float* __restrict__ qb, int Q, float* scratch /*[Q]*/) {
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) scratch[i] = __ldg(qb + i);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+        const float x = scratch[i];
+        int rank = 0;
+        for (int j = 0; j < Q; ++j) {
+            const float y = scratch[j];
+            rank += (y < x) || (y == x && j < i);
+        }
+        t.xs[rank] = x;
+        t.ord[rank] = i;
+    }
+    __syncthreads();
+}
+
+// mode 0 forward / mode 1 theta gradient
+template <int MODE>
+__global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+                                                          long qry_bs, const float* __restrict__ values, const float* __restrict__ theta,
+                                                          float* __restrict__ feat_o, float* __restrict__ dens_o, float* __restrict__ mstat_o,
+                                                          const float* __restrict__ feat_i, const float* __restrict__ mstat_i,
+                                                          const float* __restrict__ dfeat, const float* __restrict__ ddens,
+                                                          float* __restrict__ dtheta, int K, int Q, int C) {
+    extern __shared__ float smem[];
+    __shared__ float part[8];
+    const TileSmem t = carve(smem, Q);
+    float* scratch = t.invs + Q;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float th = __ldg(theta);
+    const float sigma = 1e-5f + softplus_f(th);
+    const float* kb = keys + (long)b * key_bs;
+    const float* vb = values + (long)b * K * C;
+    sort_queries(t, queries + (long)b * qry_bs, Q, scratch);
+
+    // per-query window and softmax statistics (one thread per query; windows are a few dozen keys)
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+        const float xq = t.xs[i];
+        int lo, hi;
+        window_t(kb, K, xq, sigma, lo, hi);
+        t.lo[i] = lo; t.hi[i] = hi;
+        const long oq = (long)b * Q + t.ord[i];
+        if (MODE == 0) {
+            float m = -INFINITY;
+            for (int k = lo; k <= hi; ++k) m = fmaxf(m, logit_t(xq, __ldg(kb + k), sigma));
+            float s = 0.f, d = 0.f;
+            for (int k = lo; k <= hi; ++k) {
+                const float a = logit_t(xq, __ldg(kb + k), sigma);
+                s += expf(a - m);
+                d += expf(a);
+            }
+            t.m[i] = m; t.invs[i] = 1.f / s;
+            dens_o[oq] = d;
+            mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = s;
+        } else {
+            t.m[i] = __ldg(mstat_i + oq * 2);
+            t.invs[i] = 1.f / __ldg(mstat_i + oq * 2 + 1);
+        }
+    }
+    __syncthreads();
+
+    const int c4 = lane * 4;
+    const bool ch_ok = c4 < C;
+    float warp_contrib = 0.f;
+    const int n_groups = (Q + kGroup - 1) / kGroup;
+    for (int grp = warp; grp < n_groups; grp += 8) {
+        const int t0 = grp * kGroup;
+        const int nt = min(kGroup, Q - t0);
+        int glo = t.lo[t0], ghi = t.hi[t0];
+        for (int j = 1; j < nt; ++j) { glo = min(glo, t.lo[t0 + j]); ghi = max(ghi, t.hi[t0 + j]); }
+        float4 acc[kGroup];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float a1[kGroup], a2[kGroup];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+        for (int base = glo; base <= ghi; base += 32) {
+            const int row = base + lane;
+            const float xk = (row <= ghi) ? __ldg(kb + row) : 0.f;
+            float w[kGroup];
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                w[j] = 0.f;
+                if (j < nt && row <= ghi && row >= t.lo[t0 + j] && row <= t.hi[t0 + j]) {
+                    const float a = logit_t(t.xs[t0 + j], xk, sigma);
+                    const float e = expf(a - t.m[t0 + j]) * t.invs[t0 + j];
+                    if (MODE == 0) w[j] = e;
+                    else {
+                        w[j] = e * (a - t.m[t0 + j]);
+                        a1[j] += w[j];
+                        a2[j] = fmaf(expf(a), a, a2[j]);
+                    }
+                }
+            }
+            const int cnt = min(32, ghi - base + 1);
+            for (int rr = 0; rr < cnt; ++rr) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ch_ok) v = __ldg(reinterpret_cast<const float4*>(vb + (long)(base + rr) * C + c4));
+#pragma unroll
+                for (int j = 0; j < kGroup; ++j) {
+                    const float wj = __shfl_sync(0xffffffffu, w[j], rr);
+                    acc[j].x = fmaf(wj, v.x, acc[j].x); acc[j].y = fmaf(wj, v.y, acc[j].y);
+                    acc[j].z = fmaf(wj, v.z, acc[j].z); acc[j].w = fmaf(wj, v.w, acc[j].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            if (j >= nt) continue;
+            const long oq = (long)b * Q + t.ord[t0 + j];
+            if (MODE == 0) {
+                if (ch_ok) *reinterpret_cast<float4*>(feat_o + oq * C + c4) = acc[j];
+            } else {
+                float T = 0.f, G = 0.f;
+                if (ch_ok) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(dfeat + oq * C + c4));
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(feat_i + oq * C + c4));
+                    T = g.x * acc[j].x + g.y * acc[j].y + g.z * acc[j].z + g.w * acc[j].w;
+                    G = g.x * f.x + g.y * f.y + g.z * f.z + g.w * f.w;
+                }
+                T = warp_sum(T); G = warp_sum(G);
+                const float A1 = warp_sum(a1[j]), A2 = warp_sum(a2[j]);
+                warp_contrib += T - G * A1 + __ldg(ddens + oq) * A2;
+            }
+        }
+    }
+    if (MODE == 1) {
+        if (lane == 0) part[warp] = warp_contrib;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += part[i];
+            atomicAdd(dtheta, tot * (-2.f / sigma) * sigmoid_f(th));
+        }
+    }
+}
+
+// dV[b,k,:] = sum_q w_qk dF[b,q,:]: a warp owns 8 adjacent key rows and walks the contiguous run of sorted queries whose
+// window touches them.
+__global__ void __launch_bounds__(256) setconv_grp_dv_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+                                                             long qry_bs, const float* __restrict__ theta, const float* __restrict__ mstat,
+                                                             const float* __restrict__ dfeat, float* __restrict__ dvalues, int K, int Q, int C) {
+    extern __shared__ float smem[];
+    const TileSmem t = carve(smem, Q);
+    float* scratch = t.invs + Q;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float sigma = 1e-5f + softplus_f(__ldg(theta));
+    const float* kb = keys + (long)b * key_bs;
+    sort_queries(t, queries + (long)b * qry_bs, Q, scratch);
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+        int lo, hi;
+        window_t(kb, K, t.xs[i], sigma, lo, hi);
+        t.lo[i] = lo; t.hi[i] = hi;
+        const long oq = (long)b * Q + t.ord[i];
+        t.m[i] = __ldg(mstat + oq * 2);
+        t.invs[i] = 1.f / __ldg(mstat + oq * 2 + 1);
+    }
+    __syncthreads();
+    const int c4 = lane * 4;
+    const bool ch_ok = c4 < C;
+    const int n_rgroups = (K + kGroup - 1) / kGroup;
+    for (int rg = warp; rg < n_rgroups; rg += 8) {
+        const int k0 = rg * kGroup, nr = min(kGroup, K - k0);
+        // lo[] and hi[] are non-decreasing in sorted order: queries with hi >= k0 and lo <= k0+nr-1 form one run
+        int ta = 0, tb = Q;
+        { int l = 0, h = Q; while (l < h) { const int mid = (l + h) >> 1; if (t.hi[mid] >= k0) h = mid; else l = mid + 1; } ta = l; }
+        { int l = ta, h = Q; while (l < h) { const int mid = (l + h) >> 1; if (t.lo[mid] > k0 + nr - 1) h = mid; else l = mid + 1; } tb = l; }
+        float xk[kGroup];
+#pragma unroll
+        for (int r = 0; r < kGroup; ++r) xk[r] = (r < nr) ? __ldg(kb + k0 + r) : 0.f;
+        float4 acc[kGroup];
+#pragma unroll
+        for (int r = 0; r < kGroup; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = ta; base < tb; base += 32) {
+            const int ti = base + lane;
+            float w[kGroup];
+#pragma unroll
+            for (int r = 0; r < kGroup; ++r) {
+                w[r] = 0.f;
+                if (ti < tb && r < nr && k0 + r >= t.lo[ti] && k0 + r <= t.hi[ti])
+                    w[r] = expf(logit_t(t.xs[ti], xk[r], sigma) - t.m[ti]) * t.invs[ti];
+            }
+            const int cnt = min(32, tb - base);
+            for (int tt = 0; tt < cnt; ++tt) {
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ch_ok) g = __ldg(reinterpret_cast<const float4*>(dfeat + ((long)b * Q + t.ord[base + tt]) * C + c4));
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r) {
+                    const float wr = __shfl_sync(0xffffffffu, w[r], tt);
+                    acc[r].x = fmaf(wr, g.x, acc[r].x); acc[r].y = fmaf(wr, g.y, acc[r].y);
+                    acc[r].z = fmaf(wr, g.z, acc[r].z); acc[r].w = fmaf(wr, g.w, acc[r].w);
+                }
+            }
+        }
+        if (ch_ok) {
+#pragma unroll
+            for (int r = 0; r < kGroup; ++r)
+                if (r < nr) *reinterpret_cast<float4*>(dvalues + ((long)b * K + k0 + r) * C + c4) = acc[r];
+        }
+    }
+}
+
+static bool tile_ok(int K, int Q, int C, const void* values) {
+    return C % 4 == 0 && C >= 8 && C <= 128 && Q >= 1 && Q <= kMaxQ && K >= 3 && (reinterpret_cast<uintptr_t>(values) & 15) == 0;
+}
+static size_t tile_smem(int Q) { return sizeof(float) * 7 * (size_t)Q; }
+
+int setconv_tile_fwd(const float* keys, long key_bs, const float* queries, long qry_bs, const float* values,
+                     const float* theta, float* feat, float* dens, float* mstat, int B, int K, int Q, int C,
+                     cudaStream_t st) {
+    if (!tile_ok(K, Q, C, values) || (reinterpret_cast<uintptr_t>(feat) & 15)) return NPF_ENOTSUP;
+    const size_t smem = tile_smem(Q);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(setconv_grp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+    setconv_grp_kernel<0><<<B, 256, smem, st>>>(keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, nullptr, nullptr,
+                                                nullptr, nullptr, nullptr, K, Q, C);
+    count_launch();
+    return check_launch("setconv_grp_kernel<fwd>");
+}
+
+int setconv_tile_bwd(const float* keys, long key_bs, const float* queries, long qry_bs, const float* values,
+                     const float* theta, const float* feat, const float* mstat, const float* dfeat,
+                     const float* ddens, float* dvalues, float* dtheta, int B, int K, int Q, int C, cudaStream_t st) {
+    if (!tile_ok(K, Q, C, values) || (reinterpret_cast<uintptr_t>(dfeat) & 15) || (reinterpret_cast<uintptr_t>(feat) & 15) ||
+        (dvalues && (reinterpret_cast<uintptr_t>(dvalues) & 15)))
+        return NPF_ENOTSUP;
+    const size_t smem = tile_smem(Q);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(setconv_grp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(setconv_grp_dv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr = true;
+    }
+    setconv_grp_kernel<1><<<B, 256, smem, st>>>(keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat,
+                                                dfeat, ddens, dtheta, K, Q, C);
+    count_launch();
+    int rc = check_launch("setconv_grp_kernel<dtheta>");
+    if (rc != NPF_OK || !dvalues) return rc;
+    setconv_grp_dv_kernel<<<B, 256, smem, st>>>(keys, key_bs, queries, qry_bs, theta, mstat, dfeat, dvalues, K, Q, C);
+    count_launch();
+    return check_launch("setconv_grp_dv_kernel");
+}
 
 }  // namespace npf
