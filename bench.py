@@ -314,13 +314,13 @@ def main():
     tasks = B * world * args.steps
     value = tasks / (dev_ms * 1e-3)
     peaks = measured_peaks()
-    roof = roofline(wl, ktimes, n_prof, B, peaks)
+    roof, roof_table = roofline(wl, ktimes, n_prof, B, peaks)
     line = dict(metric="tasks/sec (meta-batch fwd+bwd)", value=value, unit="tasks/s", n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype={"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (fp32-equivalent)"}[args.precision],
                 data="synthetic", config=cfg, clocks=clocks,
                 e2e=dict(value=tasks / (e2e_ms * 1e-3), unit="tasks/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
-                gpu_launches=launches, wall_ms_per_step=t_wall * 1e3 / args.steps, roofline=roof,
+                gpu_launches=launches, wall_ms_per_step=t_wall * 1e3 / args.steps, roofline=roof, kernel_rooflines=roof_table,
                 kernel_ms_per_step={k: round(v[0] / n_prof, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])})
     if not args.no_cpu_baseline:
         cb, _, _, _ = cpu_reference_timing(wl, 10, 2)
@@ -334,41 +334,30 @@ def main():
 
 
 def roofline(wl, ktimes, n_prof, B, peaks):
-    """Roofline of the dominant kernel group from the live CUDA-event breakdown.  Algorithmic bytes / flops per task are
-    SURVEY.md section 8(d)'s figures (stated in DESIGN.md)."""
+    """Roofline of the dominant C-ABI entry point (largest share of the step) plus the same figures for every timed
+    entry point.  achieved = algorithmic bytes (every operand and result once, fp32) of all its
+    launches / their summed CUDA-event time, measured live on the launching stream; peak = MEASURED_PEAKS.json."""
     if not ktimes:
-        return None
-    name = max(ktimes, key=lambda k: ktimes[k][0])
-    total_ms, calls = ktimes[name]
-    ms_per_launch = total_ms / max(calls, 1)
-    r = 128
-    out = dict(kernel=name, launches_per_step=calls // n_prof, avg_launch_ms=ms_per_launch,
-               share_of_step=total_ms / sum(v[0] for v in ktimes.values()), peak_source=peaks["source"], traffic=None)
-    if name.startswith("npf_linear"):
-        # dominant 128x128 layers: 2*M*K*N flops per launch; M = rows per launch varies, so use the step total
-        flops_step = gemm_flops_per_step(wl, B)
-        ach = flops_step / (total_ms / n_prof * 1e-3) / 1e12
-        out.update(bound="tensor", achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"],
-                   note="all npf_linear_* launches of one step: algorithmic GEMM flops / their summed CUDA-event time; "
-                        "fp32 FFMA path vs the measured bf16 tensor peak")
-    elif name.startswith("npf_setconv"):
-        I = 384
-        bytes_task = 4 * (I * r + wl["T"] * 1 + wl["T"] * r)
-        ach = bytes_task * B / (ms_per_launch * 1e-3) / 1e9
-        out.update(bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
-                   note="algorithmic bytes 4*(I*r + T*x + T*r) per task (induced->target direction)")
-    else:
-        out.update(bound="hbm", achieved=None, peak=peaks["hbm_gbs"], unit="GB/s", frac=None)
-    return out
-
-
-def gemm_flops_per_step(wl, B):
-    r, fam = 128, wl["family"]
-    if fam == "ConvCNP":
-        I, T = 384, wl["T"]
-        fwd = 3 * 2 * I * r * r + 2 * I * 2 * r + 2 * T * (r + 1) * r + 4 * 2 * T * r * r + 2 * T * r * 2
-        return 3 * fwd * B
-    return 0
+        return None, None
+    total = sum(v[0] for v in ktimes.values())
+    table = {}
+    for name, (ms, calls, nbytes, flops) in ktimes.items():
+        if not nbytes:
+            continue
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        tfs = flops / (ms * 1e-3) / 1e12
+        # the binding roof: whichever of HBM / tensor time is longer for this op mix
+        t_hbm, t_tc = nbytes / (peaks["hbm_gbs"] * 1e9), flops / (peaks["bf16_tflops"] * 1e12)
+        bound = "hbm" if t_hbm >= t_tc else "tensor"
+        table[name] = dict(bound=bound, achieved=gbs if bound == "hbm" else tfs, peak=peaks["hbm_gbs"] if bound == "hbm" else peaks["bf16_tflops"],
+                           unit="GB/s" if bound == "hbm" else "TFLOP/s", frac=(gbs / peaks["hbm_gbs"]) if bound == "hbm" else tfs / peaks["bf16_tflops"],
+                           launches_per_step=calls // n_prof, ms_per_step=ms / n_prof, share_of_step=ms / total, gbytes_per_s=gbs, tflops=tfs)
+    if not table:
+        return None, None
+    name = max(table, key=lambda k: table[k]["share_of_step"])
+    dom = dict(kernel=name, peak_source=peaks["source"], traffic=None, avg_launch_ms=table[name]["ms_per_step"] / max(table[name]["launches_per_step"], 1),
+               **{k: table[name][k] for k in ("bound", "achieved", "peak", "unit", "frac", "launches_per_step", "share_of_step")})
+    return dom, table
 
 
 if __name__ == "__main__":

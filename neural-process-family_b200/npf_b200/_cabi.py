@@ -84,7 +84,27 @@ def load():
     return lib
 
 
-_timing = None  # name -> list of (start_event, end_event) when enabled
+_timing = None  # name -> list of (start_event, end_event, algorithmic_bytes, flops) when enabled
+
+
+def _lin(M, K, N):
+    return 4 * (M * K + M * N + N * K), 2 * M * K * N
+
+
+# Algorithmic HBM bytes / flops of one call, from its arguments (SURVEY.md section 8d conventions: every operand and
+# result once, fp32).  Used only by the timing mode below.
+ALGO = {
+    "npf_linear_fwd": lambda a: _lin(a[7], a[8], a[9]),
+    "npf_linear_bwd_data": lambda a: _lin(a[6], a[7], a[8]),
+    "npf_linear_bwd_weight": lambda a: _lin(a[7], a[8], a[9]),
+    # keys/queries + values + feat (+ dens/stat): B*(K*C + Q*C)*4 dominates
+    "npf_setconv_fwd": lambda a: (4 * a[9] * (a[10] * a[12] + a[11] * a[12] + 3 * a[11] + a[10]), 2 * a[9] * a[11] * a[10] * a[12]),
+    "npf_setconv_bwd": lambda a: (4 * a[13] * (2 * a[14] * a[16] + 2 * a[15] * a[16] + 4 * a[15] + a[14]), 6 * a[13] * a[15] * a[14] * a[16]),
+    "npf_dwconv_fwd": lambda a: (4 * a[5] * a[6] * a[7] * a[8] * (3 if a[3] else 2), 2 * a[5] * a[6] * a[7] * a[8] * a[9] * a[10]),
+    "npf_dwconv_bwd": lambda a: (4 * a[6] * a[7] * a[8] * a[9] * 4, 4 * a[6] * a[7] * a[8] * a[9] * a[10] * a[11]),
+    "npf_xattn_fwd": lambda a: (4 * a[5] * a[8] * (2 * a[6] * a[9] + a[7] * a[9] + a[7] * a[10] + a[6]), 2 * a[5] * a[8] * a[6] * a[7] * (a[9] + a[10])),
+    "npf_xattn_bwd": lambda a: (4 * a[9] * a[12] * (4 * a[10] * a[13] + 2 * a[11] * a[13] + 2 * a[11] * a[14]), 5 * a[9] * a[12] * a[10] * a[11] * (a[13] + a[14])),
+}
 
 
 def enable_timing(on):
@@ -94,12 +114,12 @@ def enable_timing(on):
 
 
 def collect_timing():
-    """name -> (total_ms, n_calls); synchronises.  Clears the log."""
+    """name -> (total_ms, n_calls, algorithmic_bytes, flops); synchronises.  Clears the log."""
     import torch
     torch.cuda.synchronize()
     out = {}
     for name, evs in (_timing or {}).items():
-        out[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+        out[name] = (sum(a.elapsed_time(b) for a, b, _, _ in evs), len(evs), sum(e[2] for e in evs), sum(e[3] for e in evs))
     if _timing is not None:
         _timing.clear()
     return out
@@ -114,7 +134,8 @@ def call(name, *args):
         a.record()
         rc = getattr(lib, name)(*args)
         b.record()
-        _timing.setdefault(name, []).append((a, b))
+        nbytes, flops = ALGO[name](args) if name in ALGO else (0, 0)
+        _timing.setdefault(name, []).append((a, b, nbytes, flops))
     else:
         rc = getattr(lib, name)(*args)
     if rc != NPF_OK:
