@@ -284,18 +284,20 @@ __global__ void __launch_bounds__(256) dwconv1d_kernel(Dw1Params p) {
         reinterpret_cast<float*>(Ws4)[(size_t)j * p.C + c] = v;
     }
     __syncthreads();
-    const long gid = (long)blockIdx.x * G + g;
-    if (gid >= p.n_groups) return;
-    const long b = gid / p.groups_per_seq;
-    const int l0 = (int)(gid % p.groups_per_seq) * 8;
     const int c = 4 * q;
-    const float* xb = p.X + (b * p.L) * (long)p.C + c;
     const bool affine = p.relu_in && p.scale != nullptr;
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.scale && (p.relu_in || p.mask)) {
         sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
         sh = __ldg(reinterpret_cast<const float4*>(p.shift + c));
     }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+    // persistent: the filters are staged once per CTA, then the CTA strides over the position groups
+    for (long gid = (long)blockIdx.x * G + g; gid < p.n_groups; gid += (long)gridDim.x * G) {
+    const long b = gid / p.groups_per_seq;
+    const int l0 = (int)(gid % p.groups_per_seq) * 8;
+    const float* xb = p.X + (b * p.L) * (long)p.C + c;
     float4 xin[KW + 7];
 #pragma unroll
     for (int xc = 0; xc < KW + 7; ++xc) {
@@ -320,8 +322,6 @@ __global__ void __launch_bounds__(256) dwconv1d_kernel(Dw1Params p) {
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) acc[pp] = f4_fma(w, xin[pp + j], acc[pp]);
     }
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c));
 #pragma unroll
     for (int pp = 0; pp < 8; ++pp) {
         const int pos = l0 + pp;
@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(256) dwconv1d_kernel(Dw1Params p) {
         if (p.accum) { const float4 o = *out; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
         *out = v;
     }
+    }   // position-group loop
 }
 
 // 1-D filter + bias gradient in one pass: dWt[c,j] += sum dY[b,l,c] act(X)[b,l+j-p,c] ; dbias[c] += sum dY[b,l,c].
@@ -424,7 +425,13 @@ static int launch_dw1(Dw1Params& p, int B, cudaStream_t st) {
     p.groups_per_seq = (p.L + 7) / 8;
     p.n_groups = (long)B * p.groups_per_seq;
     const size_t smem = sizeof(float) * (size_t)KW * p.C;
-    dwconv1d_kernel<KW><<<(unsigned)cdiv(p.n_groups, G), 256, smem, st>>>(p);
+    static int occ = 0;
+    if (!occ) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dwconv1d_kernel<KW>, 256, smem) != cudaSuccess || occ < 1) { occ = 1; cudaGetLastError(); }
+    }
+    long grid = cdiv(p.n_groups, G);
+    if (grid > (long)kNumSMs * occ) grid = (long)kNumSMs * occ;
+    dwconv1d_kernel<KW><<<(unsigned)grid, 256, smem, st>>>(p);
     count_launch();
     return check_launch("dwconv1d_kernel");
 }
@@ -438,8 +445,12 @@ static int launch_dw1_wgrad(Dw1Params& p, const float* dY, float* dWt, float* db
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(dwconv1d_wgrad_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     if (smem > 200 * 1024) return NPF_ENOTSUP;
+    static int occ = 0;
+    if (!occ) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dwconv1d_wgrad_kernel<KW>, 256, smem) != cudaSuccess || occ < 1) { occ = 1; cudaGetLastError(); }
+    }
     long grid = cdiv(p.n_groups, G);
-    if (grid > 2L * kNumSMs) grid = 2L * kNumSMs;
+    if (grid > (long)kNumSMs * occ) grid = (long)kNumSMs * occ;
     dwconv1d_wgrad_kernel<KW><<<(unsigned)grid, 256, smem, st>>>(p, dY, dWt, dbias);
     count_launch();
     return check_launch("dwconv1d_wgrad_kernel");

@@ -104,12 +104,14 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // A half-warp owns one core matrix per step (conflict-free 8-byte stores; 8 full 32-byte sectors per load).
 // Loads are split from the convert+store so that a whole tile (16 x 16 B per thread = 64 KB per CTA) is in
 // flight at once, and so that the NEXT tile can be prefetched into registers under the current tile's MMA + epilogue.
-constexpr int kPre = 16;   // float4 registers per thread per batch
+constexpr int kLinThreads = 512;            // linear_tc_kernel: 16 warps (32 half-warps stage 32 core matrices per step)
+constexpr int kHW = kLinThreads / 16;
+constexpr int kPre = 8;                     // float4 registers per thread per batch: 128 x 128 tile / 4 / 512 threads
 
 __device__ __forceinline__ int ilog2(int x) { return 31 - __clz(x); }
 
 // All tile extents on this path are powers of two (checked on the host), so the (core-matrix -> row group, k chunk)
-// maps are shifts, and because 16 half-warps step through core matrices 16 at a time the k chunk of a thread is
+// maps are shifts, and because 32 half-warps step through core matrices 32 at a time the k chunk of a thread is
 // CONSTANT: only the row group advances -> one pointer increment and one smem-offset increment per step.
 __device__ __forceinline__ void load_kmajor(float4 (&pre)[kPre], const float* __restrict__ src, long ld, long row0, int rows_valid,
                                             int R, int KR, int cm_base, int vec_ok) {
@@ -119,8 +121,7 @@ __device__ __forceinline__ void load_kmajor(float4 (&pre)[kPre], const float* __
     const int cm0 = cm_base + hw;
     const int kc = cm0 & (n_kc - 1);
     int rg = cm0 >> lg;
-    const int rg_step = n_kc >= 16 ? 1 : (16 >> lg), n_rg = R >> 3;
-    // n_kc > 16 cannot happen (KR <= 128); n_kc == 16 -> each step is the next row group
+    const int rg_step = kHW >> lg, n_rg = R >> 3;   // n_kc <= 16 divides kHW = 32
     const float* g = src + (row0 + rg * 8 + r) * ld + kc * 8 + half * 4;
     const long gstep = (long)rg_step * 8 * ld;
 #pragma unroll
@@ -144,7 +145,7 @@ __device__ __forceinline__ void store_kmajor(const float4 (&pre)[kPre], uint8_t*
     const int cm0 = cm_base + hw;
     const int kc = cm0 & (n_kc - 1);
     int rg = cm0 >> lg;
-    const int rg_step = n_kc >= 16 ? 1 : (16 >> lg), n_rg = R >> 3;
+    const int rg_step = kHW >> lg, n_rg = R >> 3;
     uint32_t off = (uint32_t)kc * ((uint32_t)R * 16u) + (uint32_t)rg * 128u + (uint32_t)r * 16u + (uint32_t)half * 8u;
 #pragma unroll
     for (int i = 0; i < kPre; ++i) {
@@ -169,10 +170,10 @@ __device__ __forceinline__ void stage_kmajor_transposed(uint8_t* hi, uint8_t* lo
                                                         int KR /*reduction = N*/, int vec_ok) {
     const uint32_t lbo = (uint32_t)R * 16u;
     const int rq = R >> 2, lgq = ilog2(rq), total = rq * KR;      // float4 count; rq is a power of two <= 64
-    const int row0 = (threadIdx.x & (rq - 1)) * 4;                // constant per thread (256 is a multiple of rq)
-    for (int base = 0; base < total; base += 256 * kPre) {
+    const int row0 = (threadIdx.x & (rq - 1)) * 4;                // constant per thread (512 is a multiple of rq)
+    for (int base = 0; base < total; base += kLinThreads * kPre) {
         float4 pre[kPre];
-        const int n0 = (base + threadIdx.x) >> lgq, n_step = 256 >> lgq;
+        const int n0 = (base + threadIdx.x) >> lgq, n_step = kLinThreads >> lgq;
 #pragma unroll
         for (int i = 0; i < kPre; ++i) {
             const int n = n0 + i * n_step;
@@ -228,8 +229,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ------------------------------------------------------------------------------------------------ fwd / bwd-data
+constexpr int kScratchLd = 36;     // floats per staged row: 32 + 4 keeps both the row-wise STS.128 and the LDS.128 conflict-free
+
 template <int NSPLIT>
-__global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcLinParams p) {
+__global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
@@ -241,14 +244,16 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcL
     uint8_t* a_lo = a_hi + a_bytes;                               // only touched when NSPLIT == 3
     uint8_t* b_hi = smem_raw + (NSPLIT == 3 ? 2 : 1) * a_bytes;
     uint8_t* b_lo = b_hi + b_bytes;
+    float* scratch_all = reinterpret_cast<float*>(smem_raw + (NSPLIT == 3 ? 2 : 1) * (a_bytes + b_bytes));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* scratch = scratch_all + warp * (32 * kScratchLd);
     const uint32_t ncols = NO <= 32 ? 32u : (NO <= 64 ? 64u : (NO <= 128 ? 128u : 256u));
     if (warp == 0) tmem_alloc(&tmem_slot, ncols);
     if (tid == 0) mbar_init(&mma_bar, 1);
-    for (int c = tid; c < NO; c += 256) {
-        s_bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
-        s_w2[c] = p.w2 ? __ldg(p.w2 + (long)c * p.ldw2) : 0.f;
+    for (int c = tid; c < 256; c += kLinThreads) {
+        s_bias[c] = (p.bias && c < NO) ? __ldg(p.bias + c) : 0.f;
+        s_w2[c] = (p.w2 && c < NO) ? __ldg(p.w2 + (long)c * p.ldw2) : 0.f;
     }
 
     float4 pre[kPre];
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcL
         stage_kmajor_transposed<NSPLIT>(b_hi, b_lo, p.W, p.ldw, NO, KR, p.w_vec);
     } else {
         const int n_cm = (NO >> 3) * (KR >> 3);
-        for (int base = 0; base < n_cm; base += 16 * kPre) {
+        for (int base = 0; base < n_cm; base += kHW * kPre) {
             float4 wpre[kPre];
             load_kmajor(wpre, p.W, p.ldw, 0, NO, NO, KR, base, p.w_vec);
             store_kmajor<NSPLIT>(wpre, b_hi, b_lo, NO, KR, base, 0);
@@ -274,6 +279,13 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcL
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = make_idesc(128, NO, 0, 0);
     const uint32_t a_lbo = 128u * 16u, b_lbo = (uint32_t)NO * 16u;
+
+    // epilogue geometry: warp w drains TMEM lanes 32*(w&3)..+31 (its 32 rows) for the column chunks w>>2, w>>2 + 4, ...
+    const int CW = NO < 32 ? NO : 32;            // chunk width (16 or 32 columns)
+    const int n_chunks = NO / CW;
+    const int lane_base = 32 * (warp & 3);
+    const int qpr = CW >> 2, rpi = 32 / qpr;     // float4 per staged row, rows per coalesced instruction
+    const int r_in = lane / qpr, c4 = (lane % qpr) * 4;
 
     uint32_t phase = 0;
     for (; tile < p.n_tiles; tile += gridDim.x) {
@@ -300,44 +312,50 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) linear_tc_kernel(TcL
         phase ^= 1;
         tc_fence_after();
 
-        // epilogue: warp w drains TMEM lanes 32*(w%4) .. +31 (its rows), column half (w/4)
-        const int lane_base = 32 * (warp & 3);
-        const int row = m0 + lane_base + lane;
-        const int split = ((NO + 1) / 2 + 15) / 16 * 16;
-        const int c_begin = (warp >> 2) ? split : 0;
-        const int c_end = (warp >> 2) ? NO : min(NO, split);
-        const float up = (p.u && row < p.M) ? __ldg(p.u + row) : 0.f;
-        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);   // warp-collective
-            if (row < p.M) {
+        for (int ch = warp >> 2; ch < n_chunks; ch += 4) {
+            const int c0 = ch * CW;
+            // TMEM -> registers (thread = row) -> per-warp smem tile
+            if (CW == 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
 #pragma unroll
-                for (int j4 = 0; j4 < 16; j4 += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + j4]);
-                    const float4 ww = *reinterpret_cast<const float4*>(&s_w2[c0 + j4]);
-                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, wv[4] = {ww.x, ww.y, ww.z, ww.w};
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(scratch + lane * kScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x = v[j4 + e] + bv[e];
-                        if (p.u) x = fmaf(up, wv[e], x);
-                        if (p.relu_out) x = fmaxf(x, 0.f);
-                        v[j4 + e] = x;
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(scratch + lane * kScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            __syncwarp();
+            // smem -> global, row-contiguous: a warp instruction covers `rpi` rows x CW columns (full 32-byte sectors)
+            const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + c4]);
+            const float4 ww = *reinterpret_cast<const float4*>(&s_w2[c0 + c4]);
+            for (int r0 = 0; r0 < 32; r0 += rpi) {
+                const int r = r0 + r_in;
+                const int row = m0 + lane_base + r;
+                if (row < p.M) {
+                    float4 x = *reinterpret_cast<const float4*>(scratch + r * kScratchLd + c4);
+                    x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                    if (p.u) {
+                        const float up = __ldg(p.u + row);
+                        x.x = fmaf(up, ww.x, x.x); x.y = fmaf(up, ww.y, x.y); x.z = fmaf(up, ww.z, x.z); x.w = fmaf(up, ww.w, x.w);
                     }
-                }
-                if (p.mask) {
-                    const float* mk = p.mask + (long)row * p.ldm + c0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = (__ldg(mk + j) > 0.f) ? v[j] : 0.f;
-                }
-                float* out = p.C + (long)row * p.ldc + c0;
-                if (p.c_vec) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) out[j] = v[j];
+                    if (p.relu_out) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                    if (p.mask) {
+                        const float* mk = p.mask + (long)row * p.ldm + c0 + c4;
+                        float4 mv;
+                        if ((p.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0) mv = __ldg(reinterpret_cast<const float4*>(mk));
+                        else mv = make_float4(__ldg(mk), __ldg(mk + 1), __ldg(mk + 2), __ldg(mk + 3));
+                        x.x = mv.x > 0.f ? x.x : 0.f; x.y = mv.y > 0.f ? x.y : 0.f; x.z = mv.z > 0.f ? x.z : 0.f; x.w = mv.w > 0.f ? x.w : 0.f;
+                    }
+                    float* out = p.C + (long)row * p.ldc + c0 + c4;
+                    if (p.c_vec) *reinterpret_cast<float4*>(out) = x;
+                    else { out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w; }
                 }
             }
+            __syncwarp();
         }
         tc_fence_before();   // TMEM reads done (and the MMAs have consumed the A buffer) before it is overwritten
         __syncthreads();
@@ -532,7 +550,7 @@ static bool tc_shape_ok(int red, int out) { return pow2(red) && red >= 16 && red
 
 template <int NSPLIT>
 static int launch_lin(TcLinParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (128 + p.NO) * p.KR * 2;
+    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (128 + p.NO) * p.KR * 2 + (size_t)(kLinThreads / 32) * 32 * kScratchLd * sizeof(float);
     static size_t reserved = 0;
     if (smem > reserved) {
         if (cudaFuncSetAttribute(linear_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
@@ -544,12 +562,10 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
     if (smem > 220 * 1024) return NPF_ENOTSUP;
     p.n_tiles = (int)cdiv(p.M, 128);
     // CTAs per SM limited by shared memory; stay persistent with one CTA per resident slot
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;
+    const int per_sm = 1;   // 512 threads + ~200 KB of shared memory: one persistent CTA per SM
     int grid = kNumSMs * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    linear_tc_kernel<NSPLIT><<<grid, 256, smem, st>>>(p);
+    linear_tc_kernel<NSPLIT><<<grid, kLinThreads, smem, st>>>(p);
     count_launch();
     return check_launch("linear_tc_kernel");
 }

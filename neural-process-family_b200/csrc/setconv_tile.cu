@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
     const float* vb = values + (long)b * K * C;
     sort_queries(t, queries + (long)b * qry_bs, Q, scratch);
 
-    // per-query window and softmax statistics (one thread per query; windows are a few dozen keys)
+    // per-query window and softmax statistics (one thread per query; windows are a few dozen keys).  Every CTA of a
+    // task recomputes them (cheap); only the first one (blockIdx.y == 0) writes dens / mstat.
     for (int i = threadIdx.x; i < Q; i += blockDim.x) {
         const float xq = t.xs[i];
         int lo, hi;
@@ -119,8 +120,10 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
                 d += expf(a);
             }
             t.m[i] = m; t.invs[i] = 1.f / s;
-            dens_o[oq] = d;
-            mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = s;
+            if (blockIdx.y == 0) {
+                dens_o[oq] = d;
+                mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = s;
+            }
         } else {
             t.m[i] = __ldg(mstat_i + oq * 2);
             t.invs[i] = 1.f / __ldg(mstat_i + oq * 2 + 1);
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
     const bool ch_ok = c4 < C;
     float warp_contrib = 0.f;
     const int n_groups = (Q + kGroup - 1) / kGroup;
-    for (int grp = warp; grp < n_groups; grp += 8) {
+    for (int grp = blockIdx.y * 8 + warp; grp < n_groups; grp += 8 * gridDim.y) {
         const int t0 = grp * kGroup;
         const int nt = min(kGroup, Q - t0);
         int glo = t.lo[t0], ghi = t.hi[t0];
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(256) setconv_grp_dv_kernel(const float* __rest
     const int c4 = lane * 4;
     const bool ch_ok = c4 < C;
     const int n_rgroups = (K + kGroup - 1) / kGroup;
-    for (int rg = warp; rg < n_rgroups; rg += 8) {
+    for (int rg = blockIdx.y * 8 + warp; rg < n_rgroups; rg += 8 * gridDim.y) {
         const int k0 = rg * kGroup, nr = min(kGroup, K - k0);
         // lo[] and hi[] are non-decreasing in sorted order: queries with hi >= k0 and lo <= k0+nr-1 form one run
         int ta = 0, tb = Q;
@@ -275,6 +278,14 @@ static bool tile_ok(int K, int Q, int C, const void* values) {
     return C % 4 == 0 && C >= 8 && C <= 128 && Q >= 1 && Q <= kMaxQ && K >= 3 && (reinterpret_cast<uintptr_t>(values) & 15) == 0;
 }
 static size_t tile_smem(int Q) { return sizeof(float) * 7 * (size_t)Q; }
+// CTAs per task: enough to give every SM ~4 CTAs, but never fewer than one 8-warp pass of groups per CTA
+static unsigned split_for(int B, int n_groups) {
+    long s = cdiv(4L * kNumSMs, B);
+    const long max_s = cdiv(n_groups, 8);
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    return (unsigned)s;
+}
 
 int setconv_tile_fwd(const float* keys, long key_bs, const float* queries, long qry_bs, const float* values,
                      const float* theta, float* feat, float* dens, float* mstat, int B, int K, int Q, int C,
@@ -283,7 +294,7 @@ int setconv_tile_fwd(const float* keys, long key_bs, const float* queries, long 
     const size_t smem = tile_smem(Q);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(setconv_grp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
-    setconv_grp_kernel<0><<<B, 256, smem, st>>>(keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, nullptr, nullptr,
+    setconv_grp_kernel<0><<<dim3(B, split_for(B, (Q + kGroup - 1) / kGroup)), 256, smem, st>>>(keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, nullptr, nullptr,
                                                 nullptr, nullptr, nullptr, K, Q, C);
     count_launch();
     return check_launch("setconv_grp_kernel<fwd>");
@@ -302,12 +313,12 @@ int setconv_tile_bwd(const float* keys, long key_bs, const float* queries, long 
         cudaFuncSetAttribute(setconv_grp_dv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr = true;
     }
-    setconv_grp_kernel<1><<<B, 256, smem, st>>>(keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat,
+    setconv_grp_kernel<1><<<dim3(B, split_for(B, (Q + kGroup - 1) / kGroup)), 256, smem, st>>>(keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat,
                                                 dfeat, ddens, dtheta, K, Q, C);
     count_launch();
     int rc = check_launch("setconv_grp_kernel<dtheta>");
     if (rc != NPF_OK || !dvalues) return rc;
-    setconv_grp_dv_kernel<<<B, 256, smem, st>>>(keys, key_bs, queries, qry_bs, theta, mstat, dfeat, dvalues, K, Q, C);
+    setconv_grp_dv_kernel<<<dim3(B, split_for(B, (K + kGroup - 1) / kGroup)), 256, smem, st>>>(keys, key_bs, queries, qry_bs, theta, mstat, dfeat, dvalues, K, Q, C);
     count_launch();
     return check_launch("setconv_grp_dv_kernel");
 }

@@ -8,7 +8,7 @@ from _cfg import build_model, loss_for
 from _util import load_fixture, rel_err
 
 pytestmark = pytest.mark.gpu
-BARS = {"bf16": (1e-2, 1e-1), "bf16x3": (1e-4, 3e-3)}   # (forward max-rel, gradient L2-rel) tolerances
+BARS = {"bf16": (1e-2, 2e-1), "bf16x3": (1e-4, 3e-3)}   # (forward max-rel, gradient L2-rel) tolerances
 
 
 def l2_rel(a, b):
