@@ -243,8 +243,8 @@ int linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float*
                   int N, int flags, const float* u, const float* w2, int ldw2, int precision, cudaStream_t st);
 int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int M, int K, int N,
                        const float* mask_src, int ldm, int flags, int precision, cudaStream_t st);
-int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int K, int N,
-                         int flags, int precision, cudaStream_t st);
+int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int* db_done, int M,
+                         int K, int N, int flags, int precision, cudaStream_t st);
 
 
 }  // namespace npf
@@ -360,7 +360,11 @@ extern "C" int npf_linear_bwd_weight(const float* dY, int lddy, const float* X, 
         t.M = M; t.J = N; t.C = K;
         rc = thin_outer(t, st);
     }
-    if (rc == NPF_ENOTSUP && precision != NPF_PREC_FP32) rc = linear_bwd_weight_tc(dY, lddy, X, ldx, dW, lddw, M, K, N, flags, precision, st);
+    int db_done = 0;
+    if (rc == NPF_ENOTSUP && precision != NPF_PREC_FP32) {
+        rc = linear_bwd_weight_tc(dY, lddy, X, ldx, dW, lddw, db, &db_done, M, K, N, flags, precision, st);
+        if (rc != NPF_OK) db_done = 0;
+    }
     if (rc == NPF_ENOTSUP) {
         GemmParams p{};
         p.A = dY; p.lda = lddy; p.B = X; p.ldb = ldx; p.C = dW; p.ldc = lddw;
@@ -380,6 +384,7 @@ extern "C" int npf_linear_bwd_weight(const float* dY, int lddy, const float* X, 
         rc = launch_gemm<false, false>(p, (int)splits, st);
     }
     if (rc != NPF_OK) return rc;
+    if (db_done) db = nullptr;
     if (db || dw2) {
         long rows_per_block = cdiv(M, 2L * kNumSMs);
         if (rows_per_block < 64) rows_per_block = 64;

@@ -411,8 +411,7 @@ __device__ __forceinline__ void load_mnmajor(float4 (&pre)[2 * kWgIt], const flo
 }
 
 template <int NSPLIT>
-__device__ __forceinline__ void store_mnmajor(const float4 (&pre)[2 * kWgIt], uint8_t* hi, uint8_t* lo, int MN, int c_base, int relu) {
-    const uint32_t lbo = (uint32_t)MN * 16u;
+__device__ __forceinline__ void store_mnmajor(const float4 (&pre)[2 * kWgIt], uint8_t* hi, uint8_t* lo, int MN, int c_base, int relu, uint32_t lbo) {
     const int n_chunks = MN >> 3, lgc = ilog2(n_chunks);
     const int r = threadIdx.x & 7, q = (c_base >> 3) + (threadIdx.x >> 3);
     const int j = q & (n_chunks - 1), kg_step = 32 >> lgc;
@@ -443,6 +442,7 @@ struct TcWgParams {
     const float* dY; long lddy;    // [M, N]
     const float* X; long ldx;      // [M, K]
     float* dW; long lddw;          // [N, K], accumulated with atomics
+    float* db;                     // [N] bias gradient (+=) via an extra all-ones column of the X operand, or null
     long M; int N, K;
     int relu_in, dy_vec, x_vec;
     long rows_per_cta;
@@ -454,22 +454,32 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) wgrad_tc_kernel(TcWg
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     const int K = p.K;
-    const uint32_t a_bytes = (uint32_t)kWgRows * 128u * 2u, b_bytes = (uint32_t)kWgRows * (uint32_t)K * 2u;
+    const int KE = p.db ? K + 16 : K;    // MMA N extent: 16 extra columns, the first one all ones -> D[:, K] = sum_m dY[m, :]
+    const uint32_t a_bytes = (uint32_t)kWgRows * 128u * 2u, b_bytes = (uint32_t)kWgRows * (uint32_t)KE * 2u;
     uint8_t* a_hi = smem_raw;
     uint8_t* a_lo = a_hi + a_bytes;
     uint8_t* b_hi = smem_raw + (NSPLIT == 3 ? 2 : 1) * a_bytes;
     uint8_t* b_lo = b_hi + b_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t ncols = K <= 32 ? 32u : (K <= 64 ? 64u : (K <= 128 ? 128u : 256u));
+    const uint32_t ncols = KE <= 32 ? 32u : (KE <= 64 ? 64u : (KE <= 128 ? 128u : 256u));
     if (warp == 0) tmem_alloc(&tmem_slot, ncols);
     if (tid == 0) mbar_init(&mma_bar, 1);
+    const uint32_t a_lbo = 128u * 16u, b_lbo = (uint32_t)KE * 16u;
+    if (p.db) {
+        // constant part of the X operand: chunk K/8 of every row m holds [1,0,...,0], chunk K/8 + 1 holds zeros
+        for (int i = tid; i < kWgRows * 2; i += 256) {
+            const int m = i >> 1, jx = (K >> 3) + (i & 1);
+            const uint32_t off = (uint32_t)(m >> 3) * b_lbo + (uint32_t)jx * 128u + (uint32_t)(m & 7) * 16u;
+            *reinterpret_cast<uint4*>(b_hi + off) = make_uint4((i & 1) ? 0u : 0x00003F80u, 0u, 0u, 0u);   // bf16(1.0) = 0x3F80
+            if (NSPLIT == 3) *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = make_idesc(128, K, 1, 1);
-    const uint32_t a_lbo = 128u * 16u, b_lbo = (uint32_t)K * 16u;
+    const uint32_t idesc = make_idesc(128, KE, 1, 1);
     const int b_batches = (kWgRows * (K >> 3) + 256 * kWgIt - 1) / (256 * kWgIt);   // 1 for K <= 128, 2 for K = 256
 
     const long m_begin = (long)blockIdx.x * p.rows_per_cta;
@@ -487,11 +497,11 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) wgrad_tc_kernel(TcWg
             mbar_wait(&mma_bar, phase);
             phase ^= 1;
         }
-        store_mnmajor<NSPLIT>(pa, a_hi, a_lo, 128, 0, 0);
-        store_mnmajor<NSPLIT>(pb, b_hi, b_lo, K, 0, p.relu_in);
+        store_mnmajor<NSPLIT>(pa, a_hi, a_lo, 128, 0, 0, a_lbo);
+        store_mnmajor<NSPLIT>(pb, b_hi, b_lo, K, 0, p.relu_in, b_lbo);
         for (int bb = 1; bb < b_batches; ++bb) {       // K = 256: second half of the X sub-tile
             load_mnmajor(pb, p.X, p.ldx, m0, rows, K, K, bb * 256 * kWgIt, p.x_vec);
-            store_mnmajor<NSPLIT>(pb, b_hi, b_lo, K, bb * 256 * kWgIt, p.relu_in);
+            store_mnmajor<NSPLIT>(pb, b_hi, b_lo, K, bb * 256 * kWgIt, p.relu_in, b_lbo);
         }
         const long mn = m0 + kWgRows;
         if (mn < m_end) {    // prefetch the next sub-tile: in flight under the fence / sync / MMA issue
@@ -537,6 +547,11 @@ __global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) wgrad_tc_kernel(TcWg
                     for (int j = 0; j < 16; ++j) atomicAdd(d + j, v[j]);
                 }
             }
+        }
+        if (p.db && warp < 4) {       // the ones column: D[n, K] = sum over rows of dY[:, n]
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)K, v);
+            if (n < p.N) atomicAdd(p.db + n, v[0]);
         }
         tc_fence_before();
     }
@@ -601,7 +616,7 @@ int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float
 
 template <int NSPLIT>
 static int launch_wg(TcWgParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (kWgRows * 128 + kWgRows * p.K) * 2;
+    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (kWgRows * 128 + kWgRows * (p.K + (p.db ? 16 : 0))) * 2;
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(wgrad_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
@@ -624,12 +639,14 @@ static int launch_wg(TcWgParams& p, cudaStream_t st) {
     return check_launch("wgrad_tc_kernel");
 }
 
-int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, int M, int K, int N,
-                         int flags, int precision, cudaStream_t st) {
+int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int* db_done, int M,
+                         int K, int N, int flags, int precision, cudaStream_t st) {
     // MMA M dimension = N (rows of dW, padded to 128), MMA N dimension = K, reduction over the M rows
     if (N > 128 || N < 8 || N % 8 != 0 || !pow2(K) || K < 16 || K > 256) return NPF_ENOTSUP;
     TcWgParams p{};
     p.dY = dY; p.lddy = lddy; p.X = X; p.ldx = ldx; p.dW = dW; p.lddw = lddw;
+    p.db = (db && K + 16 <= 256) ? db : nullptr;     // fused bias gradient needs MMA N = K + 16 <= 256
+    *db_done = p.db != nullptr;
     p.M = M; p.N = N; p.K = K;
     p.relu_in = (flags & NPF_RELU_IN) ? 1 : 0;
     p.dy_vec = (lddy % 4 == 0) && aligned16(dY);

@@ -267,6 +267,87 @@ __global__ void __launch_bounds__(256) setconv_bwd_values_kernel(const float* __
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Few value channels (context -> induced: C = y_dim <= 4): one THREAD per query, the task's keys and values staged in
+// shared memory (broadcast reads).  mode 0 forward, mode 1 theta gradient.
+// ----------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+                                                            long qry_bs, const float* __restrict__ values, const float* __restrict__ theta,
+                                                            float* __restrict__ feat_o, float* __restrict__ dens_o, float* __restrict__ mstat_o,
+                                                            const float* __restrict__ feat_i, const float* __restrict__ mstat_i,
+                                                            const float* __restrict__ dfeat, const float* __restrict__ ddens,
+                                                            float* __restrict__ dtheta, int K, int Q, int C) {
+    extern __shared__ float sm[];
+    __shared__ float part[8];
+    float* sk = sm;            // [K]
+    float* sv = sm + K;        // [K][C]
+    const int b = blockIdx.y;
+    const float th = __ldg(theta);
+    const float sigma = 1e-5f + softplus_f(th);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sk[i] = __ldg(keys + (long)b * key_bs + i);
+    for (int i = threadIdx.x; i < K * C; i += blockDim.x) sv[i] = __ldg(values + (long)b * K * C + i);
+    __syncthreads();
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    float contrib = 0.f;
+    if (q < Q) {
+        const float xq = __ldg(queries + (long)b * qry_bs + q);
+        const long oq = (long)b * Q + q;
+        if (MODE == 0) {
+            float m = -INFINITY;
+            for (int k = 0; k < K; ++k) m = fmaxf(m, logit(xq, sk[k], sigma));
+            float s = 0.f, d = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < K; ++k) {
+                const float a = logit(xq, sk[k], sigma);
+                const float e = expf(a - m);
+                s += e;
+                d += expf(a);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < C) acc[c] = fmaf(e, sv[k * C + c], acc[c]);
+            }
+            const float inv = 1.f / s;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < C) feat_o[oq * C + c] = acc[c] * inv;
+            dens_o[oq] = d;
+            mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = s;
+        } else {
+            const float m = __ldg(mstat_i + oq * 2), inv_s = 1.f / __ldg(mstat_i + oq * 2 + 1);
+            float df[4], G = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                df[c] = (c < C) ? __ldg(dfeat + oq * C + c) : 0.f;
+                if (c < C) G = fmaf(df[c], __ldg(feat_i + oq * C + c), G);
+            }
+            float A1 = 0.f, A2 = 0.f, T = 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float a = logit(xq, sk[k], sigma);
+                const float wa = expf(a - m) * inv_s * (a - m);
+                A1 += wa;
+                A2 = fmaf(expf(a), a, A2);
+                float g = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < C) g = fmaf(df[c], sv[k * C + c], g);
+                T = fmaf(wa, g, T);
+            }
+            contrib = T - G * A1 + __ldg(ddens + oq) * A2;
+        }
+    }
+    if (MODE == 1) {
+        contrib = warp_sum(contrib);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = contrib;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += part[i];
+            atomicAdd(dtheta, tot * (-2.f / sigma) * sigmoid_f(th));
+        }
+    }
+}
+
 // implemented in setconv_tile.cu: shared-memory staged fast path; NPF_ENOTSUP if the shape is not covered
 int setconv_tile_fwd(const float* keys, long key_bs, const float* queries, long qry_bs, const float* values,
                      const float* theta, float* feat, float* dens, float* mstat, int B, int K, int Q, int C,
@@ -291,6 +372,13 @@ extern "C" int npf_setconv_fwd(const float* keys, long key_bs, const float* quer
     if (keys_regular) {
         int rc = setconv_tile_fwd(keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, B, K, Q, Cin, st);
         if (rc != NPF_ENOTSUP) return rc;
+    }
+    if (Cin <= 4 && !keys_regular && (size_t)K * (1 + Cin) * sizeof(float) <= 40 * 1024) {
+        dim3 grid((unsigned)cdiv(Q, 256), (unsigned)B);
+        setconv_small_kernel<0><<<grid, 256, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
+            keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, nullptr, nullptr, nullptr, nullptr, nullptr, K, Q, Cin);
+        count_launch();
+        return check_launch("setconv_small_kernel<fwd>");
     }
     dim3 grid((unsigned)cdiv(Q, 8), (unsigned)B);
     setconv_fwd_kernel<<<grid, 256, 0, st>>>(keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, K, Q, Cin,
@@ -319,7 +407,14 @@ extern "C" int npf_setconv_bwd(const float* keys, long key_bs, const float* quer
                                   dtheta, B, K, Q, Cin, st);
         if (rc != NPF_ENOTSUP) return rc;
     }
-    {
+    if (Cin <= 4 && !keys_regular && (size_t)K * (1 + Cin) * sizeof(float) <= 40 * 1024) {
+        dim3 grid((unsigned)cdiv(Q, 256), (unsigned)B);
+        setconv_small_kernel<1><<<grid, 256, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
+            keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat, dfeat, ddens, dtheta, K, Q, Cin);
+        count_launch();
+        int rc = check_launch("setconv_small_kernel<dtheta>");
+        if (rc != NPF_OK) return rc;
+    } else {
         dim3 grid((unsigned)cdiv(Q, 8), (unsigned)B);
         setconv_bwd_theta_kernel<<<grid, 256, 0, st>>>(keys, key_bs, queries, qry_bs, values, theta, feat, mstat, dfeat,
                                                        ddens, dtheta, K, Q, Cin, keys_regular);

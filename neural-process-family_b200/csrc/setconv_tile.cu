@@ -165,14 +165,21 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
                 }
             }
             const int cnt = min(32, ghi - base + 1);
-            for (int rr = 0; rr < cnt; ++rr) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ch_ok) v = __ldg(reinterpret_cast<const float4*>(vb + (long)(base + rr) * C + c4));
+            for (int rr0 = 0; rr0 < cnt; rr0 += 8) {       // 8 row loads in flight, then 8 x (8 shuffles + 32 FMAs)
+                float4 v[8];
 #pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
-                    const float wj = __shfl_sync(0xffffffffu, w[j], rr);
-                    acc[j].x = fmaf(wj, v.x, acc[j].x); acc[j].y = fmaf(wj, v.y, acc[j].y);
-                    acc[j].z = fmaf(wj, v.z, acc[j].z); acc[j].w = fmaf(wj, v.w, acc[j].w);
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ch_ok && rr0 + u < cnt) v[u] = __ldg(reinterpret_cast<const float4*>(vb + (long)(base + rr0 + u) * C + c4));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int j = 0; j < kGroup; ++j) {
+                        const float wj = __shfl_sync(0xffffffffu, w[j], rr0 + u);   // rows past the window carry weight 0
+                        acc[j].x = fmaf(wj, v[u].x, acc[j].x); acc[j].y = fmaf(wj, v[u].y, acc[j].y);
+                        acc[j].z = fmaf(wj, v[u].z, acc[j].z); acc[j].w = fmaf(wj, v[u].w, acc[j].w);
+                    }
                 }
             }
         }
@@ -255,14 +262,21 @@ __global__ void __launch_bounds__(256) setconv_grp_dv_kernel(const float* __rest
                     w[r] = expf(logit_t(t.xs[ti], xk[r], sigma) - t.m[ti]) * t.invs[ti];
             }
             const int cnt = min(32, tb - base);
-            for (int tt = 0; tt < cnt; ++tt) {
-                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ch_ok) g = __ldg(reinterpret_cast<const float4*>(dfeat + ((long)b * Q + t.ord[base + tt]) * C + c4));
+            for (int tt0 = 0; tt0 < cnt; tt0 += 8) {
+                float4 g[8];
 #pragma unroll
-                for (int r = 0; r < kGroup; ++r) {
-                    const float wr = __shfl_sync(0xffffffffu, w[r], tt);
-                    acc[r].x = fmaf(wr, g.x, acc[r].x); acc[r].y = fmaf(wr, g.y, acc[r].y);
-                    acc[r].z = fmaf(wr, g.z, acc[r].z); acc[r].w = fmaf(wr, g.w, acc[r].w);
+                for (int u = 0; u < 8; ++u) {
+                    g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ch_ok && tt0 + u < cnt) g[u] = __ldg(reinterpret_cast<const float4*>(dfeat + ((long)b * Q + t.ord[base + tt0 + u]) * C + c4));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int r = 0; r < kGroup; ++r) {
+                        const float wr = __shfl_sync(0xffffffffu, w[r], tt0 + u);   // queries past the run carry weight 0
+                        acc[r].x = fmaf(wr, g[u].x, acc[r].x); acc[r].y = fmaf(wr, g[u].y, acc[r].y);
+                        acc[r].z = fmaf(wr, g[u].z, acc[r].z); acc[r].w = fmaf(wr, g[u].w, acc[r].w);
+                    }
                 }
             }
         }

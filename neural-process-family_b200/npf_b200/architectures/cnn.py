@@ -80,7 +80,7 @@ class ResConvBlock(nn.Module):
 
     @staticmethod
     def _pointwise(x, conv):
-        return ops.linear(x, conv.weight.view(conv.weight.shape[0], conv.weight.shape[1]), conv.bias)
+        return ops.linear(x, conv.weight, conv.bias)   # 1x1 conv weight [out, in, 1(, 1)] read as [out, in]
 
     def forward(self, X):
         """X channel-last: [B, L, C] or [B, H, W, C]."""

@@ -12,7 +12,7 @@ from ._cabi import ACCUM, ADD_DY, RELU_IN, RELU_OUT, call
 __all__ = [
     "set_precision", "get_precision", "linear", "mlp_chain", "setconv", "dwconv", "channel_moments",
     "merge_relu", "mean_pool", "add_layernorm", "xattn", "gauss_head", "gauss_sum_log_prob", "latent_sample",
-    "global_latent", "gridconv_in", "range_flag", "launch_count",
+    "global_latent", "gridconv_in", "range_flag", "launch_count", "set_direct_grad_accumulation",
 ]
 
 _PRECISION = {"fp32": _cabi.PREC_FP32, "bf16": _cabi.PREC_BF16, "bf16x3": _cabi.PREC_BF16X3}
@@ -55,6 +55,30 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# ------------------------------------------------------------------------------------------------------
+# Direct gradient accumulation: every weight-gradient kernel ADDS into its output, so when a parameter already has a
+# contiguous fp32 ``.grad`` (e.g. a view into ``parallel.FlatGradients``' bucket) the kernel can write there directly
+# and the Function returns ``None`` for it -- no zeros_like fill, no autograd accumulate kernel per parameter.
+# ------------------------------------------------------------------------------------------------------
+_direct_grads = False
+
+
+def set_direct_grad_accumulation(on):
+    global _direct_grads
+    _direct_grads = bool(on)
+
+
+def _gbuf(p):
+    """(buffer to accumulate the gradient of ``p`` into, value to return to autograd for it)."""
+    if p is None:
+        return None, None
+    if _direct_grads and p.is_leaf and p.requires_grad and p.grad is not None and p.grad.is_contiguous() \
+            and p.grad.dtype == torch.float32 and p.grad.shape == p.shape and p.is_contiguous():
+        return p.grad, None
+    g = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return g, g
+
+
 # ======================================================================================================
 # Linear / MLP chain
 # ======================================================================================================
@@ -95,9 +119,10 @@ class _MLPChain(torch.autograd.Function):
         for i, (W, b) in enumerate(zip(Ws, bs)):
             last = i == n_layers - 1
             flags = RELU_OUT if (not last or final_relu) else 0
-            h = _lin_fwd(h, _c(W), None if b is None else _c(b), W.shape[0], W.shape[1], flags)
+            # W is [out, in] or a 1x1 conv weight [out, in, 1(, 1)]: same memory, K = numel / out
+            h = _lin_fwd(h, _c(W), None if b is None else _c(b), W.shape[0], W.numel() // W.shape[0], flags)
             acts.append(h)
-        ctx.save_for_backward(*acts, *Ws)
+        ctx.save_for_backward(*acts, *Ws, *(bs if has_bias else ()))
         ctx.n_layers, ctx.final_relu, ctx.has_bias = n_layers, final_relu, has_bias
         ctx.x_shape = x.shape
         return h.reshape(*lead, Ws[-1].shape[0])
@@ -106,7 +131,8 @@ class _MLPChain(torch.autograd.Function):
     def backward(ctx, dy):
         n = ctx.n_layers
         saved = ctx.saved_tensors
-        acts, Ws = saved[: n + 1], saved[n + 1:]
+        acts, Ws = saved[: n + 1], saved[n + 1: 2 * n + 1]
+        bs = saved[2 * n + 1:] if ctx.has_bias else (None,) * n
         M = acts[0].shape[0]
         dz = _c(dy).reshape(M, -1)
         if ctx.final_relu:
@@ -117,12 +143,12 @@ class _MLPChain(torch.autograd.Function):
         dx = None
         for i in range(n - 1, -1, -1):
             W = _c(Ws[i])
-            N, K = W.shape
-            dW = torch.zeros_like(W)
-            db = torch.zeros(N, device=W.device, dtype=torch.float32) if ctx.has_bias else None
+            N = W.shape[0]
+            K = W.numel() // N
+            dW, dWs[i] = _gbuf(Ws[i])
+            db, dbs[i] = _gbuf(bs[i])
             if M > 0:
                 _lin_bwd_weight(dz, acts[i], _p(dW), K, db, M, K, N)
-            dWs[i], dbs[i] = dW, db
             if i > 0:
                 dz = _lin_bwd_data(dz, _p(W), K, M, K, N, mask=acts[i])
             elif ctx.needs_input_grad[0]:
@@ -163,13 +189,14 @@ class _SetConv(torch.autograd.Function):
         mstat = torch.empty(B, Q, 2, device=dev, dtype=torch.float32)
         call("npf_setconv_fwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat), _p(dens),
              _p(mstat), B, K, Q, C, int(keys_regular), _stream())
-        W = _c(W)
+        assert W.is_contiguous(), "SetConv resizer weight must be contiguous"
         N = W.shape[0]
         out = torch.empty(B, Q, N, device=dev, dtype=torch.float32)
         if B * Q > 0:
             call("npf_linear_fwd", _p(feat), C, _p(W), C + 1, _p(b), _p(out), N, B * Q, C, N, 0, _p(dens),
                  W.data_ptr() + 4 * C, C + 1, _precision, _stream())
         ctx.save_for_backward(keys, queries, values, theta, W, feat, dens, mstat)
+        ctx.bias_ref = b
         ctx.dims = (B, K, Q, C, N, key_bs, qry_bs, int(keys_regular))
         return out
 
@@ -180,9 +207,9 @@ class _SetConv(torch.autograd.Function):
         dev = values.device
         dout = _c(dout).reshape(B * Q, N)
         M = B * Q
-        dW = torch.zeros_like(W)
-        db = torch.zeros(N, device=dev, dtype=torch.float32)
-        dtheta = torch.zeros_like(theta)
+        dW, rW = _gbuf(W)
+        db, rb = _gbuf(ctx.bias_ref)
+        dtheta, rtheta = _gbuf(theta)
         dvalues = None
         if M > 0:
             _lin_bwd_weight(dout, feat, _p(dW), C + 1, db, M, C, N, u=dens, dw2_ptr=dW.data_ptr() + 4 * C, ldw2=C + 1)
@@ -194,7 +221,7 @@ class _SetConv(torch.autograd.Function):
                  _p(mstat), _p(dfeat), _p(ddens), _p(dvalues), _p(dtheta), B, K, Q, C, regular, _stream())
         elif ctx.needs_input_grad[2]:
             dvalues = torch.zeros_like(values)
-        return None, None, dvalues, dtheta, dW, db, None
+        return None, None, dvalues, rtheta, rW, rb, None
 
 
 def setconv(keys, queries, values, theta, weight, bias, keys_regular=False):
@@ -221,12 +248,12 @@ class _DWConv(torch.autograd.Function):
         else:
             H, Wd = x.shape[1], x.shape[2]
             kh, kw = Wt.shape[-2], Wt.shape[-1]
-        Wt = _c(Wt)
+        assert Wt.is_contiguous(), "depthwise weight must be contiguous"
         y = torch.empty_like(x)
         res_c = None if res is None else _c(res)
         call("npf_dwconv_fwd", _p(x), _p(Wt), _p(bias), _p(res_c), _p(y), B, H, Wd, C, kh, kw,
              RELU_IN if relu_in else 0, _p(scale), _p(shift), _stream())
-        ctx.save_for_backward(x, Wt, scale, shift)
+        ctx.save_for_backward(x, Wt, scale, shift, bias)
         # residual == conv input (ResConvBlock with one conv layer): its gradient is folded into the dX kernel
         res_is_x = res is not None and res_c.data_ptr() == x.data_ptr() and res_c.shape == x.shape
         ctx.cfg = (B, H, Wd, C, kh, kw, relu_in, bias is not None, res is not None, res_is_x)
@@ -234,13 +261,13 @@ class _DWConv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, Wt, scale, shift = ctx.saved_tensors
+        x, Wt, scale, shift, bias = ctx.saved_tensors
         B, H, Wd, C, kh, kw, relu_in, has_bias, has_res, res_is_x = ctx.cfg
         dy = _c(dy)
         fuse_res = res_is_x and ctx.needs_input_grad[0]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dW = torch.zeros_like(Wt)
-        db = torch.zeros(C, device=x.device, dtype=torch.float32) if has_bias else None
+        dW, rW = _gbuf(Wt)
+        db, rb = _gbuf(bias)
         need_aff = scale is not None and (ctx.needs_input_grad[5] or ctx.needs_input_grad[6])
         dscale = torch.zeros_like(scale) if need_aff else None
         dshift = torch.zeros_like(shift) if need_aff else None
@@ -250,7 +277,7 @@ class _DWConv(torch.autograd.Function):
              (RELU_IN if relu_in else 0) | (ADD_DY if fuse_res else 0), _p(scale), _p(shift), _p(dscale), _p(dshift),
              _stream())
         dres = None if (fuse_res or not has_res) else dy
-        return (dx if ctx.needs_input_grad[0] else None, dW, db, dres, None, dscale, dshift)
+        return (dx if ctx.needs_input_grad[0] else None, rW, rb, dres, None, dscale, dshift)
 
 
 def dwconv(x, weight, bias=None, res=None, relu_in=False, scale=None, shift=None):
@@ -366,6 +393,7 @@ class _AddLayerNorm(torch.autograd.Function):
         rstat = torch.empty(M, 2, device=a.device, dtype=torch.float32)
         call("npf_add_layernorm_fwd", _p(a), _p(b), _p(gamma), _p(beta), _p(y), _p(rstat), M, C, _stream())
         ctx.save_for_backward(a, b, gamma, rstat)
+        ctx.beta_ref = beta
         return y
 
     @staticmethod
@@ -374,11 +402,11 @@ class _AddLayerNorm(torch.autograd.Function):
         C = a.shape[-1]
         M = a.numel() // C
         ds = torch.empty_like(a)
-        dg = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
+        dg, rg = _gbuf(gamma)
+        dbeta, rbeta = _gbuf(ctx.beta_ref)
         call("npf_add_layernorm_bwd", _p(_c(dy)), _p(a), _p(b), _p(gamma), _p(rstat), _p(ds), _p(dg), _p(dbeta), M, C,
              _stream())
-        return ds, ds, dg, dbeta
+        return ds, ds, rg, rbeta
 
 
 def add_layernorm(a, b, gamma, beta):
@@ -548,7 +576,8 @@ class _GridConvIn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, mask_u8, Wt):
         _chk(img, mask_u8, Wt)
-        img, mask_u8, Wt = _c(img), _c(mask_u8), _c(Wt)
+        img, mask_u8 = _c(img), _c(mask_u8)
+        assert Wt.is_contiguous()
         B, H, Wd, y = img.shape
         k = Wt.shape[-1]
         feat = torch.empty(B, H, Wd, 2 * y, device=img.device, dtype=torch.float32)
@@ -561,10 +590,10 @@ class _GridConvIn(torch.autograd.Function):
         img, mask_u8, Wt, feat = ctx.saved_tensors
         B, H, Wd, y = img.shape
         k = Wt.shape[-1]
-        dW = torch.zeros_like(Wt)
+        dW, rW = _gbuf(Wt)
         call("npf_gridconv_in_bwd", _p(img), _p(mask_u8), mask_u8.shape[-1], _p(Wt), _p(feat), _p(_c(dfeat)), _p(dW), B, H,
              Wd, y, k, _stream())
-        return None, None, dW
+        return None, None, rW
 
 
 def gridconv_in(img, mask, weight):

@@ -18,6 +18,9 @@ class FlatGradients:
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self._attach()
+        if dev.type == "cuda":
+            from . import ops
+            ops.set_direct_grad_accumulation(True)   # weight-gradient kernels add straight into the bucket
 
     def _attach(self):
         off = 0
