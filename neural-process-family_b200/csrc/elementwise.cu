@@ -9,7 +9,7 @@ constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2 pi)), torc
 
 static inline unsigned grid_for(long n, int block = 256) {
     long g = cdiv(n, block);
-    const long cap = 16L * kNumSMs;
+    const long cap = 64L * kNumSMs;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (unsigned)g;

@@ -78,31 +78,104 @@ __global__ void __launch_bounds__(256) rowdot_kernel(RowDotParams p) {
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-    for (long m = warp; m < p.M; m += nwarps) {
-        float acc[kThin];
+    constexpr int RU = 4;                    // rows per warp pass: RU independent row loads in flight
+    for (long m0 = warp * RU; m0 < p.M; m0 += nwarps * RU) {
+        float acc[RU][kThin];
 #pragma unroll
-        for (int j = 0; j < kThin; ++j) acc[j] = 0.f;
+        for (int u = 0; u < RU; ++u)
+#pragma unroll
+            for (int j = 0; j < kThin; ++j) acc[u][j] = 0.f;
         for (int i = lane; i < p.I; i += 32) {
-            float a = __ldg(p.A + m * p.lda + i);
-            if (p.relu_a) a = fmaxf(a, 0.f);
+            float a[RU];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                a[u] = (m0 + u < p.M) ? __ldg(p.A + (m0 + u) * p.lda + i) : 0.f;
+                if (p.relu_a) a[u] = fmaxf(a[u], 0.f);
+            }
 #pragma unroll
             for (int j = 0; j < kThin; ++j)
-                if (j < p.J) acc[j] = fmaf(a, sB[j * p.I + i], acc[j]);
+                if (j < p.J) {
+                    const float w = sB[j * p.I + i];
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) acc[u][j] = fmaf(a[u], w, acc[u][j]);
+                }
         }
 #pragma unroll
-        for (int j = 0; j < kThin; ++j)
-            if (j < p.J) acc[j] = warp_sum(acc[j]);
-        if (lane < p.J) {
-            float x = 0.f;
+        for (int u = 0; u < RU; ++u) {
 #pragma unroll
             for (int j = 0; j < kThin; ++j)
-                if (j == lane) x = acc[j];
-            if (p.bias) x += __ldg(p.bias + lane);
-            if (p.relu_out) x = fmaxf(x, 0.f);
-            if (p.mask) x = (__ldg(p.mask + m * p.ldm + lane) > 0.f) ? x : 0.f;
-            float* o = p.out + m * p.ldo + lane;
-            *o = p.accum ? *o + x : x;
+                if (j < p.J) acc[u][j] = warp_sum(acc[u][j]);
+            const long m = m0 + u;
+            if (lane < p.J && m < p.M) {
+                float x = 0.f;
+#pragma unroll
+                for (int j = 0; j < kThin; ++j)
+                    if (j == lane) x = acc[u][j];
+                if (p.bias) x += __ldg(p.bias + lane);
+                if (p.relu_out) x = fmaxf(x, 0.f);
+                if (p.mask) x = (__ldg(p.mask + m * p.ldm + lane) > 0.f) ? x : 0.f;
+                float* o = p.out + m * p.ldo + lane;
+                *o = p.accum ? *o + x : x;
+            }
         }
+    }
+}
+
+
+// float4 columns, 4 rows in flight per thread; block-level reduction through shared-memory atomics
+__global__ void __launch_bounds__(256) thin_outer_vec_kernel(ThinOuterParams p) {
+    extern __shared__ float sacc[];          // [(J + 2)][C]
+    const int nacc = (p.J + 2) * p.C;
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int CQ = p.C >> 2;
+    const int q = threadIdx.x % CQ, ry = threadIdx.x / CQ, RY = blockDim.x / CQ;
+    const long m0 = (long)blockIdx.x * p.rows_per_block, m1 = min(p.M, m0 + p.rows_per_block);
+    float4 acc[kThin + 2];
+#pragma unroll
+    for (int j = 0; j < kThin + 2; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int RU = 4;
+    for (long mb = m0 + ry * RU; mb < m1; mb += (long)RY * RU) {
+        float4 t[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mb + u < m1) t[u] = __ldg(reinterpret_cast<const float4*>(p.T + (mb + u) * p.ldt + 4 * q));
+            if (p.relu_t) { t[u].x = fmaxf(t[u].x, 0.f); t[u].y = fmaxf(t[u].y, 0.f); t[u].z = fmaxf(t[u].z, 0.f); t[u].w = fmaxf(t[u].w, 0.f); }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            if (mb + u >= m1) continue;
+#pragma unroll
+            for (int j = 0; j < kThin; ++j)
+                if (j < p.J) {
+                    float s = __ldg(p.S + (mb + u) * p.lds + j);
+                    if (p.relu_s) s = fmaxf(s, 0.f);
+                    acc[j].x = fmaf(s, t[u].x, acc[j].x); acc[j].y = fmaf(s, t[u].y, acc[j].y);
+                    acc[j].z = fmaf(s, t[u].z, acc[j].z); acc[j].w = fmaf(s, t[u].w, acc[j].w);
+                }
+            acc[kThin].x += t[u].x; acc[kThin].y += t[u].y; acc[kThin].z += t[u].z; acc[kThin].w += t[u].w;
+            if (p.u) {
+                const float uu = __ldg(p.u + mb + u);
+                acc[kThin + 1].x = fmaf(uu, t[u].x, acc[kThin + 1].x); acc[kThin + 1].y = fmaf(uu, t[u].y, acc[kThin + 1].y);
+                acc[kThin + 1].z = fmaf(uu, t[u].z, acc[kThin + 1].z); acc[kThin + 1].w = fmaf(uu, t[u].w, acc[kThin + 1].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kThin + 2; ++j) {
+        const int slot = j < kThin ? j : p.J + (j - kThin);
+        if (j < kThin && j >= p.J) continue;
+        float* d = sacc + slot * p.C + 4 * q;
+        atomicAdd(d + 0, acc[j].x); atomicAdd(d + 1, acc[j].y); atomicAdd(d + 2, acc[j].z); atomicAdd(d + 3, acc[j].w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+        const int slot = i / p.C, c = i % p.C;
+        const float v = sacc[i];
+        if (slot < p.J) atomicAdd(p.out + (long)slot * p.so_j + (long)c * p.so_c, v);
+        else if (slot == p.J) { if (p.out_ones) atomicAdd(p.out_ones + c, v); }
+        else if (p.out_u) atomicAdd(p.out_u + (long)c * p.so_u, v);
     }
 }
 
@@ -148,7 +221,7 @@ __global__ void __launch_bounds__(256) thin_outer_kernel(ThinOuterParams p) {
 
 static inline unsigned stream_grid(long work_items) {
     long g = cdiv(work_items, 256);
-    if (g > 8L * kNumSMs) g = 8L * kNumSMs;
+    if (g > 64L * kNumSMs) g = 64L * kNumSMs;
     if (g < 1) g = 1;
     return (unsigned)g;
 }
@@ -170,6 +243,16 @@ int rowdot(RowDotParams& p, cudaStream_t st) {
 }
 
 int thin_outer(ThinOuterParams& p, cudaStream_t st) {
+    const bool vec = (p.C % 4 == 0) && (p.ldt % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.T) & 15) == 0) && p.C <= 1024 &&
+                     256 % (p.C / 4) == 0 && (size_t)(p.J + 2) * p.C * sizeof(float) <= 40 * 1024;
+    if (vec) {
+        long rows = cdiv(p.M, 8L * kNumSMs);
+        if (rows < 32) rows = 32;
+        p.rows_per_block = rows;
+        thin_outer_vec_kernel<<<(unsigned)cdiv(p.M, rows), 256, sizeof(float) * (size_t)(p.J + 2) * p.C, st>>>(p);
+        count_launch();
+        return check_launch("thin_outer_vec_kernel");
+    }
     long rows = cdiv(p.M, 4L * kNumSMs);
     if (rows < 64) rows = 64;
     p.rows_per_block = rows;

@@ -14,7 +14,11 @@ class FlatGradients:
     def __init__(self, module, process_group=None):
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = process_group
-        n = sum(p.numel() for p in self.params)
+        # every parameter's slice starts on a 128-byte boundary (vectorised / float4-atomic gradient kernels need 16 B)
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 31) // 32 * 32
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self._attach()
@@ -23,10 +27,8 @@ class FlatGradients:
             ops.set_direct_grad_accumulation(True)   # weight-gradient kernels add straight into the bucket
 
     def _attach(self):
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off: off + p.numel()].view_as(p)
-            off += p.numel()
 
     def zero_(self):
         """Zero the bucket (one memset) and re-attach the views if an optimizer dropped them."""
