@@ -272,7 +272,7 @@ __device__ __forceinline__ float4 act4(float4 v, bool affine, const float4 s, co
 }
 
 template <int KW>
-__global__ void __launch_bounds__(256) dwconv1d_kernel(Dw1Params p) {
+__global__ void __launch_bounds__(256, KW <= 11 ? 2 : 1) dwconv1d_kernel(Dw1Params p) {
     extern __shared__ __align__(16) float4 Ws4[];   // [KW][CQ]
     const int CQ = p.C >> 2, G = 256 / CQ;
     const int q = threadIdx.x % CQ, g = threadIdx.x / CQ;

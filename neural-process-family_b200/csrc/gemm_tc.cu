@@ -449,7 +449,7 @@ struct TcWgParams {
 };
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(256, NSPLIT == 1 ? 2 : 1) wgrad_tc_kernel(TcWgParams p) {
+__global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(TcWgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
