@@ -263,8 +263,9 @@ __global__ void __launch_bounds__(256) xattn_bwd_dkv_kernel(AttnParams p) {
     }
 }
 
-int xattn_fwd_tc(const AttnParams& p, int B, int precision, cudaStream_t st);
-int xattn_bwd_tc(const AttnParams& p, int B, int precision, cudaStream_t st);
+// attention_tc.cu: tcgen05 path (head dim 16 / 32); NPF_ENOTSUP for other shapes
+int xattn_fwd_tc(const float* Q, const float* K, const float* V, float* O, float* LSE, int B, int Tq, int Tk, int H, int D, int Dv,
+                 float scale, int precision, cudaStream_t st);
 
 static int set_smem(const void* fn, size_t bytes) {
     if (bytes > 48 * 1024) {
@@ -289,6 +290,10 @@ extern "C" int npf_xattn_fwd(const float* Q, const float* K, const float* V, flo
     NPF_REQUIRE(B <= 65535 && H <= 65535, "npf_xattn_fwd: batch/heads > 65535");
     if (B == 0 || Tq == 0) return NPF_OK;
     cudaStream_t st = as_stream(stream);
+    if (precision != NPF_PREC_FP32) {
+        int rc = xattn_fwd_tc(Q, K, V, O, LSE, B, Tq, Tk, H, D, Dv, scale, precision, st);
+        if (rc != NPF_ENOTSUP) return rc;
+    }
     AttnParams p{};
     p.Q = Q; p.K = K; p.V = V; p.Oo = O; p.LSEo = LSE;
     p.Tq = Tq; p.Tk = Tk; p.H = H; p.D = D; p.Dv = Dv; p.scale = scale;

@@ -91,3 +91,29 @@ def test_tc_single_linear_localised(npf, prec, M, K, N):
     errs = dict(y=rel_err(res[0][0], yr), dx=rel_err(res[0][1], go @ W), dW=rel_err(res[0][2], go.t() @ x), db=rel_err(res[0][3], go.sum(0)))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), f"non-deterministic: {errs}"
     assert errs["y"] < ftol and errs["dx"] < gtol and errs["dW"] < gtol and errs["db"] < gtol, errs
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("B,Tq,Tk,H,D", [(2, 128, 128, 8, 16), (1, 33, 70, 8, 16), (2, 300, 513, 4, 32), (1, 1, 1, 8, 16), (2, 512, 512, 8, 16)])
+def test_tc_attention_forward(npf, prec, B, Tq, Tk, H, D):
+    """tcgen05 attention forward (head dim 16 / 32) vs fp64 softmax attention; backward still runs (SIMT) from its O, LSE."""
+    import math
+    npf.set_precision(prec)
+    ftol = {"bf16x3": 1e-4, "bf16": 1e-2}[prec]
+    q, k, v = _g(B, Tq, H * D, seed=1), _g(B, Tk, H * D, seed=2), _g(B, Tk, H * D, seed=3)
+
+    def heads(t):
+        return t.view(t.shape[0], t.shape[1], H, D).transpose(1, 2)
+
+    r = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    s = heads(r[0]) @ heads(r[1]).transpose(-1, -2) / math.sqrt(D)
+    yr = (s.softmax(-1) @ heads(r[2])).transpose(1, 2).reshape(B, Tq, H * D)
+    c = [t.float().cuda().requires_grad_(True) for t in (q, k, v)]
+    yc = npf.ops.xattn(c[0], c[1], c[2], H, 1.0 / math.sqrt(D))
+    assert rel_err(yc, yr) < ftol, (prec, rel_err(yc, yr))
+    go = _g(*yr.shape, seed=9)
+    yr.backward(go)
+    yc.backward(go.float().cuda())
+    gtol = {"bf16x3": 2e-3, "bf16": 5e-2}[prec]
+    for n, a, b_ in zip("qkv", c, r):
+        assert l2_rel(a.grad, b_.grad) < gtol, f"{prec} grad {n}: {l2_rel(a.grad, b_.grad)}"
