@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(256) xattn_bwd_dkv_kernel(AttnParams p) {
 // attention_tc.cu: tcgen05 path (head dim 16 / 32); NPF_ENOTSUP for other shapes
 int xattn_fwd_tc(const float* Q, const float* K, const float* V, float* O, float* LSE, int B, int Tq, int Tk, int H, int D, int Dv,
                  float scale, int precision, cudaStream_t st);
+int xattn_bwd_tc(const float* Q, const float* K, const float* V, const float* O, const float* LSE, const float* dO, float* dQ, float* dK,
+                 float* dV, int B, int Tq, int Tk, int H, int D, int Dv, float scale, int precision, cudaStream_t st);
 
 static int set_smem(const void* fn, size_t bytes) {
     if (bytes > 48 * 1024) {
@@ -319,6 +321,10 @@ extern "C" int npf_xattn_bwd(const float* Q, const float* K, const float* V, con
         cudaMemsetAsync(dK, 0, sizeof(float) * (size_t)B * Tk * H * D, st);
         cudaMemsetAsync(dV, 0, sizeof(float) * (size_t)B * Tk * H * Dv, st);
         return NPF_OK;
+    }
+    if (precision != NPF_PREC_FP32) {
+        int rc = xattn_bwd_tc(Q, K, V, O, LSE, dO, dQ, dK, dV, B, Tq, Tk, H, D, Dv, scale, precision, st);
+        if (rc != NPF_ENOTSUP) return rc;
     }
     AttnParams p{};
     p.Q = Q; p.K = K; p.V = V; p.O = O; p.LSE = LSE; p.dO = dO; p.dQ = dQ; p.dK = dK; p.dV = dV;

@@ -252,6 +252,204 @@ static int launch_fwd(AttnTcParams& p, int B, cudaStream_t st) {
     return check_launch("xattn_fwd_tc_kernel");
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Backward.  One CTA per (task, head, 128-key block); loops over the 128-query blocks.  256 threads: thread t owns
+// TMEM lane / query row r = t & 127 and the key-column half t >> 7 of the 128 x 128 score tile.
+//   S = Q K^T, dP = dO V^T                 (two MMAs, M=128 N=128 K=D|Dv)                      TMEM [0,128), [128,256)
+//   P = exp(S*scale - lse), dS = P (dP - Di) scale   -> bf16 hi/lo into the shared operand tiles Pt / dSt
+//   dV += P^T dO,  dK += dS^T Q            (M = keys, K = queries; accumulate over query blocks) TMEM [320,..), [288,..)
+//   dQ_blk = dS K                          (M = queries, K = keys)                               TMEM [256,..) -> atomics
+// Every staged tile uses ONE physical layout: 16-byte rows of 8 consecutive columns, 8 rows = a 128-byte core matrix,
+// row groups 128 B apart, column chunks 2048 B apart.  Read with (LBO=2048, SBO=128) it is a K-major operand over its
+// columns; read with (LBO=128, SBO=2048) and the MN-major flag it is the TRANSPOSED operand -- so Q, dO, K, P and dS
+// are staged once and serve both of their roles.
+// ----------------------------------------------------------------------------------------------------------------
+template <int NSPLIT>
+__device__ __forceinline__ void mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_hi, uint32_t b_lo,
+                                     uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, uint32_t acc) {
+    umma_bf16(d, make_desc(a_hi, a_lbo, a_sbo), make_desc(b_hi, b_lbo, b_sbo), idesc, acc);
+    if (NSPLIT == 3) {
+        umma_bf16(d, make_desc(a_hi, a_lbo, a_sbo), make_desc(b_lo, b_lbo, b_sbo), idesc, 1);
+        umma_bf16(d, make_desc(a_lo, a_lbo, a_sbo), make_desc(b_hi, b_lbo, b_sbo), idesc, 1);
+    }
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(256, 1) xattn_bwd_tc_kernel(AttnTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar1, bar2;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_lse2[128], s_di[128];
+    const int D = p.D, DV = p.Dv;
+    constexpr uint32_t CH = 2048u;                               // column-chunk stride of every tile (128 rows x 16 B)
+    const uint32_t t_small = (uint32_t)(D >> 3) * CH, t_small_v = (uint32_t)(DV >> 3) * CH, t_big = 16u * CH;
+    uint8_t* kt = smem_raw;
+    uint8_t* vt = kt + t_small;
+    uint8_t* qt = vt + t_small_v;
+    uint8_t* dot_ = qt + t_small;
+    uint8_t* pt = dot_ + t_small_v;
+    uint8_t* dst = pt + t_big;
+    const uint32_t half = 2u * t_small + 2u * t_small_v + 2u * t_big;
+    const uint32_t LO = half;                                     // byte offset of the "lo" copies (NSPLIT == 3)
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & 127, chalf = tid >> 7;
+    const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const long ldq = (long)p.H * D, ldv = (long)p.H * DV;
+    const float* Qb = p.Q + ((long)b * p.Tq) * ldq + h * D;
+    const float* Kb = p.K + ((long)b * p.Tk) * ldq + h * D;
+    const float* Vb = p.V + ((long)b * p.Tk) * ldv + h * DV;
+    const float* Ob = p.O + ((long)b * p.Tq) * ldv + h * DV;
+    const float* Gb = p.dO + ((long)b * p.Tq) * ldv + h * DV;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); }
+    const int key0 = kb * 128;
+    if (tid < 128) {
+        const bool k_ok = key0 + tid < p.Tk;
+        stage_rows_kmajor<NSPLIT>(kt, kt + LO, Kb + (long)key0 * ldq, ldq, tid, k_ok, D, 128);
+        stage_rows_kmajor<NSPLIT>(vt, vt + LO, Vb + (long)key0 * ldv, ldv, tid, k_ok, DV, 128);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    const uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_DK = 288, T_DV = 320;
+    const uint32_t idesc_sp = make_idesc(128, 128, 0, 0);
+    const uint32_t idesc_dv = make_idesc(128, DV, 1, 1), idesc_dk = make_idesc(128, D, 1, 1), idesc_dq = make_idesc(128, D, 0, 1);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const uint32_t s_kt = smem_u32(kt), s_vt = smem_u32(vt), s_qt = smem_u32(qt), s_dot = smem_u32(dot_), s_pt = smem_u32(pt), s_dst = smem_u32(dst);
+
+    uint32_t ph = 0, acc_kv = 0;
+    for (int q0 = 0; q0 < p.Tq; q0 += 128) {
+        if (tid < 128) {   // stage this query block: Q, dO tiles + per-row lse and Di = dO . O
+            const int q = q0 + tid;
+            const bool q_ok = q < p.Tq;
+            stage_rows_kmajor<NSPLIT>(qt, qt + LO, Qb + (long)q0 * ldq, ldq, tid, q_ok, D, 128);
+            stage_rows_kmajor<NSPLIT>(dot_, dot_ + LO, Gb + (long)q0 * ldv, ldv, tid, q_ok, DV, 128);
+            float di = 0.f;
+            if (q_ok)
+                for (int c = 0; c < DV; ++c) di = fmaf(__ldg(Gb + (long)q * ldv + c), __ldg(Ob + (long)q * ldv + c), di);
+            s_di[tid] = di;
+            s_lse2[tid] = q_ok ? __ldg(p.LSE + ((long)b * p.H + h) * p.Tq + q) * 1.4426950408889634f : INFINITY;   // +inf -> P = 0
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < D / 16; ++ks)      // S = Q K^T : both K-major over d
+                mma3<NSPLIT>(tmem + T_S, s_qt + ks * 2 * CH, s_qt + LO + ks * 2 * CH, CH, 128, s_kt + ks * 2 * CH, s_kt + LO + ks * 2 * CH, CH, 128,
+                             idesc_sp, ks > 0);
+            for (int ks = 0; ks < DV / 16; ++ks)     // dP = dO V^T
+                mma3<NSPLIT>(tmem + T_DP, s_dot + ks * 2 * CH, s_dot + LO + ks * 2 * CH, CH, 128, s_vt + ks * 2 * CH, s_vt + LO + ks * 2 * CH, CH, 128,
+                             idesc_sp, ks > 0);
+            umma_commit(&bar1);
+        }
+        mbar_wait(&bar1, ph);
+        tc_fence_after();
+
+        {   // P and dS for row r, key columns [64*chalf, 64*chalf + 64)
+            const float lse2 = s_lse2[r], di = s_di[r];
+#pragma unroll 1
+            for (int c0 = 64 * chalf; c0 < 64 * chalf + 64; c0 += 32) {
+                float sv[32], dv[32];
+                tmem_ld32(tmem + lane_addr + T_S + (uint32_t)c0, sv);
+                tmem_ld32(tmem + lane_addr + T_DP + (uint32_t)c0, dv);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const bool ok = key0 + c0 + j < p.Tk;
+                    const float pj = ok ? exp2f(fmaf(sv[j], sl2, -lse2)) : 0.f;
+                    sv[j] = pj;
+                    dv[j] = pj * (dv[j] - di) * p.scale;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float a8[8], b8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { a8[i] = sv[g * 8 + i]; b8[i] = dv[g * 8 + i]; }
+                    const uint32_t off = (uint32_t)((c0 >> 3) + g) * CH + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+                    *reinterpret_cast<uint4*>(pt + off) = pack8(a8);
+                    *reinterpret_cast<uint4*>(dst + off) = pack8(b8);
+                    if (NSPLIT == 3) {
+                        float l8[8];
+                        split8(a8, l8);
+                        *reinterpret_cast<uint4*>(pt + LO + off) = pack8(l8);
+                        split8(b8, l8);
+                        *reinterpret_cast<uint4*>(dst + LO + off) = pack8(l8);
+                    }
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < 8; ++ks) {        // reduction over the 128 query rows, 16 per step
+                // dV += P^T dO : A = P read transposed (MN-major: LBO = 128 between 8-row groups, SBO = CH between key chunks)
+                mma3<NSPLIT>(tmem + T_DV, s_pt + ks * 256, s_pt + LO + ks * 256, 128, CH, s_dot + ks * 256, s_dot + LO + ks * 256, 128, CH, idesc_dv,
+                             acc_kv | (uint32_t)(ks > 0));
+                // dK += dS^T Q
+                mma3<NSPLIT>(tmem + T_DK, s_dst + ks * 256, s_dst + LO + ks * 256, 128, CH, s_qt + ks * 256, s_qt + LO + ks * 256, 128, CH, idesc_dk,
+                             acc_kv | (uint32_t)(ks > 0));
+            }
+            for (int ks = 0; ks < 8; ++ks)          // dQ_blk = dS K : reduction over the 128 keys
+                mma3<NSPLIT>(tmem + T_DQ, s_dst + ks * 2 * CH, s_dst + LO + ks * 2 * CH, CH, 128, s_kt + ks * 256, s_kt + LO + ks * 256, 128, CH, idesc_dq,
+                             ks > 0);
+            umma_commit(&bar2);
+        }
+        acc_kv = 1;
+        mbar_wait(&bar2, ph);
+        ph ^= 1;
+        tc_fence_after();
+        if (chalf == 0) {
+            const int q = q0 + r;
+            for (int c0 = 0; c0 < D; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + lane_addr + T_DQ + (uint32_t)c0, v);
+                if (q < p.Tq) {
+                    float* d = p.dQ + ((long)b * p.Tq + q) * ldq + h * D + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (acc_kv) {
+        tc_fence_after();
+        if (chalf == 0) {
+            const int key = key0 + r;
+            for (int c0 = 0; c0 < D; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + lane_addr + T_DK + (uint32_t)c0, v);
+                if (key < p.Tk) {
+                    float* d = p.dK + ((long)b * p.Tk + key) * ldq + h * D + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        } else {
+            const int key = key0 + r;
+            for (int c0 = 0; c0 < DV; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + lane_addr + T_DV + (uint32_t)c0, v);
+                if (key < p.Tk) {
+                    float* d = p.dV + ((long)b * p.Tk + key) * ldv + h * DV + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 static bool attn_tc_ok(const AttnTcParams& p) {
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     return (p.D == 16 || p.D == 32) && (p.Dv == 16 || p.Dv == 32) && al(p.Q) && al(p.K) && al(p.V) && p.Tk >= 1;
@@ -265,6 +463,34 @@ int xattn_fwd_tc(const float* Q, const float* K, const float* V, float* O, float
     if (!attn_tc_ok(p) || (reinterpret_cast<uintptr_t>(O) & 15)) return NPF_ENOTSUP;
     if (precision == NPF_PREC_BF16X3) return Dv == 16 ? launch_fwd<3, 16>(p, B, st) : launch_fwd<3, 32>(p, B, st);
     return Dv == 16 ? launch_fwd<1, 16>(p, B, st) : launch_fwd<1, 32>(p, B, st);
+}
+
+int xattn_bwd_tc(const float* Q, const float* K, const float* V, const float* O, const float* LSE, const float* dO, float* dQ, float* dK,
+                 float* dV, int B, int Tq, int Tk, int H, int D, int Dv, float scale, int precision, cudaStream_t st) {
+    AttnTcParams p{};
+    p.Q = Q; p.K = K; p.V = V; p.O = O; p.LSE = LSE; p.dO = dO; p.dQ = dQ; p.dK = dK; p.dV = dV;
+    p.Tq = Tq; p.Tk = Tk; p.H = H; p.D = D; p.Dv = Dv; p.scale = scale;
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!attn_tc_ok(p) || !al(O) || !al(dO) || !al(dQ) || !al(dK) || !al(dV) || Tq < 1) return NPF_ENOTSUP;
+    const size_t half = (size_t)(2 * (D >> 3) + 2 * (Dv >> 3) + 32) * 2048;
+    const bool x3 = precision == NPF_PREC_BF16X3;
+    const size_t smem = half * (x3 ? 2 : 1);
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(xattn_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(xattn_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return NPF_ENOTSUP;
+        }
+        attr = true;
+    }
+    if (smem > 200 * 1024) return NPF_ENOTSUP;
+    cudaMemsetAsync(dQ, 0, sizeof(float) * (size_t)B * Tq * H * D, st);   // dQ is accumulated over key blocks with atomics
+    dim3 grid((unsigned)cdiv(Tk, 128), (unsigned)H, (unsigned)B);
+    if (x3) xattn_bwd_tc_kernel<3><<<grid, 256, smem, st>>>(p);
+    else xattn_bwd_tc_kernel<1><<<grid, 256, smem, st>>>(p);
+    count_launch();
+    return check_launch("xattn_bwd_tc_kernel");
 }
 
 }  // namespace npf

@@ -96,7 +96,7 @@ def test_tc_single_linear_localised(npf, prec, M, K, N):
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
 @pytest.mark.parametrize("B,Tq,Tk,H,D", [(2, 128, 128, 8, 16), (1, 33, 70, 8, 16), (2, 300, 513, 4, 32), (1, 1, 1, 8, 16), (2, 512, 512, 8, 16)])
 def test_tc_attention_forward(npf, prec, B, Tq, Tk, H, D):
-    """tcgen05 attention forward (head dim 16 / 32) vs fp64 softmax attention; backward still runs (SIMT) from its O, LSE."""
+    """tcgen05 attention forward + backward (head dim 16 / 32) vs fp64 softmax attention."""
     import math
     npf.set_precision(prec)
     ftol = {"bf16x3": 1e-4, "bf16": 1e-2}[prec]
@@ -115,5 +115,9 @@ def test_tc_attention_forward(npf, prec, B, Tq, Tk, H, D):
     yr.backward(go)
     yc.backward(go.float().cuda())
     gtol = {"bf16x3": 2e-3, "bf16": 5e-2}[prec]
+    gmax = max(t_.grad.norm().item() for t_ in r)
     for n, a, b_ in zip("qkv", c, r):
-        assert l2_rel(a.grad, b_.grad) < gtol, f"{prec} grad {n}: {l2_rel(a.grad, b_.grad)}"
+        # L2 error relative to the gradient's own norm, floored at 1e-3 of the largest of the three (with a single key the
+        # softmax gradient w.r.t. q and k is exactly 0)
+        err = (a.grad.double().cpu() - b_.grad).norm().item() / max(b_.grad.norm().item(), 1e-3 * gmax)
+        assert err < gtol, f"{prec} grad {n}: {err}"
