@@ -40,7 +40,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], float (&lo)[8]) {
 // rows in the tile: chunk (w/8) at (w/8)*R*16 + (row/8)*128 + (row%8)*16.
 template <int NSPLIT>
 __device__ __forceinline__ void stage_rows_kmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, long ld, int row, bool valid, int width,
-                                                  int R) {
+                                                  int R, uint8_t* lo2 = nullptr) {
     const uint32_t base = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
     for (int ch = 0; ch < (width >> 3); ++ch) {
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -55,7 +55,28 @@ __device__ __forceinline__ void stage_rows_kmajor(uint8_t* hi, uint8_t* lo, cons
             float l[8];
             split8(v, l);
             *reinterpret_cast<uint4*>(lo + off) = pack8(l);
+            if (lo2) {   // third bf16 term: x = hi + lo + lo2 to fp32 precision (operands of the softmax logits)
+                float l2[8];
+                split8(l, l2);
+                *reinterpret_cast<uint4*>(lo2 + off) = pack8(l2);
+            }
         }
+    }
+}
+
+// Logits need fp32-level accuracy (an absolute logit error is a RELATIVE error of the softmax weight, and trained
+// attention has |logit| ~ 1e2): with NSPLIT == 3 the product Q K^T uses three bf16 terms per operand and the six
+// cross products down to 2^-24: hh, hm, mh, mm, hl, lh.
+template <int NSPLIT>
+__device__ __forceinline__ void mma_logits(uint32_t d, uint32_t a_h, uint32_t a_m, uint32_t a_l, uint32_t b_h, uint32_t b_m, uint32_t b_l,
+                                           uint32_t lbo, uint32_t idesc, uint32_t acc) {
+    umma_bf16(d, make_desc(a_h, lbo, 128), make_desc(b_h, lbo, 128), idesc, acc);
+    if (NSPLIT == 3) {
+        umma_bf16(d, make_desc(a_h, lbo, 128), make_desc(b_m, lbo, 128), idesc, 1);
+        umma_bf16(d, make_desc(a_m, lbo, 128), make_desc(b_h, lbo, 128), idesc, 1);
+        umma_bf16(d, make_desc(a_m, lbo, 128), make_desc(b_m, lbo, 128), idesc, 1);
+        umma_bf16(d, make_desc(a_h, lbo, 128), make_desc(b_l, lbo, 128), idesc, 1);
+        umma_bf16(d, make_desc(a_l, lbo, 128), make_desc(b_h, lbo, 128), idesc, 1);
     }
 }
 
@@ -94,6 +115,7 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
     uint8_t* p_hi = v_hi + v_bytes;
     const uint32_t half = q_bytes + k_bytes + v_bytes + p_bytes;
     uint8_t* q_lo = q_hi + half; uint8_t* k_lo = k_hi + half; uint8_t* v_lo = v_hi + half; uint8_t* p_lo = p_hi + half;   // NSPLIT == 3 only
+    uint8_t* q_l2 = smem_raw + 2 * half; uint8_t* k_l2 = q_l2 + q_bytes;                                                  // NSPLIT == 3 only
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -107,7 +129,7 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
     constexpr uint32_t kCols = 256;   // S: [0,128), O chunk: [128, 128 + DV)
     if (warp == 0) tmem_alloc(&tmem_slot, kCols);
     if (tid == 0) { mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); }
-    stage_rows_kmajor<NSPLIT>(q_hi, q_lo, Qb + (long)qb * kQB * ldq, ldq, tid, q_ok, D, kQB);   // tile row tid <- query row q_row
+    stage_rows_kmajor<NSPLIT>(q_hi, q_lo, Qb + (long)qb * kQB * ldq, ldq, tid, q_ok, D, kQB, NSPLIT == 3 ? q_l2 : nullptr);   // tile row tid <- query row
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -129,22 +151,17 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
         // stage this chunk of K and V (thread = key row); the previous chunk's MMAs have completed (bar_o waited below)
         const int key = k0 + tid;
         const bool k_ok = key < p.Tk;
-        stage_rows_kmajor<NSPLIT>(k_hi, k_lo, Kb + (long)k0 * ldq, ldq, tid, k_ok, D, kKC);
+        stage_rows_kmajor<NSPLIT>(k_hi, k_lo, Kb + (long)k0 * ldq, ldq, tid, k_ok, D, kKC, NSPLIT == 3 ? k_l2 : nullptr);
         stage_rows_mnmajor<NSPLIT>(v_hi, v_lo, Vb + (long)k0 * ldv, ldv, tid, k_ok, DV);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            uint32_t acc = 0;
             for (int ks = 0; ks < D / 16; ++ks) {
-                const uint32_t qo = (uint32_t)ks * 2u * q_lbo, ko = (uint32_t)ks * 2u * k_lbo;
-                umma_bf16(tmem, make_desc(smem_u32(q_hi) + qo, q_lbo, 128), make_desc(smem_u32(k_hi) + ko, k_lbo, 128), idesc_s, acc);
-                acc = 1;
-                if (NSPLIT == 3) {
-                    umma_bf16(tmem, make_desc(smem_u32(q_hi) + qo, q_lbo, 128), make_desc(smem_u32(k_lo) + ko, k_lbo, 128), idesc_s, 1);
-                    umma_bf16(tmem, make_desc(smem_u32(q_lo) + qo, q_lbo, 128), make_desc(smem_u32(k_hi) + ko, k_lbo, 128), idesc_s, 1);
-                }
+                const uint32_t o = (uint32_t)ks * 2u * q_lbo;      // q_lbo == k_lbo (both tiles have 128 rows)
+                mma_logits<NSPLIT>(tmem, smem_u32(q_hi) + o, smem_u32(q_lo) + o, smem_u32(q_l2) + o, smem_u32(k_hi) + o, smem_u32(k_lo) + o,
+                                   smem_u32(k_l2) + o, q_lbo, idesc_s, ks > 0);
             }
             umma_commit(&bar_s);
         }
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
 template <int NSPLIT, int DV>
 static int launch_fwd(AttnTcParams& p, int B, cudaStream_t st) {
     const size_t half = (size_t)(kQB * p.D + kKC * p.D + kKC * DV + kQB * kKC) * 2;
-    const size_t smem = half * (NSPLIT == 3 ? 2 : 1);
+    const size_t smem = half * (NSPLIT == 3 ? 2 : 1) + (NSPLIT == 3 ? (size_t)(kQB + kKC) * p.D * 2 : 0);
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(xattn_fwd_tc_kernel<NSPLIT, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
@@ -291,6 +308,7 @@ __global__ void __launch_bounds__(256, 1) xattn_bwd_tc_kernel(AttnTcParams p) {
     uint8_t* dst = pt + t_big;
     const uint32_t half = 2u * t_small + 2u * t_small_v + 2u * t_big;
     const uint32_t LO = half;                                     // byte offset of the "lo" copies (NSPLIT == 3)
+    uint8_t* kt_l2 = smem_raw + 2 * half; uint8_t* qt_l2 = kt_l2 + t_small;   // third bf16 term of K and Q (logits only)
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & 127, chalf = tid >> 7;
@@ -307,7 +325,7 @@ __global__ void __launch_bounds__(256, 1) xattn_bwd_tc_kernel(AttnTcParams p) {
     const int key0 = kb * 128;
     if (tid < 128) {
         const bool k_ok = key0 + tid < p.Tk;
-        stage_rows_kmajor<NSPLIT>(kt, kt + LO, Kb + (long)key0 * ldq, ldq, tid, k_ok, D, 128);
+        stage_rows_kmajor<NSPLIT>(kt, kt + LO, Kb + (long)key0 * ldq, ldq, tid, k_ok, D, 128, NSPLIT == 3 ? kt_l2 : nullptr);
         stage_rows_kmajor<NSPLIT>(vt, vt + LO, Vb + (long)key0 * ldv, ldv, tid, k_ok, DV, 128);
     }
     tc_fence_before();
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(256, 1) xattn_bwd_tc_kernel(AttnTcParams p) {
         if (tid < 128) {   // stage this query block: Q, dO tiles + per-row lse and Di = dO . O
             const int q = q0 + tid;
             const bool q_ok = q < p.Tq;
-            stage_rows_kmajor<NSPLIT>(qt, qt + LO, Qb + (long)q0 * ldq, ldq, tid, q_ok, D, 128);
+            stage_rows_kmajor<NSPLIT>(qt, qt + LO, Qb + (long)q0 * ldq, ldq, tid, q_ok, D, 128, NSPLIT == 3 ? qt_l2 : nullptr);
             stage_rows_kmajor<NSPLIT>(dot_, dot_ + LO, Gb + (long)q0 * ldv, ldv, tid, q_ok, DV, 128);
             float di = 0.f;
             if (q_ok)
@@ -339,9 +357,9 @@ __global__ void __launch_bounds__(256, 1) xattn_bwd_tc_kernel(AttnTcParams p) {
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            for (int ks = 0; ks < D / 16; ++ks)      // S = Q K^T : both K-major over d
-                mma3<NSPLIT>(tmem + T_S, s_qt + ks * 2 * CH, s_qt + LO + ks * 2 * CH, CH, 128, s_kt + ks * 2 * CH, s_kt + LO + ks * 2 * CH, CH, 128,
-                             idesc_sp, ks > 0);
+            for (int ks = 0; ks < D / 16; ++ks)      // S = Q K^T : both K-major over d, fp32-level product
+                mma_logits<NSPLIT>(tmem + T_S, s_qt + ks * 2 * CH, s_qt + LO + ks * 2 * CH, smem_u32(qt_l2) + ks * 2 * CH, s_kt + ks * 2 * CH,
+                                   s_kt + LO + ks * 2 * CH, smem_u32(kt_l2) + ks * 2 * CH, CH, idesc_sp, ks > 0);
             for (int ks = 0; ks < DV / 16; ++ks)     // dP = dO V^T
                 mma3<NSPLIT>(tmem + T_DP, s_dot + ks * 2 * CH, s_dot + LO + ks * 2 * CH, CH, 128, s_vt + ks * 2 * CH, s_vt + LO + ks * 2 * CH, CH, 128,
                              idesc_sp, ks > 0);
@@ -474,7 +492,7 @@ int xattn_bwd_tc(const float* Q, const float* K, const float* V, const float* O,
     if (!attn_tc_ok(p) || !al(O) || !al(dO) || !al(dQ) || !al(dK) || !al(dV) || Tq < 1) return NPF_ENOTSUP;
     const size_t half = (size_t)(2 * (D >> 3) + 2 * (Dv >> 3) + 32) * 2048;
     const bool x3 = precision == NPF_PREC_BF16X3;
-    const size_t smem = half * (x3 ? 2 : 1);
+    const size_t smem = half * (x3 ? 2 : 1) + (x3 ? (size_t)2 * (D >> 3) * 2048 : 0);
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(xattn_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
