@@ -85,8 +85,10 @@ class MultiheadAttender(nn.Module):
         nn.init.normal_(self.value_transform.weight, mean=0, std=std)
 
     def _attend(self, keys, queries, values):
-        k = ops.linear(keys, self.key_transform.weight)
-        q = ops.linear(queries, self.query_transform.weight, self.query_transform.bias)
+        # everything upstream of the softmax logits stays in fp32: an absolute logit error is a relative error of the
+        # attention weight, and trained attention has |logit| ~ 1e2 (the 16-bit products of 'bf16x3' are not enough)
+        k = ops.linear(keys, self.key_transform.weight, precision="fp32")
+        q = ops.linear(queries, self.query_transform.weight, self.query_transform.bias, precision="fp32")
         v = ops.linear(values, self.value_transform.weight)
         return ops.xattn(q, k, v, self.n_heads, 1.0 / math.sqrt(self.kq_head_size))
 

@@ -42,6 +42,7 @@ class MLP(nn.Module):
         self.to_hidden = nn.Linear(input_size, hidden_size, bias=is_bias)
         self.linears = nn.ModuleList(nn.Linear(hidden_size, hidden_size, bias=is_bias) for _ in range(n_hidden_layers - 1))
         self.out = nn.Linear(hidden_size, output_size, bias=is_bias)
+        self.precision = None  # None: global npf_b200 precision; 'fp32' pins this MLP to the FFMA kernels
         self.reset_parameters()
 
     def _layers(self):
@@ -49,7 +50,7 @@ class MLP(nn.Module):
 
     def forward(self, x):
         layers = self._layers()
-        return ops.mlp_chain(x, [l.weight for l in layers], [l.bias for l in layers])
+        return ops.mlp_chain(x, [l.weight for l in layers], [l.bias for l in layers], precision=self.precision)
 
     def reset_parameters(self):
         for lin in self._layers()[:-1]:

@@ -26,6 +26,8 @@ class AttnCNP(NeuralProcessFamily):
             XYEncoder = self.dflt_Modules["XYEncoder"]
         self.xy_encoder = XYEncoder(self.x_transf_dim, self.y_dim, self.r_dim)
         self.attender = get_attender(attention, self.x_transf_dim, self.r_dim, self.r_dim, **attention_kwargs)
+        if hasattr(self.x_encoder, "precision"):
+            self.x_encoder.precision = "fp32"  # keys / queries of the attention: see MultiheadAttender._attend
 
     dflt_Modules = CNP.dflt_Modules
 

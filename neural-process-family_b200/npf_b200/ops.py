@@ -82,24 +82,24 @@ def _gbuf(p):
 # ======================================================================================================
 # Linear / MLP chain
 # ======================================================================================================
-def _lin_fwd(x2, W, b, N, K, flags=0, ldw=None, u=None, w2_ptr=None, ldw2=0):
+def _lin_fwd(x2, W, b, N, K, flags=0, ldw=None, u=None, w2_ptr=None, ldw2=0, prec=None):
     M = x2.shape[0]
     y = torch.empty(M, N, device=x2.device, dtype=torch.float32)
     call("npf_linear_fwd", _p(x2), x2.stride(0) if M else K, _p(W) if not isinstance(W, int) else W, ldw or K, _p(b),
-         _p(y), N, M, K, N, flags, _p(u), w2_ptr, ldw2, _precision, _stream())
+         _p(y), N, M, K, N, flags, _p(u), w2_ptr, ldw2, _precision if prec is None else prec, _stream())
     return y
 
 
-def _lin_bwd_data(dz, W_ptr, ldw, M, K, N, mask=None, out=None, accumulate=False):
+def _lin_bwd_data(dz, W_ptr, ldw, M, K, N, mask=None, out=None, accumulate=False, prec=None):
     dx = out if out is not None else torch.empty(M, K, device=dz.device, dtype=torch.float32)
     call("npf_linear_bwd_data", _p(dz), N, W_ptr, ldw, _p(dx), K, M, K, N, _p(mask), K if mask is not None else 0,
-         ACCUM if accumulate else 0, _precision, _stream())
+         ACCUM if accumulate else 0, _precision if prec is None else prec, _stream())
     return dx
 
 
-def _lin_bwd_weight(dz, x2, dW_ptr, lddw, db, M, K, N, flags=0, u=None, dw2_ptr=None, ldw2=0):
+def _lin_bwd_weight(dz, x2, dW_ptr, lddw, db, M, K, N, flags=0, u=None, dw2_ptr=None, ldw2=0, prec=None):
     call("npf_linear_bwd_weight", _p(dz), N, _p(x2), K, dW_ptr, lddw, _p(db), M, K, N, flags, _p(u), dw2_ptr, ldw2,
-         _precision, _stream())
+         _precision if prec is None else prec, _stream())
 
 
 class _MLPChain(torch.autograd.Function):
@@ -108,8 +108,9 @@ class _MLPChain(torch.autograd.Function):
     with the relu mask fused into the data-gradient GEMM epilogue."""
 
     @staticmethod
-    def forward(ctx, x, final_relu, has_bias, *params):
+    def forward(ctx, x, final_relu, has_bias, prec, *params):
         _chk(x, *params)
+        ctx.prec = prec
         n_layers = len(params) // 2 if has_bias else len(params)
         Ws = params[:n_layers]
         bs = params[n_layers:] if has_bias else (None,) * n_layers
@@ -120,7 +121,7 @@ class _MLPChain(torch.autograd.Function):
             last = i == n_layers - 1
             flags = RELU_OUT if (not last or final_relu) else 0
             # W is [out, in] or a 1x1 conv weight [out, in, 1(, 1)]: same memory, K = numel / out
-            h = _lin_fwd(h, _c(W), None if b is None else _c(b), W.shape[0], W.numel() // W.shape[0], flags)
+            h = _lin_fwd(h, _c(W), None if b is None else _c(b), W.shape[0], W.numel() // W.shape[0], flags, prec=prec)
             acts.append(h)
         ctx.save_for_backward(*acts, *Ws, *(bs if has_bias else ()))
         ctx.n_layers, ctx.final_relu, ctx.has_bias = n_layers, final_relu, has_bias
@@ -148,24 +149,25 @@ class _MLPChain(torch.autograd.Function):
             dW, dWs[i] = _gbuf(Ws[i])
             db, dbs[i] = _gbuf(bs[i])
             if M > 0:
-                _lin_bwd_weight(dz, acts[i], _p(dW), K, db, M, K, N)
+                _lin_bwd_weight(dz, acts[i], _p(dW), K, db, M, K, N, prec=ctx.prec)
             if i > 0:
-                dz = _lin_bwd_data(dz, _p(W), K, M, K, N, mask=acts[i])
+                dz = _lin_bwd_data(dz, _p(W), K, M, K, N, mask=acts[i], prec=ctx.prec)
             elif ctx.needs_input_grad[0]:
-                dx = _lin_bwd_data(dz, _p(W), K, M, K, N).reshape(ctx.x_shape)
+                dx = _lin_bwd_data(dz, _p(W), K, M, K, N, prec=ctx.prec).reshape(ctx.x_shape)
         grads = tuple(dWs) + (tuple(dbs) if ctx.has_bias else ())
-        return (dx, None, None) + grads
+        return (dx, None, None, None) + grads
 
 
-def mlp_chain(x, weights, biases, final_relu=False):
-    """weights: list of [out,in] tensors; biases: list of [out] tensors or None (all or none)."""
+def mlp_chain(x, weights, biases, final_relu=False, precision=None):
+    """weights: list of [out,in] tensors; biases: list of [out] tensors or None (all or none).
+    precision: None (global setting) or 'fp32' / 'bf16' / 'bf16x3' for this chain only."""
     has_bias = biases is not None and biases[0] is not None
     params = tuple(weights) + (tuple(biases) if has_bias else ())
-    return _MLPChain.apply(x, final_relu, has_bias, *params)
+    return _MLPChain.apply(x, final_relu, has_bias, None if precision is None else _PRECISION[precision], *params)
 
 
-def linear(x, weight, bias=None, relu=False):
-    return mlp_chain(x, [weight], None if bias is None else [bias], final_relu=relu)
+def linear(x, weight, bias=None, relu=False, precision=None):
+    return mlp_chain(x, [weight], None if bias is None else [bias], final_relu=relu, precision=precision)
 
 
 # ======================================================================================================
