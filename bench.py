@@ -323,7 +323,7 @@ def main():
                 gpu_launches=launches, wall_ms_per_step=t_wall * 1e3 / args.steps, roofline=roof, kernel_rooflines=roof_table,
                 kernel_ms_per_step={k: round(v[0] / n_prof, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])})
     if not args.no_cpu_baseline:
-        cb, _, _, _ = cpu_reference_timing(wl, 10, 2)
+        cb, _, _, _ = cpu_reference_timing(wl, 200, 2, budget_s=15.0)
         line["cpu_baseline"] = cb
     if args.kernel_times:
         for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):

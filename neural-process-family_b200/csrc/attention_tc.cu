@@ -33,7 +33,11 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 __device__ __forceinline__ void split8(const float (&v)[8], float (&lo)[8]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) lo[i] = v[i] - bf16_round(v[i]);
+    for (int i = 0; i < 8; i += 2) {     // residual against the packed bf16 pair (bf16 -> fp32 is a 16-bit shift)
+        const uint32_t h = pack_bf16(v[i], v[i + 1]);
+        lo[i] = v[i] - __uint_as_float(h << 16);
+        lo[i + 1] = v[i + 1] - __uint_as_float(h & 0xFFFF0000u);
+    }
 }
 
 // Stage `rows_valid` rows (thread = row) of a [rows, width] fp32 slice (row stride ld) as a K-major operand with `R`

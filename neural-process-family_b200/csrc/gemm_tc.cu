@@ -76,9 +76,11 @@ __device__ __forceinline__ void store_kmajor(const float4 (&pre)[kPre], uint8_t*
         if (rg < n_rg) {
             float4 v = pre[i];
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-            if (NSPLIT == 3) {
-                const float rx = v.x - bf16_round(v.x), ry = v.y - bf16_round(v.y), rz = v.z - bf16_round(v.z), rw = v.w - bf16_round(v.w);
+            const uint32_t h01 = pack_bf16(v.x, v.y), h23 = pack_bf16(v.z, v.w);
+            *reinterpret_cast<uint2*>(hi + off) = make_uint2(h01, h23);
+            if (NSPLIT == 3) {   // residuals against the packed hi halves (bf16 -> fp32 is a 16-bit shift)
+                const float rx = v.x - __uint_as_float(h01 << 16), ry = v.y - __uint_as_float(h01 & 0xFFFF0000u);
+                const float rz = v.z - __uint_as_float(h23 << 16), rw = v.w - __uint_as_float(h23 & 0xFFFF0000u);
                 *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(rx, ry), pack_bf16(rz, rw));
             }
         }
@@ -141,14 +143,17 @@ struct TcLinParams {
 // ------------------------------------------------------------------------------------------------ fwd / bwd-data
 constexpr int kScratchLd = 36;     // floats per staged row: 32 + 4 keeps both the row-wise STS.128 and the LDS.128 conflict-free
 
-template <int NSPLIT>
+// KR_T / NO_T: compile-time reduction / output extents (0 = run-time values from the parameter block); HAS_U / HAS_MASK:
+// rank-1 epilogue term / relu-mask epilogue compiled in.  The 128 x 128 instantiations are the hot ones: with the
+// extents known every staging predicate and index computation folds away.
+template <int NSPLIT, int KR_T, int NO_T, bool HAS_U, bool HAS_MASK>
 __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_bias[256], s_w2[256];
 
-    const int KR = p.KR, NO = p.NO;
+    const int KR = KR_T ? KR_T : p.KR, NO = NO_T ? NO_T : p.NO;
     const uint32_t a_bytes = 128u * KR * 2u, b_bytes = (uint32_t)NO * KR * 2u;
     uint8_t* a_hi = smem_raw;
     uint8_t* a_lo = a_hi + a_bytes;                               // only touched when NSPLIT == 3
@@ -248,12 +253,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p
                 if (row < p.M) {
                     float4 x = *reinterpret_cast<const float4*>(scratch + r * kScratchLd + c4);
                     x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                    if (p.u) {
+                    if (HAS_U && p.u) {
                         const float up = __ldg(p.u + row);
                         x.x = fmaf(up, ww.x, x.x); x.y = fmaf(up, ww.y, x.y); x.z = fmaf(up, ww.z, x.z); x.w = fmaf(up, ww.w, x.w);
                     }
                     if (p.relu_out) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                    if (p.mask) {
+                    if (HAS_MASK && p.mask) {
                         const float* mk = p.mask + (long)row * p.ldm + c0 + c4;
                         float4 mv;
                         if ((p.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0) mv = __ldg(reinterpret_cast<const float4*>(mk));
@@ -335,12 +340,15 @@ __device__ __forceinline__ void store_mnmajor(const float4 (&pre)[2 * kWgIt], ui
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
             }
-            *reinterpret_cast<uint4*>(hi + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            const uint4 h = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(hi + off) = h;
             if (NSPLIT == 3) {
-                float qd[8];
+                const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+                uint32_t ll[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) qd[e] = v[e] - bf16_round(v[e]);
-                *reinterpret_cast<uint4*>(lo + off) = make_uint4(pack_bf16(qd[0], qd[1]), pack_bf16(qd[2], qd[3]), pack_bf16(qd[4], qd[5]), pack_bf16(qd[6], qd[7]));
+                for (int e = 0; e < 4; ++e)
+                    ll[e] = pack_bf16(v[2 * e] - __uint_as_float(hh[e] << 16), v[2 * e + 1] - __uint_as_float(hh[e] & 0xFFFF0000u));
+                *reinterpret_cast<uint4*>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
             }
         }
         kg += kg_step;
@@ -478,7 +486,10 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
     const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (128 + p.NO) * p.KR * 2 + (size_t)(kLinThreads / 32) * 32 * kScratchLd * sizeof(float);
     static size_t reserved = 0;
     if (smem > reserved) {
-        if (cudaFuncSetAttribute(linear_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 0, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return NPF_ENOTSUP;
         }
@@ -490,7 +501,11 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
     const int per_sm = 1;   // 512 threads + ~200 KB of shared memory: one persistent CTA per SM
     int grid = kNumSMs * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    linear_tc_kernel<NSPLIT><<<grid, kLinThreads, smem, st>>>(p);
+    const bool hot = p.KR == 128 && p.NO == 128;
+    if (hot && !p.u && !p.mask) linear_tc_kernel<NSPLIT, 128, 128, false, false><<<grid, kLinThreads, smem, st>>>(p);
+    else if (hot && !p.u) linear_tc_kernel<NSPLIT, 128, 128, false, true><<<grid, kLinThreads, smem, st>>>(p);
+    else if (hot && !p.mask) linear_tc_kernel<NSPLIT, 128, 128, true, false><<<grid, kLinThreads, smem, st>>>(p);
+    else linear_tc_kernel<NSPLIT, 0, 0, true, true><<<grid, kLinThreads, smem, st>>>(p);
     count_launch();
     return check_launch("linear_tc_kernel");
 }
