@@ -48,6 +48,7 @@ extern "C" {
 #define NPF_RELU_IN 2    /* apply relu to the (first / activation) input on load   */
 #define NPF_ACCUM 4      /* add to the output instead of overwriting it            */
 #define NPF_ADD_DY 8     /* npf_dwconv_bwd: dX += dY (gradient of a residual branch that reads the same X) */
+#define NPF_MASK_X 16    /* npf_linear_bwd: multiply dX by the relu mask (X > 0) of the layer input X  */
 
 typedef void* npf_stream_t;
 
@@ -79,6 +80,14 @@ NPF_API int npf_linear_fwd(const float* X, int ldx, const float* W, int ldw, con
  * (post-relu) input. */
 NPF_API int npf_linear_bwd_data(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int M, int K,
                         int N, const float* mask_src, int ldm, int flags, int precision, npf_stream_t stream);
+
+/* Whole backward of one Linear in a single pass over dY and X (the layer's saved input):
+ *     dX[M,K] = (dY[M,N] . W[N,K]) (.) (X > 0 if NPF_MASK_X)      (overwritten)
+ *     dW[N,K] += dY^T . act_in(X)      db[N] += colsum(dY)        (db optional)
+ * Same results as npf_linear_bwd_weight followed by npf_linear_bwd_data(mask_src = X); for 128 -> 128 layers in the
+ * tensor-core precisions dY and X are read from HBM once instead of twice. */
+NPF_API int npf_linear_bwd(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx,
+                   float* dW, int lddw, float* db, int M, int K, int N, int flags, int precision, npf_stream_t stream);
 
 /* dW[N,K] += dY[M,N]^T . act_in(X)[M,K] ;  db[N] += sum_m dY[m,:] ;  dw2[N*ldw2] += sum_m dY[m,:] u[m]
  * db, u/dw2 optional. */

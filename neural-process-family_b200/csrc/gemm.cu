@@ -243,6 +243,8 @@ int linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float*
                   int N, int flags, const float* u, const float* w2, int ldw2, int precision, cudaStream_t st);
 int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int M, int K, int N,
                        const float* mask_src, int ldm, int flags, int precision, cudaStream_t st);
+int linear_bwd_fused_tc(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx, float* dW,
+                        int lddw, float* db, int M, int K, int N, int flags, int precision, cudaStream_t st);
 int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int* db_done, int M,
                          int K, int N, int flags, int precision, cudaStream_t st);
 
@@ -405,3 +407,20 @@ extern "C" int npf_relu_bwd(const float* dH, const float* H, float* dZ, long n, 
     count_launch();
     return check_launch("relu_bwd_kernel");
 }
+
+extern "C" int npf_linear_bwd(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx,
+                              float* dW, int lddw, float* db, int M, int K, int N, int flags, int precision, npf_stream_t stream) {
+    if (M == 0) return NPF_OK;
+    NPF_REQUIRE(dY && X && W && dX && dW, "npf_linear_bwd: null pointer");
+    NPF_REQUIRE(M >= 0 && K >= 1 && N >= 1, "npf_linear_bwd: bad shape");
+    NPF_REQUIRE(lddy >= N && ldx >= K && ldw >= K && lddx >= K && lddw >= K, "npf_linear_bwd: leading dimension too small");
+    NPF_REQUIRE(!(flags & ~(NPF_RELU_IN | NPF_MASK_X)), "npf_linear_bwd: unsupported flag");
+    if (precision != NPF_PREC_FP32) {
+        const int rc = npf::linear_bwd_fused_tc(dY, lddy, X, ldx, W, ldw, dX, lddx, dW, lddw, db, M, K, N, flags, precision, npf::as_stream(stream));
+        if (rc != NPF_ENOTSUP) return rc;
+    }
+    int rc = npf_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, db, M, K, N, flags & NPF_RELU_IN, nullptr, nullptr, 0, precision, stream);
+    if (rc != NPF_OK) return rc;
+    return npf_linear_bwd_data(dY, lddy, W, ldw, dX, lddx, M, K, N, (flags & NPF_MASK_X) ? X : nullptr, ldx, 0, precision, stream);
+}
+

@@ -17,6 +17,9 @@
 //
 // Shapes covered: reduction dim <= 128 and output dim <= 256, both multiples of 16.  Anything else reports
 // NPF_ENOTSUP and the caller uses the fp32 FFMA kernel.
+#include <cstdio>
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace npf {
@@ -37,8 +40,9 @@ __device__ __forceinline__ int ilog2(int x) { return 31 - __clz(x); }
 // All tile extents on this path are powers of two (checked on the host), so the (core-matrix -> row group, k chunk)
 // maps are shifts, and because 32 half-warps step through core matrices 32 at a time the k chunk of a thread is
 // CONSTANT: only the row group advances -> one pointer increment and one smem-offset increment per step.
+template <bool VEC>
 __device__ __forceinline__ void load_kmajor(float4 (&pre)[kPre], const float* __restrict__ src, long ld, long row0, int rows_valid,
-                                            int R, int KR, int cm_base, int vec_ok) {
+                                            int R, int KR, int cm_base) {
     const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
     const int r = l16 & 7, half = l16 >> 3;
     const int n_kc = KR >> 3, lg = ilog2(n_kc);
@@ -52,7 +56,7 @@ __device__ __forceinline__ void load_kmajor(float4 (&pre)[kPre], const float* __
     for (int i = 0; i < kPre; ++i) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rg < n_rg && rg * 8 + r < rows_valid) {
-            if (vec_ok) v = __ldg(reinterpret_cast<const float4*>(g));
+            if (VEC) v = __ldg(reinterpret_cast<const float4*>(g));
             else { v.x = __ldg(g); v.y = __ldg(g + 1); v.z = __ldg(g + 2); v.w = __ldg(g + 3); }
         }
         pre[i] = v;
@@ -146,7 +150,7 @@ constexpr int kScratchLd = 36;     // floats per staged row: 32 + 4 keeps both t
 // KR_T / NO_T: compile-time reduction / output extents (0 = run-time values from the parameter block); HAS_U / HAS_MASK:
 // rank-1 epilogue term / relu-mask epilogue compiled in.  The 128 x 128 instantiations are the hot ones: with the
 // extents known every staging predicate and index computation folds away.
-template <int NSPLIT, int KR_T, int NO_T, bool HAS_U, bool HAS_MASK>
+template <int NSPLIT, int KR_T, int NO_T, bool HAS_U, bool HAS_MASK, bool VEC>
 __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p
     float4 pre[kPre];
     int tile = blockIdx.x;
     // first activation tile: in flight while the weights are staged
-    if (tile < p.n_tiles) load_kmajor(pre, p.A, p.lda, (long)tile * 128, min(128, p.M - tile * 128), 128, KR, 0, p.a_vec);
+    if (tile < p.n_tiles) load_kmajor<VEC>(pre, p.A, p.lda, (long)tile * 128, min(128, p.M - tile * 128), 128, KR, 0);
     // weights: converted and staged once per CTA
     if (p.transposed_w) {
         stage_kmajor_transposed<NSPLIT>(b_hi, b_lo, p.W, p.ldw, NO, KR, p.w_vec);
@@ -182,7 +186,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p
         const int n_cm = (NO >> 3) * (KR >> 3);
         for (int base = 0; base < n_cm; base += kHW * kPre) {
             float4 wpre[kPre];
-            load_kmajor(wpre, p.W, p.ldw, 0, NO, NO, KR, base, p.w_vec);
+            if (p.w_vec) load_kmajor<true>(wpre, p.W, p.ldw, 0, NO, NO, KR, base);
+            else load_kmajor<false>(wpre, p.W, p.ldw, 0, NO, NO, KR, base);
             store_kmajor<NSPLIT>(wpre, b_hi, b_lo, NO, KR, base, 0);
         }
     }
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p
         }
         // prefetch the next tile into registers: in flight under this tile's MMA and epilogue
         const int next = tile + gridDim.x;
-        if (next < p.n_tiles) load_kmajor(pre, p.A, p.lda, (long)next * 128, min(128, p.M - next * 128), 128, KR, 0, p.a_vec);
+        if (next < p.n_tiles) load_kmajor<VEC>(pre, p.A, p.lda, (long)next * 128, min(128, p.M - next * 128), 128, KR, 0);
 
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
@@ -261,12 +266,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p
                     if (HAS_MASK && p.mask) {
                         const float* mk = p.mask + (long)row * p.ldm + c0 + c4;
                         float4 mv;
-                        if ((p.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0) mv = __ldg(reinterpret_cast<const float4*>(mk));
+                        if (VEC) mv = __ldg(reinterpret_cast<const float4*>(mk));
                         else mv = make_float4(__ldg(mk), __ldg(mk + 1), __ldg(mk + 2), __ldg(mk + 3));
                         x.x = mv.x > 0.f ? x.x : 0.f; x.y = mv.y > 0.f ? x.y : 0.f; x.z = mv.z > 0.f ? x.z : 0.f; x.w = mv.w > 0.f ? x.w : 0.f;
                     }
                     float* out = p.C + (long)row * p.ldc + c0 + c4;
-                    if (p.c_vec) *reinterpret_cast<float4*>(out) = x;
+                    if (VEC) *reinterpret_cast<float4*>(out) = x;
                     else { out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w; }
                 }
             }
@@ -284,6 +289,516 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
+// ------------------------------------------------------------------------------------------------ warp-specialised 128 x 128 x 128
+// The hot shape (reduction 128, output 128, 16-byte aligned rows) runs as a three-role pipeline, one persistent CTA per SM:
+//   warps 0..7  producers : fp32 tile -> registers (16 x LDG.128 per thread in flight) -> bf16 hi/lo -> smem stage s  -> full[s]
+//   warp  8     MMA       : waits full[s] + tempty[t], issues 8 (x3) tcgen05.mma into accumulator t, commits -> empty[s], tfull[t]
+//   warps 9..16 epilogue  : waits tfull[t], tcgen05.ld -> per-warp smem transpose -> bias / rank-1 / relu / mask -> coalesced STG
+// Two smem operand stages and two TMEM accumulators (2 x 128 columns): tile i+1 is loaded and converted while tile i is
+// multiplied and tile i-1 is drained, so the HBM stream never waits on the math.  The weights are staged once per CTA in the
+// row layout of W; the data gradient reads the very same staging through an MN-major descriptor (transpose for free).
+constexpr int kWsProdWarps = 8;
+constexpr int kWsEpiWarp0 = 9;
+constexpr int kWsEpiWarps = 8;
+constexpr int kWsThreads = (kWsEpiWarp0 + kWsEpiWarps) * 32;     // 544
+constexpr int kWsPre = 16;                                       // float4 per producer thread per tile
+constexpr int kWsScratchLd = 20;                                 // 16 columns + 4 pad (conflict-free STS.128)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NSPLIT>
+__device__ __forceinline__ void cvt_store(const float4& vin, uint8_t* hi, uint8_t* lo, uint32_t off, int relu) {
+    float4 v = vin;
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    const uint32_t h01 = pack_bf16(v.x, v.y), h23 = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(hi + off) = make_uint2(h01, h23);
+    if (NSPLIT == 3) {
+        const float rx = v.x - __uint_as_float(h01 << 16), ry = v.y - __uint_as_float(h01 & 0xFFFF0000u);
+        const float rz = v.z - __uint_as_float(h23 << 16), rw = v.w - __uint_as_float(h23 & 0xFFFF0000u);
+        *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(rx, ry), pack_bf16(rz, rw));
+    }
+}
+
+// producer-side tile load: thread (kc = tid/16, r = tid%8, half) owns the 16 bytes (row 8i + r, k = 8 kc + 4 half) of every
+// 8-row group i -> per instruction a half-warp covers 8 rows x 32 bytes (full sectors) and stores one 128-byte core matrix
+__device__ __forceinline__ void ws_load_tile(float4 (&pre)[kWsPre], const float* __restrict__ g, long ld, int r, int rows_valid) {
+#pragma unroll
+    for (int i = 0; i < kWsPre; ++i) {
+        pre[i] = (i * 8 + r < rows_valid) ? __ldg(reinterpret_cast<const float4*>(g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g += 8 * ld;
+    }
+}
+
+// SWIZZLE_128B K-major staging of a [128 rows x 128 k] bf16 operand: two atoms of 64 k (128 bytes per row, 16 KB per atom),
+//     byte(row, k) = (k / 64) * 16384 + row * 128 + ((((k % 64) / 8) ^ (row % 8)) * 16) + (k % 8) * 2
+// (the 16-byte chunk index XOR-ed with the row index: what the tensor core undoes in hardware; atoms 1024-byte aligned).
+// Read K-major: start + atom * 16384 + (ks % 4) * 32, SBO = 1024 (8-row groups).  The same bytes read MN-major are the
+// transpose: mn = k (two 64-wide atoms, LBO = 16384), reduction = row (8-row groups, SBO = 1024), start + ks * 2048.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_desc(saddr, lbo_bytes, sbo_bytes) | (2ull << 61);
+}
+// producer mapping (SW128): warp w owns rows 16 w .. 16 w + 15; per row the 32 lanes load the 512 contiguous bytes
+// (one LDG.128 each) and store 8 bytes of hi and of lo: per instruction 2 x 128 contiguous (permuted) bytes -> no conflicts
+__device__ __forceinline__ void ws_load_rows(float4 (&pre)[kWsPre], const float* __restrict__ g, long ld, int row_first, int rows_valid) {
+#pragma unroll
+    for (int i = 0; i < kWsPre; ++i) {
+        pre[i] = (row_first + i < rows_valid) ? __ldg(reinterpret_cast<const float4*>(g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g += ld;
+    }
+}
+
+template <int NSPLIT, bool HAS_U, bool HAS_MASK, bool SW>
+__global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_bias[128], s_w2[128];
+
+    constexpr uint32_t kTile = 128u * 128u * 2u;                 // one bf16 128 x 128 operand: 32 KB
+    constexpr uint32_t kStage = (NSPLIT == 3 ? 2u : 1u) * kTile;
+    uint8_t* b_hi = smem_raw + 2 * kStage;
+    uint8_t* b_lo = b_hi + kTile;
+    float* scratch_all = reinterpret_cast<float*>(smem_raw + 3 * kStage);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_full[i], kWsProdWarps * 32);
+            mbar_init(&bar_empty[i], 1);
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kWsEpiWarps * 32);
+        }
+    }
+    if (tid < 128) {
+        s_bias[tid] = p.bias ? __ldg(p.bias + tid) : 0.f;
+        s_w2[tid] = (HAS_U && p.w2) ? __ldg(p.w2 + (long)tid * p.ldw2) : 0.f;
+    }
+
+    // producer geometry (also used for the weight staging below)
+    const int l16 = tid & 15, pr = l16 & 7, phalf = l16 >> 3;
+    float4 pre[kWsPre];
+    int tile = blockIdx.x;
+    const int pkc = (tid >> 4) & 15;
+    // no-swizzle: thread -> (k chunk, row in group, half); SW128: thread -> (row block of the warp, float4 column = lane)
+    const float* pg = SW ? p.A + (long)(warp * 16) * p.lda + lane * 4 : p.A + (long)pr * p.lda + pkc * 8 + phalf * 4;
+    const uint32_t psoff = SW ? (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 16) * 128u + (uint32_t)(lane & 1) * 8u
+                              : (uint32_t)pkc * 2048u + (uint32_t)pr * 16u + (uint32_t)phalf * 8u;
+    const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
+    if (warp < kWsProdWarps && tile < p.n_tiles) {
+        if (SW) ws_load_rows(pre, pg + (long)tile * 128 * p.lda, p.lda, warp * 16, min(128, p.M - tile * 128));
+        else ws_load_tile(pre, pg + (long)tile * 128 * p.lda, p.lda, pr, min(128, p.M - tile * 128));
+    }
+
+    // weights [128 x 128] fp32 row-major, staged once per CTA by threads 0..511 (8 float4 each) in the layout of the A tiles
+    if (tid < 512) {
+        float4 wv[8];
+        if (SW) {                                                    // warp w: rows 8 w .. 8 w + 7
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float* g = p.W + (long)(warp * 8 + i) * p.ldw + lane * 4;
+                if (p.w_vec) wv[i] = __ldg(reinterpret_cast<const float4*>(g));
+                else wv[i] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                cvt_store<NSPLIT>(wv[i], b_hi, b_lo, (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8 + i) * 128u + ((pchunk ^ (uint32_t)i) << 4) + (uint32_t)(lane & 1) * 8u, 0);
+        } else {
+            const int rg0 = tid >> 8;                                // float4 index f = tid + 512 i: kc = (tid/16)%16, rg = tid/256 + 2i
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float* g = p.W + (long)((rg0 + 2 * i) * 8 + pr) * p.ldw + pkc * 8 + phalf * 4;
+                if (p.w_vec) wv[i] = __ldg(reinterpret_cast<const float4*>(g));
+                else wv[i] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cvt_store<NSPLIT>(wv[i], b_hi, b_lo, psoff + (uint32_t)(rg0 + 2 * i) * 128u, 0);
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < kWsProdWarps) {
+        // ------------------------------------------------------------------ producers
+        for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int s = it & 1;
+            mbar_wait(&bar_empty[s], ((it >> 1) & 1) ^ 1);
+            uint8_t* hi = smem_raw + s * kStage;
+            uint8_t* lo = hi + kTile;
+#pragma unroll
+            for (int i = 0; i < kWsPre; ++i)
+                cvt_store<NSPLIT>(pre[i], hi, lo, SW ? psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4) : psoff + (uint32_t)i * 128u, p.relu_in);
+            fence_async_smem();
+            mbar_arrive(&bar_full[s]);
+            const int next = tile + gridDim.x;
+            if (next < p.n_tiles) {
+                if (SW) ws_load_rows(pre, pg + (long)next * 128 * p.lda, p.lda, warp * 16, min(128, p.M - next * 128));
+                else ws_load_tile(pre, pg + (long)next * 128 * p.lda, p.lda, pr, min(128, p.M - next * 128));
+            }
+        }
+    } else if (warp == kWsProdWarps) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 128, 0, p.transposed_w ? 1 : 0);
+            const uint32_t sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+            // fwd: B = W rows (n) K-major in k.  bwd-data: B = W^T, i.e. the same bytes read MN-major (mn = k_out, red = n)
+            const uint32_t b_step = p.transposed_w ? 256u : 4096u, b_lbo = p.transposed_w ? 128u : 2048u, b_sbo = p.transposed_w ? 2048u : 128u;
+            for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const int s = it & 1;
+                const uint32_t par = (it >> 1) & 1;
+                mbar_wait(&bar_full[s], par);
+                mbar_wait(&bar_tempty[s], par ^ 1);
+                tc_fence_after();
+                const uint32_t sa_hi = smem_u32(smem_raw + s * kStage), sa_lo = sa_hi + kTile;
+                const uint32_t d = tmem + (uint32_t)s * 128u;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    uint64_t a_h, a_l, b_h, b_l;
+                    if (SW) {
+                        const uint32_t ao = (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u;
+                        a_h = make_desc_sw128(sa_hi + ao, 16, 1024);
+                        a_l = make_desc_sw128(sa_lo + ao, 16, 1024);
+                        if (p.transposed_w) {
+                            b_h = make_desc_sw128(sb_hi + ks * 2048u, 16384, 1024);
+                            b_l = make_desc_sw128(sb_lo + ks * 2048u, 16384, 1024);
+                        } else {
+                            b_h = make_desc_sw128(sb_hi + ao, 16, 1024);
+                            b_l = make_desc_sw128(sb_lo + ao, 16, 1024);
+                        }
+                    } else {
+                        a_h = make_desc(sa_hi + ks * 4096u, 2048, 128);
+                        a_l = make_desc(sa_lo + ks * 4096u, 2048, 128);
+                        b_h = make_desc(sb_hi + ks * b_step, b_lbo, b_sbo);
+                        b_l = make_desc(sb_lo + ks * b_step, b_lbo, b_sbo);
+                    }
+                    umma_bf16(d, a_h, b_h, idesc, ks ? 1u : 0u);
+                    if (NSPLIT == 3) {
+                        umma_bf16(d, a_h, b_l, idesc, 1);
+                        umma_bf16(d, a_l, b_h, idesc, 1);
+                    }
+                }
+                umma_commit(&bar_empty[s]);      // operand stage s free once these MMAs retire
+                umma_commit(&bar_tfull[s]);      // accumulator s complete
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int e = warp - kWsEpiWarp0;
+        const int lane_base = 32 * (warp & 3);                    // the TMEM lane quadrant this warp may read
+        const int col_base = (e >> 2) * 64;                       // two warps per quadrant: 64 columns each, 4 chunks of 16
+        float* scratch = scratch_all + e * (32 * kWsScratchLd);
+        const int r_in = lane >> 2, c4 = (lane & 3) * 4;          // store geometry: 8 rows x 64 bytes per instruction
+        for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int s = it & 1;
+            const int m0 = tile * 128 + lane_base;
+            float4 mk[4];
+            if (HAS_MASK) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = m0 + j * 8 + r_in;
+                    mk[j] = row < p.M ? __ldg(reinterpret_cast<const float4*>(p.mask + (long)row * p.ldm + col_base + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            mbar_wait(&bar_tfull[s], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int c0 = col_base + ch * 16;
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(s * 128 + c0), v);
+                if (ch == 3) {                                     // accumulator drained: hand it back before the stores
+                    tc_fence_before();
+                    mbar_arrive(&bar_tempty[s]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(scratch + lane * kWsScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                float4 mn[4];
+                if (HAS_MASK && ch < 3) {                          // next chunk's mask in flight under this chunk's stores
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = m0 + j * 8 + r_in;
+                        mn[j] = row < p.M ? __ldg(reinterpret_cast<const float4*>(p.mask + (long)row * p.ldm + c0 + 16 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + c4]);
+                const float4 ww = *reinterpret_cast<const float4*>(&s_w2[c0 + c4]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = j * 8 + r_in;
+                    const int row = m0 + r;
+                    if (row < p.M) {
+                        float4 x = *reinterpret_cast<const float4*>(scratch + r * kWsScratchLd + c4);
+                        x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                        if (HAS_U) {
+                            const float up = __ldg(p.u + row);
+                            x.x = fmaf(up, ww.x, x.x); x.y = fmaf(up, ww.y, x.y); x.z = fmaf(up, ww.z, x.z); x.w = fmaf(up, ww.w, x.w);
+                        }
+                        if (p.relu_out) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        if (HAS_MASK) {
+                            x.x = mk[j].x > 0.f ? x.x : 0.f; x.y = mk[j].y > 0.f ? x.y : 0.f;
+                            x.z = mk[j].z > 0.f ? x.z : 0.f; x.w = mk[j].w > 0.f ? x.w : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(p.C + (long)row * p.ldc + c0 + c4) = x;
+                    }
+                }
+                if (HAS_MASK && ch < 3) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mk[j] = mn[j];
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ fused backward 128 x 128 x 128
+// dX = (dY W) (.) (X > 0)   and   dW += dY^T X,  db += colsum(dY)   in ONE pass over dY and X (hot shape only).
+// The dY and X row tiles are staged once (SW128, bf16 hi/lo) and each is read by the tensor core two ways:
+//     dX tile  = dY[K-major view] x W^T[MN-major view of the row-staged W]                 -> TMEM accumulator t (double buffered)
+//     dW      += dY^T[MN-major view of the SAME dY bytes] x X[MN-major view of the X tile] -> one TMEM accumulator for the CTA
+//     db      += column sums of dY, taken by the producers from the registers the tile passes through (exact fp32)
+// so the separate weight-gradient kernel's second read of dY and X (2/5 of the backward traffic of a layer) disappears and
+// the relu mask comes from the staged X tile instead of a third global stream.  Roles: 16 producer warps (next tile held in
+// registers: 8 + 8 LDG.128 per thread in flight), 1 MMA warp, 8 epilogue warps.  TMEM: [0,256) dX x2, [256,384) dW.
+constexpr int kFbProdWarps = 16;
+constexpr int kFbEpiWarp0 = 17;
+constexpr int kFbThreads = (kFbEpiWarp0 + kWsEpiWarps) * 32;     // 800
+
+struct TcFusedParams {
+    const float* dY; long lddy;     // [M, 128]
+    const float* X; long ldx;       // [M, 128]  layer input (post-relu activations): wgrad operand and relu mask
+    const float* W; long ldw;       // [128 (n), 128 (k)]
+    float* dX; long lddx;           // [M, 128]
+    float* dW; long lddw;           // [128, 128]  +=
+    float* db;                      // [128] += or null
+    int M, n_tiles;
+    int relu_x, use_mask, w_vec, dw_vec;
+};
+
+__device__ __forceinline__ void fb_load_rows(float4 (&pre)[8], const float* __restrict__ g, long ld, int row_first, int rows_valid) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        pre[i] = (row_first + i < rows_valid) ? __ldg(reinterpret_cast<const float4*>(g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g += ld;
+    }
+}
+
+template <int NSPLIT, bool HAS_MASK>
+__global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_mask, bar_dwfull, bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_db[128];
+
+    constexpr uint32_t kTile = 128u * 128u * 2u;                  // 32 KB
+    constexpr uint32_t kOp = (NSPLIT == 3 ? 2u : 1u) * kTile;     // one operand (hi [+ lo])
+    uint8_t* y_hi = smem_raw;            uint8_t* y_lo = y_hi + kTile;
+    uint8_t* x_hi = smem_raw + kOp;      uint8_t* x_lo = x_hi + kTile;
+    uint8_t* w_hi = smem_raw + 2 * kOp;  uint8_t* w_lo = w_hi + kTile;
+    float* scratch_all = reinterpret_cast<float*>(smem_raw + 3 * kOp);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (tid == 32) {
+        mbar_init(&bar_full, kFbProdWarps * 32);
+        mbar_init(&bar_empty, 1);
+        mbar_init(&bar_mask, kWsEpiWarps * 32);
+        mbar_init(&bar_dwfull, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kWsEpiWarps * 32);
+        }
+    }
+    if (tid < 128) s_db[tid] = 0.f;
+
+    // producer / weight-staging geometry: warp w owns rows 8 w .. 8 w + 7, lane = float4 column
+    const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
+    const uint32_t psoff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
+    float4 py[8], px[8];
+    int tile = blockIdx.x;
+    if (warp < kFbProdWarps) {
+        const int rv = min(128, p.M - tile * 128);
+        fb_load_rows(py, p.dY + ((long)tile * 128 + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
+        fb_load_rows(px, p.X + ((long)tile * 128 + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
+        float4 wv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float* g = p.W + (long)(warp * 8 + i) * p.ldw + lane * 4;
+            if (p.w_vec) wv[i] = __ldg(reinterpret_cast<const float4*>(g));
+            else wv[i] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cvt_store<NSPLIT>(wv[i], w_hi, w_lo, psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4), 0);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < kFbProdWarps) {
+        // ------------------------------------------------------------------ producers
+        float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { dbs.x += py[i].x; dbs.y += py[i].y; dbs.z += py[i].z; dbs.w += py[i].w; }
+            if (it > 0) {
+                mbar_wait(&bar_empty, (it - 1) & 1);               // both MMA groups of the previous tile have read the stage
+                if (HAS_MASK) mbar_wait(&bar_mask, (it - 1) & 1);  // and the epilogue has taken its relu mask from it
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t off = psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4);
+                cvt_store<NSPLIT>(py[i], y_hi, y_lo, off, 0);
+                cvt_store<NSPLIT>(px[i], x_hi, x_lo, off, p.relu_x);
+            }
+            fence_async_smem();
+            mbar_arrive(&bar_full);
+            const int next = tile + gridDim.x;
+            if (next < p.n_tiles) {
+                const int rv = min(128, p.M - next * 128);
+                fb_load_rows(py, p.dY + ((long)next * 128 + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
+                fb_load_rows(px, p.X + ((long)next * 128 + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
+            }
+        }
+        if (p.db) {                                                  // bias gradient: warps -> smem -> one global atomic per column
+            atomicAdd(&s_db[lane * 4 + 0], dbs.x); atomicAdd(&s_db[lane * 4 + 1], dbs.y);
+            atomicAdd(&s_db[lane * 4 + 2], dbs.z); atomicAdd(&s_db[lane * 4 + 3], dbs.w);
+            asm volatile("bar.sync 1, %0;" ::"n"(kFbProdWarps * 32) : "memory");
+            if (tid < 128) atomicAdd(p.db + tid, s_db[tid]);
+        }
+    } else if (warp == kFbProdWarps) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_dx = make_idesc(128, 128, 0, 1);    // A = dY K-major, B = W^T (MN-major view)
+            const uint32_t idesc_dw = make_idesc(128, 128, 1, 1);    // A = dY^T, B = X: both MN-major views (reduction over rows)
+            const uint32_t sy_hi = smem_u32(y_hi), sy_lo = smem_u32(y_lo), sx_hi = smem_u32(x_hi), sx_lo = smem_u32(x_lo);
+            const uint32_t sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
+            const uint32_t d_dw = tmem + 256u;
+            for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const int t = it & 1;
+                mbar_wait(&bar_full, it & 1);
+                mbar_wait(&bar_tempty[t], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_dx = tmem + (uint32_t)t * 128u;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {                     // reduction over n
+                    const uint32_t ao = (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u;
+                    const uint64_t a_h = make_desc_sw128(sy_hi + ao, 16, 1024), b_h = make_desc_sw128(sw_hi + ks * 2048u, 16384, 1024);
+                    umma_bf16(d_dx, a_h, b_h, idesc_dx, ks ? 1u : 0u);
+                    if (NSPLIT == 3) {
+                        umma_bf16(d_dx, a_h, make_desc_sw128(sw_lo + ks * 2048u, 16384, 1024), idesc_dx, 1);
+                        umma_bf16(d_dx, make_desc_sw128(sy_lo + ao, 16, 1024), b_h, idesc_dx, 1);
+                    }
+                }
+                umma_commit(&bar_tfull[t]);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {                     // reduction over the 128 rows of the tile
+                    const uint32_t acc = (it | ks) ? 1u : 0u;
+                    const uint64_t a_h = make_desc_sw128(sy_hi + ks * 2048u, 16384, 1024), b_h = make_desc_sw128(sx_hi + ks * 2048u, 16384, 1024);
+                    umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
+                    if (NSPLIT == 3) {
+                        const uint64_t a_l = make_desc_sw128(sy_lo + ks * 2048u, 16384, 1024);
+                        umma_bf16(d_dw, a_h, make_desc_sw128(sx_lo + ks * 2048u, 16384, 1024), idesc_dw, 1);
+                        umma_bf16(d_dw, a_l, b_h, idesc_dw, 1);
+                    }
+                }
+                umma_commit(&bar_empty);
+            }
+            umma_commit(&bar_dwfull);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int e = warp - kFbEpiWarp0;
+        const int lane_base = 32 * (warp & 3);
+        const int col_base = (e >> 2) * 64;
+        float* scratch = scratch_all + e * (32 * kWsScratchLd);
+        const int r_in = lane >> 2, c4 = (lane & 3) * 4;
+        for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int t = it & 1;
+            const int m0 = tile * 128 + lane_base;
+            mbar_wait(&bar_tfull[t], (it >> 1) & 1);
+            tc_fence_after();
+            unsigned long long mbits = ~0ull;
+            if (HAS_MASK) {          // relu mask of this thread's 16 float4 outputs, from the staged (relu'd) X tile: bf16 > 0 <=> int16 > 0
+                mbits = 0ull;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = lane_base + j * 8 + r_in, c = col_base + ch * 16 + c4;
+                        const uint2 xb = *reinterpret_cast<const uint2*>(x_hi + (uint32_t)(c >> 6) * 16384u + (uint32_t)r * 128u +
+                                                                       ((((uint32_t)(c & 63) >> 3) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)(c & 7) * 2u);
+                        const unsigned long long b4 = ((short)(xb.x & 0xFFFFu) > 0 ? 1ull : 0ull) | ((short)(xb.x >> 16) > 0 ? 2ull : 0ull) |
+                                                      ((short)(xb.y & 0xFFFFu) > 0 ? 4ull : 0ull) | ((short)(xb.y >> 16) > 0 ? 8ull : 0ull);
+                        mbits |= b4 << ((ch * 4 + j) * 4);
+                    }
+                }
+                mbar_arrive(&bar_mask);
+            }
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int c0 = col_base + ch * 16;
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 128 + c0), v);
+                if (ch == 3) {
+                    tc_fence_before();
+                    mbar_arrive(&bar_tempty[t]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(scratch + lane * kWsScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = j * 8 + r_in;
+                    const int row = m0 + r;
+                    if (row < p.M) {
+                        float4 x = *reinterpret_cast<const float4*>(scratch + r * kWsScratchLd + c4);
+                        if (HAS_MASK) {
+                            const unsigned b4 = (unsigned)(mbits >> ((ch * 4 + j) * 4));
+                            x.x = (b4 & 1u) ? x.x : 0.f; x.y = (b4 & 2u) ? x.y : 0.f; x.z = (b4 & 4u) ? x.z : 0.f; x.w = (b4 & 8u) ? x.w : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(p.dX + (long)row * p.lddx + c0 + c4) = x;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- flush of the CTA's weight / bias gradient: thread = row n of dW, 64 columns per warp
+        mbar_wait(&bar_dwfull, 0);
+        tc_fence_after();
+        const int n = lane_base + lane;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            const int c0 = col_base + ch * 16;
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(256 + c0), v);
+            float* d = p.dW + (long)n * p.lddw + c0;
+            if (p.dw_vec) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(d + j, v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[n, k] += sum_m dY[m, n] X[m, k].  MMA shape M = N_out (rows of dW, <= 128 -> padded to 128), N = K_out, K = rows m.
 // Both operands MN-major, no swizzle: element (mn, k) at byte (k/8)*LBO + (mn/8)*128 + (k%8)*16 + (mn%8)*2,
@@ -295,8 +810,10 @@ constexpr int kWgIt = 4;     // 16-byte chunks per thread per batch: 64 rows x 1
 // chunk c of a [64 rows x MN] operand: 8 lanes cover 8 consecutive rows of one 8-wide column chunk.  MN/8 is a power
 // of two <= 32 and a thread block advances 32 chunk columns per step, so a thread's column chunk j is constant and only
 // the 8-row group kg advances.
-__device__ __forceinline__ void load_mnmajor(float4 (&pre)[2 * kWgIt], const float* __restrict__ src, long ld, long row0, int rows_valid, int MN,
-                                             int mn_valid, int c_base, int vec_ok) {
+template <bool VEC>
+__device__ __forceinline__ void load_mnmajor_t(float4 (&pre)[2 * kWgIt], const float* __restrict__ src, long ld, long row0, int rows_valid, int MN,
+                                               int mn_valid, int c_base) {
+    const int vec_ok = VEC;
     const int n_chunks = MN >> 3, lgc = ilog2(n_chunks);
     const int r = threadIdx.x & 7, q = (c_base >> 3) + (threadIdx.x >> 3);
     const int j = q & (n_chunks - 1), kg_step = 32 >> lgc;
@@ -323,6 +840,12 @@ __device__ __forceinline__ void load_mnmajor(float4 (&pre)[2 * kWgIt], const flo
         kg += kg_step;
         g += gstep;
     }
+}
+
+__device__ __forceinline__ void load_mnmajor(float4 (&pre)[2 * kWgIt], const float* __restrict__ src, long ld, long row0, int rows_valid, int MN,
+                                             int mn_valid, int c_base, int vec_ok) {
+    if (vec_ok && mn_valid == MN) load_mnmajor_t<true>(pre, src, ld, row0, rows_valid, MN, mn_valid, c_base);   // all-vector fast path
+    else load_mnmajor_t<false>(pre, src, ld, row0, rows_valid, MN, mn_valid, c_base);
 }
 
 template <int NSPLIT>
@@ -486,10 +1009,11 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
     const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (128 + p.NO) * p.KR * 2 + (size_t)(kLinThreads / 32) * 32 * kScratchLd * sizeof(float);
     static size_t reserved = 0;
     if (smem > reserved) {
-        if (cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 0, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 128, 128, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 0, 0, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(linear_tc_kernel<NSPLIT, 0, 0, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return NPF_ENOTSUP;
         }
@@ -501,11 +1025,43 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
     const int per_sm = 1;   // 512 threads + ~200 KB of shared memory: one persistent CTA per SM
     int grid = kNumSMs * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    const bool hot = p.KR == 128 && p.NO == 128;
-    if (hot && !p.u && !p.mask) linear_tc_kernel<NSPLIT, 128, 128, false, false><<<grid, kLinThreads, smem, st>>>(p);
-    else if (hot && !p.u) linear_tc_kernel<NSPLIT, 128, 128, false, true><<<grid, kLinThreads, smem, st>>>(p);
-    else if (hot && !p.mask) linear_tc_kernel<NSPLIT, 128, 128, true, false><<<grid, kLinThreads, smem, st>>>(p);
-    else linear_tc_kernel<NSPLIT, 0, 0, true, true><<<grid, kLinThreads, smem, st>>>(p);
+    // VEC: every activation / output / mask access is a 16-byte one (leading dimensions % 4 == 0, 16-byte aligned bases)
+    const bool vec = p.a_vec && p.c_vec && (!p.mask || ((p.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0));
+    const bool hot = vec && p.KR == 128 && p.NO == 128;
+    if (hot && !(p.u && p.mask)) {
+        // warp-specialised pipeline (2 operand stages + weights + epilogue scratch)
+        const size_t ws_smem = (size_t)3 * (NSPLIT == 3 ? 2 : 1) * 32768 + (size_t)kWsEpiWarps * 32 * kWsScratchLd * sizeof(float);
+        static const bool sw = getenv("NPF_WS_SW") ? atoi(getenv("NPF_WS_SW")) != 0 : true;
+        static bool ws_attr = false;
+        if (!ws_attr) {
+            bool ok = true;
+#define NPF_WS_ATTR(U, MK, S) ok = ok && cudaFuncSetAttribute(linear_ws_kernel<NSPLIT, U, MK, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess
+            NPF_WS_ATTR(false, false, true); NPF_WS_ATTR(true, false, true); NPF_WS_ATTR(false, true, true);
+            NPF_WS_ATTR(false, false, false); NPF_WS_ATTR(true, false, false); NPF_WS_ATTR(false, true, false);
+#undef NPF_WS_ATTR
+            if (!ok) {
+                cudaGetLastError();
+                return NPF_ENOTSUP;
+            }
+            ws_attr = true;
+        }
+        if (sw) {
+            if (p.u) linear_ws_kernel<NSPLIT, true, false, true><<<grid, kWsThreads, ws_smem, st>>>(p);
+            else if (p.mask) linear_ws_kernel<NSPLIT, false, true, true><<<grid, kWsThreads, ws_smem, st>>>(p);
+            else linear_ws_kernel<NSPLIT, false, false, true><<<grid, kWsThreads, ws_smem, st>>>(p);
+        } else {
+            if (p.u) linear_ws_kernel<NSPLIT, true, false, false><<<grid, kWsThreads, ws_smem, st>>>(p);
+            else if (p.mask) linear_ws_kernel<NSPLIT, false, true, false><<<grid, kWsThreads, ws_smem, st>>>(p);
+            else linear_ws_kernel<NSPLIT, false, false, false><<<grid, kWsThreads, ws_smem, st>>>(p);
+        }
+        count_launch();
+        return check_launch("linear_ws_kernel");
+    }
+    if (hot && !p.u && !p.mask) linear_tc_kernel<NSPLIT, 128, 128, false, false, true><<<grid, kLinThreads, smem, st>>>(p);
+    else if (hot && !p.u) linear_tc_kernel<NSPLIT, 128, 128, false, true, true><<<grid, kLinThreads, smem, st>>>(p);
+    else if (hot && !p.mask) linear_tc_kernel<NSPLIT, 128, 128, true, false, true><<<grid, kLinThreads, smem, st>>>(p);
+    else if (vec) linear_tc_kernel<NSPLIT, 0, 0, true, true, true><<<grid, kLinThreads, smem, st>>>(p);
+    else linear_tc_kernel<NSPLIT, 0, 0, true, true, false><<<grid, kLinThreads, smem, st>>>(p);
     count_launch();
     return check_launch("linear_tc_kernel");
 }
@@ -537,6 +1093,43 @@ int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float
     p.w_vec = (ldw % 4 == 0) && aligned16(W);
     p.c_vec = (lddx % 4 == 0) && aligned16(dX);
     return precision == NPF_PREC_BF16X3 ? launch_lin<3>(p, st) : launch_lin<1>(p, st);
+}
+
+
+// Fused data + weight (+ bias) gradient of a 128 -> 128 layer; NPF_ENOTSUP for any other shape / alignment (the caller
+// then runs the two separate kernels).
+template <int NSPLIT>
+static int launch_fused(TcFusedParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)3 * (NSPLIT == 3 ? 2 : 1) * 32768 + (size_t)kWsEpiWarps * 32 * kWsScratchLd * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(linear_bwd_fused_kernel<NSPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(linear_bwd_fused_kernel<NSPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return NPF_ENOTSUP;
+        }
+        attr = true;
+    }
+    p.n_tiles = (int)cdiv(p.M, 128);
+    const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+    if (p.use_mask) linear_bwd_fused_kernel<NSPLIT, true><<<grid, kFbThreads, smem, st>>>(p);
+    else linear_bwd_fused_kernel<NSPLIT, false><<<grid, kFbThreads, smem, st>>>(p);
+    count_launch();
+    return check_launch("linear_bwd_fused_kernel");
+}
+
+int linear_bwd_fused_tc(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx, float* dW,
+                        int lddw, float* db, int M, int K, int N, int flags, int precision, cudaStream_t st) {
+    if (K != 128 || N != 128 || M < 128) return NPF_ENOTSUP;
+    if ((lddy | ldx | lddx) % 4 != 0 || !aligned16(dY) || !aligned16(X) || !aligned16(dX)) return NPF_ENOTSUP;
+    TcFusedParams p{};
+    p.dY = dY; p.lddy = lddy; p.X = X; p.ldx = ldx; p.W = W; p.ldw = ldw; p.dX = dX; p.lddx = lddx;
+    p.dW = dW; p.lddw = lddw; p.db = db; p.M = M;
+    p.relu_x = (flags & NPF_RELU_IN) ? 1 : 0;
+    p.use_mask = (flags & NPF_MASK_X) ? 1 : 0;
+    p.w_vec = (ldw % 4 == 0) && aligned16(W);
+    p.dw_vec = (lddw % 4 == 0) && aligned16(dW);
+    return precision == NPF_PREC_BF16X3 ? launch_fused<3>(p, st) : launch_fused<1>(p, st);
 }
 
 template <int NSPLIT>

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnpf_b200.so")
 # error codes / flags (mirror include/npf_b200.h)
 NPF_OK, NPF_EINVAL, NPF_ECUDA, NPF_ENOTSUP = 0, -1, -2, -3
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
-RELU_OUT, RELU_IN, ACCUM, ADD_DY = 1, 2, 4, 8
+RELU_OUT, RELU_IN, ACCUM, ADD_DY, MASK_X = 1, 2, 4, 8, 16
 
 P, I, L, F = c_void_p, c_int, c_long, c_float
 
@@ -23,6 +23,7 @@ SIGNATURES = {
     "npf_linear_fwd": [P, I, P, I, P, P, I, I, I, I, I, P, P, I, I, P],
     "npf_linear_bwd_data": [P, I, P, I, P, I, I, I, I, P, I, I, I, P],
     "npf_linear_bwd_weight": [P, I, P, I, P, I, P, I, I, I, I, P, P, I, I, P],
+    "npf_linear_bwd": [P, I, P, I, P, I, P, I, P, I, P, I, I, I, I, I, P],
     "npf_relu_bwd": [P, P, P, L, P],
     "npf_setconv_fwd": [P, L, P, L, P, P, P, P, P, I, I, I, I, I, P],
     "npf_setconv_bwd": [P, L, P, L, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
@@ -97,6 +98,8 @@ ALGO = {
     "npf_linear_fwd": lambda a: _lin(a[7], a[8], a[9]),
     "npf_linear_bwd_data": lambda a: _lin(a[6], a[7], a[8]),
     "npf_linear_bwd_weight": lambda a: _lin(a[7], a[8], a[9]),
+    # dY and X read once, dX written once: the same bytes as the data gradient alone; twice its flops
+    "npf_linear_bwd": lambda a: (4 * a[11] * (a[13] + 2 * a[12]), 4 * a[11] * a[12] * a[13]),
     # keys/queries + values + feat (+ dens/stat): B*(K*C + Q*C)*4 dominates
     "npf_setconv_fwd": lambda a: (4 * a[9] * (a[10] * a[12] + a[11] * a[12] + 3 * a[11] + a[10]), 2 * a[9] * a[11] * a[10] * a[12]),
     "npf_setconv_bwd": lambda a: (4 * a[13] * (2 * a[14] * a[16] + 2 * a[15] * a[16] + 4 * a[15] + a[14]), 6 * a[13] * a[15] * a[14] * a[16]),

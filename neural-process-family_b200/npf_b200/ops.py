@@ -7,7 +7,7 @@ fp32, contiguous, on a CUDA device.  No CPU fallback: calling an op with CPU ten
 import torch
 
 from . import _cabi
-from ._cabi import ACCUM, ADD_DY, RELU_IN, RELU_OUT, call
+from ._cabi import ACCUM, ADD_DY, MASK_X, RELU_IN, RELU_OUT, call
 
 __all__ = [
     "set_precision", "get_precision", "linear", "mlp_chain", "setconv", "dwconv", "channel_moments",
@@ -97,6 +97,14 @@ def _lin_bwd_data(dz, W_ptr, ldw, M, K, N, mask=None, out=None, accumulate=False
     return dx
 
 
+def _lin_bwd(dz, x2, W_ptr, ldw, dW_ptr, lddw, db, M, K, N, mask, prec=None):
+    """dX, dW +=, db += of one Linear in a single call (one pass over dz and x2 for 128 -> 128 layers)."""
+    dx = torch.empty(M, K, device=dz.device, dtype=torch.float32)
+    call("npf_linear_bwd", _p(dz), N, _p(x2), K, W_ptr, ldw, _p(dx), K, dW_ptr, lddw, _p(db), M, K, N,
+         MASK_X if mask else 0, _precision if prec is None else prec, _stream())
+    return dx
+
+
 def _lin_bwd_weight(dz, x2, dW_ptr, lddw, db, M, K, N, flags=0, u=None, dw2_ptr=None, ldw2=0, prec=None):
     call("npf_linear_bwd_weight", _p(dz), N, _p(x2), K, dW_ptr, lddw, _p(db), M, K, N, flags, _p(u), dw2_ptr, ldw2,
          _precision if prec is None else prec, _stream())
@@ -148,12 +156,15 @@ class _MLPChain(torch.autograd.Function):
             K = W.numel() // N
             dW, dWs[i] = _gbuf(Ws[i])
             db, dbs[i] = _gbuf(bs[i])
-            if M > 0:
+            need_dx = i > 0 or ctx.needs_input_grad[0]
+            if M > 0 and need_dx:        # one pass over dz and acts[i]: data + weight + bias gradient
+                dz = _lin_bwd(dz, acts[i], _p(W), K, _p(dW), K, db, M, K, N, mask=i > 0, prec=ctx.prec)
+            elif M > 0:
                 _lin_bwd_weight(dz, acts[i], _p(dW), K, db, M, K, N, prec=ctx.prec)
-            if i > 0:
-                dz = _lin_bwd_data(dz, _p(W), K, M, K, N, mask=acts[i], prec=ctx.prec)
-            elif ctx.needs_input_grad[0]:
-                dx = _lin_bwd_data(dz, _p(W), K, M, K, N, prec=ctx.prec).reshape(ctx.x_shape)
+            elif need_dx:
+                dz = torch.empty(0, K, device=dz.device, dtype=torch.float32)
+            if i == 0 and need_dx:
+                dx = dz.reshape(ctx.x_shape)
         grads = tuple(dWs) + (tuple(dbs) if ctx.has_bias else ())
         return (dx, None, None, None) + grads
 

@@ -33,7 +33,8 @@ def _g(*shape, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
-@pytest.mark.parametrize("M,K,H,N", [(1, 128, 128, 128), (300, 128, 128, 128), (1000, 64, 128, 32), (4099, 128, 256, 16), (130, 128, 128, 2)])
+@pytest.mark.parametrize("M,K,H,N", [(1, 128, 128, 128), (300, 128, 128, 128), (1000, 64, 128, 32), (4099, 128, 256, 16), (130, 128, 128, 2),
+                                     (32768, 128, 128, 128)])
 def test_tc_mlp_chain(npf, prec, M, K, H, N):
     npf.set_precision(prec)
     ftol, gtol = BARS[prec]
@@ -50,6 +51,46 @@ def test_tc_mlp_chain(npf, prec, M, K, H, N):
     for n, a, b in zip("x W1 b1 W2 b2 W3 b3".split(), c, r):
         err = l2_rel(a.grad, b.grad)
         assert err < gtol, f"{prec} grad {n}: {err}"
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,mask,bias", [(128, True, True), (1000, True, True), (4099, False, True), (75776, True, False), (640, False, False)])
+def test_tc_fused_linear_backward(npf, prec, M, mask, bias):
+    """npf_linear_bwd on the 128 -> 128 hot shape (one pass: dX, dW +=, db +=) against fp64, including row tails, the relu
+    mask taken from the staged X tile, accumulation into non-zero dW / db, and agreement with the two-kernel path."""
+    from npf_b200 import _cabi
+    K = N = 128
+    pr = {"bf16": 1, "bf16x3": 2}[prec]
+    _, gtol = BARS[prec]
+    dY, W = _g(M, N, seed=1), _g(N, K, seed=2, scale=K ** -0.5)
+    X = torch.relu(_g(M, K, seed=3))
+    dW0, db0 = _g(N, K, seed=4), _g(N, seed=5)
+    dXr = dY @ W
+    if mask:
+        dXr = dXr * (X > 0)
+    dWr, dbr = dW0 + dY.t() @ X, db0 + dY.sum(0)
+    c = lambda t: t.float().cuda().contiguous()
+    dYc, Wc, Xc, dWc, dbc = c(dY), c(W), c(X), c(dW0), c(db0)
+    dXc = torch.full((M, K), float("nan"), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _cabi.call("npf_linear_bwd", dYc.data_ptr(), N, Xc.data_ptr(), K, Wc.data_ptr(), K, dXc.data_ptr(), K, dWc.data_ptr(), K,
+               dbc.data_ptr() if bias else 0, M, K, N, 16 if mask else 0, pr, st)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dXc).all()
+    assert l2_rel(dXc, dXr) < gtol, l2_rel(dXc, dXr)
+    assert l2_rel(dWc - c(dW0), dWr - dW0) < gtol, l2_rel(dWc - c(dW0), dWr - dW0)
+    if bias:
+        assert l2_rel(dbc - c(db0), dbr - db0) < gtol
+    else:
+        assert torch.equal(dbc, c(db0))
+    if mask:   # masked entries are exact zeros
+        assert (dXc[(Xc <= 0)] == 0).all()
+    # the separate kernels give the same numbers to rounding
+    dW2, dX2 = c(dW0), torch.empty(M, K, device="cuda")
+    _cabi.call("npf_linear_bwd_weight", dYc.data_ptr(), N, Xc.data_ptr(), K, dW2.data_ptr(), K, 0, M, K, N, 0, 0, 0, 0, pr, st)
+    _cabi.call("npf_linear_bwd_data", dYc.data_ptr(), N, Wc.data_ptr(), K, dX2.data_ptr(), K, M, K, N, Xc.data_ptr() if mask else 0,
+               K if mask else 0, 0, pr, st)
+    assert l2_rel(dXc, dX2) < 1e-5 and l2_rel(dWc - c(dW0), dW2 - c(dW0)) < (1e-5 if prec == "bf16x3" else 1e-4)
 
 
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
