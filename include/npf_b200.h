@@ -82,10 +82,11 @@ NPF_API int npf_linear_bwd_data(const float* dY, int lddy, const float* W, int l
                         int N, const float* mask_src, int ldm, int flags, int precision, npf_stream_t stream);
 
 /* Whole backward of one Linear in a single pass over dY and X (the layer's saved input):
- *     dX[M,K] = (dY[M,N] . W[N,K]) (.) (X > 0 if NPF_MASK_X)      (overwritten)
+ *     dX[M,K] = (dY[M,N] . W[N,K]) (.) (X > 0 if NPF_MASK_X)      (overwritten; NULL to skip)
  *     dW[N,K] += dY^T . act_in(X)      db[N] += colsum(dY)        (db optional)
  * Same results as npf_linear_bwd_weight followed by npf_linear_bwd_data(mask_src = X); for 128 -> 128 layers in the
- * tensor-core precisions dY and X are read from HBM once instead of twice. */
+ * tensor-core precisions, and for thin layers (K <= 8 or N <= 8 against a 128-wide side) in every precision, dY and X
+ * are read from HBM once instead of twice. */
 NPF_API int npf_linear_bwd(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx,
                    float* dW, int lddw, float* db, int M, int K, int N, int flags, int precision, npf_stream_t stream);
 
@@ -108,16 +109,19 @@ NPF_API int npf_relu_bwd(const float* dH, const float* H, float* dZ, long n, npf
  * increasing, uniformly spaced grid and the kernel only visits the run-time sigma-window of keys whose
  * softmax weight is not below 2^-60 of the largest one (exact in fp32); otherwise all keys are visited.
  * mstat[B,Q,2] receives (max logit, sum_k exp(a - max)) per query (saved for backward).
+ * ldf / ldd: row stride of feat (and dfeat) / element stride of dens (and ddens), in floats.  Cin and 1 for dense
+ * buffers; the few-channel path (Cin <= 4, irregular keys) also takes ldf = ldd = Cin + 1 with dens = feat + Cin, i.e.
+ * [feat | dens] interleaved as the [B*Q, Cin+1] input of SetConv's resizer Linear (no concatenation pass).
  * ------------------------------------------------------------------------------------------------ */
 NPF_API int npf_setconv_fwd(const float* keys, long key_bs, const float* queries, long qry_bs, const float* values,
                     const float* theta, float* feat, float* dens, float* mstat, int B, int K, int Q, int Cin,
-                    int keys_regular, npf_stream_t stream);
+                    int keys_regular, int ldf, int ldd, npf_stream_t stream);
 
 /* Given dfeat[B,Q,Cin], ddens[B,Q]:  dvalues[B,K,Cin] (overwritten; may be NULL) and dtheta[1] (+=). */
 NPF_API int npf_setconv_bwd(const float* keys, long key_bs, const float* queries, long qry_bs, const float* values,
                     const float* theta, const float* feat, const float* dens, const float* mstat,
                     const float* dfeat, const float* ddens, float* dvalues, float* dtheta, int B, int K, int Q,
-                    int Cin, int keys_regular, npf_stream_t stream);
+                    int Cin, int keys_regular, int ldf, int ldd, npf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Depthwise convolution, channel-last, zero padding k/2  (depthwise half of make_depth_sep_conv,

@@ -243,6 +243,14 @@ int linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float*
                   int N, int flags, const float* u, const float* w2, int ldw2, int precision, cudaStream_t st);
 int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float* dX, int lddx, int M, int K, int N,
                        const float* mask_src, int ldm, int flags, int precision, cudaStream_t st);
+int thin128_in_fwd(const float* X, long ldx, const float* W, long ldw, const float* b, float* Y, long ldy, long M, int R, int relu_in,
+                   int relu_out, cudaStream_t st);
+int thin128_in_bwd(const float* dY, long lddy, const float* X, long ldx, const float* W, long ldw, float* dX, long lddx, float* dW, long lddw,
+                   float* db, long M, int R, int relu_in, cudaStream_t st);
+int thin128_out_fwd(const float* X, long ldx, const float* W, long ldw, const float* b, float* Y, long ldy, long M, int J, int relu_in,
+                    int relu_out, cudaStream_t st);
+int thin128_out_bwd(const float* dY, long lddy, const float* X, long ldx, const float* W, long ldw, float* dX, long lddx, float* dW, long lddw,
+                    float* db, long M, int J, int relu_in, int use_mask, cudaStream_t st);
 int linear_bwd_fused_tc(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx, float* dW,
                         int lddw, float* db, int M, int K, int N, int flags, int precision, cudaStream_t st);
 int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int* db_done, int M,
@@ -263,6 +271,12 @@ extern "C" int npf_linear_fwd(const float* X, int ldx, const float* W, int ldw, 
     NPF_REQUIRE((u == nullptr) == (w2 == nullptr), "npf_linear_fwd: u and w2 must be given together");
     if (M == 0) return NPF_OK;
     cudaStream_t st = as_stream(stream);
+    if (!u && !(flags & NPF_ACCUM)) {      // wide side exactly 128: the specialised one-pass kernels
+        int rc = NPF_ENOTSUP;
+        if (K <= kThinMax && N == 128) rc = thin128_in_fwd(X, ldx, W, ldw, b, Y, ldy, M, K, (flags & NPF_RELU_IN) != 0, (flags & NPF_RELU_OUT) != 0, st);
+        else if (N <= kThinMax && K == 128) rc = thin128_out_fwd(X, ldx, W, ldw, b, Y, ldy, M, N, (flags & NPF_RELU_IN) != 0, (flags & NPF_RELU_OUT) != 0, st);
+        if (rc != NPF_ENOTSUP) return rc;
+    }
     if (K <= kThinMax) {
         ThinRedParams t{};
         t.A = X; t.lda = ldx; t.relu_a = (flags & NPF_RELU_IN) ? 1 : 0;
@@ -346,6 +360,13 @@ extern "C" int npf_linear_bwd_weight(const float* dY, int lddy, const float* X, 
     NPF_REQUIRE((u == nullptr) == (dw2 == nullptr), "npf_linear_bwd_weight: u and dw2 must be given together");
     if (M == 0) return NPF_OK;
     cudaStream_t st = as_stream(stream);
+    if (!u) {
+        int rc128 = NPF_ENOTSUP;
+        if (K <= kThinMax && N == 128) rc128 = thin128_in_bwd(dY, lddy, X, ldx, nullptr, 0, nullptr, 0, dW, lddw, db, M, K, (flags & NPF_RELU_IN) != 0, st);
+        else if (N <= kThinMax && K == 128)
+            rc128 = thin128_out_bwd(dY, lddy, X, ldx, nullptr, 0, nullptr, 0, dW, lddw, db, M, N, (flags & NPF_RELU_IN) != 0, 0, st);
+        if (rc128 != NPF_ENOTSUP) return rc128;
+    }
     if (K <= kThinMax) {   // one pass over dY: dW, db and the rank-1 column together
         ThinOuterParams t{};
         t.S = X; t.lds = ldx; t.relu_s = (flags & NPF_RELU_IN) ? 1 : 0;
@@ -411,16 +432,25 @@ extern "C" int npf_relu_bwd(const float* dH, const float* H, float* dZ, long n, 
 extern "C" int npf_linear_bwd(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx,
                               float* dW, int lddw, float* db, int M, int K, int N, int flags, int precision, npf_stream_t stream) {
     if (M == 0) return NPF_OK;
-    NPF_REQUIRE(dY && X && W && dX && dW, "npf_linear_bwd: null pointer");
+    NPF_REQUIRE(dY && X && W && dW, "npf_linear_bwd: null pointer");
     NPF_REQUIRE(M >= 0 && K >= 1 && N >= 1, "npf_linear_bwd: bad shape");
-    NPF_REQUIRE(lddy >= N && ldx >= K && ldw >= K && lddx >= K && lddw >= K, "npf_linear_bwd: leading dimension too small");
+    NPF_REQUIRE(lddy >= N && ldx >= K && ldw >= K && (!dX || lddx >= K) && lddw >= K, "npf_linear_bwd: leading dimension too small");
     NPF_REQUIRE(!(flags & ~(NPF_RELU_IN | NPF_MASK_X)), "npf_linear_bwd: unsupported flag");
-    if (precision != NPF_PREC_FP32) {
+    {
+        cudaStream_t st = npf::as_stream(stream);
+        int rc = NPF_ENOTSUP;
+        if (K <= npf::kThinMax && N == 128 && !(flags & NPF_MASK_X))
+            rc = npf::thin128_in_bwd(dY, lddy, X, ldx, W, ldw, dX, lddx, dW, lddw, db, M, K, (flags & NPF_RELU_IN) != 0, st);
+        else if (N <= npf::kThinMax && K == 128)
+            rc = npf::thin128_out_bwd(dY, lddy, X, ldx, W, ldw, dX, lddx, dW, lddw, db, M, N, (flags & NPF_RELU_IN) != 0, (flags & NPF_MASK_X) != 0, st);
+        if (rc != NPF_ENOTSUP) return rc;
+    }
+    if (precision != NPF_PREC_FP32 && dX) {
         const int rc = npf::linear_bwd_fused_tc(dY, lddy, X, ldx, W, ldw, dX, lddx, dW, lddw, db, M, K, N, flags, precision, npf::as_stream(stream));
         if (rc != NPF_ENOTSUP) return rc;
     }
     int rc = npf_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, db, M, K, N, flags & NPF_RELU_IN, nullptr, nullptr, 0, precision, stream);
-    if (rc != NPF_OK) return rc;
+    if (rc != NPF_OK || !dX) return rc;
     return npf_linear_bwd_data(dY, lddy, W, ldw, dX, lddx, M, K, N, (flags & NPF_MASK_X) ? X : nullptr, ldx, 0, precision, stream);
 }
 

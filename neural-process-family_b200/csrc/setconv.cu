@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
                                                             float* __restrict__ feat_o, float* __restrict__ dens_o, float* __restrict__ mstat_o,
                                                             const float* __restrict__ feat_i, const float* __restrict__ mstat_i,
                                                             const float* __restrict__ dfeat, const float* __restrict__ ddens,
-                                                            float* __restrict__ dtheta, int K, int Q, int C) {
+                                                            float* __restrict__ dtheta, int K, int Q, int C, int ldf, int ldd) {
     extern __shared__ float sm[];
     __shared__ float part[8];
     float* sk = sm;            // [K]
@@ -309,16 +309,16 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
             const float inv = 1.f / s;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                if (c < C) feat_o[oq * C + c] = acc[c] * inv;
-            dens_o[oq] = d;
+                if (c < C) feat_o[oq * ldf + c] = acc[c] * inv;
+            dens_o[oq * ldd] = d;
             mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = s;
         } else {
             const float m = __ldg(mstat_i + oq * 2), inv_s = 1.f / __ldg(mstat_i + oq * 2 + 1);
             float df[4], G = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                df[c] = (c < C) ? __ldg(dfeat + oq * C + c) : 0.f;
-                if (c < C) G = fmaf(df[c], __ldg(feat_i + oq * C + c), G);
+                df[c] = (c < C) ? __ldg(dfeat + oq * ldf + c) : 0.f;
+                if (c < C) G = fmaf(df[c], __ldg(feat_i + oq * ldf + c), G);
             }
             float A1 = 0.f, A2 = 0.f, T = 0.f;
             for (int k = 0; k < K; ++k) {
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
                     if (c < C) g = fmaf(df[c], sv[k * C + c], g);
                 T = fmaf(wa, g, T);
             }
-            contrib = T - G * A1 + __ldg(ddens + oq) * A2;
+            contrib = T - G * A1 + __ldg(ddens + oq * ldd) * A2;
         }
     }
     if (MODE == 1) {
@@ -362,8 +362,11 @@ using namespace npf;
 
 extern "C" int npf_setconv_fwd(const float* keys, long key_bs, const float* queries, long qry_bs,
                                const float* values, const float* theta, float* feat, float* dens, float* mstat,
-                               int B, int K, int Q, int Cin, int keys_regular, npf_stream_t stream) {
+                               int B, int K, int Q, int Cin, int keys_regular, int ldf, int ldd, npf_stream_t stream) {
     NPF_REQUIRE(keys && queries && values && theta && feat && dens && mstat, "npf_setconv_fwd: null pointer");
+    const bool small = Cin <= 4 && !keys_regular && (size_t)K * (1 + Cin) * sizeof(float) <= 40 * 1024;
+    NPF_REQUIRE(ldf >= Cin && ldd >= 1, "npf_setconv_fwd: feat / dens strides too small");
+    NPF_REQUIRE((ldf == Cin && ldd == 1) || small, "npf_setconv_fwd: strided feat / dens only on the few-channel path (Cin <= 4, irregular keys)");
     NPF_REQUIRE(B >= 0 && K >= 1 && Q >= 0 && Cin >= 1, "npf_setconv_fwd: bad shape B=%d K=%d Q=%d C=%d", B, K, Q, Cin);
     NPF_REQUIRE(Cin <= 32 * kMaxChunks, "npf_setconv_fwd: at most %d channels", 32 * kMaxChunks);
     NPF_REQUIRE(B <= 65535, "npf_setconv_fwd: batch > 65535");
@@ -373,10 +376,10 @@ extern "C" int npf_setconv_fwd(const float* keys, long key_bs, const float* quer
         int rc = setconv_tile_fwd(keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, B, K, Q, Cin, st);
         if (rc != NPF_ENOTSUP) return rc;
     }
-    if (Cin <= 4 && !keys_regular && (size_t)K * (1 + Cin) * sizeof(float) <= 40 * 1024) {
+    if (small) {
         dim3 grid((unsigned)cdiv(Q, 256), (unsigned)B);
         setconv_small_kernel<0><<<grid, 256, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
-            keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, nullptr, nullptr, nullptr, nullptr, nullptr, K, Q, Cin);
+            keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, nullptr, nullptr, nullptr, nullptr, nullptr, K, Q, Cin, ldf, ldd);
         count_launch();
         return check_launch("setconv_small_kernel<fwd>");
     }
@@ -390,8 +393,11 @@ extern "C" int npf_setconv_fwd(const float* keys, long key_bs, const float* quer
 extern "C" int npf_setconv_bwd(const float* keys, long key_bs, const float* queries, long qry_bs,
                                const float* values, const float* theta, const float* feat, const float* dens,
                                const float* mstat, const float* dfeat, const float* ddens, float* dvalues,
-                               float* dtheta, int B, int K, int Q, int Cin, int keys_regular, npf_stream_t stream) {
+                               float* dtheta, int B, int K, int Q, int Cin, int keys_regular, int ldf, int ldd, npf_stream_t stream) {
     (void)dens;
+    const bool small = Cin <= 4 && !keys_regular && (size_t)K * (1 + Cin) * sizeof(float) <= 40 * 1024;
+    NPF_REQUIRE(ldf >= Cin && ldd >= 1, "npf_setconv_bwd: feat / dens strides too small");
+    NPF_REQUIRE((ldf == Cin && ldd == 1) || (small && !dvalues), "npf_setconv_bwd: strided feat / dens only on the few-channel path without dvalues");
     NPF_REQUIRE(keys && queries && values && theta && feat && mstat && dfeat && ddens && dtheta,
                 "npf_setconv_bwd: null pointer");
     NPF_REQUIRE(B >= 0 && K >= 1 && Q >= 0 && Cin >= 1 && Cin <= 32 * kMaxChunks, "npf_setconv_bwd: bad shape");
@@ -407,10 +413,10 @@ extern "C" int npf_setconv_bwd(const float* keys, long key_bs, const float* quer
                                   dtheta, B, K, Q, Cin, st);
         if (rc != NPF_ENOTSUP) return rc;
     }
-    if (Cin <= 4 && !keys_regular && (size_t)K * (1 + Cin) * sizeof(float) <= 40 * 1024) {
+    if (small) {
         dim3 grid((unsigned)cdiv(Q, 256), (unsigned)B);
         setconv_small_kernel<1><<<grid, 256, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
-            keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat, dfeat, ddens, dtheta, K, Q, Cin);
+            keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat, dfeat, ddens, dtheta, K, Q, Cin, ldf, ldd);
         count_launch();
         int rc = check_launch("setconv_small_kernel<dtheta>");
         if (rc != NPF_OK) return rc;

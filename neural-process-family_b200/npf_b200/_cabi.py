@@ -25,8 +25,8 @@ SIGNATURES = {
     "npf_linear_bwd_weight": [P, I, P, I, P, I, P, I, I, I, I, P, P, I, I, P],
     "npf_linear_bwd": [P, I, P, I, P, I, P, I, P, I, P, I, I, I, I, I, P],
     "npf_relu_bwd": [P, P, P, L, P],
-    "npf_setconv_fwd": [P, L, P, L, P, P, P, P, P, I, I, I, I, I, P],
-    "npf_setconv_bwd": [P, L, P, L, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
+    "npf_setconv_fwd": [P, L, P, L, P, P, P, P, P, I, I, I, I, I, I, I, P],
+    "npf_setconv_bwd": [P, L, P, L, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "npf_dwconv_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P],
     "npf_dwconv_bwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "npf_channel_stats": [P, P, P, P, L, I, P],

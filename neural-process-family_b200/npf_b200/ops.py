@@ -185,8 +185,10 @@ def linear(x, weight, bias=None, relu=False, precision=None):
 # SetConv
 # ======================================================================================================
 class _SetConv(torch.autograd.Function):
-    """out = Linear([ sum_k softmax_k(a) v_k ; sum_k exp(a) ]) with the exp-quadratic RBF.  The density column of the
-    Linear is applied as a rank-1 epilogue term, so the [.., C+1] concatenation never exists."""
+    """out = Linear([ sum_k softmax_k(a) v_k ; sum_k exp(a) ]) with the exp-quadratic RBF.  The [.., C+1] concatenation
+    never exists as a separate pass: with many channels the density column of the Linear is a rank-1 epilogue term of the
+    GEMM; with few channels (context -> induced, C = y_dim) the SetConv kernel writes [feat | dens] interleaved and the
+    resizer and its whole backward are single streaming passes (npf_linear_fwd / npf_linear_bwd, K = C + 1)."""
 
     @staticmethod
     def forward(ctx, keys, queries, values, theta, W, b, keys_regular):
@@ -197,41 +199,58 @@ class _SetConv(torch.autograd.Function):
         key_bs = 0 if keys.dim() == 1 else K
         qry_bs = 0 if queries.dim() == 1 else Q
         dev = values.device
-        feat = torch.empty(B, Q, C, device=dev, dtype=torch.float32)
-        dens = torch.empty(B, Q, device=dev, dtype=torch.float32)
-        mstat = torch.empty(B, Q, 2, device=dev, dtype=torch.float32)
-        call("npf_setconv_fwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat), _p(dens),
-             _p(mstat), B, K, Q, C, int(keys_regular), _stream())
         assert W.is_contiguous(), "SetConv resizer weight must be contiguous"
         N = W.shape[0]
+        M = B * Q
+        ilv = C <= 4 and not keys_regular and K * (1 + C) * 4 <= 40 * 1024 and not ctx.needs_input_grad[2]
+        mstat = torch.empty(B, Q, 2, device=dev, dtype=torch.float32)
         out = torch.empty(B, Q, N, device=dev, dtype=torch.float32)
-        if B * Q > 0:
-            call("npf_linear_fwd", _p(feat), C, _p(W), C + 1, _p(b), _p(out), N, B * Q, C, N, 0, _p(dens),
-                 W.data_ptr() + 4 * C, C + 1, _precision, _stream())
+        if ilv:
+            feat = torch.empty(B, Q, C + 1, device=dev, dtype=torch.float32)       # [feat | dens]
+            dens = feat
+            call("npf_setconv_fwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat),
+                 feat.data_ptr() + 4 * C, _p(mstat), B, K, Q, C, 0, C + 1, C + 1, _stream())
+            if M > 0:
+                call("npf_linear_fwd", _p(feat), C + 1, _p(W), C + 1, _p(b), _p(out), N, M, C + 1, N, 0, None, None, 0,
+                     _precision, _stream())
+        else:
+            feat = torch.empty(B, Q, C, device=dev, dtype=torch.float32)
+            dens = torch.empty(B, Q, device=dev, dtype=torch.float32)
+            call("npf_setconv_fwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat), _p(dens),
+                 _p(mstat), B, K, Q, C, int(keys_regular), C, 1, _stream())
+            if M > 0:
+                call("npf_linear_fwd", _p(feat), C, _p(W), C + 1, _p(b), _p(out), N, M, C, N, 0, _p(dens),
+                     W.data_ptr() + 4 * C, C + 1, _precision, _stream())
         ctx.save_for_backward(keys, queries, values, theta, W, feat, dens, mstat)
         ctx.bias_ref = b
-        ctx.dims = (B, K, Q, C, N, key_bs, qry_bs, int(keys_regular))
+        ctx.dims = (B, K, Q, C, N, key_bs, qry_bs, int(keys_regular), ilv)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         keys, queries, values, theta, W, feat, dens, mstat = ctx.saved_tensors
-        B, K, Q, C, N, key_bs, qry_bs, regular = ctx.dims
-        dev = values.device
+        B, K, Q, C, N, key_bs, qry_bs, regular, ilv = ctx.dims
         dout = _c(dout).reshape(B * Q, N)
         M = B * Q
         dW, rW = _gbuf(W)
         db, rb = _gbuf(ctx.bias_ref)
         dtheta, rtheta = _gbuf(theta)
         dvalues = None
-        if M > 0:
+        if M > 0 and ilv:
+            dxe = torch.empty(M, C + 1, device=dout.device, dtype=torch.float32)   # [dfeat | ddens]
+            call("npf_linear_bwd", _p(dout), N, _p(feat), C + 1, _p(W), C + 1, _p(dxe), C + 1, _p(dW), C + 1, _p(db), M,
+                 C + 1, N, 0, _precision, _stream())
+            call("npf_setconv_bwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat),
+                 feat.data_ptr() + 4 * C, _p(mstat), _p(dxe), dxe.data_ptr() + 4 * C, None, _p(dtheta), B, K, Q, C, 0,
+                 C + 1, C + 1, _stream())
+        elif M > 0:
             _lin_bwd_weight(dout, feat, _p(dW), C + 1, db, M, C, N, u=dens, dw2_ptr=dW.data_ptr() + 4 * C, ldw2=C + 1)
             dfeat = _lin_bwd_data(dout, _p(W), C + 1, M, C, N)
             ddens = _lin_bwd_data(dout, W.data_ptr() + 4 * C, C + 1, M, 1, N)
             if ctx.needs_input_grad[2]:
                 dvalues = torch.empty_like(values)
             call("npf_setconv_bwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat), _p(dens),
-                 _p(mstat), _p(dfeat), _p(ddens), _p(dvalues), _p(dtheta), B, K, Q, C, regular, _stream())
+                 _p(mstat), _p(dfeat), _p(ddens), _p(dvalues), _p(dtheta), B, K, Q, C, regular, C, 1, _stream())
         elif ctx.needs_input_grad[2]:
             dvalues = torch.zeros_like(values)
         return None, None, dvalues, rtheta, rW, rb, None

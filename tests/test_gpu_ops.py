@@ -55,6 +55,24 @@ def test_mlp_chain(ops, M, K, N):
     _check_grads(cu_in, ref_in, yc, yr, ["x", "W1", "b1", "W2", "b2"])
 
 
+@pytest.mark.parametrize("M,K,J", [(5, 1, 1), (1037, 2, 2), (4099, 3, 6), (130, 8, 8), (40000, 2, 2)])
+def test_thin_128_layers(ops, M, K, J):
+    """x[M,K<=8] -> 128 -> relu -> J<=8: the one-pass thin kernels (forward, fused backward with / without input gradient,
+    relu mask taken from the saved activations), rows that do not fill the last warp pass."""
+    x = _g(M, K, seed=1)
+    W1, b1, W2, b2 = _g(128, K, seed=2, scale=K ** -0.5), _g(128, seed=3), _g(J, 128, seed=4, scale=128 ** -0.5), _g(J, seed=5)
+    for x_grad in (True, False):
+        ref_in = [t.clone().requires_grad_(True) for t in (x, W1, b1, W2, b2)]
+        cu_in = [_cu(t, True) for t in (x, W1, b1, W2, b2)]
+        ref_in[0].requires_grad_(x_grad)
+        cu_in[0].requires_grad_(x_grad)
+        yr = F.linear(torch.relu(F.linear(ref_in[0], ref_in[1], ref_in[2])), ref_in[3], ref_in[4])
+        yc = ops.mlp_chain(cu_in[0], [cu_in[1], cu_in[3]], [cu_in[2], cu_in[4]])
+        assert rel_err(yc, yr) < TOL
+        _check_grads(cu_in, ref_in, yc, yr, ["x", "W1", "b1", "W2", "b2"])
+        assert (cu_in[0].grad is not None) == x_grad
+
+
 def test_linear_final_relu_no_bias(ops):
     x, W = _g(4, 50, 96, seed=1), _g(64, 96, seed=2, scale=0.1)
     xr, Wr = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
