@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--workload", default="convcnp1d_b256_c128_t128", choices=list(WORKLOADS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay of the step (npf_b200.GraphedStep)")
     ap.add_argument("--kernel-times", action="store_true", help="print the per-kernel CUDA-event breakdown to stderr")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -205,7 +206,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = dict(workload=args.workload, description=wl["desc"], tasks_per_gpu=wl["B"], global_batch=wl["B"] * max(world, 1),
                n_cntxt=wl["C"], n_trgt=wl["T"], parallelism=f"dp{max(world, 1)} (tasks sharded, flat-gradient all-reduce)",
-               l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)")
+               l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)",
+               launch="eager" if args.no_graph else "cuda graph replay (npf_b200.GraphedStep)")
 
     if args.impl == "reference":
         if rank != 0:
@@ -240,13 +242,21 @@ def main():
     host_inputs = [make_inputs(wl, B, seed=100 * rank + i, pin=True) for i in range(n_sets)]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
-    def step(inp):
+    def eager_step(inp):
         flat.zero_()
         out = model(inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"])
         loss = crit(out, inp["Y_trgt"])
         loss.backward()
         flat.all_reduce_mean()
         return loss
+
+    # the public training-step API: the whole step recorded once into a CUDA graph and replayed (one host call per step)
+    gstep = None if args.no_graph else npf_b200.GraphedStep(model, crit, flat=flat)
+
+    def step(inp):
+        if gstep is None:
+            return eager_step(inp)
+        return gstep(inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"])
 
     def barrier():
         if dist is not None:
@@ -272,7 +282,7 @@ def main():
         evs[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall
-    launches = ops.launch_count() - n0
+    launches = ops.launch_count() - n0 if gstep is None else gstep.last_launches * args.steps   # replays launch the recorded kernels
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -296,7 +306,7 @@ def main():
     _cabi.enable_timing(True)
     for i in range(min(args.steps, 10)):
         flush.fill_(0.0)
-        step(dev_inputs[i % n_sets])
+        eager_step(dev_inputs[i % n_sets])
     torch.cuda.synchronize()
     ktimes = _cabi.collect_timing()  # name -> (total_ms, calls)
     _cabi.enable_timing(False)

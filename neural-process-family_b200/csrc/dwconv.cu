@@ -456,6 +456,110 @@ static int launch_dw1_wgrad(Dw1Params& p, const float* dY, float* dWt, float* db
     return check_launch("dwconv1d_wgrad_kernel");
 }
 
+// Whole 1-D backward in one pass over dY and X (KW <= 11): the data gradient needs the dY window around 8 positions, and
+// with the substitution m = l + j - pw the filter gradient needs the SAME window against act(X) at the 8 centres:
+//     dX[m]  = act'(X[m]) * sum_j Wt[j] dY[m + pw - j]  (+ dY[m] for the residual branch)
+//     dWt[j] += sum_m act(X)[m] dY[m + pw - j]          dbias += sum_m dY[m]
+// so one register window of dY (KW + 7 float4) and the 8 centre X values feed both; X and dY are read once, dX written once.
+template <int KW>
+__global__ void __launch_bounds__(256, 1) dwconv1d_bwd_fused_kernel(Dw1Params p, float* __restrict__ dWt, float* __restrict__ dbias) {
+    extern __shared__ __align__(16) float4 dyn4[];   // [KW][CQ] flipped filters, then [G][KW + 1][CQ] reduction scratch
+    const int CQ = p.C >> 2, G = 256 / CQ;
+    float4* Ws4 = dyn4;
+    float4* red4 = dyn4 + (size_t)KW * CQ;
+    const int q = threadIdx.x % CQ, g = threadIdx.x / CQ;
+    const int pw = KW / 2, joff = (KW - p.kw) / 2;
+    for (int idx = threadIdx.x; idx < KW * p.C; idx += 256) {
+        const int c = idx % p.C, j = idx / p.C, jr = j - joff;
+        reinterpret_cast<float*>(Ws4)[(size_t)j * p.C + c] = (jr >= 0 && jr < p.kw) ? __ldg(p.Wt + (long)c * p.kw + (p.kw - 1 - jr)) : 0.f;
+    }
+    __syncthreads();
+    const int c = 4 * q;
+    const bool affine = p.mask && p.scale != nullptr;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (affine) {
+        sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+        sh = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+    }
+    float4 accw[KW], accb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < KW; ++j) accw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long gid = (long)blockIdx.x * G + g; gid < p.n_groups; gid += (long)gridDim.x * G) {
+        const long b = gid / p.groups_per_seq;
+        const int l0 = (int)(gid % p.groups_per_seq) * 8;
+        const float* gb = p.X + (b * p.L) * (long)p.C + c;          // dY
+        const float* xb = p.Xorig + (b * p.L) * (long)p.C + c;      // layer input
+        float4 dyw[KW + 7], xv[8];
+#pragma unroll
+        for (int xc = 0; xc < KW + 7; ++xc) {
+            const int pos = l0 + xc - pw;
+            dyw[xc] = (pos >= 0 && pos < p.L) ? __ldg(reinterpret_cast<const float4*>(gb + (long)pos * p.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+            xv[pp] = (l0 + pp < p.L) ? __ldg(reinterpret_cast<const float4*>(xb + (long)(l0 + pp) * p.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc[8];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) acc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            const float4 w = Ws4[j * CQ + q];
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) acc[pp] = f4_fma(w, dyw[pp + j], acc[pp]);
+        }
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            const int pos = l0 + pp;
+            if (pos >= p.L) continue;
+            const float4 x = xv[pp];
+            float4 v = acc[pp], ax = x;
+            if (p.mask) {
+                const float4 pre = make_float4(fmaf(sc.x, x.x, sh.x), fmaf(sc.y, x.y, sh.y), fmaf(sc.z, x.z, sh.z), fmaf(sc.w, x.w, sh.w));
+                v.x = pre.x > 0.f ? v.x * sc.x : 0.f; v.y = pre.y > 0.f ? v.y * sc.y : 0.f;
+                v.z = pre.z > 0.f ? v.z * sc.z : 0.f; v.w = pre.w > 0.f ? v.w * sc.w : 0.f;
+                ax = make_float4(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f), fmaxf(pre.z, 0.f), fmaxf(pre.w, 0.f));
+            }
+            const float4 dyc = dyw[pp + pw];
+            if (p.addgrad) { v.x += dyc.x; v.y += dyc.y; v.z += dyc.z; v.w += dyc.w; }
+            *reinterpret_cast<float4*>(p.Y + ((b * p.L) + pos) * (long)p.C + c) = v;
+            accb.x += dyc.x; accb.y += dyc.y; accb.z += dyc.z; accb.w += dyc.w;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) accw[j] = f4_fma(ax, dyw[pp + j], accw[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KW; ++j) red4[((size_t)g * (KW + 1) + j) * CQ + q] = accw[j];
+    red4[((size_t)g * (KW + 1) + KW) * CQ + q] = accb;
+    __syncthreads();
+    const float* red = reinterpret_cast<const float*>(red4);
+    for (int idx = threadIdx.x; idx < (KW + 1) * p.C; idx += 256) {
+        const int ch = idx % p.C, j = idx / p.C;
+        float s = 0.f;
+        for (int gg = 0; gg < G; ++gg) s += red[((size_t)gg * (KW + 1) + j) * p.C + ch];
+        if (j == KW) { if (dbias) atomicAdd(dbias + ch, s); }
+        else {
+            const int jr = j - joff;           // accw[j] pairs with the flipped tap: dWt[kw - 1 - jr]
+            if (jr >= 0 && jr < p.kw) atomicAdd(dWt + (long)ch * p.kw + (p.kw - 1 - jr), s);
+        }
+    }
+}
+
+template <int KW>
+static int launch_dw1_bwd_fused(Dw1Params& p, float* dWt, float* dbias, int B, cudaStream_t st) {
+    const int CQ = p.C / 4, G = 256 / CQ;
+    p.groups_per_seq = (p.L + 7) / 8;
+    p.n_groups = (long)B * p.groups_per_seq;
+    const size_t smem = sizeof(float) * ((size_t)KW * p.C + (size_t)G * (KW + 1) * p.C);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(dwconv1d_bwd_fused_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    if (smem > 200 * 1024) return NPF_ENOTSUP;
+    long grid = cdiv(p.n_groups, G);
+    if (grid > (long)kNumSMs) grid = kNumSMs;
+    dwconv1d_bwd_fused_kernel<KW><<<(unsigned)grid, 256, smem, st>>>(p, dWt, dbias);
+    count_launch();
+    return check_launch("dwconv1d_bwd_fused_kernel");
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // 2-D fast path (GridConvCNP / GridConvLNP, 32x32-ish images, k = 9 / 11): FFMA-bound (121 taps per output), so the
 // kernel is organised around register reuse.  CTA tile = 16 rows x 32 columns x 16 channels (halo tile in shared
@@ -854,6 +958,14 @@ extern "C" int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, 
     const int kwsel = pick_kw(kw);
     if (kwsel < 0) { set_error("npf_dwconv_bwd: kernel width %d > 19", kw); return NPF_ENOTSUP; }
     const bool fast1d = dw1_ok(H, C) && !dpre_scale;
+    if (fast1d && dX && dWt && !(flags & NPF_ACCUM) && kwsel <= 11) {   // one pass: data + filter + bias gradient
+        Dw1Params q{};
+        q.X = dY; q.Wt = Wt; q.Y = dX; q.Xorig = X; q.scale = pre_scale; q.shift = pre_shift;
+        q.addgrad = (flags & NPF_ADD_DY) ? dY : nullptr;
+        q.L = Wd; q.C = C; q.kw = kw; q.mask = relu_in;
+        rc = kwsel == 9 ? launch_dw1_bwd_fused<9>(q, dWt, dbias, B, st) : launch_dw1_bwd_fused<11>(q, dWt, dbias, B, st);
+        if (rc != NPF_ENOTSUP) return rc;
+    }
     if (fast1d) {
         if (dX) {
             Dw1Params q{};

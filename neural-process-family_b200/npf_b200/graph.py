@@ -1,0 +1,106 @@
+"""CUDA-graph capture of the training step (forward + loss + backward).
+
+A ConvCNP meta-batch step is ~50 kernels of 10-50 us each: eager PyTorch dispatch (autograd Function bookkeeping + one
+ctypes call per kernel) costs about as much host time as the kernels cost device time, so the GPU idles between launches.
+``GraphedStep`` records the whole step once per input-shape signature into a ``torch.cuda.CUDAGraph`` and replays it:
+one host call per step, kernels back to back on the device.
+
+    step = GraphedStep(model, criterion)            # optionally flat=FlatGradients(model, process_group)
+    loss = step(X_cntxt, Y_cntxt, X_trgt, Y_trgt)   # gradients are in p.grad (views of step.flat.flat) afterwards
+    optimizer.step()
+
+What is captured: ``flat.zero_()``, ``model(...)``, ``criterion(...)``, ``loss.backward()``.  What stays outside: the
+host->device copies of the inputs into the graph's static buffers, the flat-gradient all-reduce (multi-GPU), the
+optimizer, and the host side of the asynchronous [-1, 1] range validation (``_validate_inputs`` only launches the check
+kernel while capturing; the flag is read back after every replay).
+
+Constraints (the usual ones of whole-network capture): shapes are static per graph -- a new (n_cntxt, n_trgt, batch)
+signature records a new graph (LRU cache of ``max_graphs``); Python-side control flow is frozen at capture (number of
+latent samples, train/eval mode -- the mode is part of the signature); the returned loss is a static tensor that the
+next replay overwrites.
+"""
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from .parallel import FlatGradients
+
+__all__ = ["GraphedStep"]
+
+
+class _Entry:
+    __slots__ = ("graph", "inputs", "loss", "launches")
+
+
+class GraphedStep:
+    def __init__(self, model, criterion, flat=None, n_warmup=2, max_graphs=8):
+        self.model, self.criterion = model, criterion
+        self.flat = flat if flat is not None else FlatGradients(model)
+        self.n_warmup, self.max_graphs = n_warmup, max_graphs
+        self._graphs = OrderedDict()
+
+    # the eager body; also what gets recorded
+    def _body(self, xc, yc, xt, yt):
+        self.flat.zero_()
+        out = self.model(xc, yc, xt, yt)
+        loss = self.criterion(out, yt)
+        loss.backward()
+        return loss.detach()
+
+    def _signature(self, tensors):
+        return (self.model.training,) + tuple((tuple(t.shape), t.dtype) for t in tensors)
+
+    def _capture(self, sig, tensors):
+        dev = next(self.model.parameters()).device
+        e = _Entry()
+        e.inputs = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in tensors]
+        for d, s in zip(e.inputs, tensors):
+            d.copy_(s, non_blocking=True)
+        # warm-up on a side stream (lazy one-time initialisation inside the library, allocator pools); the running
+        # statistics / step counters it advances are restored so that capture has no side effect on the model
+        saved = [(b, b.clone()) for b in self.model.buffers()]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.n_warmup):
+                self._body(*e.inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.model.validate_now() if hasattr(self.model, "validate_now") else None
+        e.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(e.graph):
+            e.loss = self._body(*e.inputs)
+        e.launches = ops.launch_count() - n0
+        with torch.no_grad():
+            for b, v in saved:
+                b.copy_(v)
+        self._graphs[sig] = e
+        while len(self._graphs) > self.max_graphs:
+            self._graphs.popitem(last=False)
+        return e
+
+    def __call__(self, X_cntxt, Y_cntxt, X_trgt, Y_trgt):
+        tensors = (X_cntxt, Y_cntxt, X_trgt, Y_trgt)
+        sig = self._signature(tensors)
+        e = self._graphs.get(sig)
+        if e is None:
+            e = self._capture(sig, tensors)
+        else:
+            self._graphs.move_to_end(sig)
+        for d, s in zip(e.inputs, tensors):
+            if d.data_ptr() != s.data_ptr():
+                d.copy_(s, non_blocking=True)
+        e.graph.replay()
+        if hasattr(self.model, "_after_graph_replay"):
+            self.model._after_graph_replay()
+        self.flat.all_reduce_mean()
+        self.last_launches = e.launches
+        return e.loss
+
+    def static_inputs(self, X_cntxt, Y_cntxt, X_trgt, Y_trgt):
+        """The graph's own input buffers for this signature (write the next batch into them to skip the copies)."""
+        tensors = (X_cntxt, Y_cntxt, X_trgt, Y_trgt)
+        sig = self._signature(tensors)
+        e = self._graphs.get(sig) or self._capture(sig, tensors)
+        return tuple(e.inputs)

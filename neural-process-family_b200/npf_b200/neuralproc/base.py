@@ -111,13 +111,27 @@ class NeuralProcessFamily(nn.Module, abc.ABC):
             st = dict(flag=torch.zeros(1, dtype=torch.int32, device=X_cntxt.device),
                       host=torch.zeros(1, dtype=torch.int32).pin_memory(), event=None)
             self._range_state = st
+        if torch.cuda.is_current_stream_capturing():     # CUDA-graph capture (graph.GraphedStep): record the check kernel only;
+            ops.range_flag(st["flag"], X_cntxt, X_trgt, lo=-1.0, hi=1.0)   # the flag is read back after each replay
+            return
         self._raise_if_flagged(wait=False)
         ops.range_flag(st["flag"], X_cntxt, X_trgt, lo=-1.0, hi=1.0)
+        self._post_range_check()
+
+    def _post_range_check(self):
+        st = self._range_state
         st["host"].copy_(st["flag"], non_blocking=True)
         st["event"] = torch.cuda.Event()
         st["event"].record()
         if self.strict_validation:
             self._raise_if_flagged(wait=True)
+
+    def _after_graph_replay(self):
+        """Host side of the range validation for a replayed step: raise for the previous replay, queue this one's read."""
+        if self._range_state is None or not self.training:
+            return
+        self._raise_if_flagged(wait=False)
+        self._post_range_check()
 
     def _raise_if_flagged(self, wait):
         st = self._range_state

@@ -244,9 +244,9 @@ class _SetConv(torch.autograd.Function):
                  feat.data_ptr() + 4 * C, _p(mstat), _p(dxe), dxe.data_ptr() + 4 * C, None, _p(dtheta), B, K, Q, C, 0,
                  C + 1, C + 1, _stream())
         elif M > 0:
-            _lin_bwd_weight(dout, feat, _p(dW), C + 1, db, M, C, N, u=dens, dw2_ptr=dW.data_ptr() + 4 * C, ldw2=C + 1)
-            dfeat = _lin_bwd_data(dout, _p(W), C + 1, M, C, N)
-            ddens = _lin_bwd_data(dout, W.data_ptr() + 4 * C, C + 1, M, 1, N)
+            # feature block of the resizer: dfeat, dW[:, :C], db in one pass; density column: ddens and dW[:, C] in a thin one
+            dfeat = _lin_bwd(dout, feat, _p(W), C + 1, _p(dW), C + 1, db, M, C, N, mask=False)
+            ddens = _lin_bwd(dout, dens, W.data_ptr() + 4 * C, C + 1, dW.data_ptr() + 4 * C, C + 1, None, M, 1, N, mask=False)
             if ctx.needs_input_grad[2]:
                 dvalues = torch.empty_like(values)
             call("npf_setconv_bwd", _p(keys), key_bs, _p(queries), qry_bs, _p(values), _p(theta), _p(feat), _p(dens),
