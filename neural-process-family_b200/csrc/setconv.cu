@@ -271,6 +271,11 @@ __global__ void __launch_bounds__(256) setconv_bwd_values_kernel(const float* __
 // Few value channels (context -> induced: C = y_dim <= 4): one THREAD per query, the task's keys and values staged in
 // shared memory (broadcast reads).  mode 0 forward, mode 1 theta gradient.
 // ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float logit_r(float xq, float xk, float inv_sigma) {
+    const float t = (xk - xq) * inv_sigma;
+    return -(t * t);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
                                                             long qry_bs, const float* __restrict__ values, const float* __restrict__ theta,
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
     const int b = blockIdx.y;
     const float th = __ldg(theta);
     const float sigma = 1e-5f + softplus_f(th);
+    const float inv_sigma = 1.f / sigma;       // one division per thread instead of one per (query, key) pair
     for (int i = threadIdx.x; i < K; i += blockDim.x) sk[i] = __ldg(keys + (long)b * key_bs + i);
     for (int i = threadIdx.x; i < K * C; i += blockDim.x) sv[i] = __ldg(values + (long)b * K * C + i);
     __syncthreads();
@@ -295,18 +301,19 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
         const long oq = (long)b * Q + q;
         if (MODE == 0) {
             float m = -INFINITY;
-            for (int k = 0; k < K; ++k) m = fmaxf(m, logit(xq, sk[k], sigma));
-            float s = 0.f, d = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int k = 0; k < K; ++k) m = fmaxf(m, logit_r(xq, sk[k], inv_sigma));
+            float s = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
             for (int k = 0; k < K; ++k) {
-                const float a = logit(xq, sk[k], sigma);
-                const float e = expf(a - m);
+                const float e = expf(logit_r(xq, sk[k], inv_sigma) - m);
                 s += e;
-                d += expf(a);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     if (c < C) acc[c] = fmaf(e, sv[k * C + c], acc[c]);
             }
             const float inv = 1.f / s;
+            const float d = expf(m) * s;           // sum_k exp(a_k) = exp(m) sum_k exp(a_k - m): one exp per query, not per pair
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 if (c < C) feat_o[oq * ldf + c] = acc[c] * inv;
@@ -321,8 +328,9 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
                 if (c < C) G = fmaf(df[c], __ldg(feat_i + oq * ldf + c), G);
             }
             float A1 = 0.f, A2 = 0.f, T = 0.f;
+#pragma unroll 4
             for (int k = 0; k < K; ++k) {
-                const float a = logit(xq, sk[k], sigma);
+                const float a = logit_r(xq, sk[k], inv_sigma);
                 const float wa = expf(a - m) * inv_s * (a - m);
                 A1 += wa;
                 A2 = fmaf(expf(a), a, A2);
@@ -341,8 +349,7 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
         __syncthreads();
         if (threadIdx.x == 0) {
             float tot = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tot += part[i];
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += part[i];
             atomicAdd(dtheta, tot * (-2.f / sigma) * sigmoid_f(th));
         }
     }
@@ -377,8 +384,9 @@ extern "C" int npf_setconv_fwd(const float* keys, long key_bs, const float* quer
         if (rc != NPF_ENOTSUP) return rc;
     }
     if (small) {
-        dim3 grid((unsigned)cdiv(Q, 256), (unsigned)B);
-        setconv_small_kernel<0><<<grid, 256, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
+        const int nblk = (int)cdiv(Q, 256), thr = (int)cdiv(cdiv(Q, nblk), 32) * 32;   // e.g. Q = 296 -> 2 x 160 threads (92 % of lanes busy)
+        dim3 grid((unsigned)nblk, (unsigned)B);
+        setconv_small_kernel<0><<<grid, thr, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
             keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, nullptr, nullptr, nullptr, nullptr, nullptr, K, Q, Cin, ldf, ldd);
         count_launch();
         return check_launch("setconv_small_kernel<fwd>");
@@ -414,8 +422,9 @@ extern "C" int npf_setconv_bwd(const float* keys, long key_bs, const float* quer
         if (rc != NPF_ENOTSUP) return rc;
     }
     if (small) {
-        dim3 grid((unsigned)cdiv(Q, 256), (unsigned)B);
-        setconv_small_kernel<1><<<grid, 256, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
+        const int nblk = (int)cdiv(Q, 256), thr = (int)cdiv(cdiv(Q, nblk), 32) * 32;
+        dim3 grid((unsigned)nblk, (unsigned)B);
+        setconv_small_kernel<1><<<grid, thr, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
             keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat, dfeat, ddens, dtheta, K, Q, Cin, ldf, ldd);
         count_launch();
         int rc = check_launch("setconv_small_kernel<dtheta>");

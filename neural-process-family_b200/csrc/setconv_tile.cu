@@ -17,10 +17,12 @@ namespace npf {
 
 constexpr float kWindowLogT = 41.6f;
 constexpr int kGroup = 8;        // queries (or rows) per warp pass
+constexpr int kRowBatch = 4;     // value rows loaded per batch (3 CTAs x 8 warps per SM keep >= 96 16-byte loads per lane slot in flight)
 constexpr int kMaxQ = 2048;      // queries per task handled in shared memory
 
-__device__ __forceinline__ float logit_t(float xq, float xk, float sigma) {
-    const float t = fabsf(xk - xq) / sigma;
+// logits use 1 / sigma (one division per kernel instead of one per pair; <= 1 ulp from the quotient form)
+__device__ __forceinline__ float logit_t(float xq, float xk, float inv_sigma) {
+    const float t = (xk - xq) * inv_sigma;
     return -(t * t);
 }
 
@@ -71,8 +73,15 @@ __device__ __forceinline__ void sort_queries(const TileSmem& t, const float* __r
     __syncthreads();
     for (int i = threadIdx.x; i < Q; i += blockDim.x) {
         const float x = scratch[i];
-        int rank = 0;
-        for (int j = 0; j < Q; ++j) {
+        int rank = 0, j = 0;
+        if ((Q & 3) == 0) {                                // scratch sits 6 Q floats into the 16-byte aligned dynamic smem: float4 reads
+            for (; j < Q; j += 4) {
+                const float4 y = *reinterpret_cast<const float4*>(scratch + j);
+                rank += (y.x < x) + (y.y < x) + (y.z < x) + (y.w < x);
+                rank += (y.x == x && j < i) + (y.y == x && j + 1 < i) + (y.z == x && j + 2 < i) + (y.w == x && j + 3 < i);
+            }
+        }
+        for (; j < Q; ++j) {
             const float y = scratch[j];
             rank += (y < x) || (y == x && j < i);
         }
@@ -84,7 +93,7 @@ __device__ __forceinline__ void sort_queries(const TileSmem& t, const float* __r
 
 // mode 0 forward / mode 1 theta gradient
 template <int MODE>
-__global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+__global__ void __launch_bounds__(256, 3) setconv_grp_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
                                                           long qry_bs, const float* __restrict__ values, const float* __restrict__ theta,
                                                           float* __restrict__ feat_o, float* __restrict__ dens_o, float* __restrict__ mstat_o,
                                                           const float* __restrict__ feat_i, const float* __restrict__ mstat_i,
@@ -98,33 +107,30 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float th = __ldg(theta);
     const float sigma = 1e-5f + softplus_f(th);
+    const float inv_sigma = 1.f / sigma;
     const float* kb = keys + (long)b * key_bs;
     const float* vb = values + (long)b * K * C;
     sort_queries(t, queries + (long)b * qry_bs, Q, scratch);
 
-    // per-query window and softmax statistics (one thread per query; windows are a few dozen keys).  Every CTA of a
-    // task recomputes them (cheap); only the first one (blockIdx.y == 0) writes dens / mstat.
+    // per-query window (one thread per query).  Forward: the max logit is the one of the nearest grid row (the window code's
+    // n0 or a neighbour: all three are tried); the softmax denominator is accumulated by the group pass below from the very
+    // weights it applies, so no thread walks its window serially.
     for (int i = threadIdx.x; i < Q; i += blockDim.x) {
         const float xq = t.xs[i];
         int lo, hi;
         window_t(kb, K, xq, sigma, lo, hi);
         t.lo[i] = lo; t.hi[i] = hi;
-        const long oq = (long)b * Q + t.ord[i];
         if (MODE == 0) {
-            float m = -INFINITY;
-            for (int k = lo; k <= hi; ++k) m = fmaxf(m, logit_t(xq, __ldg(kb + k), sigma));
-            float s = 0.f, d = 0.f;
-            for (int k = lo; k <= hi; ++k) {
-                const float a = logit_t(xq, __ldg(kb + k), sigma);
-                s += expf(a - m);
-                d += expf(a);
-            }
-            t.m[i] = m; t.invs[i] = 1.f / s;
-            if (blockIdx.y == 0) {
-                dens_o[oq] = d;
-                mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = s;
-            }
+            const float x0 = __ldg(kb), dx = (__ldg(kb + K - 1) - x0) / (float)(K - 1);
+            int n0 = (dx > 0.f) ? (int)rintf(fminf(fmaxf((xq - x0) / dx, 0.f), (float)(K - 1))) : lo;
+            n0 = min(max(n0, lo), hi);
+            float m = logit_t(xq, __ldg(kb + n0), inv_sigma);
+            if (n0 > lo) m = fmaxf(m, logit_t(xq, __ldg(kb + n0 - 1), inv_sigma));
+            if (n0 < hi) m = fmaxf(m, logit_t(xq, __ldg(kb + n0 + 1), inv_sigma));
+            if (!(dx > 0.f)) for (int k = lo; k <= hi; ++k) m = fmaxf(m, logit_t(xq, __ldg(kb + k), inv_sigma));   // degenerate grid
+            t.m[i] = m;
         } else {
+            const long oq = (long)b * Q + t.ord[i];
             t.m[i] = __ldg(mstat_i + oq * 2);
             t.invs[i] = 1.f / __ldg(mstat_i + oq * 2 + 1);
         }
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
         float4 acc[kGroup];
 #pragma unroll
         for (int j = 0; j < kGroup; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float a1[kGroup], a2[kGroup];
+        float a1[kGroup], a2[kGroup];      // forward: a1 = this lane's share of sum_k exp(a - m);  theta gradient: A1, A2
 #pragma unroll
         for (int j = 0; j < kGroup; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
         for (int base = glo; base <= ghi; base += 32) {
@@ -154,26 +160,27 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
             for (int j = 0; j < kGroup; ++j) {
                 w[j] = 0.f;
                 if (j < nt && row <= ghi && row >= t.lo[t0 + j] && row <= t.hi[t0 + j]) {
-                    const float a = logit_t(t.xs[t0 + j], xk, sigma);
-                    const float e = expf(a - t.m[t0 + j]) * t.invs[t0 + j];
-                    if (MODE == 0) w[j] = e;
-                    else {
-                        w[j] = e * (a - t.m[t0 + j]);
+                    const float a = logit_t(t.xs[t0 + j], xk, inv_sigma);
+                    if (MODE == 0) {
+                        w[j] = expf(a - t.m[t0 + j]);          // unnormalised: divided by the sum once per query below
+                        a1[j] += w[j];
+                    } else {
+                        w[j] = expf(a - t.m[t0 + j]) * t.invs[t0 + j] * (a - t.m[t0 + j]);
                         a1[j] += w[j];
                         a2[j] = fmaf(expf(a), a, a2[j]);
                     }
                 }
             }
             const int cnt = min(32, ghi - base + 1);
-            for (int rr0 = 0; rr0 < cnt; rr0 += 8) {       // 8 row loads in flight, then 8 x (8 shuffles + 32 FMAs)
-                float4 v[8];
+            for (int rr0 = 0; rr0 < cnt; rr0 += kRowBatch) {   // kRowBatch row loads in flight, then kRowBatch x (8 shuffles + 32 FMAs)
+                float4 v[kRowBatch];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < kRowBatch; ++u) {
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ch_ok && rr0 + u < cnt) v[u] = __ldg(reinterpret_cast<const float4*>(vb + (long)(base + rr0 + u) * C + c4));
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < kRowBatch; ++u) {
 #pragma unroll
                     for (int j = 0; j < kGroup; ++j) {
                         const float wj = __shfl_sync(0xffffffffu, w[j], rr0 + u);   // rows past the window carry weight 0
@@ -188,7 +195,13 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
             if (j >= nt) continue;
             const long oq = (long)b * Q + t.ord[t0 + j];
             if (MODE == 0) {
-                if (ch_ok) *reinterpret_cast<float4*>(feat_o + oq * C + c4) = acc[j];
+                const float ssum = warp_sum(a1[j]), inv = 1.f / ssum;
+                if (ch_ok) *reinterpret_cast<float4*>(feat_o + oq * C + c4) = make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
+                if (lane == 0) {                               // dens = sum_k exp(a) = exp(m) * sum_k exp(a - m)
+                    const float m = t.m[t0 + j];
+                    dens_o[oq] = expf(m) * ssum;
+                    mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = ssum;
+                }
             } else {
                 float T = 0.f, G = 0.f;
                 if (ch_ok) {
@@ -217,7 +230,7 @@ __global__ void __launch_bounds__(256) setconv_grp_kernel(const float* __restric
 
 // dV[b,k,:] = sum_q w_qk dF[b,q,:]: a warp owns 8 adjacent key rows and walks the contiguous run of sorted queries whose
 // window touches them.
-__global__ void __launch_bounds__(256) setconv_grp_dv_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+__global__ void __launch_bounds__(256, 3) setconv_grp_dv_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
                                                              long qry_bs, const float* __restrict__ theta, const float* __restrict__ mstat,
                                                              const float* __restrict__ dfeat, float* __restrict__ dvalues, int K, int Q, int C) {
     extern __shared__ float smem[];
@@ -226,6 +239,7 @@ __global__ void __launch_bounds__(256) setconv_grp_dv_kernel(const float* __rest
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float sigma = 1e-5f + softplus_f(__ldg(theta));
+    const float inv_sigma = 1.f / sigma;
     const float* kb = keys + (long)b * key_bs;
     sort_queries(t, queries + (long)b * qry_bs, Q, scratch);
     for (int i = threadIdx.x; i < Q; i += blockDim.x) {
@@ -259,18 +273,18 @@ __global__ void __launch_bounds__(256) setconv_grp_dv_kernel(const float* __rest
             for (int r = 0; r < kGroup; ++r) {
                 w[r] = 0.f;
                 if (ti < tb && r < nr && k0 + r >= t.lo[ti] && k0 + r <= t.hi[ti])
-                    w[r] = expf(logit_t(t.xs[ti], xk[r], sigma) - t.m[ti]) * t.invs[ti];
+                    w[r] = expf(logit_t(t.xs[ti], xk[r], inv_sigma) - t.m[ti]) * t.invs[ti];
             }
             const int cnt = min(32, tb - base);
-            for (int tt0 = 0; tt0 < cnt; tt0 += 8) {
-                float4 g[8];
+            for (int tt0 = 0; tt0 < cnt; tt0 += kRowBatch) {
+                float4 g[kRowBatch];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < kRowBatch; ++u) {
                     g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ch_ok && tt0 + u < cnt) g[u] = __ldg(reinterpret_cast<const float4*>(dfeat + ((long)b * Q + t.ord[base + tt0 + u]) * C + c4));
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < kRowBatch; ++u) {
 #pragma unroll
                     for (int r = 0; r < kGroup; ++r) {
                         const float wr = __shfl_sync(0xffffffffu, w[r], tt0 + u);   // queries past the run carry weight 0
