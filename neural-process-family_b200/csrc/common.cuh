@@ -43,4 +43,31 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 
 static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A kernel launched with launch_pdl may begin while its stream predecessor is still draining: its CTAs are scheduled as
+// soon as every predecessor CTA has passed pdl_trigger() (or exited) and SM resources free up, so launch latency, the
+// prologue that touches only parameters (TMEM allocation, barrier init, weight staging) and the predecessor's tail
+// overlap.  CONTRACT: such a kernel executes pdl_wait() before its first access to anything a preceding kernel may have
+// written (activations, gradients, statistics) and before its first global write; pdl_wait returns once the predecessor
+// grid has completed and its memory is visible.
+// The early start is requested only while the stream is being captured into a CUDA graph (GraphedStep): there the kernel
+// order is the library's own, and no kernel that writes PARAMETERS (an optimizer step) can sit directly in front of a
+// kernel whose pre-wait prologue reads them.  Eager launches keep plain stream order (the wait is then a no-op).
+bool pdl_enabled();     // NPF_PDL=0 disables it everywhere
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool early = pdl_enabled() && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
+    attr[0].val.programmaticStreamSerializationAllowed = early ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace npf

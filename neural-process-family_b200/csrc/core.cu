@@ -1,5 +1,6 @@
 // Error plumbing and launch accounting for libnpf_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -19,6 +20,11 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("NPF_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

@@ -283,7 +283,9 @@ __global__ void __launch_bounds__(256, KW <= 11 ? 2 : 1) dwconv1d_kernel(Dw1Para
         if (jr >= 0 && jr < p.kw) v = __ldg(p.Wt + (long)c * p.kw + (p.flip ? p.kw - 1 - jr : jr));
         reinterpret_cast<float*>(Ws4)[(size_t)j * p.C + c] = v;
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();          // filters are parameters; the folded norm affine and the activations come from preceding kernels
     const int c = 4 * q;
     const bool affine = p.relu_in && p.scale != nullptr;
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -431,7 +433,7 @@ static int launch_dw1(Dw1Params& p, int B, cudaStream_t st) {
     }
     long grid = cdiv(p.n_groups, G);
     if (grid > (long)kNumSMs * occ) grid = (long)kNumSMs * occ;
-    dwconv1d_kernel<KW><<<(unsigned)grid, 256, smem, st>>>(p);
+    launch_pdl(dwconv1d_kernel<KW>, dim3((unsigned)grid), dim3(256), smem, st, p);
     count_launch();
     return check_launch("dwconv1d_kernel");
 }
@@ -473,7 +475,9 @@ __global__ void __launch_bounds__(256, 1) dwconv1d_bwd_fused_kernel(Dw1Params p,
         const int c = idx % p.C, j = idx / p.C, jr = j - joff;
         reinterpret_cast<float*>(Ws4)[(size_t)j * p.C + c] = (jr >= 0 && jr < p.kw) ? __ldg(p.Wt + (long)c * p.kw + (p.kw - 1 - jr)) : 0.f;
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();
     const int c = 4 * q;
     const bool affine = p.mask && p.scale != nullptr;
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -555,7 +559,7 @@ static int launch_dw1_bwd_fused(Dw1Params& p, float* dWt, float* dbias, int B, c
     if (smem > 200 * 1024) return NPF_ENOTSUP;
     long grid = cdiv(p.n_groups, G);
     if (grid > (long)kNumSMs) grid = kNumSMs;
-    dwconv1d_bwd_fused_kernel<KW><<<(unsigned)grid, 256, smem, st>>>(p, dWt, dbias);
+    launch_pdl(dwconv1d_bwd_fused_kernel<KW>, dim3((unsigned)grid), dim3(256), smem, st, p, dWt, dbias);
     count_launch();
     return check_launch("dwconv1d_bwd_fused_kernel");
 }

@@ -304,10 +304,6 @@ constexpr int kWsThreads = (kWsEpiWarp0 + kWsEpiWarps) * 32;     // 544
 constexpr int kWsPre = 16;                                       // float4 per producer thread per tile
 constexpr int kWsScratchLd = 20;                                 // 16 columns + 4 pad (conflict-free STS.128)
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <int NSPLIT>
 __device__ __forceinline__ void cvt_store(const float4& vin, uint8_t* hi, uint8_t* lo, uint32_t off, int relu) {
     float4 v = vin;
@@ -349,6 +345,16 @@ __device__ __forceinline__ void ws_load_rows(float4 (&pre)[kWsPre], const float*
     }
 }
 
+// L2 prefetch of a 128-row x 512-byte tile (512 lines of 128 bytes) by `nthreads` threads: the tile AFTER the one whose loads
+// were just issued.  DRAM latency under load (~4 us) then overlaps two tile periods and the register-staged loads of the next
+// iteration hit L2, without spending registers or shared memory on a deeper ring.
+__device__ __forceinline__ void prefetch_tile_l2(const float* __restrict__ base, long ld, long row0, int rows_valid, int t, int nthreads) {
+    for (int l = t; l < 512; l += nthreads) {
+        const int r = l >> 2;
+        if (r < rows_valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (row0 + r) * ld + (l & 3) * 32));
+    }
+}
+
 template <int NSPLIT, bool HAS_U, bool HAS_MASK, bool SW>
 __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -387,10 +393,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
     const uint32_t psoff = SW ? (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 16) * 128u + (uint32_t)(lane & 1) * 8u
                               : (uint32_t)pkc * 2048u + (uint32_t)pr * 16u + (uint32_t)phalf * 8u;
     const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
-    if (warp < kWsProdWarps && tile < p.n_tiles) {
-        if (SW) ws_load_rows(pre, pg + (long)tile * 128 * p.lda, p.lda, warp * 16, min(128, p.M - tile * 128));
-        else ws_load_tile(pre, pg + (long)tile * 128 * p.lda, p.lda, pr, min(128, p.M - tile * 128));
-    }
+    pdl_trigger();      // the next kernel may start its own parameter-only prologue as SMs free up
 
     // weights [128 x 128] fp32 row-major, staged once per CTA by threads 0..511 (8 float4 each) in the layout of the A tiles
     if (tid < 512) {
@@ -422,9 +425,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    // everything above touched parameters only (weights, bias); activations of the preceding kernel from here on
+    pdl_wait();
 
     if (warp < kWsProdWarps) {
         // ------------------------------------------------------------------ producers
+        if (tile < p.n_tiles) {
+            if (SW) ws_load_rows(pre, pg + (long)tile * 128 * p.lda, p.lda, warp * 16, min(128, p.M - tile * 128));
+            else ws_load_tile(pre, pg + (long)tile * 128 * p.lda, p.lda, pr, min(128, p.M - tile * 128));
+            const int nn = tile + gridDim.x;
+            if (nn < p.n_tiles) prefetch_tile_l2(p.A, p.lda, (long)nn * 128, min(128, p.M - nn * 128), tid, kWsProdWarps * 32);
+        }
         for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
             mbar_wait(&bar_empty[s], ((it >> 1) & 1) ^ 1);
@@ -439,6 +450,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
             if (next < p.n_tiles) {
                 if (SW) ws_load_rows(pre, pg + (long)next * 128 * p.lda, p.lda, warp * 16, min(128, p.M - next * 128));
                 else ws_load_tile(pre, pg + (long)next * 128 * p.lda, p.lda, pr, min(128, p.M - next * 128));
+                const int nn = next + gridDim.x;
+                if (nn < p.n_tiles) prefetch_tile_l2(p.A, p.lda, (long)nn * 128, min(128, p.M - nn * 128), tid, kWsProdWarps * 32);
             }
         }
     } else if (warp == kWsProdWarps) {
@@ -626,10 +639,8 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
     const uint32_t psoff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
     float4 py[8], px[8];
     int tile = blockIdx.x;
+    pdl_trigger();
     if (warp < kFbProdWarps) {
-        const int rv = min(128, p.M - tile * 128);
-        fb_load_rows(py, p.dY + ((long)tile * 128 + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
-        fb_load_rows(px, p.X + ((long)tile * 128 + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
         float4 wv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -645,9 +656,20 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();         // weights only so far; dY / X of the preceding kernels (and our dX / dW / db writes) from here on
 
     if (warp < kFbProdWarps) {
         // ------------------------------------------------------------------ producers
+        {
+            const int rv = min(128, p.M - tile * 128);
+            fb_load_rows(py, p.dY + ((long)tile * 128 + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
+            fb_load_rows(px, p.X + ((long)tile * 128 + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
+            const int nn = tile + gridDim.x;
+            if (nn < p.n_tiles) {
+                prefetch_tile_l2(p.dY, p.lddy, (long)nn * 128, min(128, p.M - nn * 128), tid, kFbProdWarps * 32);
+                prefetch_tile_l2(p.X, p.ldx, (long)nn * 128, min(128, p.M - nn * 128), tid, kFbProdWarps * 32);
+            }
+        }
         float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
 #pragma unroll
@@ -669,6 +691,11 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
                 const int rv = min(128, p.M - next * 128);
                 fb_load_rows(py, p.dY + ((long)next * 128 + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
                 fb_load_rows(px, p.X + ((long)next * 128 + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
+                const int nn = next + gridDim.x;
+                if (nn < p.n_tiles) {
+                    prefetch_tile_l2(p.dY, p.lddy, (long)nn * 128, min(128, p.M - nn * 128), tid, kFbProdWarps * 32);
+                    prefetch_tile_l2(p.X, p.ldx, (long)nn * 128, min(128, p.M - nn * 128), tid, kFbProdWarps * 32);
+                }
             }
         }
         if (p.db) {                                                  // bias gradient: warps -> smem -> one global atomic per column
@@ -1046,13 +1073,13 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
             ws_attr = true;
         }
         if (sw) {
-            if (p.u) linear_ws_kernel<NSPLIT, true, false, true><<<grid, kWsThreads, ws_smem, st>>>(p);
-            else if (p.mask) linear_ws_kernel<NSPLIT, false, true, true><<<grid, kWsThreads, ws_smem, st>>>(p);
-            else linear_ws_kernel<NSPLIT, false, false, true><<<grid, kWsThreads, ws_smem, st>>>(p);
+            if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, true>, grid, kWsThreads, ws_smem, st, p);
+            else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, true>, grid, kWsThreads, ws_smem, st, p);
+            else launch_pdl(linear_ws_kernel<NSPLIT, false, false, true>, grid, kWsThreads, ws_smem, st, p);
         } else {
-            if (p.u) linear_ws_kernel<NSPLIT, true, false, false><<<grid, kWsThreads, ws_smem, st>>>(p);
-            else if (p.mask) linear_ws_kernel<NSPLIT, false, true, false><<<grid, kWsThreads, ws_smem, st>>>(p);
-            else linear_ws_kernel<NSPLIT, false, false, false><<<grid, kWsThreads, ws_smem, st>>>(p);
+            if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, false>, grid, kWsThreads, ws_smem, st, p);
+            else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, false>, grid, kWsThreads, ws_smem, st, p);
+            else launch_pdl(linear_ws_kernel<NSPLIT, false, false, false>, grid, kWsThreads, ws_smem, st, p);
         }
         count_launch();
         return check_launch("linear_ws_kernel");
@@ -1112,8 +1139,8 @@ static int launch_fused(TcFusedParams& p, cudaStream_t st) {
     }
     p.n_tiles = (int)cdiv(p.M, 128);
     const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
-    if (p.use_mask) linear_bwd_fused_kernel<NSPLIT, true><<<grid, kFbThreads, smem, st>>>(p);
-    else linear_bwd_fused_kernel<NSPLIT, false><<<grid, kFbThreads, smem, st>>>(p);
+    if (p.use_mask) launch_pdl(linear_bwd_fused_kernel<NSPLIT, true>, grid, kFbThreads, smem, st, p);
+    else launch_pdl(linear_bwd_fused_kernel<NSPLIT, false>, grid, kFbThreads, smem, st, p);
     count_launch();
     return check_launch("linear_bwd_fused_kernel");
 }

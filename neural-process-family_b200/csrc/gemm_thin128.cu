@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(kT128Threads) thin_in128_fwd_kernel(Thin128Par
         w[r] = make_float4(__ldg(p.W + (long)(4 * lane + 0) * p.ldw + r), __ldg(p.W + (long)(4 * lane + 1) * p.ldw + r),
                            __ldg(p.W + (long)(4 * lane + 2) * p.ldw + r), __ldg(p.W + (long)(4 * lane + 3) * p.ldw + r));
     const float4 bias = p.b ? __ldg(reinterpret_cast<const float4*>(p.b) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_trigger();
+    pdl_wait();          // weights / bias above are parameters; x is a preceding kernel's output
     for (long m0 = warp * kT128Rows; m0 < p.M; m0 += nwarps * kT128Rows) {
         float x[kT128Rows][R];
 #pragma unroll
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(kT128Threads) thin_in128_bwd_kernel(Thin128Par
             w[r] = make_float4(__ldg(p.W + (long)(4 * lane + 0) * p.ldw + r), __ldg(p.W + (long)(4 * lane + 1) * p.ldw + r),
                                __ldg(p.W + (long)(4 * lane + 2) * p.ldw + r), __ldg(p.W + (long)(4 * lane + 3) * p.ldw + r));
     }
+    pdl_trigger();
+    pdl_wait();
     for (long m0 = warp * kT128Rows; m0 < p.M; m0 += nwarps * kT128Rows) {
         float4 dy[kT128Rows];
         float x[kT128Rows][R];
@@ -142,6 +146,8 @@ __global__ void __launch_bounds__(kT128Threads) thin_out128_fwd_kernel(Thin128Pa
 #pragma unroll
     for (int j = 0; j < J; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(p.W + (long)j * p.ldw) + lane);
     const float bias = (p.b && lane < J) ? __ldg(p.b + lane) : 0.f;
+    pdl_trigger();
+    pdl_wait();
     for (long m0 = warp * kT128Rows; m0 < p.M; m0 += nwarps * kT128Rows) {
         float4 x[kT128Rows];
 #pragma unroll
@@ -181,6 +187,8 @@ __global__ void __launch_bounds__(kT128Threads) thin_out128_bwd_kernel(Thin128Pa
         aw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         ab[j] = 0.f;
     }
+    pdl_trigger();
+    pdl_wait();
     for (long m0 = warp * kT128Rows; m0 < p.M; m0 += nwarps * kT128Rows) {
         float4 x[kT128Rows];
         float dy[kT128Rows][J];
@@ -228,14 +236,14 @@ static inline unsigned t128_grid(long M, int per_sm) {
 }
 #define NPF_T128_SWITCH(n, KERNEL, grid)                                                  \
     switch (n) {                                                                            \
-        case 1: KERNEL<1><<<grid, kT128Threads, 0, st>>>(p); break;                         \
-        case 2: KERNEL<2><<<grid, kT128Threads, 0, st>>>(p); break;                         \
-        case 3: KERNEL<3><<<grid, kT128Threads, 0, st>>>(p); break;                         \
-        case 4: KERNEL<4><<<grid, kT128Threads, 0, st>>>(p); break;                         \
-        case 5: KERNEL<5><<<grid, kT128Threads, 0, st>>>(p); break;                         \
-        case 6: KERNEL<6><<<grid, kT128Threads, 0, st>>>(p); break;                         \
-        case 7: KERNEL<7><<<grid, kT128Threads, 0, st>>>(p); break;                         \
-        case 8: KERNEL<8><<<grid, kT128Threads, 0, st>>>(p); break;                         \
+        case 1: launch_pdl(KERNEL<1>, dim3(grid), dim3(kT128Threads), 0, st, p); break;                         \
+        case 2: launch_pdl(KERNEL<2>, dim3(grid), dim3(kT128Threads), 0, st, p); break;                         \
+        case 3: launch_pdl(KERNEL<3>, dim3(grid), dim3(kT128Threads), 0, st, p); break;                         \
+        case 4: launch_pdl(KERNEL<4>, dim3(grid), dim3(kT128Threads), 0, st, p); break;                         \
+        case 5: launch_pdl(KERNEL<5>, dim3(grid), dim3(kT128Threads), 0, st, p); break;                         \
+        case 6: launch_pdl(KERNEL<6>, dim3(grid), dim3(kT128Threads), 0, st, p); break;                         \
+        case 7: launch_pdl(KERNEL<7>, dim3(grid), dim3(kT128Threads), 0, st, p); break;                         \
+        case 8: launch_pdl(KERNEL<8>, dim3(grid), dim3(kT128Threads), 0, st, p); break;                         \
         default: return NPF_ENOTSUP;                                                        \
     }
 

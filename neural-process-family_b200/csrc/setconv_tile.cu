@@ -11,7 +11,7 @@
 //   mode 0: feat = sum_k softmax_k(a) V_k, dens, (max logit, sum exp)            (forward)
 //   mode 1: d theta: T - G*A1 + ddens*A2 with max-shifted logits (see setconv.cu)
 //   dV    : dV[k] = sum_q w_qk dF_q                                               (gather, no atomics)
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace npf {
 
@@ -45,6 +45,15 @@ __device__ __forceinline__ void window_t(const float* __restrict__ keys, int K, 
     hi = fminf(fmaxf(hi, 0.f), (float)(K - 1));
     lo_o = min((int)lo, n0);
     hi_o = max((int)hi, n0);
+}
+
+// Pull a contiguous range into L2 ahead of use (one prefetch per 128-byte line, spread over the CTA): the DRAM latency of
+// the task's value rows then overlaps the sort / window phase instead of stalling every batch of the group pass.
+__device__ __forceinline__ void prefetch_l2_range(const void* base, size_t bytes, int part, int n_parts) {
+    const char* p = reinterpret_cast<const char*>(base);
+    const size_t lines = (bytes + 127) >> 7;
+    const size_t per = (lines + n_parts - 1) / n_parts, l0 = per * part, l1 = min(lines, l0 + per);
+    for (size_t l = l0 + threadIdx.x; l < l1; l += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (l << 7)));
 }
 
 struct TileSmem {
@@ -110,6 +119,11 @@ __global__ void __launch_bounds__(256, 3) setconv_grp_kernel(const float* __rest
     const float inv_sigma = 1.f / sigma;
     const float* kb = keys + (long)b * key_bs;
     const float* vb = values + (long)b * K * C;
+    prefetch_l2_range(vb, sizeof(float) * (size_t)K * C, blockIdx.y, gridDim.y);
+    if (MODE == 1) {
+        prefetch_l2_range(dfeat + (long)b * Q * C, sizeof(float) * (size_t)Q * C, blockIdx.y, gridDim.y);
+        prefetch_l2_range(feat_i + (long)b * Q * C, sizeof(float) * (size_t)Q * C, blockIdx.y, gridDim.y);
+    }
     sort_queries(t, queries + (long)b * qry_bs, Q, scratch);
 
     // per-query window (one thread per query).  Forward: the max logit is the one of the nearest grid row (the window code's
@@ -241,6 +255,7 @@ __global__ void __launch_bounds__(256, 3) setconv_grp_dv_kernel(const float* __r
     const float sigma = 1e-5f + softplus_f(__ldg(theta));
     const float inv_sigma = 1.f / sigma;
     const float* kb = keys + (long)b * key_bs;
+    prefetch_l2_range(dfeat + (long)b * Q * C, sizeof(float) * (size_t)Q * C, blockIdx.y, gridDim.y);
     sort_queries(t, queries + (long)b * qry_bs, Q, scratch);
     for (int i = threadIdx.x; i < Q; i += blockDim.x) {
         int lo, hi;
@@ -302,6 +317,313 @@ __global__ void __launch_bounds__(256, 3) setconv_grp_dv_kernel(const float* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Task-resident variant (C == 128, K * 512 B <= ~190 KB): ONE persistent CTA per SM walks the tasks; the task's whole value
+// matrix V[K,128] is brought into shared memory by the TMA (cp.async.bulk, one mbarrier per 32-row chunk) while the CTA sorts
+// the queries, so HBM sees every byte exactly once, fully coalesced, and the group pass reads rows with LDS.128 instead of
+// waiting on batches of global loads.  A warp owns 8 position-adjacent queries; the lanes compute the 8 x 32 weights of a
+// 32-row slab once (one row per lane), park them in the warp's shared-memory slab and every row step is then
+// 2 broadcast LDS.128 (weights) + 1 LDS.128 (values) + 32 FFMA.  Warps start on a slab as soon as its chunk has landed.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kTaskThreads = 512;
+constexpr int kTaskWarps = kTaskThreads / 32;
+constexpr int kChunkRows = 32;
+constexpr int kMaxChunks = 16;          // K <= 512
+
+// rank-counting sort with every thread busy: `parts` threads share one query and split the comparison range
+__device__ __forceinline__ void sort_queries_wide(const TileSmem& t, const float* __restrict__ qb, int Q, float* scratch, int* rank_acc) {
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) { scratch[i] = __ldg(qb + i); rank_acc[i] = 0; }
+    __syncthreads();
+    const int parts = (int)blockDim.x / Q >= 4 ? 4 : ((int)blockDim.x / Q >= 2 ? 2 : 1);
+    const int span = (Q + parts - 1) / parts;
+    for (int w = threadIdx.x; w < Q * parts; w += blockDim.x) {
+        const int i = w % Q, part = w / Q;
+        const float x = scratch[i];
+        const int j0 = part * span, j1 = min(Q, j0 + span);
+        int r0 = 0, r1 = 0;
+        int j = j0;
+        for (; j + 2 <= j1; j += 2) {
+            const float y0 = scratch[j], y1 = scratch[j + 1];
+            r0 += (y0 < x) || (y0 == x && j < i);
+            r1 += (y1 < x) || (y1 == x && j + 1 < i);
+        }
+        if (j < j1) { const float y = scratch[j]; r0 += (y < x) || (y == x && j < i); }
+        if (parts == 1) rank_acc[i] = r0 + r1; else atomicAdd(&rank_acc[i], r0 + r1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+        const int rank = rank_acc[i];
+        t.xs[rank] = scratch[i];
+        t.ord[rank] = i;
+    }
+    __syncthreads();
+}
+
+// per-query constants of the task, packed for one broadcast LDS.128: (position, max logit, 1 / sum, window lo | hi << 16)
+__device__ __forceinline__ float4 pack_qc(float x, float m, float invs, int lo, int hi) { return make_float4(x, m, invs, __int_as_float(lo | (hi << 16))); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kTaskThreads, 1) setconv_task_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+                                                                       long qry_bs, const float* __restrict__ values, const float* __restrict__ theta,
+                                                                       float* __restrict__ feat_o, float* __restrict__ dens_o, float* __restrict__ mstat_o,
+                                                                       const float* __restrict__ feat_i, const float* __restrict__ mstat_i,
+                                                                       const float* __restrict__ dfeat, const float* __restrict__ ddens,
+                                                                       float* __restrict__ dtheta, int B, int K, int Q) {
+    constexpr int C = 128;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bars[kMaxChunks];
+    __shared__ float part[kTaskWarps];
+    const int n_chunks = (K + kChunkRows - 1) / kChunkRows;
+    float* Vs = smem;                                              // [n_chunks * 32][128]
+    float* wbuf_all = Vs + (size_t)n_chunks * kChunkRows * C;      // [16 warps][32 rows][8 queries]
+    float4* qc = reinterpret_cast<float4*>(wbuf_all + kTaskWarps * kChunkRows * kGroup);   // [Q]
+    const TileSmem t = carve(reinterpret_cast<float*>(qc + Q), Q);
+    float* scratch = t.invs + Q;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wbuf = wbuf_all + warp * (kChunkRows * kGroup);
+    const float th = __ldg(theta);
+    const float sigma = 1e-5f + softplus_f(th);
+    const float inv_sigma = 1.f / sigma;
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < n_chunks; ++c) mbar_init(&bars[c], 1);
+    }
+    __syncthreads();
+    float warp_contrib = 0.f;
+    uint32_t parity = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, parity ^= 1) {
+        const float* kb = keys + (long)b * key_bs;
+        const float* vb = values + (long)b * K * C;
+        if (threadIdx.x == 0) {
+            fence_async_smem();                    // the previous task's generic reads of Vs are ordered before the new async writes
+            for (int c = 0; c < n_chunks; ++c) {
+                const int rows = min(kChunkRows, K - c * kChunkRows);
+                const uint32_t bytes = (uint32_t)rows * C * sizeof(float);
+                mbar_expect_tx(&bars[c], bytes);
+                bulk_g2s(Vs + (size_t)c * kChunkRows * C, vb + (size_t)c * kChunkRows * C, bytes, &bars[c]);
+            }
+        }
+        sort_queries_wide(t, queries + (long)b * qry_bs, Q, scratch, t.lo);
+        const float x0 = __ldg(kb), dx = (__ldg(kb + K - 1) - x0) / (float)(K - 1);
+        for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+            const float xq = t.xs[i];
+            int lo, hi;
+            window_t(kb, K, xq, sigma, lo, hi);
+            float m, invs = 0.f;
+            if (MODE == 0) {
+                int n0 = (dx > 0.f) ? (int)rintf(fminf(fmaxf((xq - x0) / dx, 0.f), (float)(K - 1))) : lo;
+                n0 = min(max(n0, lo), hi);
+                m = logit_t(xq, __ldg(kb + n0), inv_sigma);
+                if (n0 > lo) m = fmaxf(m, logit_t(xq, __ldg(kb + n0 - 1), inv_sigma));
+                if (n0 < hi) m = fmaxf(m, logit_t(xq, __ldg(kb + n0 + 1), inv_sigma));
+                if (!(dx > 0.f)) for (int k = lo; k <= hi; ++k) m = fmaxf(m, logit_t(xq, __ldg(kb + k), inv_sigma));
+            } else {
+                const long oq = (long)b * Q + t.ord[i];
+                m = __ldg(mstat_i + oq * 2);
+                invs = 1.f / __ldg(mstat_i + oq * 2 + 1);
+            }
+            qc[i] = pack_qc(xq, m, invs, lo, hi);
+        }
+        __syncthreads();
+
+        const int c4 = lane * 4;
+        const int n_groups = (Q + kGroup - 1) / kGroup;
+        for (int grp = warp; grp < n_groups; grp += kTaskWarps) {
+            const int t0 = grp * kGroup;
+            const int nt = min(kGroup, Q - t0);
+            // the group's 8 query records in registers (broadcast 16-byte reads), union window
+            float qx[kGroup], qm[kGroup], qi[kGroup];
+            int qlo[kGroup], qhi[kGroup];
+            int glo = K, ghi = -1;
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                const float4 r = qc[min(t0 + j, Q - 1)];
+                const int lh = __float_as_int(r.w);
+                qx[j] = r.x; qm[j] = r.y; qi[j] = r.z;
+                qlo[j] = (j < nt) ? (lh & 0xFFFF) : K;              // empty window for the padding queries of the last group
+                qhi[j] = (j < nt) ? (lh >> 16) : -1;
+                glo = min(glo, qlo[j]); ghi = max(ghi, qhi[j]);
+            }
+            float4 acc[kGroup];
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float a1[kGroup], a2[kGroup];
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+            for (int base = glo; base <= ghi; base += 32) {
+                const int row = base + lane;
+                const float xk = __ldg(kb + min(row, K - 1));
+                float w[kGroup];
+#pragma unroll
+                for (int j = 0; j < kGroup; ++j) {                   // branch-free: 8 independent exp chains per lane
+                    const bool in = row >= qlo[j] && row <= qhi[j];
+                    const float a = logit_t(qx[j], xk, inv_sigma);
+                    const float e = expf(a - qm[j]);
+                    if (MODE == 0) {
+                        w[j] = in ? e : 0.f;
+                        a1[j] += w[j];
+                    } else {
+                        w[j] = in ? e * qi[j] * (a - qm[j]) : 0.f;
+                        a1[j] += w[j];
+                        a2[j] += in ? expf(a) * a : 0.f;
+                    }
+                }
+                __syncwarp();                                       // previous slab fully consumed
+                *reinterpret_cast<float4*>(wbuf + lane * kGroup) = make_float4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<float4*>(wbuf + lane * kGroup + 4) = make_float4(w[4], w[5], w[6], w[7]);
+                __syncwarp();
+                const int cnt = min(32, ghi - base + 1);
+                // the rows base .. base+cnt-1 live in at most two chunks
+                mbar_wait(&bars[base / kChunkRows], parity);
+                mbar_wait(&bars[(base + cnt - 1) / kChunkRows], parity);
+                const float* vrow = Vs + (size_t)base * C + c4;
+#pragma unroll 4
+                for (int r = 0; r < cnt; ++r) {
+                    const float4 wa = *reinterpret_cast<const float4*>(wbuf + r * kGroup);
+                    const float4 wb = *reinterpret_cast<const float4*>(wbuf + r * kGroup + 4);
+                    const float4 v = *reinterpret_cast<const float4*>(vrow + (size_t)r * C);
+                    const float ws[kGroup] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int j = 0; j < kGroup; ++j) {
+                        acc[j].x = fmaf(ws[j], v.x, acc[j].x); acc[j].y = fmaf(ws[j], v.y, acc[j].y);
+                        acc[j].z = fmaf(ws[j], v.z, acc[j].z); acc[j].w = fmaf(ws[j], v.w, acc[j].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                if (j >= nt) continue;
+                const long oq = (long)b * Q + t.ord[t0 + j];
+                if (MODE == 0) {
+                    const float ssum = warp_sum(a1[j]), inv = 1.f / ssum;
+                    *reinterpret_cast<float4*>(feat_o + oq * C + c4) = make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
+                    if (lane == 0) {
+                        dens_o[oq] = expf(qm[j]) * ssum;
+                        mstat_o[oq * 2] = qm[j]; mstat_o[oq * 2 + 1] = ssum;
+                    }
+                } else {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(dfeat + oq * C + c4));
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(feat_i + oq * C + c4));
+                    float T = g.x * acc[j].x + g.y * acc[j].y + g.z * acc[j].z + g.w * acc[j].w;
+                    float G = g.x * f.x + g.y * f.y + g.z * f.z + g.w * f.w;
+                    T = warp_sum(T); G = warp_sum(G);
+                    const float A1 = warp_sum(a1[j]), A2 = warp_sum(a2[j]);
+                    warp_contrib += T - G * A1 + __ldg(ddens + oq) * A2;
+                }
+            }
+        }
+        // every chunk must have landed before its barrier is re-armed and its rows overwritten (the last chunks may lie outside all windows)
+        if (warp == 0) for (int c = lane; c < n_chunks; c += 32) mbar_wait(&bars[c], parity);
+        __syncthreads();                                            // Vs, the query arrays and the slabs are reused by the next task
+    }
+    if (MODE == 1) {
+        if (lane == 0) part[warp] = warp_contrib;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < kTaskWarps; ++i) tot += part[i];
+            atomicAdd(dtheta, tot * (-2.f / sigma) * sigmoid_f(th));
+        }
+    }
+}
+
+// dV[b,k,:] = sum_q w_qk dF[b,q,:] with the task's dF[Q,128] resident in shared memory (one bulk copy).
+__global__ void __launch_bounds__(kTaskThreads, 1) setconv_task_dv_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+                                                                          long qry_bs, const float* __restrict__ theta, const float* __restrict__ mstat,
+                                                                          const float* __restrict__ dfeat, float* __restrict__ dvalues, int B, int K, int Q) {
+    constexpr int C = 128;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    float* Fs = smem;                                               // [Q][128]
+    float* wbuf_all = Fs + (size_t)Q * C;                           // [16 warps][32 queries][8 rows]
+    float4* qc = reinterpret_cast<float4*>(wbuf_all + kTaskWarps * kChunkRows * kGroup);
+    const TileSmem t = carve(reinterpret_cast<float*>(qc + Q), Q);
+    float* scratch = t.invs + Q;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wbuf = wbuf_all + warp * (kChunkRows * kGroup);
+    const float sigma = 1e-5f + softplus_f(__ldg(theta));
+    const float inv_sigma = 1.f / sigma;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, parity ^= 1) {
+        const float* kb = keys + (long)b * key_bs;
+        if (threadIdx.x == 0) {
+            fence_async_smem();
+            const uint32_t bytes = (uint32_t)Q * C * sizeof(float);
+            mbar_expect_tx(&bar, bytes);
+            bulk_g2s(Fs, dfeat + (long)b * Q * C, bytes, &bar);
+        }
+        sort_queries_wide(t, queries + (long)b * qry_bs, Q, scratch, t.lo);
+        for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+            int lo, hi;
+            window_t(kb, K, t.xs[i], sigma, lo, hi);
+            t.lo[i] = lo; t.hi[i] = hi;
+            const long oq = (long)b * Q + t.ord[i];
+            qc[i] = pack_qc(t.xs[i], __ldg(mstat + oq * 2), 1.f / __ldg(mstat + oq * 2 + 1), lo, hi);
+        }
+        __syncthreads();
+        mbar_wait(&bar, parity);
+        const int c4 = lane * 4;
+        const int n_rgroups = (K + kGroup - 1) / kGroup;
+        for (int rg = warp; rg < n_rgroups; rg += kTaskWarps) {
+            const int k0 = rg * kGroup, nr = min(kGroup, K - k0);
+            int ta = 0, tb = Q;
+            { int l = 0, h = Q; while (l < h) { const int mid = (l + h) >> 1; if (t.hi[mid] >= k0) h = mid; else l = mid + 1; } ta = l; }
+            { int l = ta, h = Q; while (l < h) { const int mid = (l + h) >> 1; if (t.lo[mid] > k0 + nr - 1) h = mid; else l = mid + 1; } tb = l; }
+            float xk[kGroup];
+#pragma unroll
+            for (int r = 0; r < kGroup; ++r) xk[r] = __ldg(kb + min(k0 + r, K - 1));
+            float4 acc[kGroup];
+#pragma unroll
+            for (int r = 0; r < kGroup; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int base = ta; base < tb; base += 32) {
+                const int ti = base + lane;
+                const float4 rec = qc[min(ti, Q - 1)];
+                const int lh = __float_as_int(rec.w);
+                const int lo = (ti < tb) ? (lh & 0xFFFF) : K, hi = (ti < tb) ? (lh >> 16) : -1;
+                float w[kGroup];
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r) {
+                    const bool in = r < nr && k0 + r >= lo && k0 + r <= hi;
+                    const float e = expf(logit_t(rec.x, xk[r], inv_sigma) - rec.y) * rec.z;
+                    w[r] = in ? e : 0.f;
+                }
+                __syncwarp();
+                *reinterpret_cast<float4*>(wbuf + lane * kGroup) = make_float4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<float4*>(wbuf + lane * kGroup + 4) = make_float4(w[4], w[5], w[6], w[7]);
+                __syncwarp();
+                const int cnt = min(32, tb - base);
+                const int my_ord = t.ord[min(ti, Q - 1)];
+#pragma unroll 4
+                for (int q = 0; q < cnt; ++q) {
+                    const float4 wa = *reinterpret_cast<const float4*>(wbuf + q * kGroup);
+                    const float4 wb = *reinterpret_cast<const float4*>(wbuf + q * kGroup + 4);
+                    const int o = __shfl_sync(0xffffffffu, my_ord, q);
+                    const float4 g = *reinterpret_cast<const float4*>(Fs + (size_t)o * C + c4);
+                    const float ws[kGroup] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int r = 0; r < kGroup; ++r) {
+                        acc[r].x = fmaf(ws[r], g.x, acc[r].x); acc[r].y = fmaf(ws[r], g.y, acc[r].y);
+                        acc[r].z = fmaf(ws[r], g.z, acc[r].z); acc[r].w = fmaf(ws[r], g.w, acc[r].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kGroup; ++r)
+                if (r < nr) *reinterpret_cast<float4*>(dvalues + ((long)b * K + k0 + r) * C + c4) = acc[r];
+        }
+        __syncthreads();
+    }
+}
+
+static size_t task_smem_fwd(int K, int Q) {
+    return sizeof(float) * ((size_t)((K + kChunkRows - 1) / kChunkRows) * kChunkRows * 128 + (size_t)kTaskWarps * kChunkRows * kGroup + 11 * (size_t)Q);
+}
+static size_t task_smem_dv(int Q) { return sizeof(float) * ((size_t)Q * 128 + (size_t)kTaskWarps * kChunkRows * kGroup + 11 * (size_t)Q); }
+constexpr size_t kTaskSmemMax = 200 * 1024;
+static bool task_ok(int K, int Q, int C) { return C == 128 && K <= kMaxChunks * kChunkRows && K < 32768 && task_smem_fwd(K, Q) <= kTaskSmemMax; }
+
 static bool tile_ok(int K, int Q, int C, const void* values) {
     return C % 4 == 0 && C >= 8 && C <= 128 && Q >= 1 && Q <= kMaxQ && K >= 3 && (reinterpret_cast<uintptr_t>(values) & 15) == 0;
 }
@@ -319,6 +641,14 @@ int setconv_tile_fwd(const float* keys, long key_bs, const float* queries, long 
                      const float* theta, float* feat, float* dens, float* mstat, int B, int K, int Q, int C,
                      cudaStream_t st) {
     if (!tile_ok(K, Q, C, values) || (reinterpret_cast<uintptr_t>(feat) & 15)) return NPF_ENOTSUP;
+    if (task_ok(K, Q, C)) {
+        static bool tattr = false;
+        if (!tattr) { cudaFuncSetAttribute(setconv_task_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaskSmemMax); tattr = true; }
+        setconv_task_kernel<0><<<B < kNumSMs ? B : kNumSMs, kTaskThreads, task_smem_fwd(K, Q), st>>>(keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat,
+                                                                                                     nullptr, nullptr, nullptr, nullptr, nullptr, B, K, Q);
+        count_launch();
+        return check_launch("setconv_task_kernel<fwd>");
+    }
     const size_t smem = tile_smem(Q);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(setconv_grp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
@@ -334,6 +664,30 @@ int setconv_tile_bwd(const float* keys, long key_bs, const float* queries, long 
     if (!tile_ok(K, Q, C, values) || (reinterpret_cast<uintptr_t>(dfeat) & 15) || (reinterpret_cast<uintptr_t>(feat) & 15) ||
         (dvalues && (reinterpret_cast<uintptr_t>(dvalues) & 15)))
         return NPF_ENOTSUP;
+    if (task_ok(K, Q, C)) {
+        static bool tattr = false;
+        if (!tattr) {
+            cudaFuncSetAttribute(setconv_task_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaskSmemMax);
+            cudaFuncSetAttribute(setconv_task_dv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaskSmemMax);
+            tattr = true;
+        }
+        const int grid = B < kNumSMs ? B : kNumSMs;
+        setconv_task_kernel<1><<<grid, kTaskThreads, task_smem_fwd(K, Q), st>>>(keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat,
+                                                                              dfeat, ddens, dtheta, B, K, Q);
+        count_launch();
+        int rc = check_launch("setconv_task_kernel<dtheta>");
+        if (rc != NPF_OK || !dvalues) return rc;
+        if (task_smem_dv(Q) <= kTaskSmemMax) {
+            setconv_task_dv_kernel<<<grid, kTaskThreads, task_smem_dv(Q), st>>>(keys, key_bs, queries, qry_bs, theta, mstat, dfeat, dvalues, B, K, Q);
+            count_launch();
+            return check_launch("setconv_task_dv_kernel");
+        }
+        static bool dattr = false;
+        if (!dattr) { cudaFuncSetAttribute(setconv_grp_dv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); dattr = true; }
+        setconv_grp_dv_kernel<<<dim3(B, split_for(B, (K + kGroup - 1) / kGroup)), 256, tile_smem(Q), st>>>(keys, key_bs, queries, qry_bs, theta, mstat, dfeat, dvalues, K, Q, C);
+        count_launch();
+        return check_launch("setconv_grp_dv_kernel");
+    }
     const size_t smem = tile_smem(Q);
     static bool attr = false;
     if (!attr) {

@@ -102,6 +102,9 @@ def _setconv_ref(keys, queries, values, theta, W, b):
     (1, 192, 33, 64, 96, True, 5.0),      # sigma >> grid: dense fallback inside the window code
     (2, 640, 40, 128, 128, True, 0.012),  # extrapolation grid, queries outside [-1, 1]
     (1, 1, 5, 3, 8, False, 0.1),          # single key
+    (3, 296, 128, 128, 128, True, 0.012),  # task-resident path (V in shared memory via TMA bulk copies), bench geometry
+    (2, 296, 40, 128, 128, True, 0.2),    # task-resident, windows spanning several 32-row chunks
+    (149, 296, 9, 128, 128, True, 0.012),  # more tasks than SMs: the persistent CTA loop re-arms its barriers
 ])
 def test_setconv(ops, B, K, Q, C, N, regular, sigma):
     gen = torch.Generator().manual_seed(K * 7 + Q)
