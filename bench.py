@@ -87,12 +87,25 @@ def make_inputs(wl, B, seed, device="cpu", pin=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region: NVML in a background thread every
+    ~2 ms (the graph-replayed timed region lasts tens of milliseconds, far shorter than one `nvidia-smi -lms` period);
+    falls back to the nvidia-smi loop of the B200_PROFILING.md recipe if NVML cannot be loaded."""
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
@@ -103,14 +116,42 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & bit else "Not Active" for _, bit in names])
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append([s.strip() for s in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        elif self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml and nvidia-smi unavailable"], samples=0)
+        else:
+            self.proc.terminate()
         mhz = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
         reasons = set()
         for s in self.samples:
@@ -119,7 +160,7 @@ class ClockSampler:
                     reasons.add(name)
         mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
         return dict(sm_mhz=mhz[len(mhz) // 2] if mhz else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
-                    samples=len(mhz))
+                    samples=len(mhz), source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -191,11 +232,13 @@ def cpu_reference_timing(wl, steps, warmup, budget_s=25.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="convcnp1d_b256_c128_t128", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16", "bf16x3"],
+                    help="bf16x3 (default): tcgen05 linear layers with 3-term split-bf16 operands, fp32 accumulate -- meets the fp32 parity bar (1e-4); "
+                         "fp32: FFMA GEMMs; bf16: single-pass bf16 operands (1e-2 bar)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay of the step (npf_b200.GraphedStep)")
     ap.add_argument("--kernel-times", action="store_true", help="print the per-kernel CUDA-event breakdown to stderr")
@@ -308,9 +351,34 @@ def main():
         flush.fill_(0.0)
         eager_step(dev_inputs[i % n_sets])
     torch.cuda.synchronize()
-    ktimes = _cabi.collect_timing()  # name -> (total_ms, calls)
+    shaped = _cabi.collect_timing(by_shape=True)   # (name, bytes/call, flops/call) -> (total_ms, calls)
     _cabi.enable_timing(False)
     n_prof = min(args.steps, 10)
+    ktimes = {}
+    for (name, nb, fl), (ms, n) in shaped.items():
+        t = ktimes.get(name, (0.0, 0, 0, 0))
+        ktimes[name] = (t[0] + ms, t[1] + n, t[2] + nb * n, t[3] + fl * n)
+
+    # ---- the fp32 (FFMA) path of the same step, for reference next to the default precision -------------------------
+    fp32_path = None
+    if args.precision != "fp32":
+        npf_b200.set_precision("fp32")
+        g32 = None if args.no_graph else npf_b200.GraphedStep(model, crit, flat=flat)
+        step32 = (lambda inp: eager_step(inp)) if g32 is None else (lambda inp: g32(inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"]))
+        for i in range(3):
+            step32(dev_inputs[i % n_sets])
+        barrier()
+        n32 = max(5, args.steps // 3)
+        ev32 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n32)]
+        for i in range(n32):
+            flush.fill_(float(i))
+            ev32[i][0].record()
+            step32(dev_inputs[i % n_sets])
+            ev32[i][1].record()
+        barrier()
+        ms32 = sum(a.elapsed_time(b) for a, b in ev32) / n32
+        fp32_path = dict(ms_per_step=ms32, value=B * world / (ms32 * 1e-3), unit="tasks/s", steps=n32, note="same step with precision=fp32 (FFMA GEMMs), rank-local time")
+        npf_b200.set_precision(args.precision)
 
     tot = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -324,14 +392,18 @@ def main():
     tasks = B * world * args.steps
     value = tasks / (dev_ms * 1e-3)
     peaks = measured_peaks()
-    roof, roof_table = roofline(wl, ktimes, n_prof, B, peaks)
+    roof, roof_table = roofline(wl, ktimes, n_prof, B, peaks, shaped)
     line = dict(metric="tasks/sec (meta-batch fwd+bwd)", value=value, unit="tasks/s", n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype={"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (fp32-equivalent)"}[args.precision],
                 data="synthetic", config=cfg, clocks=clocks,
                 e2e=dict(value=tasks / (e2e_ms * 1e-3), unit="tasks/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
                 gpu_launches=launches, wall_ms_per_step=t_wall * 1e3 / args.steps, roofline=roof, kernel_rooflines=roof_table,
-                kernel_ms_per_step={k: round(v[0] / n_prof, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])})
+                kernel_ms_per_step={k: round(v[0] / n_prof, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
+                kernel_timing="per-call CUDA events on the launching stream in 10 instrumented eager steps after the timed region "
+                              "(the timed region itself replays a CUDA graph: no per-kernel events inside it)")
+    if fp32_path is not None:
+        line["fp32_path"] = fp32_path
     if not args.no_cpu_baseline:
         cb, _, _, _ = cpu_reference_timing(wl, 200, 2, budget_s=15.0)
         line["cpu_baseline"] = cb
@@ -343,30 +415,45 @@ def main():
         dist.destroy_process_group()
 
 
-def roofline(wl, ktimes, n_prof, B, peaks):
-    """Roofline of the dominant C-ABI entry point (largest share of the step) plus the same figures for every timed
-    entry point.  achieved = algorithmic bytes (every operand and result once, fp32) of all its
-    launches / their summed CUDA-event time, measured live on the launching stream; peak = MEASURED_PEAKS.json."""
+def roofline(wl, ktimes, n_prof, B, peaks, shaped):
+    """Roofline of the dominant kernel = the (C-ABI entry point, problem size) class with the largest share of the step,
+    plus aggregate figures for every timed entry point.  achieved = algorithmic bytes of ONE launch (SURVEY.md section 8d:
+    every operand and result once, fp32; table in npf_b200/_cabi.py) / the average duration of that launch, measured with
+    CUDA events on the launching stream; peak = MEASURED_PEAKS.json (sustained figures: the kernels run inside a long
+    step); traffic = DRAM bytes of the same launch from the committed `ncu --set full` capture (profiles/traffic_r1.json)."""
     if not ktimes:
         return None, None
     total = sum(v[0] for v in ktimes.values())
     table = {}
-    for name, (ms, calls, nbytes, flops) in ktimes.items():
-        if not nbytes:
-            continue
+
+    def entry(ms, calls, nbytes, flops):
         gbs = nbytes / (ms * 1e-3) / 1e9
         tfs = flops / (ms * 1e-3) / 1e12
         # the binding roof: whichever of HBM / tensor time is longer for this op mix
         t_hbm, t_tc = nbytes / (peaks["hbm_gbs"] * 1e9), flops / (peaks["bf16_tflops"] * 1e12)
         bound = "hbm" if t_hbm >= t_tc else "tensor"
-        table[name] = dict(bound=bound, achieved=gbs if bound == "hbm" else tfs, peak=peaks["hbm_gbs"] if bound == "hbm" else peaks["bf16_tflops"],
-                           unit="GB/s" if bound == "hbm" else "TFLOP/s", frac=(gbs / peaks["hbm_gbs"]) if bound == "hbm" else tfs / peaks["bf16_tflops"],
-                           launches_per_step=calls // n_prof, ms_per_step=ms / n_prof, share_of_step=ms / total, gbytes_per_s=gbs, tflops=tfs)
-    if not table:
-        return None, None
-    name = max(table, key=lambda k: table[k]["share_of_step"])
-    dom = dict(kernel=name, peak_source=peaks["source"], traffic=None, avg_launch_ms=table[name]["ms_per_step"] / max(table[name]["launches_per_step"], 1),
-               **{k: table[name][k] for k in ("bound", "achieved", "peak", "unit", "frac", "launches_per_step", "share_of_step")})
+        return dict(bound=bound, achieved=gbs if bound == "hbm" else tfs, peak=peaks["hbm_gbs"] if bound == "hbm" else peaks["bf16_tflops"],
+                    unit="GB/s" if bound == "hbm" else "TFLOP/s", frac=(gbs / peaks["hbm_gbs"]) if bound == "hbm" else tfs / peaks["bf16_tflops"],
+                    launches_per_step=calls // n_prof, ms_per_step=ms / n_prof, share_of_step=ms / total, gbytes_per_s=gbs, tflops=tfs)
+
+    for name, (ms, calls, nbytes, flops) in ktimes.items():
+        if nbytes:
+            table[name] = entry(ms, calls, nbytes, flops)
+    classes = {k: v for k, v in shaped.items() if k[1]}
+    if not classes:
+        return None, table or None
+    (name, nb, fl), (ms, calls) = max(classes.items(), key=lambda kv: kv[1][0])
+    e = entry(ms, calls, nb * calls, fl * calls)
+    traffic, cuda_kernel = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+            for rec in json.load(f)["kernels"]:
+                if rec["entry"] == name and rec["algorithmic_bytes"] == nb:
+                    traffic, cuda_kernel = rec["dram_bytes"], rec["cuda_kernel"]
+    except (OSError, KeyError, ValueError):
+        pass
+    dom = dict(kernel=name, cuda_kernel=cuda_kernel, algorithmic_bytes_per_launch=nb, flops_per_launch=fl, peak_source=peaks["source"], traffic=traffic,
+               avg_launch_ms=ms / calls, **{k: e[k] for k in ("bound", "achieved", "peak", "unit", "frac", "launches_per_step", "share_of_step")})
     return dom, table
 
 

@@ -142,6 +142,7 @@ struct TcLinParams {
     int M, KR, NO;
     int relu_in, relu_out, transposed_w, a_vec, w_vec, c_vec;
     int n_tiles;
+    int rows_per_cta;   // linear_ws_kernel: contiguous row range per CTA (multiple of 8)
 };
 
 // ------------------------------------------------------------------------------------------------ fwd / bwd-data
@@ -386,7 +387,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
     // producer geometry (also used for the weight staging below)
     const int l16 = tid & 15, pr = l16 & 7, phalf = l16 >> 3;
     float4 pre[kWsPre];
-    int tile = blockIdx.x;
+    // balanced contiguous row ranges: every CTA gets M / gridDim rows (8-row granularity) = whole 128-row tiles + one partial
+    // tile, instead of 128-row tiles dealt round-robin (768 tiles over 148 SMs would cost 6 rounds for 5.2 tiles of work)
+    const int r_begin = blockIdx.x * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);
+    const int n_local = r_end > r_begin ? (r_end - r_begin + 127) >> 7 : 0;
     const int pkc = (tid >> 4) & 15;
     // no-swizzle: thread -> (k chunk, row in group, half); SW128: thread -> (row block of the warp, float4 column = lane)
     const float* pg = SW ? p.A + (long)(warp * 16) * p.lda + lane * 4 : p.A + (long)pr * p.lda + pkc * 8 + phalf * 4;
@@ -430,13 +434,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
 
     if (warp < kWsProdWarps) {
         // ------------------------------------------------------------------ producers
-        if (tile < p.n_tiles) {
-            if (SW) ws_load_rows(pre, pg + (long)tile * 128 * p.lda, p.lda, warp * 16, min(128, p.M - tile * 128));
-            else ws_load_tile(pre, pg + (long)tile * 128 * p.lda, p.lda, pr, min(128, p.M - tile * 128));
-            const int nn = tile + gridDim.x;
-            if (nn < p.n_tiles) prefetch_tile_l2(p.A, p.lda, (long)nn * 128, min(128, p.M - nn * 128), tid, kWsProdWarps * 32);
+        if (n_local > 0) {
+            if (SW) ws_load_rows(pre, pg + (long)r_begin * p.lda, p.lda, warp * 16, min(128, r_end - r_begin));
+            else ws_load_tile(pre, pg + (long)r_begin * p.lda, p.lda, pr, min(128, r_end - r_begin));
+            if (n_local > 1) prefetch_tile_l2(p.A, p.lda, (long)r_begin + 128, min(128, r_end - r_begin - 128), tid, kWsProdWarps * 32);
         }
-        for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < n_local; ++it) {
             const int s = it & 1;
             mbar_wait(&bar_empty[s], ((it >> 1) & 1) ^ 1);
             uint8_t* hi = smem_raw + s * kStage;
@@ -446,12 +449,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
                 cvt_store<NSPLIT>(pre[i], hi, lo, SW ? psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4) : psoff + (uint32_t)i * 128u, p.relu_in);
             fence_async_smem();
             mbar_arrive(&bar_full[s]);
-            const int next = tile + gridDim.x;
-            if (next < p.n_tiles) {
-                if (SW) ws_load_rows(pre, pg + (long)next * 128 * p.lda, p.lda, warp * 16, min(128, p.M - next * 128));
-                else ws_load_tile(pre, pg + (long)next * 128 * p.lda, p.lda, pr, min(128, p.M - next * 128));
-                const int nn = next + gridDim.x;
-                if (nn < p.n_tiles) prefetch_tile_l2(p.A, p.lda, (long)nn * 128, min(128, p.M - nn * 128), tid, kWsProdWarps * 32);
+            if (it + 1 < n_local) {
+                const int nrow = r_begin + (it + 1) * 128;
+                if (SW) ws_load_rows(pre, pg + (long)nrow * p.lda, p.lda, warp * 16, min(128, r_end - nrow));
+                else ws_load_tile(pre, pg + (long)nrow * p.lda, p.lda, pr, min(128, r_end - nrow));
+                if (it + 2 < n_local) prefetch_tile_l2(p.A, p.lda, (long)nrow + 128, min(128, r_end - nrow - 128), tid, kWsProdWarps * 32);
             }
         }
     } else if (warp == kWsProdWarps) {
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
             const uint32_t sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
             // fwd: B = W rows (n) K-major in k.  bwd-data: B = W^T, i.e. the same bytes read MN-major (mn = k_out, red = n)
             const uint32_t b_step = p.transposed_w ? 256u : 4096u, b_lbo = p.transposed_w ? 128u : 2048u, b_sbo = p.transposed_w ? 2048u : 128u;
-            for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            for (int it = 0; it < n_local; ++it) {
                 const int s = it & 1;
                 const uint32_t par = (it >> 1) & 1;
                 mbar_wait(&bar_full[s], par);
@@ -506,15 +508,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
         const int col_base = (e >> 2) * 64;                       // two warps per quadrant: 64 columns each, 4 chunks of 16
         float* scratch = scratch_all + e * (32 * kWsScratchLd);
         const int r_in = lane >> 2, c4 = (lane & 3) * 4;          // store geometry: 8 rows x 64 bytes per instruction
-        for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < n_local; ++it) {
             const int s = it & 1;
-            const int m0 = tile * 128 + lane_base;
+            const int m0 = r_begin + it * 128 + lane_base;
             float4 mk[4];
             if (HAS_MASK) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int row = m0 + j * 8 + r_in;
-                    mk[j] = row < p.M ? __ldg(reinterpret_cast<const float4*>(p.mask + (long)row * p.ldm + col_base + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    mk[j] = row < r_end ? __ldg(reinterpret_cast<const float4*>(p.mask + (long)row * p.ldm + col_base + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             mbar_wait(&bar_tfull[s], (it >> 1) & 1);
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int row = m0 + j * 8 + r_in;
-                        mn[j] = row < p.M ? __ldg(reinterpret_cast<const float4*>(p.mask + (long)row * p.ldm + c0 + 16 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        mn[j] = row < r_end ? __ldg(reinterpret_cast<const float4*>(p.mask + (long)row * p.ldm + c0 + 16 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
                 const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + c4]);
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
                 for (int j = 0; j < 4; ++j) {
                     const int r = j * 8 + r_in;
                     const int row = m0 + r;
-                    if (row < p.M) {
+                    if (row < r_end) {
                         float4 x = *reinterpret_cast<const float4*>(scratch + r * kWsScratchLd + c4);
                         x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
                         if (HAS_U) {
@@ -594,7 +596,7 @@ struct TcFusedParams {
     float* dX; long lddx;           // [M, 128]
     float* dW; long lddw;           // [128, 128]  +=
     float* db;                      // [128] += or null
-    int M, n_tiles;
+    int M, n_tiles, rows_per_cta;
     int relu_x, use_mask, w_vec, dw_vec;
 };
 
@@ -638,7 +640,8 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
     const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
     const uint32_t psoff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
     float4 py[8], px[8];
-    int tile = blockIdx.x;
+    const int r_begin = blockIdx.x * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);     // balanced contiguous row ranges
+    const int n_local = r_end > r_begin ? (r_end - r_begin + 127) >> 7 : 0;
     pdl_trigger();
     if (warp < kFbProdWarps) {
         float4 wv[8];
@@ -661,17 +664,16 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
     if (warp < kFbProdWarps) {
         // ------------------------------------------------------------------ producers
         {
-            const int rv = min(128, p.M - tile * 128);
-            fb_load_rows(py, p.dY + ((long)tile * 128 + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
-            fb_load_rows(px, p.X + ((long)tile * 128 + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
-            const int nn = tile + gridDim.x;
-            if (nn < p.n_tiles) {
-                prefetch_tile_l2(p.dY, p.lddy, (long)nn * 128, min(128, p.M - nn * 128), tid, kFbProdWarps * 32);
-                prefetch_tile_l2(p.X, p.ldx, (long)nn * 128, min(128, p.M - nn * 128), tid, kFbProdWarps * 32);
+            const int rv = min(128, r_end - r_begin);
+            fb_load_rows(py, p.dY + ((long)r_begin + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
+            fb_load_rows(px, p.X + ((long)r_begin + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
+            if (n_local > 1) {
+                prefetch_tile_l2(p.dY, p.lddy, (long)r_begin + 128, min(128, r_end - r_begin - 128), tid, kFbProdWarps * 32);
+                prefetch_tile_l2(p.X, p.ldx, (long)r_begin + 128, min(128, r_end - r_begin - 128), tid, kFbProdWarps * 32);
             }
         }
         float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < n_local; ++it) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { dbs.x += py[i].x; dbs.y += py[i].y; dbs.z += py[i].z; dbs.w += py[i].w; }
             if (it > 0) {
@@ -686,15 +688,13 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
             }
             fence_async_smem();
             mbar_arrive(&bar_full);
-            const int next = tile + gridDim.x;
-            if (next < p.n_tiles) {
-                const int rv = min(128, p.M - next * 128);
-                fb_load_rows(py, p.dY + ((long)next * 128 + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
-                fb_load_rows(px, p.X + ((long)next * 128 + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
-                const int nn = next + gridDim.x;
-                if (nn < p.n_tiles) {
-                    prefetch_tile_l2(p.dY, p.lddy, (long)nn * 128, min(128, p.M - nn * 128), tid, kFbProdWarps * 32);
-                    prefetch_tile_l2(p.X, p.ldx, (long)nn * 128, min(128, p.M - nn * 128), tid, kFbProdWarps * 32);
+            if (it + 1 < n_local) {
+                const int nrow = r_begin + (it + 1) * 128, rv = min(128, r_end - nrow);
+                fb_load_rows(py, p.dY + ((long)nrow + warp * 8) * p.lddy + lane * 4, p.lddy, warp * 8, rv);
+                fb_load_rows(px, p.X + ((long)nrow + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, rv);
+                if (it + 2 < n_local) {
+                    prefetch_tile_l2(p.dY, p.lddy, (long)nrow + 128, min(128, r_end - nrow - 128), tid, kFbProdWarps * 32);
+                    prefetch_tile_l2(p.X, p.ldx, (long)nrow + 128, min(128, r_end - nrow - 128), tid, kFbProdWarps * 32);
                 }
             }
         }
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
             const uint32_t sy_hi = smem_u32(y_hi), sy_lo = smem_u32(y_lo), sx_hi = smem_u32(x_hi), sx_lo = smem_u32(x_lo);
             const uint32_t sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
             const uint32_t d_dw = tmem + 256u;
-            for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            for (int it = 0; it < n_local; ++it) {
                 const int t = it & 1;
                 mbar_wait(&bar_full, it & 1);
                 mbar_wait(&bar_tempty[t], ((it >> 1) & 1) ^ 1);
@@ -751,9 +751,9 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
         const int col_base = (e >> 2) * 64;
         float* scratch = scratch_all + e * (32 * kWsScratchLd);
         const int r_in = lane >> 2, c4 = (lane & 3) * 4;
-        for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < n_local; ++it) {
             const int t = it & 1;
-            const int m0 = tile * 128 + lane_base;
+            const int m0 = r_begin + it * 128 + lane_base;
             mbar_wait(&bar_tfull[t], (it >> 1) & 1);
             tc_fence_after();
             unsigned long long mbits = ~0ull;
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
                 for (int j = 0; j < 4; ++j) {
                     const int r = j * 8 + r_in;
                     const int row = m0 + r;
-                    if (row < p.M) {
+                    if (row < r_end) {
                         float4 x = *reinterpret_cast<const float4*>(scratch + r * kWsScratchLd + c4);
                         if (HAS_MASK) {
                             const unsigned b4 = (unsigned)(mbits >> ((ch * 4 + j) * 4));
@@ -1056,6 +1056,8 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
     const bool vec = p.a_vec && p.c_vec && (!p.mask || ((p.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0));
     const bool hot = vec && p.KR == 128 && p.NO == 128;
     if (hot && !(p.u && p.mask)) {
+        p.rows_per_cta = (int)(cdiv(cdiv(p.M, grid), 8) * 8);
+        const int ws_grid = (int)cdiv(p.M, p.rows_per_cta);
         // warp-specialised pipeline (2 operand stages + weights + epilogue scratch)
         const size_t ws_smem = (size_t)3 * (NSPLIT == 3 ? 2 : 1) * 32768 + (size_t)kWsEpiWarps * 32 * kWsScratchLd * sizeof(float);
         static const bool sw = getenv("NPF_WS_SW") ? atoi(getenv("NPF_WS_SW")) != 0 : true;
@@ -1073,13 +1075,13 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
             ws_attr = true;
         }
         if (sw) {
-            if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, true>, grid, kWsThreads, ws_smem, st, p);
-            else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, true>, grid, kWsThreads, ws_smem, st, p);
-            else launch_pdl(linear_ws_kernel<NSPLIT, false, false, true>, grid, kWsThreads, ws_smem, st, p);
+            if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, true>, ws_grid, kWsThreads, ws_smem, st, p);
+            else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, true>, ws_grid, kWsThreads, ws_smem, st, p);
+            else launch_pdl(linear_ws_kernel<NSPLIT, false, false, true>, ws_grid, kWsThreads, ws_smem, st, p);
         } else {
-            if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, false>, grid, kWsThreads, ws_smem, st, p);
-            else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, false>, grid, kWsThreads, ws_smem, st, p);
-            else launch_pdl(linear_ws_kernel<NSPLIT, false, false, false>, grid, kWsThreads, ws_smem, st, p);
+            if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, false>, ws_grid, kWsThreads, ws_smem, st, p);
+            else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, false>, ws_grid, kWsThreads, ws_smem, st, p);
+            else launch_pdl(linear_ws_kernel<NSPLIT, false, false, false>, ws_grid, kWsThreads, ws_smem, st, p);
         }
         count_launch();
         return check_launch("linear_ws_kernel");
@@ -1138,7 +1140,9 @@ static int launch_fused(TcFusedParams& p, cudaStream_t st) {
         attr = true;
     }
     p.n_tiles = (int)cdiv(p.M, 128);
-    const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+    int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+    p.rows_per_cta = (int)(cdiv(cdiv(p.M, grid), 8) * 8);
+    grid = (int)cdiv(p.M, p.rows_per_cta);
     if (p.use_mask) launch_pdl(linear_bwd_fused_kernel<NSPLIT, true>, grid, kFbThreads, smem, st, p);
     else launch_pdl(linear_bwd_fused_kernel<NSPLIT, false>, grid, kFbThreads, smem, st, p);
     count_launch();

@@ -116,13 +116,21 @@ def enable_timing(on):
     _timing = {} if on else None
 
 
-def collect_timing():
-    """name -> (total_ms, n_calls, algorithmic_bytes, flops); synchronises.  Clears the log."""
+def collect_timing(by_shape=False):
+    """name -> (total_ms, n_calls, algorithmic_bytes, flops); synchronises.  Clears the log.
+    by_shape=True keys by (name, algorithmic bytes per call, flops per call) instead, i.e. one row per entry point AND
+    problem size (the 128 x 128 x 75776 layer and the 2 x 128 head are different kernels behind the same entry point)."""
     import torch
     torch.cuda.synchronize()
     out = {}
     for name, evs in (_timing or {}).items():
-        out[name] = (sum(a.elapsed_time(b) for a, b, _, _ in evs), len(evs), sum(e[2] for e in evs), sum(e[3] for e in evs))
+        if by_shape:
+            for a, b, nb, fl in evs:
+                k = (name, nb, fl)
+                ms, n = out.get(k, (0.0, 0))
+                out[k] = (ms + a.elapsed_time(b), n + 1)
+        else:
+            out[name] = (sum(a.elapsed_time(b) for a, b, _, _ in evs), len(evs), sum(e[2] for e in evs), sum(e[3] for e in evs))
     if _timing is not None:
         _timing.clear()
     return out
