@@ -1125,6 +1125,241 @@ int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float
 }
 
 
+// ------------------------------------------------------------------------------------------------ fused backward, 64-row tiles
+// Same mathematics as linear_bwd_fused_kernel, re-cut so that the operand stage fits TWICE in shared memory (x3: 2 x 64 KB +
+// 64 KB of weights): with 128-row tiles a single stage forces "convert+store tile i+1" to wait for "multiply tile i"
+// (14 k cycles per tile measured, against 8.7 k of HBM time).  With 64-row tiles the tensor-core M dimension is kept at
+// 128 by computing the TRANSPOSED data gradient:
+//     dX^T[k, m] = sum_n W[n, k] dY[m, n]      A = W^T (MN-major view of the row-staged W),  B = dY tile (K-major),  N = 64
+//     dW[n, k]  += sum_m dY[m, n] X[m, k]      A = dY^T, B = X (MN-major views), 4 k-steps of 16 rows
+// The accumulator then has k on the TMEM lanes and the tile's rows on the columns, so an epilogue thread owns ONE column k
+// of dX and every register it reads is one row: a warp store covers 128 contiguous bytes without any shared-memory
+// transpose, and the relu mask is a 2-byte read of the staged X tile.  Producers keep TWO tiles in flight in registers.
+constexpr int kF64Rows = 64;
+#ifndef NPF_F64_AHEAD
+#define NPF_F64_AHEAD 4
+#endif
+constexpr int kF64Ahead = NPF_F64_AHEAD;
+
+__device__ __forceinline__ void f64_load_rows(float4 (&pre)[4], const float* __restrict__ g, long ld, int row_first, int rows_valid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pre[i] = (row_first + i < rows_valid) ? __ldg(reinterpret_cast<const float4*>(g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g += ld;
+    }
+}
+__device__ __forceinline__ void f64_prefetch(const float* __restrict__ base, long ld, long row0, int rows_valid, int t) {
+    // 64 rows x 512 bytes = 256 lines; threads 0..255 take dY / 256..511 are given the X tile by the caller
+    const int l = t & 255, r = l >> 2;
+    if (r < rows_valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (row0 + r) * ld + (l & 3) * 32));
+}
+
+template <int NSPLIT, bool HAS_MASK>
+__global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused64_kernel(TcFusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_mask[2], bar_dwfull, bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_db[128];
+
+    constexpr uint32_t kHalf = 64u * 128u * 2u;                    // one bf16 64 x 128 operand image: 16 KB
+    constexpr uint32_t kOp = (NSPLIT == 3 ? 2u : 1u) * kHalf;      // hi [+ lo]
+    constexpr uint32_t kStage = 2u * kOp;                          // dY + X
+    constexpr uint32_t kWTile = 128u * 128u * 2u;                  // 32 KB
+    uint8_t* w_hi = smem_raw + 2 * kStage;
+    uint8_t* w_lo = w_hi + kWTile;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (tid == 32) {
+        mbar_init(&bar_dwfull, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_full[i], kFbProdWarps * 32);
+            mbar_init(&bar_empty[i], 1);
+            mbar_init(&bar_mask[i], kWsEpiWarps * 32);
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kWsEpiWarps * 32);
+        }
+    }
+    if (tid < 128) s_db[tid] = 0.f;
+
+    const int r_begin = blockIdx.x * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);
+    const int n_local = r_end > r_begin ? (r_end - r_begin + kF64Rows - 1) / kF64Rows : 0;
+    const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
+    pdl_trigger();
+    if (warp < kFbProdWarps) {          // weights: warp w stages rows 8 w .. 8 w + 7 of W (two 64-column atoms of 16 KB)
+        const uint32_t woff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
+        float4 wv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float* g = p.W + (long)(warp * 8 + i) * p.ldw + lane * 4;
+            if (p.w_vec) wv[i] = __ldg(reinterpret_cast<const float4*>(g));
+            else wv[i] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cvt_store<NSPLIT>(wv[i], w_hi, w_lo, woff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4), 0);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    pdl_wait();
+
+    if (warp < kFbProdWarps) {
+        // ------------------------------------------------------------------ producers: warp w owns rows 4 w .. 4 w + 3 of a tile
+        const int prow = warp * 4;
+        const uint32_t psoff = (uint32_t)(lane >> 4) * 8192u + (uint32_t)prow * 128u + (uint32_t)(lane & 1) * 8u;
+        const uint32_t rsw = (uint32_t)(prow & 7);                   // row % 8 of the warp's first row (0 or 4)
+        float4 ya[4], xa[4], yb[4], xb[4];
+        float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_tile = [&](float4 (&yy)[4], float4 (&xx)[4], int it) {
+            const int row0 = r_begin + it * kF64Rows, rv = min(kF64Rows, r_end - row0);
+            f64_load_rows(yy, p.dY + ((long)row0 + prow) * p.lddy + lane * 4, p.lddy, prow, rv);
+            f64_load_rows(xx, p.X + ((long)row0 + prow) * p.ldx + lane * 4, p.ldx, prow, rv);
+        };
+        auto put_tile = [&](float4 (&yy)[4], float4 (&xx)[4], int it) {
+            const int s = it & 1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { dbs.x += yy[i].x; dbs.y += yy[i].y; dbs.z += yy[i].z; dbs.w += yy[i].w; }
+            if (it >= 2) {
+                mbar_wait(&bar_empty[s], ((it >> 1) - 1) & 1);               // the MMAs of tile it-2 have read this stage
+                if (HAS_MASK) mbar_wait(&bar_mask[s], ((it >> 1) - 1) & 1);  // and the epilogue has taken its relu mask
+            }
+            uint8_t* y_hi = smem_raw + s * kStage;
+            uint8_t* x_hi = y_hi + kOp;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t off = psoff + (uint32_t)i * 128u + ((pchunk ^ (rsw + (uint32_t)i)) << 4);
+                cvt_store<NSPLIT>(yy[i], y_hi, y_hi + kHalf, off, 0);
+                cvt_store<NSPLIT>(xx[i], x_hi, x_hi + kHalf, off, p.relu_x);
+            }
+            fence_async_smem();
+            mbar_arrive(&bar_full[s]);
+            if (it + 2 < n_local) load_tile(yy, xx, it + 2);
+            if (it + kF64Ahead < n_local) {        // L2 prefetch kF64Ahead tiles ahead (2 tiles are in flight in registers)
+                const int row0 = r_begin + (it + kF64Ahead) * kF64Rows, rv = min(kF64Rows, r_end - row0);
+                if (tid < 256) f64_prefetch(p.dY, p.lddy, row0, rv, tid); else f64_prefetch(p.X, p.ldx, row0, rv, tid);
+            }
+        };
+        if (n_local > 0) load_tile(ya, xa, 0);
+        if (n_local > 1) load_tile(yb, xb, 1);
+        for (int a = 2; a < kF64Ahead && a < n_local; ++a) {
+            const int row0 = r_begin + a * kF64Rows, rv = min(kF64Rows, r_end - row0);
+            if (tid < 256) f64_prefetch(p.dY, p.lddy, row0, rv, tid); else f64_prefetch(p.X, p.ldx, row0, rv, tid);
+        }
+        for (int it = 0; it < n_local; it += 2) {
+            put_tile(ya, xa, it);
+            if (it + 1 < n_local) put_tile(yb, xb, it + 1);
+        }
+        if (p.db) {
+            atomicAdd(&s_db[lane * 4 + 0], dbs.x); atomicAdd(&s_db[lane * 4 + 1], dbs.y);
+            atomicAdd(&s_db[lane * 4 + 2], dbs.z); atomicAdd(&s_db[lane * 4 + 3], dbs.w);
+            asm volatile("bar.sync 1, %0;" ::"n"(kFbProdWarps * 32) : "memory");
+            if (tid < 128) atomicAdd(p.db + tid, s_db[tid]);
+        }
+    } else if (warp == kFbProdWarps) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_dx = make_idesc(128, 64, 1, 0);     // A = W^T (MN-major view), B = dY tile (K-major), D = dX^T [k x m]
+            const uint32_t idesc_dw = make_idesc(128, 128, 1, 1);    // A = dY^T, B = X: MN-major views (reduction over the tile's rows)
+            const uint32_t sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
+            const uint32_t d_dw = tmem + 128u;
+            for (int it = 0; it < n_local; ++it) {
+                const int s = it & 1;
+                const uint32_t par = (it >> 1) & 1;
+                mbar_wait(&bar_full[s], par);
+                mbar_wait(&bar_tempty[s], par ^ 1);
+                tc_fence_after();
+                const uint32_t sy_hi = smem_u32(smem_raw + s * kStage), sy_lo = sy_hi + kHalf, sx_hi = sy_hi + kOp, sx_lo = sx_hi + kHalf;
+                const uint32_t d_dx = tmem + (uint32_t)s * 64u;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {                     // reduction over n (16 per step)
+                    const uint32_t bo = (uint32_t)(ks >> 2) * 8192u + (uint32_t)(ks & 3) * 32u;
+                    const uint64_t a_h = make_desc_sw128(sw_hi + ks * 2048u, 16384, 1024), b_h = make_desc_sw128(sy_hi + bo, 16, 1024);
+                    umma_bf16(d_dx, a_h, b_h, idesc_dx, ks ? 1u : 0u);
+                    if (NSPLIT == 3) {
+                        umma_bf16(d_dx, a_h, make_desc_sw128(sy_lo + bo, 16, 1024), idesc_dx, 1);
+                        umma_bf16(d_dx, make_desc_sw128(sw_lo + ks * 2048u, 16384, 1024), b_h, idesc_dx, 1);
+                    }
+                }
+                umma_commit(&bar_tfull[s]);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {                     // reduction over the 64 rows of the tile
+                    const uint32_t acc = (it | ks) ? 1u : 0u;
+                    const uint64_t a_h = make_desc_sw128(sy_hi + ks * 2048u, 8192, 1024), b_h = make_desc_sw128(sx_hi + ks * 2048u, 8192, 1024);
+                    umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
+                    if (NSPLIT == 3) {
+                        umma_bf16(d_dw, a_h, make_desc_sw128(sx_lo + ks * 2048u, 8192, 1024), idesc_dw, 1);
+                        umma_bf16(d_dw, make_desc_sw128(sy_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
+                    }
+                }
+                umma_commit(&bar_empty[s]);
+            }
+            umma_commit(&bar_dwfull);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: thread = column k of dX, 32 rows of the tile
+        const int e = warp - kFbEpiWarp0;
+        const int lane_base = 32 * (warp & 3);
+        const int k = lane_base + lane;
+        const int mh = (e >> 2) * 32;                                  // this warp's half of the tile's 64 rows
+        const uint32_t xk_off = (uint32_t)(k >> 6) * 8192u + (uint32_t)(k & 7) * 2u, xk_chunk = (uint32_t)(k & 63) >> 3;
+        for (int it = 0; it < n_local; ++it) {
+            const int s = it & 1;
+            const int row0 = r_begin + it * kF64Rows + mh;
+            mbar_wait(&bar_tfull[s], (it >> 1) & 1);
+            tc_fence_after();
+            uint32_t mbits = 0xFFFFFFFFu;
+            if (HAS_MASK) {          // relu mask of column k for the 32 rows, from the staged (relu'd) X tile: bf16 > 0 <=> int16 > 0
+                const uint8_t* x_hi = smem_raw + s * kStage + kOp;
+                mbits = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t m = (uint32_t)(mh + j);
+                    const short xb = *reinterpret_cast<const short*>(x_hi + xk_off + m * 128u + ((xk_chunk ^ (m & 7u)) << 4));
+                    mbits |= (xb > 0 ? 1u : 0u) << j;
+                }
+                mbar_arrive(&bar_mask[s]);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(s * 64 + mh + c * 16), v);
+                if (c == 1) {
+                    tc_fence_before();
+                    mbar_arrive(&bar_tempty[s]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int row = row0 + c * 16 + j;
+                    if (row < r_end) p.dX[(long)row * p.lddx + k] = ((mbits >> (c * 16 + j)) & 1u) ? v[j] : 0.f;
+                }
+            }
+        }
+        // ---- flush of the CTA's weight gradient: thread = row n of dW, 64 columns per warp
+        mbar_wait(&bar_dwfull, 0);
+        tc_fence_after();
+        const int col_base = (e >> 2) * 64;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            const int c0 = col_base + ch * 16;
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(128 + c0), v);
+            float* d = p.dW + (long)k * p.lddw + c0;
+            if (p.dw_vec) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(d + j, v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // Fused data + weight (+ bias) gradient of a 128 -> 128 layer; NPF_ENOTSUP for any other shape / alignment (the caller
 // then runs the two separate kernels).
 template <int NSPLIT>
@@ -1143,6 +1378,23 @@ static int launch_fused(TcFusedParams& p, cudaStream_t st) {
     int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
     p.rows_per_cta = (int)(cdiv(cdiv(p.M, grid), 8) * 8);
     grid = (int)cdiv(p.M, p.rows_per_cta);
+    static const bool v64 = getenv("NPF_FUSED64") ? atoi(getenv("NPF_FUSED64")) != 0 : true;
+    if (v64) {      // 64-row tiles, two operand stages (no epilogue scratch)
+        static bool attr64 = false;
+        if (!attr64) {
+            if (cudaFuncSetAttribute(linear_bwd_fused64_kernel<NSPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute(linear_bwd_fused64_kernel<NSPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) {
+                cudaGetLastError();
+                return NPF_ENOTSUP;
+            }
+            attr64 = true;
+        }
+        const size_t smem64 = (size_t)(NSPLIT == 3 ? 2 : 1) * (4 * 16384 + 32768);
+        if (p.use_mask) launch_pdl(linear_bwd_fused64_kernel<NSPLIT, true>, grid, kFbThreads, smem64, st, p);
+        else launch_pdl(linear_bwd_fused64_kernel<NSPLIT, false>, grid, kFbThreads, smem64, st, p);
+        count_launch();
+        return check_launch("linear_bwd_fused64_kernel");
+    }
     if (p.use_mask) launch_pdl(linear_bwd_fused_kernel<NSPLIT, true>, grid, kFbThreads, smem, st, p);
     else launch_pdl(linear_bwd_fused_kernel<NSPLIT, false>, grid, kFbThreads, smem, st, p);
     count_launch();
