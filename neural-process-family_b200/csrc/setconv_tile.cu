@@ -11,6 +11,7 @@
 //   mode 0: feat = sum_k softmax_k(a) V_k, dens, (max logit, sum exp)            (forward)
 //   mode 1: d theta: T - G*A1 + ddens*A2 with max-shifted logits (see setconv.cu)
 //   dV    : dV[k] = sum_q w_qk dF_q                                               (gather, no atomics)
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace npf {
@@ -617,6 +618,263 @@ __global__ void __launch_bounds__(kTaskThreads, 1) setconv_task_dv_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core forward for the induced -> target direction (C == 128, regular key grid):
+//     feat[b] = diag(1 / s) . E[b] . V[b],    E[q, k] = exp(a_qk - m_q),   s_q = sum_k E[q, k]
+// is a [128 queries x K keys] x [K x 128 channels] GEMM per task whose left operand is never stored: W-producer warps evaluate
+// E in registers (one exp per pair, ex2.approx), split it into bf16 hi + lo and write it straight into the UMMA SWIZZLE_128B
+// operand layout; V-producer warps stream the task's value rows from HBM (each byte once), split them the same way and stage
+// them row-major, which the tensor core reads as the MN-major B operand; tcgen05.mma accumulates hi.hi + hi.lo + lo.hi over
+// 64-key chunks (2-stage ring) into a TMEM accumulator that is double-buffered across tasks, and the epilogue scales row q by
+// 1 / s_q and writes coalesced rows.  No query sort and no windows: keys outside a query's sigma-window get E = 0 by fp32
+// underflow exactly as in the reference's dense softmax.  The SIMT version is bounded by the FFMA pipe (~ the HBM time
+// itself); here the FMA work rides on the tensor pipe and the kernel is bounded by the V stream.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kTcKeys = 64;                 // keys per chunk (one 128-byte swizzle atom of bf16 along the reduction)
+constexpr int kTcVProd = 8, kTcWProd = 8, kTcEpi = 8;
+constexpr int kTcMmaWarp = kTcVProd + kTcWProd;
+constexpr int kTcEpiWarp0 = kTcMmaWarp + 1;
+constexpr int kTcThreads = (kTcEpiWarp0 + kTcEpi) * 32;      // 800
+constexpr int kTcScratchLd = 20;
+
+__device__ __forceinline__ uint64_t make_desc_sw128_t(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_desc(saddr, lbo_bytes, sbo_bytes) | (2ull << 61);
+}
+__device__ __forceinline__ void split_store8(const float (&v)[8], uint8_t* hi, uint8_t* lo, uint32_t off) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        h[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+        l[e] = pack_bf16(v[2 * e] - __uint_as_float(h[e] << 16), v[2 * e + 1] - __uint_as_float(h[e] & 0xFFFF0000u));
+    }
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) setconv_tc_fwd_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+                                                                      long qry_bs, const float* __restrict__ values, const float* __restrict__ theta,
+                                                                      float* __restrict__ feat_o, float* __restrict__ dens_o, float* __restrict__ mstat_o,
+                                                                      int B, int K, int Q) {
+    constexpr int C = 128;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_vfull[2], bar_wfull[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_sum[2][128];
+    __shared__ __align__(16) float s_keys[kMaxChunks * kChunkRows + kTcKeys];   // shared key grid, padded with +inf to whole chunks
+
+    constexpr uint32_t kWTile = 128u * kTcKeys * 2u;            // E chunk, one bf16 image: 16 KB
+    constexpr uint32_t kVTile = kTcKeys * 128u * 2u;            // V chunk, one bf16 image: 16 KB
+    constexpr uint32_t kStage = 2u * kWTile + 2u * kVTile;      // hi + lo of both: 64 KB
+    float* scratch_all = reinterpret_cast<float*>(smem_raw + 2 * kStage);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_vfull[i], kTcVProd * 32);
+            mbar_init(&bar_wfull[i], kTcWProd * 32);
+            mbar_init(&bar_empty[i], 1);
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kTcEpi * 32);
+        }
+    }
+    const float sigma = 1e-5f + softplus_f(__ldg(theta));
+    const float inv_sigma = 1.f / sigma;
+    const int n_chunks = (K + kTcKeys - 1) / kTcKeys;
+    const int n_qt = (Q + 127) >> 7;
+    const int n_units = B * n_qt;                                // (task, 128-query tile)
+    pdl_trigger();
+    for (int i = tid; i < n_chunks * kTcKeys; i += kTcThreads) s_keys[i] = i < K ? __ldg(keys + i) : INFINITY;   // the grid is an input of the step
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    pdl_wait();
+
+    if (warp < kTcVProd) {
+        // ------------------------------------------------------------------ V producers: warp w owns rows 8 w .. 8 w + 7 of a 64-key chunk
+        const uint32_t vchunk = (uint32_t)(lane >> 1) & 7u;
+        const uint32_t voff = (uint32_t)(lane >> 4) * 8192u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
+        int g = 0;
+        // the value rows of a unit are pulled into L2 one whole unit ahead (the register-staged loads keep only 32 KB in flight
+        // per SM, far too little against ~5 us of loaded DRAM latency; an L2 hit costs ~1 k cycles)
+        auto prefetch_unit = [&](int u) {
+            if (u >= n_units) return;
+            const char* base = reinterpret_cast<const char*>(values + (long)(u / n_qt) * K * C);
+            const int lines = (K * C * 4 + 127) >> 7;
+            for (int l = tid; l < lines; l += kTcVProd * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((long)l << 7)));
+        };
+        prefetch_unit(blockIdx.x);
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int b = u / n_qt;
+            const float* vb = values + (long)b * K * C;
+            prefetch_unit(u + gridDim.x);
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                const int s = g & 1;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = c * kTcKeys + warp * 8 + i;
+                    v[i] = row < K ? __ldg(reinterpret_cast<const float4*>(vb + (long)row * C) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (g >= 2) mbar_wait(&bar_empty[s], ((g >> 1) - 1) & 1);
+                uint8_t* v_hi = smem_raw + s * kStage + 2 * kWTile;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t off = voff + (uint32_t)i * 128u + ((vchunk ^ (uint32_t)i) << 4);
+                    const uint32_t h01 = pack_bf16(v[i].x, v[i].y), h23 = pack_bf16(v[i].z, v[i].w);
+                    *reinterpret_cast<uint2*>(v_hi + off) = make_uint2(h01, h23);
+                    *reinterpret_cast<uint2*>(v_hi + kVTile + off) =
+                        make_uint2(pack_bf16(v[i].x - __uint_as_float(h01 << 16), v[i].y - __uint_as_float(h01 & 0xFFFF0000u)),
+                                   pack_bf16(v[i].z - __uint_as_float(h23 << 16), v[i].w - __uint_as_float(h23 & 0xFFFF0000u)));
+                }
+                fence_async_smem();
+                mbar_arrive(&bar_vfull[s]);
+            }
+        }
+    } else if (warp < kTcMmaWarp) {
+        // ------------------------------------------------------------------ E producers: thread = (query, half of the chunk's keys)
+        const int wt = tid - kTcVProd * 32;                       // 0..255
+        const int ql = wt >> 1, half = wt & 1;                     // query row of the tile, keys [32 half, 32 half + 32) of the chunk
+        const float x0 = s_keys[0], inv_dx = (float)(K - 1) / (s_keys[K - 1] - x0);
+        const float is2 = inv_sigma * 1.2011224087864498f;         // exp(a - m) = exp2(-(d is2)^2 - m log2 e),  is2 = sqrt(log2 e) / sigma
+        int g = 0, tcount = 0;
+        // padding queries sit at +inf: every weight underflows to exactly 0 without a select in the inner loop.  The NEXT
+        // unit's position is fetched a whole unit ahead (a cold load under load costs several microseconds).
+        auto load_xq = [&](int u) {
+            if (u >= n_units) return INFINITY;
+            const int q = (u % n_qt) * 128 + ql;
+            return q < Q ? __ldg(queries + (long)(u / n_qt) * qry_bs + q) : INFINITY;
+        };
+        float xq_next = load_xq(blockIdx.x);
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++tcount) {
+            const int b = u / n_qt, q = (u % n_qt) * 128 + ql;
+            const bool qok = q < Q;
+            const float xq = xq_next;
+            xq_next = load_xq(u + gridDim.x);
+            // max logit: the nearest grid row (three candidates), as in the SIMT kernels
+            float m = 0.f;
+            if (qok) {
+                const int n0 = (int)rintf(fminf(fmaxf((xq - x0) * inv_dx, 0.f), (float)(K - 1)));
+                m = logit_t(xq, s_keys[n0], inv_sigma);
+                if (n0 > 0) m = fmaxf(m, logit_t(xq, s_keys[n0 - 1], inv_sigma));
+                if (n0 < K - 1) m = fmaxf(m, logit_t(xq, s_keys[n0 + 1], inv_sigma));
+            }
+            const float m2 = m * 1.4426950408889634f;
+            float ssum = 0.f;
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                const int s = g & 1;
+                if (g >= 2) mbar_wait(&bar_empty[s], ((g >> 1) - 1) & 1);
+                uint8_t* w_hi = smem_raw + s * kStage;
+                const float4* kp = reinterpret_cast<const float4*>(s_keys + c * kTcKeys + half * 32);     // broadcast reads; rows >= K hold +inf
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                     // 8 keys = one 16-byte bf16 chunk of row ql
+                    const float4 ka = kp[2 * j], kb2 = kp[2 * j + 1];
+                    const float kk[8] = {ka.x, ka.y, ka.z, ka.w, kb2.x, kb2.y, kb2.z, kb2.w};
+                    float e[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float t = (kk[i] - xq) * is2;
+                        float ev;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ev) : "f"(fmaf(-t, t, -m2)));
+                        e[i] = ev;
+                        ssum += ev;
+                    }
+                    const uint32_t chunk = (uint32_t)(half * 4 + j);
+                    split_store8(e, w_hi, w_hi + kWTile, (uint32_t)ql * 128u + ((chunk ^ (uint32_t)(ql & 7)) << 4));
+                }
+                fence_async_smem();
+                if (c == n_chunks - 1) {                           // denominators of this unit, before the last chunk is released
+                    const float tot = ssum + __shfl_xor_sync(0xffffffffu, ssum, 1);
+                    if (half == 0) {
+                        s_sum[tcount & 1][ql] = qok ? tot : 1.f;
+                        if (qok) {
+                            const long oq = (long)b * Q + q;
+                            dens_o[oq] = expf(m) * tot;
+                            mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = tot;
+                        }
+                    }
+                }
+                mbar_arrive(&bar_wfull[s]);
+            }
+        }
+    } else if (warp == kTcMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 128, 0, 1);     // A = E chunk (K-major), B = V chunk rows (MN-major view)
+            int g = 0, tcount = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++tcount) {
+                const int t = tcount & 1;
+                mbar_wait(&bar_tempty[t], ((tcount >> 1) & 1) ^ 1);
+                const uint32_t d = tmem + (uint32_t)t * 128u;
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const int s = g & 1;
+                    const uint32_t par = (g >> 1) & 1;
+                    mbar_wait(&bar_vfull[s], par);
+                    mbar_wait(&bar_wfull[s], par);
+                    tc_fence_after();
+                    const uint32_t sw_hi = smem_u32(smem_raw + s * kStage), sw_lo = sw_hi + kWTile, sv_hi = sw_hi + 2 * kWTile, sv_lo = sv_hi + kVTile;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t a_h = make_desc_sw128_t(sw_hi + ks * 32u, 16, 1024), b_h = make_desc_sw128_t(sv_hi + ks * 2048u, 8192, 1024);
+                        umma_bf16(d, a_h, b_h, idesc, (c | ks) ? 1u : 0u);
+                        umma_bf16(d, a_h, make_desc_sw128_t(sv_lo + ks * 2048u, 8192, 1024), idesc, 1);
+                        umma_bf16(d, make_desc_sw128_t(sw_lo + ks * 32u, 16, 1024), b_h, idesc, 1);
+                    }
+                    umma_commit(&bar_empty[s]);
+                }
+                umma_commit(&bar_tfull[t]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: TMEM -> scale by 1 / s -> coalesced rows of feat
+        const int e = warp - kTcEpiWarp0;
+        const int lane_base = 32 * (warp & 3);
+        const int col_base = (e >> 2) * 64;
+        float* scratch = scratch_all + e * (32 * kTcScratchLd);
+        const int r_in = lane >> 2, c4 = (lane & 3) * 4;
+        int tcount = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++tcount) {
+            const int t = tcount & 1;
+            const int b = u / n_qt, q0 = (u % n_qt) * 128;
+            mbar_wait(&bar_tfull[t], (tcount >> 1) & 1);
+            tc_fence_after();
+            const float inv = 1.f / s_sum[t][lane_base + lane];    // this thread's TMEM lane = query row
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int c0 = col_base + ch * 16;
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 128 + c0), v);
+                if (ch == 3) {
+                    tc_fence_before();
+                    mbar_arrive(&bar_tempty[t]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(scratch + lane * kTcScratchLd + j) = make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = j * 8 + r_in;
+                    const int q = q0 + lane_base + r;
+                    if (q < Q)
+                        *reinterpret_cast<float4*>(feat_o + ((long)b * Q + q) * C + c0 + c4) = *reinterpret_cast<const float4*>(scratch + r * kTcScratchLd + c4);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static bool tc_fwd_ok(int K, int Q, int C, long key_bs) {
+    static const bool on = [] { const char* e = getenv("NPF_SETCONV_TC"); return !(e && e[0] == '0'); }();
+    (void)Q;
+    return on && C == 128 && key_bs == 0 && K <= kMaxChunks * kChunkRows && K > 2 * kTcKeys;     // >= 3 chunks: the per-unit denominators are double-buffered against the 2-stage ring
+}
+
 static size_t task_smem_fwd(int K, int Q) {
     return sizeof(float) * ((size_t)((K + kChunkRows - 1) / kChunkRows) * kChunkRows * 128 + (size_t)kTaskWarps * kChunkRows * kGroup + 11 * (size_t)Q);
 }
@@ -641,6 +899,16 @@ int setconv_tile_fwd(const float* keys, long key_bs, const float* queries, long 
                      const float* theta, float* feat, float* dens, float* mstat, int B, int K, int Q, int C,
                      cudaStream_t st) {
     if (!tile_ok(K, Q, C, values) || (reinterpret_cast<uintptr_t>(feat) & 15)) return NPF_ENOTSUP;
+    if (tc_fwd_ok(K, Q, C, key_bs)) {
+        static bool cattr = false;
+        if (!cattr) { cudaFuncSetAttribute(setconv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); cattr = true; }
+        const int units = B * ((Q + 127) / 128);
+        const size_t smem = 2 * 65536 + (size_t)kTcEpi * 32 * kTcScratchLd * sizeof(float);
+        launch_pdl(setconv_tc_fwd_kernel, dim3(units < kNumSMs ? units : kNumSMs), dim3(kTcThreads), smem, st, keys, key_bs, queries, qry_bs, values, theta, feat, dens,
+                   mstat, B, K, Q);
+        count_launch();
+        return check_launch("setconv_tc_fwd_kernel");
+    }
     if (task_ok(K, Q, C)) {
         static bool tattr = false;
         if (!tattr) { cudaFuncSetAttribute(setconv_task_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTaskSmemMax); tattr = true; }
