@@ -1,5 +1,5 @@
 import os, sys, torch
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "neural-process-family_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "neural-process-family_b200"))
 from npf_b200 import _cabi
 M = int(os.environ.get("M", 75776)); K = N = 128
 dY = torch.randn(M, N, device="cuda"); X = torch.relu(torch.randn(M, K, device="cuda")); W = torch.randn(N, K, device="cuda") / 11

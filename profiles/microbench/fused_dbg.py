@@ -1,5 +1,5 @@
 import os, sys, torch
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "neural-process-family_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "neural-process-family_b200"))
 from npf_b200 import _cabi
 K = N = 128
 st = torch.cuda.current_stream().cuda_stream

@@ -1,6 +1,6 @@
 """micro-benchmark of npf_linear_fwd / bwd_data on the hot shape (attribution experiments; not a bench value)"""
 import os, sys, torch
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "neural-process-family_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "neural-process-family_b200"))
 from npf_b200 import _cabi
 M = int(os.environ.get("M", 75776)); K = N = 128
 dev = "cuda"

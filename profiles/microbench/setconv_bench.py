@@ -1,6 +1,6 @@
 """micro-benchmark of the induced -> target SetConv (regular keys, 128 channels): per-entry-point CUDA-event times"""
 import os, sys, torch
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "neural-process-family_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "neural-process-family_b200"))
 import npf_b200
 from npf_b200 import _cabi, ops
 npf_b200.set_precision("bf16x3")
