@@ -294,31 +294,45 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
     for (int i = threadIdx.x; i < K; i += blockDim.x) sk[i] = __ldg(keys + (long)b * key_bs + i);
     for (int i = threadIdx.x; i < K * C; i += blockDim.x) sv[i] = __ldg(values + (long)b * K * C + i);
     __syncthreads();
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    // four lanes per query, each sweeping every fourth key: 4x the warps of a thread-per-query layout (this kernel is bound by
+    // the latency of its exp chains, not by issue slots), partial maxima / sums joined with two shuffles
+    const int q = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2), kpart = threadIdx.x & 3;
     float contrib = 0.f;
-    if (q < Q) {
-        const float xq = __ldg(queries + (long)b * qry_bs + q);
-        const long oq = (long)b * Q + q;
+    const bool qok = q < Q;
+    {
+        const int qq = qok ? q : Q - 1;            // padding lanes shadow the last query (they must take part in the shuffles)
+        const float xq = __ldg(queries + (long)b * qry_bs + qq);
+        const long oq = (long)b * Q + qq;
         if (MODE == 0) {
             float m = -INFINITY;
 #pragma unroll 8
-            for (int k = 0; k < K; ++k) m = fmaxf(m, logit_r(xq, sk[k], inv_sigma));
+            for (int k = kpart; k < K; k += 4) m = fmaxf(m, logit_r(xq, sk[k], inv_sigma));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
             float s = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-            for (int k = 0; k < K; ++k) {
+            for (int k = kpart; k < K; k += 4) {
                 const float e = expf(logit_r(xq, sk[k], inv_sigma) - m);
                 s += e;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     if (c < C) acc[c] = fmaf(e, sv[k * C + c], acc[c]);
             }
-            const float inv = 1.f / s;
-            const float d = expf(m) * s;           // sum_k exp(a_k) = exp(m) sum_k exp(a_k - m): one exp per query, not per pair
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c < C) feat_o[oq * ldf + c] = acc[c] * inv;
-            dens_o[oq * ldd] = d;
-            mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = s;
+            for (int c = 0; c < 4; ++c) {
+                acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+                acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+            }
+            if (qok && kpart == 0) {
+                const float inv = 1.f / s;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < C) feat_o[oq * ldf + c] = acc[c] * inv;
+                dens_o[oq * ldd] = expf(m) * s;    // sum_k exp(a_k) = exp(m) sum_k exp(a_k - m): one exp per query, not per pair
+                mstat_o[oq * 2] = m; mstat_o[oq * 2 + 1] = s;
+            }
         } else {
             const float m = __ldg(mstat_i + oq * 2), inv_s = 1.f / __ldg(mstat_i + oq * 2 + 1);
             float df[4], G = 0.f;
@@ -329,18 +343,22 @@ __global__ void __launch_bounds__(256) setconv_small_kernel(const float* __restr
             }
             float A1 = 0.f, A2 = 0.f, T = 0.f;
 #pragma unroll 4
-            for (int k = 0; k < K; ++k) {
+            for (int k = kpart; k < K; k += 4) {
                 const float a = logit_r(xq, sk[k], inv_sigma);
-                const float wa = expf(a - m) * inv_s * (a - m);
+                const float e = expf(a - m);
+                const float wa = e * inv_s * (a - m);
                 A1 += wa;
-                A2 = fmaf(expf(a), a, A2);
+                A2 = fmaf(e, a, A2);               // sum_k exp(a_k) a_k = exp(m) sum_k exp(a_k - m) a_k
                 float g = 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     if (c < C) g = fmaf(df[c], sv[k * C + c], g);
                 T = fmaf(wa, g, T);
             }
-            contrib = T - G * A1 + __ldg(ddens + oq * ldd) * A2;
+            A1 += __shfl_xor_sync(0xffffffffu, A1, 1); A1 += __shfl_xor_sync(0xffffffffu, A1, 2);
+            A2 += __shfl_xor_sync(0xffffffffu, A2, 1); A2 += __shfl_xor_sync(0xffffffffu, A2, 2);
+            T += __shfl_xor_sync(0xffffffffu, T, 1); T += __shfl_xor_sync(0xffffffffu, T, 2);
+            if (qok && kpart == 0) contrib = T - G * A1 + __ldg(ddens + oq * ldd) * (A2 * expf(m));
         }
     }
     if (MODE == 1) {
@@ -384,7 +402,7 @@ extern "C" int npf_setconv_fwd(const float* keys, long key_bs, const float* quer
         if (rc != NPF_ENOTSUP) return rc;
     }
     if (small) {
-        const int nblk = (int)cdiv(Q, 256), thr = (int)cdiv(cdiv(Q, nblk), 32) * 32;   // e.g. Q = 296 -> 2 x 160 threads (92 % of lanes busy)
+        const int nblk = (int)cdiv(Q, 64), thr = 256;                                  // 64 queries x 4 key lanes per block
         dim3 grid((unsigned)nblk, (unsigned)B);
         setconv_small_kernel<0><<<grid, thr, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
             keys, key_bs, queries, qry_bs, values, theta, feat, dens, mstat, nullptr, nullptr, nullptr, nullptr, nullptr, K, Q, Cin, ldf, ldd);
@@ -422,7 +440,7 @@ extern "C" int npf_setconv_bwd(const float* keys, long key_bs, const float* quer
         if (rc != NPF_ENOTSUP) return rc;
     }
     if (small) {
-        const int nblk = (int)cdiv(Q, 256), thr = (int)cdiv(cdiv(Q, nblk), 32) * 32;
+        const int nblk = (int)cdiv(Q, 64), thr = 256;
         dim3 grid((unsigned)nblk, (unsigned)B);
         setconv_small_kernel<1><<<grid, thr, (size_t)K * (1 + Cin) * sizeof(float), st>>>(
             keys, key_bs, queries, qry_bs, values, theta, nullptr, nullptr, nullptr, feat, mstat, dfeat, ddens, dtheta, K, Q, Cin, ldf, ldd);
