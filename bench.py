@@ -33,6 +33,8 @@ WORKLOADS = {
     "cnp_b16_c32_t64": dict(family="CNP", B=16, C=32, T=64, loss="cnpf", desc="BASELINE configs[0]: CNP toy"),
     "attncnp_b64_c512_t512": dict(family="AttnCNP", B=64, C=512, T=512, loss="cnpf",
                                   desc="BASELINE configs[2]: AttnCNP transformer attention 512 ctx / 512 tgt"),
+    "attncnp_b256_c512_t512": dict(family="AttnCNP", B=256, C=512, T=512, loss="cnpf",
+                                   desc="BASELINE configs[2] at the SURVEY 8(d) batch: AttnCNP transformer attention 512 ctx / 512 tgt, 256 tasks"),
     "gridconvcnp_b128_32x32": dict(family="GridConvCNP", B=128, C=0, T=0, loss="cnpf",
                                    desc="BASELINE configs[3]: GridConvCNP 32x32x3, 128 images per GPU"),
     "gridconvlnp_b64_32x32_nz16": dict(family="GridConvLNP", B=64, C=0, T=0, loss="nll",

@@ -39,6 +39,7 @@ class GraphedStep:
         self.flat = flat if flat is not None else FlatGradients(model)
         self.n_warmup, self.max_graphs = n_warmup, max_graphs
         self._graphs = OrderedDict()
+        self._side = None
 
     # the eager body; also what gets recorded
     def _body(self, xc, yc, xt, yt):
@@ -60,7 +61,12 @@ class GraphedStep:
         # warm-up on a side stream (lazy one-time initialisation inside the library, allocator pools); the running
         # statistics / step counters it advances are restored so that capture has no side effect on the model
         saved = [(b, b.clone()) for b in self.model.buffers()]
-        side = torch.cuda.Stream(device=dev)
+        # warm-up AND capture run on one dedicated side stream: autograd nodes that outlive a backward pass (the parameters'
+        # gradient accumulators) remember the stream they were created on, and the engine joins that stream with the caller's
+        # at the end of backward() -- a join with a stream outside the capture would be an illegal cross-stream dependency
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(self.n_warmup):
@@ -69,7 +75,7 @@ class GraphedStep:
         self.model.validate_now() if hasattr(self.model, "validate_now") else None
         e.graph = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
-        with torch.cuda.graph(e.graph):
+        with torch.cuda.graph(e.graph, stream=side):
             e.loss = self._body(*e.inputs)
         e.launches = ops.launch_count() - n0
         with torch.no_grad():
