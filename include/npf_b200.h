@@ -90,6 +90,15 @@ NPF_API int npf_linear_bwd_data(const float* dY, int lddy, const float* W, int l
 NPF_API int npf_linear_bwd(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx,
                    float* dW, int lddw, float* db, int M, int K, int N, int flags, int precision, npf_stream_t stream);
 
+/* L consecutive square layers of one MLP (mlp.py:95-109, the hidden stack):  H_0 = act_in(X),
+ *     Y_l = act_l( H_l . W_l^T + b_l ),  H_{l+1} = Y_l,   act_l = relu if bit l of relu_mask else identity,
+ * every Y_l [M,width] stored (they are the activations saved for backward).  W / b / Y are HOST arrays of L device
+ * pointers (b may be NULL, or hold NULL entries); W_l is [width,width] row-major contiguous, Y_l contiguous.
+ * For width 128 in the tensor-core precisions and M <= 37 888 rows the row block stays on chip between layers
+ * (one kernel: no intermediate activation is read back); otherwise identical to L npf_linear_fwd calls. */
+NPF_API int npf_mlp_chain_fwd(const float* X, int ldx, const float* const* W, const float* const* b, float* const* Y, int L, int M,
+                      int width, int relu_in, unsigned relu_mask, int precision, npf_stream_t stream);
+
 /* dW[N,K] += dY[M,N]^T . act_in(X)[M,K] ;  db[N] += sum_m dY[m,:] ;  dw2[N*ldw2] += sum_m dY[m,:] u[m]
  * db, u/dw2 optional. */
 NPF_API int npf_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db,

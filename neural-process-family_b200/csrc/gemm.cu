@@ -251,6 +251,8 @@ int thin128_out_fwd(const float* X, long ldx, const float* W, long ldw, const fl
                     int relu_out, cudaStream_t st);
 int thin128_out_bwd(const float* dY, long lddy, const float* X, long ldx, const float* W, long ldw, float* dX, long lddx, float* dW, long lddw,
                     float* db, long M, int J, int relu_in, int use_mask, cudaStream_t st);
+int mlp_chain_fwd_tc(const float* X, int ldx, const float* const* W, const int* ldw, const float* const* b, float* const* Y, const int* ldy, int L, int M,
+                     int relu_in, unsigned relu_mask, int precision, cudaStream_t st);
 int linear_bwd_fused_tc(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx, float* dW,
                         int lddw, float* db, int M, int K, int N, int flags, int precision, cudaStream_t st);
 int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int* db_done, int M,
@@ -452,5 +454,29 @@ extern "C" int npf_linear_bwd(const float* dY, int lddy, const float* X, int ldx
     int rc = npf_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, db, M, K, N, flags & NPF_RELU_IN, nullptr, nullptr, 0, precision, stream);
     if (rc != NPF_OK || !dX) return rc;
     return npf_linear_bwd_data(dY, lddy, W, ldw, dX, lddx, M, K, N, (flags & NPF_MASK_X) ? X : nullptr, ldx, 0, precision, stream);
+}
+
+extern "C" int npf_mlp_chain_fwd(const float* X, int ldx, const float* const* W, const float* const* b, float* const* Y, int L, int M, int width,
+                                 int relu_in, unsigned relu_mask, int precision, npf_stream_t stream) {
+    if (M == 0) return NPF_OK;
+    NPF_REQUIRE(X && W && Y && L >= 1 && L <= 8, "npf_mlp_chain_fwd: null pointer or bad layer count");
+    NPF_REQUIRE(M >= 0 && width >= 1 && ldx >= width, "npf_mlp_chain_fwd: bad shape");
+    for (int l = 0; l < L; ++l) NPF_REQUIRE(W[l] && Y[l], "npf_mlp_chain_fwd: null layer pointer");
+    int ld[8];
+    for (int l = 0; l < L; ++l) ld[l] = width;
+    if (width == 128) {
+        const int rc = npf::mlp_chain_fwd_tc(X, ldx, W, ld, b, Y, ld, L, M, relu_in, relu_mask, precision, npf::as_stream(stream));
+        if (rc != NPF_ENOTSUP) return rc;
+    }
+    // layer by layer (any width, any precision)
+    const float* in = X;
+    int ldin = ldx;
+    for (int l = 0; l < L; ++l) {
+        const int flags = ((l == 0 && relu_in) ? NPF_RELU_IN : 0) | (((relu_mask >> l) & 1u) ? NPF_RELU_OUT : 0);
+        const int rc = npf_linear_fwd(in, ldin, W[l], width, b ? b[l] : nullptr, Y[l], width, M, width, width, flags, nullptr, nullptr, 0, precision, stream);
+        if (rc != NPF_OK) return rc;
+        in = Y[l]; ldin = width;
+    }
+    return NPF_OK;
 }
 

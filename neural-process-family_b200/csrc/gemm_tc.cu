@@ -576,6 +576,192 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// ------------------------------------------------------------------------------------------------ MLP chain forward (128-wide)
+// L consecutive Linear(128 -> 128) [+ ReLU] layers for a row block that stays ON CHIP between layers: a CTA owns up to 256
+// rows (two 128-row tiles); layer l's output leaves the tensor core through TMEM, gets its bias / ReLU in the epilogue, is
+// written once to HBM as the saved activation Y_l AND re-split into bf16 hi / lo straight into the shared-memory A-operand
+// image of layer l+1.  Against one kernel per layer this removes the read of every intermediate activation, L - 1 launches
+// with their parameter prologues and pipeline fill / drain -- the per-layer kernels of the 32 768-row decoder MLP spend
+// most of their 15 us there (1.7 tiles per SM).  Roles: 8 stager warps (X rows at the start, then W_l per layer, prefetched
+// into registers while layer l-1 is multiplied), 1 MMA warp, 8 epilogue warps.
+constexpr int kChainMaxLayers = 8;
+constexpr int kChainRows = 256;
+struct ChainParams {
+    const float* X; long ldx;
+    const float* W[kChainMaxLayers]; long ldw[kChainMaxLayers];
+    const float* b[kChainMaxLayers];
+    float* Y[kChainMaxLayers]; long ldy[kChainMaxLayers];
+    int L, M, rows_per_cta, relu_in;
+    unsigned relu_mask;          // bit l: ReLU after layer l
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_wfull, bar_wfree, bar_xready[2], bar_aready[2], bar_mma[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_bias[kChainMaxLayers][128];     // all layers' biases (parameters), staged once
+
+    constexpr uint32_t kTile = 128u * 128u * 2u;                   // one bf16 128 x 128 image: 32 KB
+    constexpr uint32_t kImg = (NSPLIT == 3 ? 2u : 1u) * kTile;     // hi [+ lo]
+    uint8_t* w_hi = smem_raw + 2 * kImg;
+    uint8_t* w_lo = w_hi + kTile;
+    float* scratch_all = reinterpret_cast<float*>(smem_raw + 3 * kImg);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (tid == 32) {
+        mbar_init(&bar_wfull, kWsProdWarps * 32);
+        mbar_init(&bar_wfree, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_xready[i], kWsProdWarps * 32);
+            mbar_init(&bar_aready[i], kWsEpiWarps * 32);
+            mbar_init(&bar_mma[i], 1);
+        }
+    }
+    const int r_begin = blockIdx.x * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);
+    const int n_tiles = r_end > r_begin ? (r_end - r_begin + 127) >> 7 : 0;     // 1 or 2
+    const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
+    for (int i = tid; i < p.L * 128; i += kWsThreads) s_bias[i >> 7][i & 127] = p.b[i >> 7] ? __ldg(p.b[i >> 7] + (i & 127)) : 0.f;
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < kWsProdWarps) {
+        // ------------------------------------------------------------------ stagers: warp w owns rows 16 w .. 16 w + 15 of a 128-row image
+        const uint32_t psoff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 16) * 128u + (uint32_t)(lane & 1) * 8u;
+        float4 pre[kWsPre];
+        // layer 0 weights first (parameters: may be read before the predecessor kernel has finished)
+        auto load_w = [&](int l) {
+#pragma unroll
+            for (int i = 0; i < kWsPre; ++i) pre[i] = __ldg(reinterpret_cast<const float4*>(p.W[l] + (long)(warp * 16 + i) * p.ldw[l]) + lane);
+        };
+        auto store_w = [&]() {
+#pragma unroll
+            for (int i = 0; i < kWsPre; ++i) cvt_store<NSPLIT>(pre[i], w_hi, w_lo, psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4), 0);
+            fence_async_smem();
+            mbar_arrive(&bar_wfull);
+        };
+        load_w(0);
+        store_w();
+        pdl_wait();
+        for (int t = 0; t < n_tiles; ++t) {                         // the block's input rows -> A images
+            const int row0 = r_begin + t * 128;
+            ws_load_rows(pre, p.X + ((long)row0 + warp * 16) * p.ldx + lane * 4, p.ldx, warp * 16, min(128, r_end - row0));
+            uint8_t* hi = smem_raw + t * kImg;
+#pragma unroll
+            for (int i = 0; i < kWsPre; ++i) cvt_store<NSPLIT>(pre[i], hi, hi + kTile, psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4), p.relu_in);
+            fence_async_smem();
+            mbar_arrive(&bar_xready[t]);
+        }
+        for (int l = 1; l < p.L; ++l) {
+            load_w(l);                                               // in flight while layer l-1 is multiplied
+            mbar_wait(&bar_wfree, (l - 1) & 1);                      // the MMAs of layer l-1 have read the weight buffer
+            store_w();
+        }
+    } else if (warp == kWsProdWarps) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 128, 0, 0);
+            const uint32_t sb_hi = smem_u32(w_hi), sb_lo = smem_u32(w_lo);
+            for (int l = 0; l < p.L; ++l) {
+                mbar_wait(&bar_wfull, l & 1);
+                for (int t = 0; t < n_tiles; ++t) {
+                    if (l == 0) mbar_wait(&bar_xready[t], 0);
+                    else mbar_wait(&bar_aready[t], (l - 1) & 1);     // epilogue of layer l-1 has rewritten the image and drained TMEM
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_u32(smem_raw + t * kImg), sa_lo = sa_hi + kTile;
+                    const uint32_t d = tmem + (uint32_t)t * 128u;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t ao = (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u;
+                        const uint64_t a_h = make_desc_sw128(sa_hi + ao, 16, 1024), b_h = make_desc_sw128(sb_hi + ao, 16, 1024);
+                        umma_bf16(d, a_h, b_h, idesc, ks ? 1u : 0u);
+                        if (NSPLIT == 3) {
+                            umma_bf16(d, a_h, make_desc_sw128(sb_lo + ao, 16, 1024), idesc, 1);
+                            umma_bf16(d, make_desc_sw128(sa_lo + ao, 16, 1024), b_h, idesc, 1);
+                        }
+                    }
+                    umma_commit(&bar_mma[t]);
+                }
+                umma_commit(&bar_wfree);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: 8 warps, tile after tile
+        const int e = warp - kWsEpiWarp0;
+        const int lane_base = 32 * (warp & 3);
+        const int col_base = (e >> 2) * 64;
+        float* scratch = scratch_all + e * (32 * kWsScratchLd);
+        const int r_in = lane >> 2, c4 = (lane & 3) * 4;
+        const int row_img = lane_base + lane;                        // this thread's row of the image (TMEM lane)
+        pdl_wait();
+        for (int l = 0; l < p.L; ++l) {
+            const bool relu = (p.relu_mask >> l) & 1u;
+            const bool feed = l + 1 < p.L;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int m0 = r_begin + t * 128 + lane_base;
+                mbar_wait(&bar_mma[t], l & 1);
+                tc_fence_after();
+                uint8_t* img_hi = smem_raw + t * kImg;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int c0 = col_base + ch * 16;
+                    float v[16];
+                    tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 128 + c0), v);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[l][c0 + j]);
+                        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (feed) {                                      // next layer's A operand: row row_img, columns c0 .. c0 + 15 (two 16-byte chunks)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c = c0 + h * 8;
+                            const uint32_t off = (uint32_t)(c >> 6) * 16384u + (uint32_t)row_img * 128u + ((((uint32_t)(c & 63) >> 3) ^ (uint32_t)(row_img & 7)) << 4);
+                            uint32_t hh[4], ll[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float a = v[h * 8 + 2 * q], b2 = v[h * 8 + 2 * q + 1];
+                                hh[q] = pack_bf16(a, b2);
+                                ll[q] = pack_bf16(a - __uint_as_float(hh[q] << 16), b2 - __uint_as_float(hh[q] & 0xFFFF0000u));
+                            }
+                            *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                            if (NSPLIT == 3) *reinterpret_cast<uint4*>(img_hi + kTile + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(scratch + lane * kWsScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = j * 8 + r_in;
+                        const int row = m0 + r;
+                        if (row < r_end)
+                            *reinterpret_cast<float4*>(p.Y[l] + (long)row * p.ldy[l] + c0 + c4) = *reinterpret_cast<const float4*>(scratch + r * kWsScratchLd + c4);
+                    }
+                    __syncwarp();
+                }
+                if (feed) {
+                    tc_fence_before();                               // TMEM tile drained
+                    fence_async_smem();                              // image writes visible to the tensor core
+                    mbar_arrive(&bar_aready[t]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // ------------------------------------------------------------------------------------------------ fused backward 128 x 128 x 128
 // dX = (dY W) (.) (X > 0)   and   dW += dY^T X,  db += colsum(dY)   in ONE pass over dY and X (hot shape only).
 // The dY and X row tiles are staged once (SW128, bf16 hi/lo) and each is read by the tensor core two ways:
@@ -1413,6 +1599,40 @@ int linear_bwd_fused_tc(const float* dY, int lddy, const float* X, int ldx, cons
     p.w_vec = (ldw % 4 == 0) && aligned16(W);
     p.dw_vec = (lddw % 4 == 0) && aligned16(dW);
     return precision == NPF_PREC_BF16X3 ? launch_fused<3>(p, st) : launch_fused<1>(p, st);
+}
+
+// Chain of L Linear(128 -> 128) layers with bias / ReLU epilogues, all outputs stored (saved activations).  NPF_ENOTSUP unless
+// every layer is 128 x 128, rows are 16-byte aligned and M fits one wave of 256-row CTAs.
+template <int NSPLIT>
+static int launch_chain(ChainParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)3 * (NSPLIT == 3 ? 2 : 1) * 32768 + (size_t)kWsEpiWarps * 32 * kWsScratchLd * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(mlp_chain_fwd_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return NPF_ENOTSUP;
+        }
+        attr = true;
+    }
+    int grid = (int)cdiv(p.M, kChainRows);
+    p.rows_per_cta = (int)(cdiv(cdiv(p.M, grid), 8) * 8);
+    grid = (int)cdiv(p.M, p.rows_per_cta);
+    launch_pdl(mlp_chain_fwd_kernel<NSPLIT>, dim3(grid), dim3(kWsThreads), smem, st, p);
+    count_launch();
+    return check_launch("mlp_chain_fwd_kernel");
+}
+
+int mlp_chain_fwd_tc(const float* X, int ldx, const float* const* W, const int* ldw, const float* const* b, float* const* Y, const int* ldy, int L, int M,
+                     int relu_in, unsigned relu_mask, int precision, cudaStream_t st) {
+    if (L < 2 || L > kChainMaxLayers || M < 1 || M > kNumSMs * kChainRows || precision == NPF_PREC_FP32) return NPF_ENOTSUP;
+    if (ldx % 4 != 0 || !aligned16(X)) return NPF_ENOTSUP;
+    ChainParams p{};
+    p.X = X; p.ldx = ldx; p.L = L; p.M = M; p.relu_in = relu_in; p.relu_mask = relu_mask;
+    for (int l = 0; l < L; ++l) {
+        if (ldw[l] % 4 != 0 || !aligned16(W[l]) || ldy[l] % 4 != 0 || !aligned16(Y[l])) return NPF_ENOTSUP;
+        p.W[l] = W[l]; p.ldw[l] = ldw[l]; p.b[l] = b ? b[l] : nullptr; p.Y[l] = Y[l]; p.ldy[l] = ldy[l];
+    }
+    return precision == NPF_PREC_BF16X3 ? launch_chain<3>(p, st) : launch_chain<1>(p, st);
 }
 
 template <int NSPLIT>

@@ -4,6 +4,8 @@ PyTorch is used for device memory (torch.empty / zeros from the caching allocato
 and autograd bookkeeping; every arithmetic op on the hot path is a kernel of the library.  All tensors are
 fp32, contiguous, on a CUDA device.  No CPU fallback: calling an op with CPU tensors raises.
 """
+import ctypes
+
 import torch
 
 from . import _cabi
@@ -79,6 +81,9 @@ def _gbuf(p):
     return g, g
 
 
+_CHAIN_MAX_ROWS = 148 * 256      # npf_mlp_chain_fwd keeps a row block on chip only within one wave of 256-row CTAs
+
+
 # ======================================================================================================
 # Linear / MLP chain
 # ======================================================================================================
@@ -125,12 +130,37 @@ class _MLPChain(torch.autograd.Function):
         lead = x.shape[:-1]
         h = _c(x).reshape(-1, x.shape[-1])
         acts = [h]
-        for i, (W, b) in enumerate(zip(Ws, bs)):
+        p_eff = _precision if prec is None else prec
+        i = 0
+        while i < n_layers:
+            W, b = Ws[i], bs[i]
+            K = W.numel() // W.shape[0]
+            # run of consecutive square 128-wide layers: one kernel keeps the row block on chip between layers
+            j = i
+            if p_eff != _PRECISION["fp32"] and K == 128 and h.shape[0] > 0:
+                while j < n_layers and Ws[j].shape[0] == 128 and Ws[j].numel() == 128 * 128 and Ws[j].is_contiguous():
+                    j += 1
+            if j - i >= 2 and h.shape[0] <= _CHAIN_MAX_ROWS:
+                L, M = j - i, h.shape[0]
+                ys = [torch.empty(M, 128, device=h.device, dtype=torch.float32) for _ in range(L)]
+                mask = 0
+                for l in range(L):
+                    if (i + l) != n_layers - 1 or final_relu:
+                        mask |= 1 << l
+                Wp = (ctypes.c_void_p * L)(*[Ws[i + l].data_ptr() for l in range(L)])
+                bp = (ctypes.c_void_p * L)(*[(bs[i + l].data_ptr() if bs[i + l] is not None else None) for l in range(L)])
+                Yp = (ctypes.c_void_p * L)(*[y.data_ptr() for y in ys])
+                call("npf_mlp_chain_fwd", _p(h), h.stride(0), Wp, bp, Yp, L, M, 128, 0, mask, p_eff, _stream())
+                acts.extend(ys)
+                h = ys[-1]
+                i = j
+                continue
             last = i == n_layers - 1
             flags = RELU_OUT if (not last or final_relu) else 0
             # W is [out, in] or a 1x1 conv weight [out, in, 1(, 1)]: same memory, K = numel / out
-            h = _lin_fwd(h, _c(W), None if b is None else _c(b), W.shape[0], W.numel() // W.shape[0], flags, prec=prec)
+            h = _lin_fwd(h, _c(W), None if b is None else _c(b), W.shape[0], K, flags, prec=prec)
             acts.append(h)
+            i += 1
         ctx.save_for_backward(*acts, *Ws, *(bs if has_bias else ()))
         ctx.n_layers, ctx.final_relu, ctx.has_bias = n_layers, final_relu, has_bias
         ctx.x_shape = x.shape
