@@ -94,6 +94,42 @@ def test_tc_fused_linear_backward(npf, prec, M, mask, bias):
 
 
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("L,M,relu_mask,relu_in", [(2, 1, 0b01, 0), (5, 257, 0b01111, 0), (8, 4099, 0b10110101, 1), (4, 37888, 0b0111, 0), (3, 40000, 0b011, 0)])
+def test_tc_mlp_chain_entry(npf, prec, L, M, relu_mask, relu_in):
+    """npf_mlp_chain_fwd (row block kept on chip between layers) against the same layers run one npf_linear_fwd at a time and
+    against fp64: every saved activation, missing biases, arbitrary ReLU pattern, partial tiles, and the size fallback."""
+    import ctypes
+    from npf_b200 import _cabi
+    pr = {"bf16": 1, "bf16x3": 2}[prec]
+    ftol, _ = BARS[prec]
+    st = torch.cuda.current_stream().cuda_stream
+    X = _g(M, 128, seed=1)
+    Ws = [_g(128, 128, seed=10 + l, scale=128 ** -0.5) for l in range(L)]
+    bs = [None if l % 3 == 1 else _g(128, seed=30 + l) for l in range(L)]
+    Xc, Wc = X.float().cuda(), [w.float().cuda() for w in Ws]
+    bc = [None if b is None else b.float().cuda() for b in bs]
+    Ys = [torch.full((M, 128), float("nan"), device="cuda") for _ in range(L)]
+    Wp = (ctypes.c_void_p * L)(*[w.data_ptr() for w in Wc])
+    bp = (ctypes.c_void_p * L)(*[None if b is None else b.data_ptr() for b in bc])
+    Yp = (ctypes.c_void_p * L)(*[y.data_ptr() for y in Ys])
+    _cabi.call("npf_mlp_chain_fwd", Xc.data_ptr(), 128, Wp, bp, Yp, L, M, 128, relu_in, relu_mask, pr, st)
+    h64 = torch.relu(X) if relu_in else X
+    hseq = Xc
+    for l in range(L):
+        h64 = h64 @ Ws[l].t() + (0 if bs[l] is None else bs[l])
+        if (relu_mask >> l) & 1:
+            h64 = torch.relu(h64)
+        y = torch.empty(M, 128, device="cuda")
+        flags = (2 if (l == 0 and relu_in) else 0) | (1 if (relu_mask >> l) & 1 else 0)
+        _cabi.call("npf_linear_fwd", hseq.data_ptr(), 128, Wc[l].data_ptr(), 128, 0 if bc[l] is None else bc[l].data_ptr(), y.data_ptr(), 128, M, 128, 128,
+                   flags, 0, 0, 0, pr, st)
+        hseq = y
+        assert torch.isfinite(Ys[l]).all()
+        assert rel_err(Ys[l], h64) < ftol * (l + 1), (l, rel_err(Ys[l], h64))
+        assert l2_rel(Ys[l], y) < (2e-5 if prec == "bf16x3" else 1e-2) * (l + 1), (l, l2_rel(Ys[l], y))
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
 def test_tc_model_parity_convcnp(npf, prec):
     """Whole ConvCNP (pointwise convs, SetConv resizer with the rank-1 density column, decoder MLP) on tensor cores."""
     npf.set_precision(prec)
