@@ -598,7 +598,7 @@ struct ChainParams {
 template <int NSPLIT>
 __global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_wfull, bar_wfree, bar_xready[2], bar_aready[2], bar_mma[2];
+    __shared__ __align__(8) uint64_t bar_wfull, bar_wfree, bar_xready[2], bar_aready[2], bar_drained[2], bar_mma[2];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_bias[kChainMaxLayers][128];     // all layers' biases (parameters), staged once
 
@@ -616,13 +616,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParam
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_xready[i], kWsProdWarps * 32);
             mbar_init(&bar_aready[i], kWsEpiWarps * 32);
+            mbar_init(&bar_drained[i], kWsEpiWarps * 32);
             mbar_init(&bar_mma[i], 1);
         }
     }
-    const int r_begin = blockIdx.x * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);
-    const int n_tiles = r_end > r_begin ? (r_end - r_begin + 127) >> 7 : 0;     // 1 or 2
+    // row blocks of rows_per_cta (<= 256) rows: block k of this CTA is blockIdx.x + k gridDim.x; `it` counts (block, layer) pairs
+    const int n_blocks = (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
+    const int L = p.L;
     const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
-    for (int i = tid; i < p.L * 128; i += kWsThreads) s_bias[i >> 7][i & 127] = p.b[i >> 7] ? __ldg(p.b[i >> 7] + (i & 127)) : 0.f;
+    for (int i = tid; i < L * 128; i += kWsThreads) s_bias[i >> 7][i & 127] = p.b[i >> 7] ? __ldg(p.b[i >> 7] + (i & 127)) : 0.f;
     pdl_trigger();
     tc_fence_before();
     __syncthreads();
@@ -633,7 +635,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParam
         // ------------------------------------------------------------------ stagers: warp w owns rows 16 w .. 16 w + 15 of a 128-row image
         const uint32_t psoff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 16) * 128u + (uint32_t)(lane & 1) * 8u;
         float4 pre[kWsPre];
-        // layer 0 weights first (parameters: may be read before the predecessor kernel has finished)
         auto load_w = [&](int l) {
 #pragma unroll
             for (int i = 0; i < kWsPre; ++i) pre[i] = __ldg(reinterpret_cast<const float4*>(p.W[l] + (long)(warp * 16 + i) * p.ldw[l]) + lane);
@@ -644,49 +645,65 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParam
             fence_async_smem();
             mbar_arrive(&bar_wfull);
         };
-        load_w(0);
-        store_w();
-        pdl_wait();
-        for (int t = 0; t < n_tiles; ++t) {                         // the block's input rows -> A images
-            const int row0 = r_begin + t * 128;
-            ws_load_rows(pre, p.X + ((long)row0 + warp * 16) * p.ldx + lane * 4, p.ldx, warp * 16, min(128, r_end - row0));
-            uint8_t* hi = smem_raw + t * kImg;
-#pragma unroll
-            for (int i = 0; i < kWsPre; ++i) cvt_store<NSPLIT>(pre[i], hi, hi + kTile, psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4), p.relu_in);
-            fence_async_smem();
-            mbar_arrive(&bar_xready[t]);
-        }
-        for (int l = 1; l < p.L; ++l) {
-            load_w(l);                                               // in flight while layer l-1 is multiplied
-            mbar_wait(&bar_wfree, (l - 1) & 1);                      // the MMAs of layer l-1 have read the weight buffer
+        int it = 0;
+        for (int blk = blockIdx.x, bi = 0; blk < n_blocks; blk += gridDim.x, ++bi) {
+            const int r_begin = blk * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);
+            const int n_tiles = (r_end - r_begin + 127) >> 7;
+            load_w(0);                                               // weights are parameters: may be read before the predecessor kernel is done
+            if (it > 0) mbar_wait(&bar_wfree, (it - 1) & 1);         // last layer of the previous block has read W and both images
             store_w();
+            if (bi == 0) pdl_wait();
+            for (int t = 0; t < n_tiles; ++t) {                      // the block's input rows -> A images
+                const int row0 = r_begin + t * 128;
+                ws_load_rows(pre, p.X + ((long)row0 + warp * 16) * p.ldx + lane * 4, p.ldx, warp * 16, min(128, r_end - row0));
+                uint8_t* hi = smem_raw + t * kImg;
+#pragma unroll
+                for (int i = 0; i < kWsPre; ++i) cvt_store<NSPLIT>(pre[i], hi, hi + kTile, psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4), p.relu_in);
+                fence_async_smem();
+                mbar_arrive(&bar_xready[t]);
+            }
+            ++it;
+            for (int l = 1; l < L; ++l, ++it) {
+                load_w(l);                                           // in flight while layer l-1 is multiplied
+                mbar_wait(&bar_wfree, (it - 1) & 1);                 // the MMAs of layer l-1 have read the weight buffer
+                store_w();
+            }
         }
     } else if (warp == kWsProdWarps) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, 128, 0, 0);
             const uint32_t sb_hi = smem_u32(w_hi), sb_lo = smem_u32(w_lo);
-            for (int l = 0; l < p.L; ++l) {
-                mbar_wait(&bar_wfull, l & 1);
-                for (int t = 0; t < n_tiles; ++t) {
-                    if (l == 0) mbar_wait(&bar_xready[t], 0);
-                    else mbar_wait(&bar_aready[t], (l - 1) & 1);     // epilogue of layer l-1 has rewritten the image and drained TMEM
-                    tc_fence_after();
-                    const uint32_t sa_hi = smem_u32(smem_raw + t * kImg), sa_lo = sa_hi + kTile;
-                    const uint32_t d = tmem + (uint32_t)t * 128u;
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t ao = (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u;
-                        const uint64_t a_h = make_desc_sw128(sa_hi + ao, 16, 1024), b_h = make_desc_sw128(sb_hi + ao, 16, 1024);
-                        umma_bf16(d, a_h, b_h, idesc, ks ? 1u : 0u);
-                        if (NSPLIT == 3) {
-                            umma_bf16(d, a_h, make_desc_sw128(sb_lo + ao, 16, 1024), idesc, 1);
-                            umma_bf16(d, make_desc_sw128(sa_lo + ao, 16, 1024), b_h, idesc, 1);
+            int it = 0;
+            for (int blk = blockIdx.x, bi = 0; blk < n_blocks; blk += gridDim.x, ++bi) {
+                const int r_begin = blk * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);
+                const int n_tiles = (r_end - r_begin + 127) >> 7;
+                for (int l = 0; l < L; ++l, ++it) {
+                    mbar_wait(&bar_wfull, it & 1);
+                    for (int t = 0; t < n_tiles; ++t) {
+                        if (l == 0) {
+                            mbar_wait(&bar_xready[t], bi & 1);
+                            if (bi > 0) mbar_wait(&bar_drained[t], (bi - 1) & 1);                     // previous block's last accumulator read out
+                        } else {
+                            mbar_wait(&bar_aready[t], (bi * (L - 1) + l - 1) & 1);                    // image rewritten and TMEM drained by layer l-1's epilogue
                         }
+                        tc_fence_after();
+                        const uint32_t sa_hi = smem_u32(smem_raw + t * kImg), sa_lo = sa_hi + kTile;
+                        const uint32_t d = tmem + (uint32_t)t * 128u;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint32_t ao = (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u;
+                            const uint64_t a_h = make_desc_sw128(sa_hi + ao, 16, 1024), b_h = make_desc_sw128(sb_hi + ao, 16, 1024);
+                            umma_bf16(d, a_h, b_h, idesc, ks ? 1u : 0u);
+                            if (NSPLIT == 3) {
+                                umma_bf16(d, a_h, make_desc_sw128(sb_lo + ao, 16, 1024), idesc, 1);
+                                umma_bf16(d, make_desc_sw128(sa_lo + ao, 16, 1024), b_h, idesc, 1);
+                            }
+                        }
+                        umma_commit(&bar_mma[t]);
                     }
-                    umma_commit(&bar_mma[t]);
+                    umma_commit(&bar_wfree);
                 }
-                umma_commit(&bar_wfree);
             }
         }
     } else {
@@ -698,61 +715,70 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParam
         const int r_in = lane >> 2, c4 = (lane & 3) * 4;
         const int row_img = lane_base + lane;                        // this thread's row of the image (TMEM lane)
         pdl_wait();
-        for (int l = 0; l < p.L; ++l) {
-            const bool relu = (p.relu_mask >> l) & 1u;
-            const bool feed = l + 1 < p.L;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int m0 = r_begin + t * 128 + lane_base;
-                mbar_wait(&bar_mma[t], l & 1);
-                tc_fence_after();
-                uint8_t* img_hi = smem_raw + t * kImg;
+        int it = 0;
+        for (int blk = blockIdx.x, bi = 0; blk < n_blocks; blk += gridDim.x, ++bi) {
+            const int r_begin = blk * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);
+            const int n_tiles = (r_end - r_begin + 127) >> 7;
+            for (int l = 0; l < L; ++l, ++it) {
+                const bool relu = (p.relu_mask >> l) & 1u;
+                const bool feed = l + 1 < L;
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int m0 = r_begin + t * 128 + lane_base;
+                    mbar_wait(&bar_mma[t], it & 1);
+                    tc_fence_after();
+                    uint8_t* img_hi = smem_raw + t * kImg;
 #pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    const int c0 = col_base + ch * 16;
-                    float v[16];
-                    tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 128 + c0), v);
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[l][c0 + j]);
-                        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-                    }
-                    if (relu) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-                    if (feed) {                                      // next layer's A operand: row row_img, columns c0 .. c0 + 15 (two 16-byte chunks)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int c = c0 + h * 8;
-                            const uint32_t off = (uint32_t)(c >> 6) * 16384u + (uint32_t)row_img * 128u + ((((uint32_t)(c & 63) >> 3) ^ (uint32_t)(row_img & 7)) << 4);
-                            uint32_t hh[4], ll[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float a = v[h * 8 + 2 * q], b2 = v[h * 8 + 2 * q + 1];
-                                hh[q] = pack_bf16(a, b2);
-                                ll[q] = pack_bf16(a - __uint_as_float(hh[q] << 16), b2 - __uint_as_float(hh[q] & 0xFFFF0000u));
-                            }
-                            *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                            if (NSPLIT == 3) *reinterpret_cast<uint4*>(img_hi + kTile + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int c0 = col_base + ch * 16;
+                        float v[16];
+                        tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 128 + c0), v);
+                        if (!feed && ch == 3) {                      // last layer: the accumulator may be reused by the next block
+                            tc_fence_before();
+                            mbar_arrive(&bar_drained[t]);
                         }
-                    }
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(scratch + lane * kWsScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    __syncwarp();
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(&s_bias[l][c0 + j]);
+                            v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+                        }
+                        if (relu) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = j * 8 + r_in;
-                        const int row = m0 + r;
-                        if (row < r_end)
-                            *reinterpret_cast<float4*>(p.Y[l] + (long)row * p.ldy[l] + c0 + c4) = *reinterpret_cast<const float4*>(scratch + r * kWsScratchLd + c4);
+                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        if (feed) {                                  // next layer's A operand: row row_img, columns c0 .. c0 + 15 (two 16-byte chunks)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int c = c0 + h * 8;
+                                const uint32_t off = (uint32_t)(c >> 6) * 16384u + (uint32_t)row_img * 128u + ((((uint32_t)(c & 63) >> 3) ^ (uint32_t)(row_img & 7)) << 4);
+                                uint32_t hh[4], ll[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float a = v[h * 8 + 2 * q], b2 = v[h * 8 + 2 * q + 1];
+                                    hh[q] = pack_bf16(a, b2);
+                                    ll[q] = pack_bf16(a - __uint_as_float(hh[q] << 16), b2 - __uint_as_float(hh[q] & 0xFFFF0000u));
+                                }
+                                *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                                if (NSPLIT == 3) *reinterpret_cast<uint4*>(img_hi + kTile + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(scratch + lane * kWsScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int r = j * 8 + r_in;
+                            const int row = m0 + r;
+                            if (row < r_end)
+                                *reinterpret_cast<float4*>(p.Y[l] + (long)row * p.ldy[l] + c0 + c4) = *reinterpret_cast<const float4*>(scratch + r * kWsScratchLd + c4);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
-                }
-                if (feed) {
-                    tc_fence_before();                               // TMEM tile drained
-                    fence_async_smem();                              // image writes visible to the tensor core
-                    mbar_arrive(&bar_aready[t]);
+                    if (feed) {
+                        tc_fence_before();                           // TMEM tile drained
+                        fence_async_smem();                          // image writes visible to the tensor core
+                        mbar_arrive(&bar_aready[t]);
+                    }
                 }
             }
         }
@@ -1615,8 +1641,13 @@ static int launch_chain(ChainParams& p, cudaStream_t st) {
         attr = true;
     }
     int grid = (int)cdiv(p.M, kChainRows);
-    p.rows_per_cta = (int)(cdiv(cdiv(p.M, grid), 8) * 8);
-    grid = (int)cdiv(p.M, p.rows_per_cta);
+    if (grid <= kNumSMs) {                       // one balanced block per CTA
+        p.rows_per_cta = (int)(cdiv(cdiv(p.M, grid), 8) * 8);
+        grid = (int)cdiv(p.M, p.rows_per_cta);
+    } else {                                     // persistent CTAs walk 256-row blocks (weights re-staged per block and layer from L2)
+        p.rows_per_cta = kChainRows;
+        grid = kNumSMs;
+    }
     launch_pdl(mlp_chain_fwd_kernel<NSPLIT>, dim3(grid), dim3(kWsThreads), smem, st, p);
     count_launch();
     return check_launch("mlp_chain_fwd_kernel");
@@ -1624,7 +1655,7 @@ static int launch_chain(ChainParams& p, cudaStream_t st) {
 
 int mlp_chain_fwd_tc(const float* X, int ldx, const float* const* W, const int* ldw, const float* const* b, float* const* Y, const int* ldy, int L, int M,
                      int relu_in, unsigned relu_mask, int precision, cudaStream_t st) {
-    if (L < 2 || L > kChainMaxLayers || M < 1 || M > kNumSMs * kChainRows || precision == NPF_PREC_FP32) return NPF_ENOTSUP;
+    if (L < 2 || L > kChainMaxLayers || M < 1 || precision == NPF_PREC_FP32) return NPF_ENOTSUP;
     if (ldx % 4 != 0 || !aligned16(X)) return NPF_ENOTSUP;
     ChainParams p{};
     p.X = X; p.ldx = ldx; p.L = L; p.M = M; p.relu_in = relu_in; p.relu_mask = relu_mask;

@@ -81,7 +81,7 @@ def _gbuf(p):
     return g, g
 
 
-_CHAIN_MAX_ROWS = 148 * 256      # npf_mlp_chain_fwd keeps a row block on chip only within one wave of 256-row CTAs
+_CHAIN_MAX_ROWS = 1 << 30       # npf_mlp_chain_fwd: one 256-row block per CTA up to 37 888 rows, persistent CTAs over blocks beyond
 
 
 # ======================================================================================================

@@ -94,7 +94,7 @@ def test_tc_fused_linear_backward(npf, prec, M, mask, bias):
 
 
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
-@pytest.mark.parametrize("L,M,relu_mask,relu_in", [(2, 1, 0b01, 0), (5, 257, 0b01111, 0), (8, 4099, 0b10110101, 1), (4, 37888, 0b0111, 0), (3, 40000, 0b011, 0)])
+@pytest.mark.parametrize("L,M,relu_mask,relu_in", [(2, 1, 0b01, 0), (5, 257, 0b01111, 0), (8, 4099, 0b10110101, 1), (4, 37888, 0b0111, 0), (3, 40000, 0b011, 0), (4, 131072, 0b1111, 0)])
 def test_tc_mlp_chain_entry(npf, prec, L, M, relu_mask, relu_in):
     """npf_mlp_chain_fwd (row block kept on chip between layers) against the same layers run one npf_linear_fwd at a time and
     against fp64: every saved activation, missing biases, arbitrary ReLU pattern, partial tiles, and the size fallback."""
