@@ -298,11 +298,11 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(TcLinParams p
 // Two smem operand stages and two TMEM accumulators (2 x 128 columns): tile i+1 is loaded and converted while tile i is
 // multiplied and tile i-1 is drained, so the HBM stream never waits on the math.  The weights are staged once per CTA in the
 // row layout of W; the data gradient reads the very same staging through an MN-major descriptor (transpose for free).
-constexpr int kWsProdWarps = 8;
-constexpr int kWsEpiWarp0 = 9;
+constexpr int kWsProdWarps = 16;
+constexpr int kWsEpiWarp0 = 17;
 constexpr int kWsEpiWarps = 8;
-constexpr int kWsThreads = (kWsEpiWarp0 + kWsEpiWarps) * 32;     // 544
-constexpr int kWsPre = 16;                                       // float4 per producer thread per tile
+constexpr int kWsThreads = (kWsEpiWarp0 + kWsEpiWarps) * 32;     // 800
+constexpr int kWsPre = 8;                                        // float4 per producer thread per tile
 constexpr int kWsScratchLd = 20;                                 // 16 columns + 4 pad (conflict-free STS.128)
 
 template <int NSPLIT>
@@ -384,45 +384,30 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
         s_w2[tid] = (HAS_U && p.w2) ? __ldg(p.w2 + (long)tid * p.ldw2) : 0.f;
     }
 
-    // producer geometry (also used for the weight staging below)
-    const int l16 = tid & 15, pr = l16 & 7, phalf = l16 >> 3;
-    float4 pre[kWsPre];
+    static_assert(SW, "the warp-specialised kernel stages SWIZZLE_128B operands");
+    // producer geometry (also used for the weight staging below): warp w owns rows 8 w .. 8 w + 7 of a 128-row tile; per row
+    // the 32 lanes load the 512 contiguous bytes (one LDG.128 each) and store 8 bytes of hi and of lo.  SIXTEEN producer warps
+    // with 8 loads each rather than 8 x 16: at equal bytes in flight a streaming kernel on this part gets 5.7 vs 4.7 TB/s
+    // (profiles/microbench/stream_probe.cu) -- the memory pipe wants warps, not deep per-warp queues.
     // balanced contiguous row ranges: every CTA gets M / gridDim rows (8-row granularity) = whole 128-row tiles + one partial
     // tile, instead of 128-row tiles dealt round-robin (768 tiles over 148 SMs would cost 6 rounds for 5.2 tiles of work)
     const int r_begin = blockIdx.x * p.rows_per_cta, r_end = min(p.M, r_begin + p.rows_per_cta);
     const int n_local = r_end > r_begin ? (r_end - r_begin + 127) >> 7 : 0;
-    const int pkc = (tid >> 4) & 15;
-    // no-swizzle: thread -> (k chunk, row in group, half); SW128: thread -> (row block of the warp, float4 column = lane)
-    const float* pg = SW ? p.A + (long)(warp * 16) * p.lda + lane * 4 : p.A + (long)pr * p.lda + pkc * 8 + phalf * 4;
-    const uint32_t psoff = SW ? (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 16) * 128u + (uint32_t)(lane & 1) * 8u
-                              : (uint32_t)pkc * 2048u + (uint32_t)pr * 16u + (uint32_t)phalf * 8u;
     const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
+    const uint32_t psoff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
     pdl_trigger();      // the next kernel may start its own parameter-only prologue as SMs free up
 
-    // weights [128 x 128] fp32 row-major, staged once per CTA by threads 0..511 (8 float4 each) in the layout of the A tiles
-    if (tid < 512) {
+    // weights [128 x 128] fp32 row-major, staged once per CTA by the 16 producer warps in the layout of the A tiles
+    if (warp < kWsProdWarps) {
         float4 wv[8];
-        if (SW) {                                                    // warp w: rows 8 w .. 8 w + 7
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float* g = p.W + (long)(warp * 8 + i) * p.ldw + lane * 4;
-                if (p.w_vec) wv[i] = __ldg(reinterpret_cast<const float4*>(g));
-                else wv[i] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                cvt_store<NSPLIT>(wv[i], b_hi, b_lo, (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8 + i) * 128u + ((pchunk ^ (uint32_t)i) << 4) + (uint32_t)(lane & 1) * 8u, 0);
-        } else {
-            const int rg0 = tid >> 8;                                // float4 index f = tid + 512 i: kc = (tid/16)%16, rg = tid/256 + 2i
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float* g = p.W + (long)((rg0 + 2 * i) * 8 + pr) * p.ldw + pkc * 8 + phalf * 4;
-                if (p.w_vec) wv[i] = __ldg(reinterpret_cast<const float4*>(g));
-                else wv[i] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cvt_store<NSPLIT>(wv[i], b_hi, b_lo, psoff + (uint32_t)(rg0 + 2 * i) * 128u, 0);
+        for (int i = 0; i < 8; ++i) {
+            const float* g = p.W + (long)(warp * 8 + i) * p.ldw + lane * 4;
+            if (p.w_vec) wv[i] = __ldg(reinterpret_cast<const float4*>(g));
+            else wv[i] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cvt_store<NSPLIT>(wv[i], b_hi, b_lo, psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4), 0);
     }
     fence_async_smem();
     tc_fence_before();
@@ -434,9 +419,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
 
     if (warp < kWsProdWarps) {
         // ------------------------------------------------------------------ producers
+        const float* pg = p.A + (long)(warp * 8) * p.lda + lane * 4;
+        float4 pre[kWsPre];
         if (n_local > 0) {
-            if (SW) ws_load_rows(pre, pg + (long)r_begin * p.lda, p.lda, warp * 16, min(128, r_end - r_begin));
-            else ws_load_tile(pre, pg + (long)r_begin * p.lda, p.lda, pr, min(128, r_end - r_begin));
+            ws_load_rows(pre, pg + (long)r_begin * p.lda, p.lda, warp * 8, min(128, r_end - r_begin));
             if (n_local > 1) prefetch_tile_l2(p.A, p.lda, (long)r_begin + 128, min(128, r_end - r_begin - 128), tid, kWsProdWarps * 32);
         }
         for (int it = 0; it < n_local; ++it) {
@@ -445,14 +431,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
             uint8_t* hi = smem_raw + s * kStage;
             uint8_t* lo = hi + kTile;
 #pragma unroll
-            for (int i = 0; i < kWsPre; ++i)
-                cvt_store<NSPLIT>(pre[i], hi, lo, SW ? psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4) : psoff + (uint32_t)i * 128u, p.relu_in);
+            for (int i = 0; i < kWsPre; ++i) cvt_store<NSPLIT>(pre[i], hi, lo, psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4), p.relu_in);
             fence_async_smem();
             mbar_arrive(&bar_full[s]);
             if (it + 1 < n_local) {
                 const int nrow = r_begin + (it + 1) * 128;
-                if (SW) ws_load_rows(pre, pg + (long)nrow * p.lda, p.lda, warp * 16, min(128, r_end - nrow));
-                else ws_load_tile(pre, pg + (long)nrow * p.lda, p.lda, pr, min(128, r_end - nrow));
+                ws_load_rows(pre, pg + (long)nrow * p.lda, p.lda, warp * 8, min(128, r_end - nrow));
                 if (it + 2 < n_local) prefetch_tile_l2(p.A, p.lda, (long)nrow + 128, min(128, r_end - nrow - 128), tid, kWsProdWarps * 32);
             }
         }
@@ -582,7 +566,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
 // written once to HBM as the saved activation Y_l AND re-split into bf16 hi / lo straight into the shared-memory A-operand
 // image of layer l+1.  Against one kernel per layer this removes the read of every intermediate activation, L - 1 launches
 // with their parameter prologues and pipeline fill / drain -- the per-layer kernels of the 32 768-row decoder MLP spend
-// most of their 15 us there (1.7 tiles per SM).  Roles: 8 stager warps (X rows at the start, then W_l per layer, prefetched
+// most of their 15 us there (1.7 tiles per SM).  Roles: 16 stager warps (X rows at the start, then W_l per layer, prefetched
 // into registers while layer l-1 is multiplied), 1 MMA warp, 8 epilogue warps.
 constexpr int kChainMaxLayers = 8;
 constexpr int kChainRows = 256;
@@ -632,12 +616,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParam
     const uint32_t tmem = tmem_slot;
 
     if (warp < kWsProdWarps) {
-        // ------------------------------------------------------------------ stagers: warp w owns rows 16 w .. 16 w + 15 of a 128-row image
-        const uint32_t psoff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 16) * 128u + (uint32_t)(lane & 1) * 8u;
+        // ------------------------------------------------------------------ stagers: warp w owns rows 8 w .. 8 w + 7 of a 128-row image
+        const uint32_t psoff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
         float4 pre[kWsPre];
         auto load_w = [&](int l) {
 #pragma unroll
-            for (int i = 0; i < kWsPre; ++i) pre[i] = __ldg(reinterpret_cast<const float4*>(p.W[l] + (long)(warp * 16 + i) * p.ldw[l]) + lane);
+            for (int i = 0; i < kWsPre; ++i) pre[i] = __ldg(reinterpret_cast<const float4*>(p.W[l] + (long)(warp * 8 + i) * p.ldw[l]) + lane);
         };
         auto store_w = [&]() {
 #pragma unroll
@@ -655,7 +639,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParam
             if (bi == 0) pdl_wait();
             for (int t = 0; t < n_tiles; ++t) {                      // the block's input rows -> A images
                 const int row0 = r_begin + t * 128;
-                ws_load_rows(pre, p.X + ((long)row0 + warp * 16) * p.ldx + lane * 4, p.ldx, warp * 16, min(128, r_end - row0));
+                ws_load_rows(pre, p.X + ((long)row0 + warp * 8) * p.ldx + lane * 4, p.ldx, warp * 8, min(128, r_end - row0));
                 uint8_t* hi = smem_raw + t * kImg;
 #pragma unroll
                 for (int i = 0; i < kWsPre; ++i) cvt_store<NSPLIT>(pre[i], hi, hi + kTile, psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4), p.relu_in);
@@ -1272,13 +1256,11 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
         const int ws_grid = (int)cdiv(p.M, p.rows_per_cta);
         // warp-specialised pipeline (2 operand stages + weights + epilogue scratch)
         const size_t ws_smem = (size_t)3 * (NSPLIT == 3 ? 2 : 1) * 32768 + (size_t)kWsEpiWarps * 32 * kWsScratchLd * sizeof(float);
-        static const bool sw = getenv("NPF_WS_SW") ? atoi(getenv("NPF_WS_SW")) != 0 : true;
         static bool ws_attr = false;
         if (!ws_attr) {
             bool ok = true;
 #define NPF_WS_ATTR(U, MK, S) ok = ok && cudaFuncSetAttribute(linear_ws_kernel<NSPLIT, U, MK, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess
             NPF_WS_ATTR(false, false, true); NPF_WS_ATTR(true, false, true); NPF_WS_ATTR(false, true, true);
-            NPF_WS_ATTR(false, false, false); NPF_WS_ATTR(true, false, false); NPF_WS_ATTR(false, true, false);
 #undef NPF_WS_ATTR
             if (!ok) {
                 cudaGetLastError();
@@ -1286,15 +1268,9 @@ static int launch_lin(TcLinParams& p, cudaStream_t st) {
             }
             ws_attr = true;
         }
-        if (sw) {
-            if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, true>, ws_grid, kWsThreads, ws_smem, st, p);
-            else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, true>, ws_grid, kWsThreads, ws_smem, st, p);
-            else launch_pdl(linear_ws_kernel<NSPLIT, false, false, true>, ws_grid, kWsThreads, ws_smem, st, p);
-        } else {
-            if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, false>, ws_grid, kWsThreads, ws_smem, st, p);
-            else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, false>, ws_grid, kWsThreads, ws_smem, st, p);
-            else launch_pdl(linear_ws_kernel<NSPLIT, false, false, false>, ws_grid, kWsThreads, ws_smem, st, p);
-        }
+        if (p.u) launch_pdl(linear_ws_kernel<NSPLIT, true, false, true>, ws_grid, kWsThreads, ws_smem, st, p);
+        else if (p.mask) launch_pdl(linear_ws_kernel<NSPLIT, false, true, true>, ws_grid, kWsThreads, ws_smem, st, p);
+        else launch_pdl(linear_ws_kernel<NSPLIT, false, false, true>, ws_grid, kWsThreads, ws_smem, st, p);
         count_launch();
         return check_launch("linear_ws_kernel");
     }
