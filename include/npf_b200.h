@@ -250,6 +250,15 @@ NPF_API int npf_global_latent_fwd(const float* zin, float* out, int N, int P, in
 NPF_API int npf_global_latent_bwd(const float* dout, float* dzin, int N, int P, int C, npf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Optimizer step on flat buffers -- the step AFTER the path (torch.optim.Adam as configured by utils/train.py:50, 237-254).
+ * One pass over n contiguous fp32 parameters and their gradient / first / second moment buffers; `step` is the 1-based
+ * step count (bias corrections computed on the host in double), grad_scale multiplies the gradient first (1 / world
+ * size, or a clipping factor), weight_decay is the L2 (non-decoupled) form of torch.optim.Adam.
+ * ------------------------------------------------------------------------------------------------ */
+NPF_API int npf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int step, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Input validation without a host sync  (NeuralProcessFamily._validate_inputs npf/neuralproc/base.py:241-247,
  * isin_range npf/utils/helpers.py:55-57): flag[0] |= 1 if any x outside [lo, hi]  (flag is device int32)
  * ------------------------------------------------------------------------------------------------ */

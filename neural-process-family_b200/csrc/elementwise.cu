@@ -1,6 +1,8 @@
 // Small fused element-wise / reduction kernels around the three hot kernel groups: sum-merge, context mean
 // pooling, add+LayerNorm, predictive head, Gaussian log-likelihood, latent sampling, global latent, input check.
 // All HBM-bound streaming kernels: grid-stride, coalesced on the channel (last) axis.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace npf {
@@ -306,6 +308,24 @@ __global__ void range_check_kernel(const float* __restrict__ X, long n, float lo
 
 using namespace npf;
 
+
+// ------------------------------------------------------------------------------------------------ optimizer (next row)
+// torch.optim.Adam (utils/train.py:50, the optimizer every notebook passes to skorch) on flat fp32 buffers: one elementwise pass
+// over (param, grad, exp_avg, exp_avg_sq) instead of ~40 small foreach launches.  Same update order as torch's single-tensor path:
+//   g' = g * grad_scale + wd * p;  m = b1 m + (1 - b1) g';  v = b2 v + (1 - b2) g'^2;  p -= step_size * m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void adam_kernel(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ Mo, float* __restrict__ V, long n, float step_size,
+                            float inv_sqrt_bc2, float b1, float b2, float eps, float wd, float grad_scale) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float p = P[i];
+        const float g = fmaf(wd, p, G[i] * grad_scale);
+        const float m = fmaf(b1, Mo[i], (1.f - b1) * g);
+        const float v = fmaf(b2, V[i], (1.f - b2) * g * g);
+        Mo[i] = m;
+        V[i] = v;
+        P[i] = p - step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+    }
+}
+
 #define LAUNCH_1D(kernel, n, st, ...)                                    \
     do {                                                                 \
         kernel<<<grid_for(n), 256, 0, st>>>(__VA_ARGS__);                \
@@ -444,3 +464,14 @@ extern "C" int npf_range_check(const float* X, long n, float lo, float hi, int* 
     if (n <= 0) return NPF_OK;
     LAUNCH_1D(range_check_kernel, n, as_stream(stream), X, n, lo, hi, flag);
 }
+
+extern "C" int npf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int step, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, float grad_scale, npf_stream_t stream) {
+    NPF_REQUIRE(param && grad && exp_avg && exp_avg_sq, "npf_adam_step: null pointer");
+    NPF_REQUIRE(n >= 0 && step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "npf_adam_step: bad hyper-parameter");
+    if (n == 0) return NPF_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    LAUNCH_1D(adam_kernel, n, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps,
+              weight_decay, grad_scale);
+}
+

@@ -50,6 +50,7 @@ SIGNATURES = {
     "npf_latent_sample_bwd": [P, P, P, P, P, P, I, L, I, P],
     "npf_global_latent_fwd": [P, P, I, I, I, P],
     "npf_global_latent_bwd": [P, P, I, I, I, P],
+    "npf_adam_step": [P, P, P, P, L, I, F, F, F, F, F, F, P],
     "npf_range_check": [P, L, F, F, P, P],
 }
 BOOKKEEPING = {

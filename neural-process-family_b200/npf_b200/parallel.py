@@ -7,7 +7,7 @@ NVSwitch).  Works with any ``torch.distributed`` backend (``gloo`` on CPU for th
 import torch
 import torch.distributed as dist
 
-__all__ = ["FlatGradients", "shard_tasks"]
+__all__ = ["FlatGradients", "FlatAdam", "shard_tasks"]
 
 
 class FlatGradients:
@@ -52,6 +52,49 @@ class FlatGradients:
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.flat.mul_(1.0 / w)
         return self.flat
+
+
+class FlatAdam:
+    """torch.optim.Adam (the optimizer of upstream utils/train.py:50) over the flat gradient bucket: the parameters are
+    re-pointed into ONE contiguous fp32 buffer laid out like ``flat`` (same 128-byte aligned slots), so a step is a single
+    elementwise kernel (``npf_adam_step``) over (param, grad, exp_avg, exp_avg_sq) instead of ~40 small foreach launches.
+    ``lr`` may be changed between steps (``opt.lr = ...``: ExponentialLR is ``opt.lr *= gamma`` per epoch);
+    ``grad_scale`` pre-multiplies the gradient (gradient clipping by global norm: ``min(1, max_norm / norm)``)."""
+
+    def __init__(self, flat, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
+        self.step_count = 0
+        g = flat.flat
+        self.param = torch.zeros_like(g)
+        with torch.no_grad():
+            for p, off in zip(flat.params, flat.offsets):
+                view = self.param[off: off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view                     # the module now reads / the kernels now update the flat storage
+        self.exp_avg = torch.zeros_like(g)
+        self.exp_avg_sq = torch.zeros_like(g)
+
+    def global_grad_norm(self):
+        return self.flat.flat.norm()              # padding between slots is zero
+
+    def step(self, grad_scale=1.0):
+        from . import _cabi
+        self.step_count += 1
+        n = self.param.numel()
+        if self.param.is_cuda:
+            _cabi.call("npf_adam_step", self.param.data_ptr(), self.flat.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), n,
+                       self.step_count, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                       float(grad_scale), torch.cuda.current_stream().cuda_stream)
+            return
+        raise RuntimeError("FlatAdam: CUDA only (there is no CPU fallback)")
+
+    def state_dict(self):
+        return dict(step=self.step_count, lr=self.lr, exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone())
+
+    def load_state_dict(self, sd):
+        self.step_count, self.lr = int(sd["step"]), float(sd["lr"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
 
 
 def shard_tasks(batch, rank, world_size):
