@@ -1323,6 +1323,9 @@ int linear_bwd_data_tc(const float* dY, int lddy, const float* W, int ldw, float
 // The accumulator then has k on the TMEM lanes and the tile's rows on the columns, so an epilogue thread owns ONE column k
 // of dX and every register it reads is one row: a warp store covers 128 contiguous bytes without any shared-memory
 // transpose, and the relu mask is a 2-byte read of the staged X tile.  Producers keep TWO tiles in flight in registers.
+#ifndef F64_DEPTH
+#define F64_DEPTH 1
+#endif
 constexpr int kF64Rows = 64;
 #ifndef NPF_F64_AHEAD
 #define NPF_F64_AHEAD 4
@@ -1423,21 +1426,26 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused64_kernel(TcFus
             }
             fence_async_smem();
             mbar_arrive(&bar_full[s]);
-            if (it + 2 < n_local) load_tile(yy, xx, it + 2);
+            if (it + F64_DEPTH < n_local) load_tile(yy, xx, it + F64_DEPTH);
             if (it + kF64Ahead < n_local) {        // L2 prefetch kF64Ahead tiles ahead (2 tiles are in flight in registers)
                 const int row0 = r_begin + (it + kF64Ahead) * kF64Rows, rv = min(kF64Rows, r_end - row0);
                 if (tid < 256) f64_prefetch(p.dY, p.lddy, row0, rv, tid); else f64_prefetch(p.X, p.ldx, row0, rv, tid);
             }
         };
+        static const int kDepth = F64_DEPTH;
         if (n_local > 0) load_tile(ya, xa, 0);
-        if (n_local > 1) load_tile(yb, xb, 1);
-        for (int a = 2; a < kF64Ahead && a < n_local; ++a) {
+        if (kDepth == 2 && n_local > 1) load_tile(yb, xb, 1);
+        for (int a = kDepth; a < kF64Ahead && a < n_local; ++a) {
             const int row0 = r_begin + a * kF64Rows, rv = min(kF64Rows, r_end - row0);
             if (tid < 256) f64_prefetch(p.dY, p.lddy, row0, rv, tid); else f64_prefetch(p.X, p.ldx, row0, rv, tid);
         }
-        for (int it = 0; it < n_local; it += 2) {
-            put_tile(ya, xa, it);
-            if (it + 1 < n_local) put_tile(yb, xb, it + 1);
+        if (kDepth == 2) {
+            for (int it = 0; it < n_local; it += 2) {
+                put_tile(ya, xa, it);
+                if (it + 1 < n_local) put_tile(yb, xb, it + 1);
+            }
+        } else {
+            for (int it = 0; it < n_local; ++it) put_tile(ya, xa, it);
         }
         if (p.db) {
             atomicAdd(&s_db[lane * 4 + 0], dbs.x); atomicAdd(&s_db[lane * 4 + 1], dbs.y);
