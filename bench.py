@@ -126,6 +126,23 @@ class ClockSampler:
                 return int(ids[self.index])
         return self.index
 
+    def sample_now(self):
+        """One synchronous sample from the caller's thread (the polling thread can be starved of the GIL by the launch loop)."""
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            bits = (n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown, n.nvmlClocksEventReasonSwThermalSlowdown,
+                    n.nvmlClocksEventReasonSwPowerCap)
+            self.samples.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & b else "Not Active" for b in bits])
+        except Exception:
+            pass
+
     def _poll(self):
         n = self.nvml
         names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
@@ -325,6 +342,8 @@ def main():
         evs[i][0].record()
         step(dev_inputs[i % n_sets])
         evs[i][1].record()
+        if rank == 0 and i % 8 == 4:
+            sampler.sample_now()            # under load: the GPU is several replays behind the host here
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = ops.launch_count() - n0 if gstep is None else gstep.last_launches * args.steps   # replays launch the recorded kernels
