@@ -6,7 +6,7 @@ path is CUDA-only and raises if its extension is missing.
 
 What it is: a *functional* restatement (plain functions over a ``state_dict``; no ``nn.Module``) of
 the algorithm the reference implements in ``npf/`` for the per-task forward / loss of CNP, AttnCNP,
-ConvCNP, GridConvCNP, ConvLNP, GridConvLNP (+ LNP).  Arithmetic is torch CPU (fp32 or fp64), which is
+ConvCNP, GridConvCNP, ConvLNP, GridConvLNP (+ LNP, AttnLNP, self-attention encoders).  Arithmetic is torch CPU (fp32 or fp64), which is
 the reference's own third-party arithmetic (every FLOP of the reference is an
 ATen op); gradients come from torch autograd over this restatement.  Each function cites the
 reference ``file:line`` it follows (paths relative to the upstream repo root).
@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 __all__ = [
     "mlp", "merge_flat_sum", "setconv", "res_conv_cnn", "dot_attention", "multihead_attention",
-    "transformer_attention", "cnp_forward", "attncnp_forward", "convcnp_forward",
+    "transformer_attention", "self_attention", "cnp_forward", "attncnp_forward", "attnlnp_forward", "convcnp_forward",
     "gridconvcnp_forward", "lnp_forward", "convlnp_forward", "gridconvlnp_forward",
     "gauss_sum_log_prob", "cnpf_loss", "nll_lnpf_loss", "elbo_lnpf_loss", "induced_grid",
     "p_y_scale", "q_z_scale",
@@ -198,6 +198,47 @@ def transformer_attention(sd, prefix, keys, queries, values, n_heads=8):
     return ctx
 
 
+def self_attention(sd, prefix, X, attention="transformer", n_attn_layers=2, n_heads=8):
+    """SelfAttention.forward, npf/architectures/selfattn.py:82-100 with positional=None: every layer
+    attends the set to itself (keys = queries = values = previous output); Linear ``resize`` at the end
+    when an output size was given."""
+    out = X
+    for i in range(n_attn_layers):
+        pre = prefix + f"attn_layers.{i}."
+        if attention == "scaledot":
+            out = dot_attention(out, out, out)
+        elif attention == "multihead":
+            out = multihead_attention(sd, pre, out, out, out, n_heads)
+        elif attention == "transformer":
+            out = transformer_attention(sd, pre, out, out, out, n_heads)
+        else:
+            raise ValueError(f"Unknown attention method {attention}")
+    if (prefix + "resize.weight") in sd:
+        out = _lin(sd, prefix + "resize.", out)
+    return out
+
+
+def _attn_xy_encode(sd, Xe, Y, is_self_attn, self_attention_type="transformer"):
+    """The per-point context encoder of AttnCNP / AttnLNP: MergeFlatInputs around an MLP, or around
+    SelfAttention when ``is_self_attn`` (npf/neuralproc/attnnp.py:88-96).  The self-attention layers
+    take their type from ``self_attention_kwargs`` (default "transformer", selfattn.py:50), NOT from the
+    ``attention`` argument, which only selects the cross-attention."""
+    if not is_self_attn:
+        return merge_flat_sum(sd, "xy_encoder.", Xe, Y)
+    h = torch.relu(Xe + mlp(sd, "xy_encoder.resizer.", Y))
+    return self_attention(sd, "xy_encoder.flat_module.", h, self_attention_type)
+
+
+def _attend(sd, Xe_c, Xe_t, R_c, attention, n_heads):
+    if attention == "scaledot":
+        return dot_attention(Xe_c, Xe_t, R_c)
+    if attention == "multihead":
+        return multihead_attention(sd, "attender.", Xe_c, Xe_t, R_c, n_heads)
+    if attention == "transformer":
+        return transformer_attention(sd, "attender.", Xe_c, Xe_t, R_c, n_heads)
+    raise ValueError(f"Unknown attention method {attention}")
+
+
 # --------------------------------------------------------------------------------------------
 # models (npf/neuralproc): each returns (loc, scale) of shape [n_z, B, *n_trgt, y_dim] (+ latents)
 # --------------------------------------------------------------------------------------------
@@ -229,25 +270,18 @@ def cnp_forward(sd, X_cntxt, Y_cntxt, X_trgt):
     return _decode(sd, Xe_t, R_trgt, y_dim)
 
 
-def attncnp_forward(sd, X_cntxt, Y_cntxt, X_trgt, attention="transformer", n_heads=8):
+def attncnp_forward(sd, X_cntxt, Y_cntxt, X_trgt, attention="transformer", n_heads=8, is_self_attn=False):
     """AttnCNP, npf/neuralproc/attnnp.py:105-131.  attention in {"scaledot","multihead","transformer"}."""
     y_dim = Y_cntxt.shape[-1]
     Xe_c = mlp(sd, "x_encoder.", X_cntxt)
     Xe_t = mlp(sd, "x_encoder.", X_trgt)
     B, C, _ = Xe_c.shape
-    r_dim = sd["xy_encoder.flat_module.out.weight"].shape[0]
+    r_dim = sd["decoder.resizer.to_hidden.weight"].shape[1]  # MergeFlatInputs resizes R (r_dim) onto x
     if C == 0:
         R_trgt = torch.zeros(B, X_trgt.shape[1], r_dim, dtype=Xe_t.dtype)
     else:
-        R_c = merge_flat_sum(sd, "xy_encoder.", Xe_c, Y_cntxt)
-        if attention == "scaledot":
-            R_trgt = dot_attention(Xe_c, Xe_t, R_c)
-        elif attention == "multihead":
-            R_trgt = multihead_attention(sd, "attender.", Xe_c, Xe_t, R_c, n_heads)
-        elif attention == "transformer":
-            R_trgt = transformer_attention(sd, "attender.", Xe_c, Xe_t, R_c, n_heads)
-        else:
-            raise ValueError(f"Unknown attention method {attention}")
+        R_c = _attn_xy_encode(sd, Xe_c, Y_cntxt, is_self_attn)
+        R_trgt = _attend(sd, Xe_c, Xe_t, R_c, attention, n_heads)
     return _decode(sd, Xe_t, R_trgt.unsqueeze(0), y_dim)
 
 
@@ -336,6 +370,47 @@ def lnp_forward(sd, X_cntxt, Y_cntxt, X_trgt, eps, encoded_path="latent"):
     R_trgt = R_trgt.expand(z.shape[0], B, X_trgt.shape[1], r_dim)
     loc, scale = _decode(sd, Xe_t, R_trgt, y_dim)
     return loc, scale, z, q_loc, q_scale
+
+
+def attnlnp_forward(sd, X_cntxt, Y_cntxt, X_trgt, eps, attention="transformer", n_heads=8, is_self_attn=False,
+                    Y_trgt=None):
+    """AttnLNP (encoded_path="both"), npf/neuralproc/attnnp.py:134-202 with base.py:495-514, 554-575:
+    deterministic path = AttnCNP's cross-attention; latent path = one global z per task inferred from
+    the MEAN of the per-context representations (zeros without context).  With ``Y_trgt`` given, z is
+    sampled from q(z | targets) (is_q_zCct=True in training, base.py:501-506): the target set goes
+    through the same xy-encoder.  Returns loc, scale, z, q_c (loc, scale), q_ct (loc, scale) or None."""
+    y_dim = Y_cntxt.shape[-1]
+    Xe_c = mlp(sd, "x_encoder.", X_cntxt)
+    Xe_t = mlp(sd, "x_encoder.", X_trgt)
+    B, C, _ = Xe_c.shape
+    r_dim = sd["decoder.resizer.to_hidden.weight"].shape[1]  # MergeFlatInputs resizes R (r_dim) onto x
+    z_dim = sd["latent_encoder.out.weight"].shape[0] // 2
+
+    def pooled(R):
+        if R.shape[1] == 0:
+            return torch.zeros(R.shape[0], 1, r_dim, dtype=Xe_t.dtype)
+        return R.mean(dim=1, keepdim=True)
+
+    R_c = (_attn_xy_encode(sd, Xe_c, Y_cntxt, is_self_attn) if C > 0
+           else torch.zeros(B, 0, r_dim, dtype=Xe_t.dtype))
+    q_loc, q_scale = _latent_dist(sd, pooled(R_c), z_dim)
+    q_ct = None
+    if Y_trgt is not None:
+        q_ct = _latent_dist(sd, pooled(_attn_xy_encode(sd, Xe_t, Y_trgt, is_self_attn)), z_dim)
+        z = q_ct[0].unsqueeze(0) + q_ct[1].unsqueeze(0) * eps
+    else:
+        z = q_loc.unsqueeze(0) + q_scale.unsqueeze(0) * eps
+    T = X_trgt.shape[1]
+    if C == 0:
+        R_det = torch.zeros(B, T, r_dim, dtype=Xe_t.dtype)
+    else:
+        R_det = _attend(sd, Xe_c, Xe_t, R_c, attention, n_heads)
+    n_z = z.shape[0]
+    Rz = R_det.unsqueeze(0).expand(n_z, B, T, r_dim)
+    zz = z.expand(n_z, B, T, z_dim)
+    R_trgt = torch.relu(_lin(sd, "r_z_merger.", torch.cat((Rz, zz), dim=-1)))
+    loc, scale = _decode(sd, Xe_t, R_trgt, y_dim)
+    return loc, scale, z, (q_loc, q_scale), q_ct
 
 
 def convlnp_forward(sd, X_cntxt, Y_cntxt, X_trgt, eps, X_induced=None, is_global=False, training=True):

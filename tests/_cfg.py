@@ -5,7 +5,7 @@ from functools import partial
 import torch.nn as nn
 
 import npf_b200
-from npf_b200 import CNP, LNP, AttnCNP, ConvCNP, ConvLNP, GridConvCNP, GridConvLNP
+from npf_b200 import CNP, LNP, AttnCNP, AttnLNP, ConvCNP, ConvLNP, GridConvCNP, GridConvLNP
 from npf_b200.architectures import CNN, MLP, ResConvBlock, SetConv, discard_ith_arg, merge_flat_input
 
 R_DIM = 128
@@ -18,9 +18,11 @@ def build_model(cfg):
         if fam in ("CNP", "AttnCNP", "LNP"):
             kw["XEncoder"] = partial(MLP, n_hidden_layers=1, hidden_size=R_DIM)
             kw["Decoder"] = merge_flat_input(partial(MLP, n_hidden_layers=4, hidden_size=R_DIM), is_sum_merge=True)
+        if fam in ("CNP", "AttnCNP", "LNP", "AttnLNP"):
             kw["r_dim"] = R_DIM
-            kw["XYEncoder"] = merge_flat_input(
-                partial(MLP, n_hidden_layers=2, hidden_size=cfg["xy_hidden"]), is_sum_merge=True)
+            if not cfg.get("is_self_attn"):
+                kw["XYEncoder"] = merge_flat_input(
+                    partial(MLP, n_hidden_layers=2, hidden_size=cfg["xy_hidden"]), is_sum_merge=True)
         elif fam in ("ConvCNP", "GridConvCNP"):
             kw["r_dim"] = R_DIM
             kw["Decoder"] = discard_ith_arg(partial(MLP, n_hidden_layers=4, hidden_size=R_DIM), i=0)
@@ -35,12 +37,12 @@ def build_model(cfg):
         kw["CNN"] = partial(CNN, ConvBlock=ResConvBlock, Conv=Conv, Normalization=Norm, n_blocks=c["n_blocks"],
                             kernel_size=c["kernel_size"], is_chan_last=True, n_conv_layers=c["n_conv_layers"])
     for k in ("density_induced", "attention", "n_z_samples_train", "n_z_samples_test", "is_global", "encoded_path",
-              "is_q_zCct"):
+              "is_q_zCct", "is_self_attn"):
         if k in cfg:
             kw[k] = cfg[k]
     if fam in ("ConvCNP", "ConvLNP") and cfg.get("notebook"):
         kw["Interpolator"] = SetConv
-    cls = dict(CNP=CNP, LNP=LNP, AttnCNP=AttnCNP, ConvCNP=ConvCNP, ConvLNP=ConvLNP, GridConvCNP=GridConvCNP,
+    cls = dict(CNP=CNP, LNP=LNP, AttnCNP=AttnCNP, AttnLNP=AttnLNP, ConvCNP=ConvCNP, ConvLNP=ConvLNP, GridConvCNP=GridConvCNP,
                GridConvLNP=GridConvLNP)[fam]
     return cls(cfg["x_dim"], cfg["y_dim"], **kw)
 

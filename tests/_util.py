@@ -61,7 +61,16 @@ def oracle_run(cfg, state_dict, case, dtype=torch.float32, with_grads=False):
     if fam == "CNP":
         loc, scale = O.cnp_forward(sd, Xc, Yc, Xt)
     elif fam == "AttnCNP":
-        loc, scale = O.attncnp_forward(sd, Xc, Yc, Xt, attention=cfg.get("attention", "scaledot"))
+        loc, scale = O.attncnp_forward(sd, Xc, Yc, Xt, attention=cfg.get("attention", "scaledot"),
+                                       is_self_attn=cfg.get("is_self_attn", False))
+    elif fam == "AttnLNP":
+        # z ~ q(z | targets) whenever the targets are known and is_q_zCct (base.py:501), train or eval
+        loc, scale, z, (q_loc, q_scale), q_ct = O.attnlnp_forward(
+            sd, Xc, Yc, Xt, cast(case["eps"]), attention=cfg.get("attention", "scaledot"),
+            is_self_attn=cfg.get("is_self_attn", False), Y_trgt=Yt if cfg.get("is_q_zCct") else None)
+        extra.update(q_loc=q_loc, q_scale=q_scale)
+        if q_ct is not None:
+            extra.update(q_ct_loc=q_ct[0], q_ct_scale=q_ct[1])
     elif fam == "ConvCNP":
         Xi = _induced(cfg, case, dtype)
         loc, scale = O.convcnp_forward(sd, Xc, Yc, Xt, X_induced=Xi, training=training)

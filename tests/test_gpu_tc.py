@@ -207,9 +207,11 @@ from _util import fixture_names  # noqa: E402
 def test_tc_x3_all_models_match_golden(npf, name):
     """Every model family in the split-bf16 tensor-core mode (linear layers, attention) against the reference's golden
     vectors.  The products of this mode carry ~16 bits (2^-16 ~ 1.5e-5): 1e-4 on mu, sigma, loss holds for every fixture
-    except the upstream-pretrained transformer AttnCNP, whose sharp attention / large weights amplify it to ~3e-4 (bar 5e-4
-    here; the fp32 mode meets 1e-4 on it, tests/test_gpu_parity.py)."""
-    tol = 5e-4 if name == "attncnp_transformer_pretrained" else 1e-4
+    except the upstream-pretrained transformer-attention checkpoints (AttnCNP / AttnLNP, cross- and self-attention), whose
+    sharp attention / large weights amplify it to 1e-4 .. 3e-4 (bar 5e-4 here; the fp32 mode meets 1e-4 on all of them,
+    tests/test_gpu_parity.py; measured per case by profiles/microbench/fixture_errors.py)."""
+    tol = 5e-4 if name in ("attncnp_transformer_pretrained", "attncnp_selfattn_pretrained", "attnlnp_pretrained",
+                           "attnlnp_selfattn_pretrained") else 1e-4
     npf.set_precision("bf16x3")
     fx = load_fixture(name)
     model = build_model(fx["cfg"])
