@@ -258,6 +258,15 @@ NPF_API int npf_global_latent_bwd(const float* dout, float* dzin, int N, int P, 
 NPF_API int npf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int step, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, npf_stream_t stream);
 
+/* Gradient clipping by global norm without a host sync (skorch GradientNormClipping -> torch.nn.utils.clip_grad_norm_,
+ * the callback of the ConvLNP / AttnLNP notebooks):  npf_sqnorm overwrites the device scalar sqnorm[0] with sum_i x_i^2
+ * over the flat gradient bucket; npf_adam_step_clipped is npf_adam_step with the gradient additionally multiplied by
+ * min(1, max_norm / (grad_scale * sqrt(sqnorm[0]) + 1e-6)), read on the device. */
+NPF_API int npf_sqnorm(const float* x, long n, float* sqnorm, npf_stream_t stream);
+NPF_API int npf_adam_step_clipped(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int step, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale, const float* sqnorm,
+                  float max_norm, npf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Input validation without a host sync  (NeuralProcessFamily._validate_inputs npf/neuralproc/base.py:241-247,
  * isin_range npf/utils/helpers.py:55-57): flag[0] |= 1 if any x outside [lo, hi]  (flag is device int32)

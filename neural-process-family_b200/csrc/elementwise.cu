@@ -326,6 +326,43 @@ __global__ void adam_kernel(float* __restrict__ P, const float* __restrict__ G, 
     }
 }
 
+// sum of squares of a flat buffer (global gradient norm for clipping): warp shuffle + one atomic per block
+__global__ void sqnorm_kernel(const float* __restrict__ X, long n, float* __restrict__ out) {
+    float s = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float v = __ldg(X + i);
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+        atomicAdd(out, t);
+    }
+}
+
+// Adam with the clipping factor of torch.nn.utils.clip_grad_norm_ taken from a DEVICE scalar (no host sync):
+//   coef = min(1, max_norm / (grad_scale * sqrt(sqnorm) + 1e-6))
+__global__ void adam_clipped_kernel(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ Mo, float* __restrict__ V, long n,
+                                    float step_size, float inv_sqrt_bc2, float b1, float b2, float eps, float wd, float grad_scale,
+                                    const float* __restrict__ sqnorm, float max_norm) {
+    const float coef = fminf(1.f, max_norm / (grad_scale * sqrtf(__ldg(sqnorm)) + 1e-6f));
+    const float gs = grad_scale * coef;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float p = P[i];
+        const float g = fmaf(wd, p, G[i] * gs);
+        const float m = fmaf(b1, Mo[i], (1.f - b1) * g);
+        const float v = fmaf(b2, V[i], (1.f - b2) * g * g);
+        Mo[i] = m;
+        V[i] = v;
+        P[i] = p - step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+    }
+}
+
 #define LAUNCH_1D(kernel, n, st, ...)                                    \
     do {                                                                 \
         kernel<<<grid_for(n), 256, 0, st>>>(__VA_ARGS__);                \
@@ -475,3 +512,23 @@ extern "C" int npf_adam_step(float* param, const float* grad, float* exp_avg, fl
               weight_decay, grad_scale);
 }
 
+extern "C" int npf_sqnorm(const float* x, long n, float* sqnorm, npf_stream_t stream) {
+    NPF_REQUIRE(sqnorm && (x || n == 0), "npf_sqnorm: null pointer");
+    NPF_REQUIRE(n >= 0, "npf_sqnorm: bad size");
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(sqnorm, 0, sizeof(float), st) != cudaSuccess) return check_launch("npf_sqnorm memset");
+    if (n == 0) return NPF_OK;
+    LAUNCH_1D(sqnorm_kernel, n, st, x, n, sqnorm);
+}
+
+extern "C" int npf_adam_step_clipped(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int step, float lr,
+                                     float beta1, float beta2, float eps, float weight_decay, float grad_scale, const float* sqnorm,
+                                     float max_norm, npf_stream_t stream) {
+    NPF_REQUIRE(param && grad && exp_avg && exp_avg_sq && sqnorm, "npf_adam_step_clipped: null pointer");
+    NPF_REQUIRE(n >= 0 && step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && max_norm > 0.f,
+                "npf_adam_step_clipped: bad hyper-parameter");
+    if (n == 0) return NPF_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    LAUNCH_1D(adam_clipped_kernel, n, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), beta1,
+              beta2, eps, weight_decay, grad_scale, sqnorm, max_norm);
+}

@@ -51,6 +51,8 @@ SIGNATURES = {
     "npf_global_latent_fwd": [P, P, I, I, I, P],
     "npf_global_latent_bwd": [P, P, I, I, I, P],
     "npf_adam_step": [P, P, P, P, L, I, F, F, F, F, F, F, P],
+    "npf_sqnorm": [P, L, P, P],
+    "npf_adam_step_clipped": [P, P, P, P, L, I, F, F, F, F, F, F, P, F, P],
     "npf_range_check": [P, L, F, F, P, P],
 }
 BOOKKEEPING = {

@@ -59,7 +59,9 @@ class FlatAdam:
     re-pointed into ONE contiguous fp32 buffer laid out like ``flat`` (same 128-byte aligned slots), so a step is a single
     elementwise kernel (``npf_adam_step``) over (param, grad, exp_avg, exp_avg_sq) instead of ~40 small foreach launches.
     ``lr`` may be changed between steps (``opt.lr = ...``: ExponentialLR is ``opt.lr *= gamma`` per epoch);
-    ``grad_scale`` pre-multiplies the gradient (gradient clipping by global norm: ``min(1, max_norm / norm)``)."""
+    ``grad_scale`` pre-multiplies the gradient (1 / world size); ``max_grad_norm`` clips by the global norm like
+    ``torch.nn.utils.clip_grad_norm_`` (skorch ``GradientNormClipping`` of the latent notebooks) with the norm reduced and
+    consumed on the device (``npf_sqnorm`` + ``npf_adam_step_clipped``): no host sync, capturable in a CUDA graph."""
 
     def __init__(self, flat, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
@@ -73,14 +75,28 @@ class FlatAdam:
                 p.data = view                     # the module now reads / the kernels now update the flat storage
         self.exp_avg = torch.zeros_like(g)
         self.exp_avg_sq = torch.zeros_like(g)
+        self._sqnorm = torch.zeros(1, dtype=torch.float32, device=g.device)
+
+    def last_grad_norm(self):
+        """Global gradient norm seen by the last clipped step (device scalar; reading it synchronises)."""
+        return self._sqnorm.sqrt()
 
     def global_grad_norm(self):
         return self.flat.flat.norm()              # padding between slots is zero
 
-    def step(self, grad_scale=1.0):
+    def step(self, grad_scale=1.0, max_grad_norm=None):
         from . import _cabi
+        if not self.param.is_cuda:
+            raise RuntimeError("FlatAdam: CUDA only (there is no CPU fallback)")
         self.step_count += 1
         n = self.param.numel()
+        if max_grad_norm is not None:
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.call("npf_sqnorm", self.flat.flat.data_ptr(), n, self._sqnorm.data_ptr(), st)
+            _cabi.call("npf_adam_step_clipped", self.param.data_ptr(), self.flat.flat.data_ptr(), self.exp_avg.data_ptr(),
+                       self.exp_avg_sq.data_ptr(), n, self.step_count, float(self.lr), float(self.betas[0]), float(self.betas[1]),
+                       float(self.eps), float(self.weight_decay), float(grad_scale), self._sqnorm.data_ptr(), float(max_grad_norm), st)
+            return
         if self.param.is_cuda:
             _cabi.call("npf_adam_step", self.param.data_ptr(), self.flat.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), n,
                        self.step_count, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),

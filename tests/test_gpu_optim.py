@@ -69,3 +69,30 @@ def test_flat_adam_grad_scale_and_state():
     opt2 = FlatAdam(FlatGradients(copy.deepcopy(lin)), lr=5.0)
     opt2.load_state_dict(sd)
     assert opt2.step_count == 3 and opt2.lr == 1e-2 and torch.equal(opt2.exp_avg, opt.exp_avg)
+
+
+def test_flat_adam_device_side_clipping():
+    """max_grad_norm: the global norm is reduced and applied on the device (npf_sqnorm + npf_adam_step_clipped) and must
+    track torch.nn.utils.clip_grad_norm_ + torch.optim.Adam, both when the clip is active and when it is not."""
+    from npf_b200.parallel import FlatAdam, FlatGradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 33), torch.nn.ReLU(), torch.nn.Linear(33, 4)).cuda()
+    ref = copy.deepcopy(net)
+    flat = FlatGradients(net)
+    opt = FlatAdam(flat, lr=1e-2, weight_decay=1e-3)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-2, weight_decay=1e-3)
+    x = torch.randn(64, 8, device="cuda")
+    for it, max_norm in enumerate([0.05, 0.05, 1e3, 0.2, 1e3]):
+        flat.zero_()
+        (net(x).square().mean() * 3).backward()
+        ropt.zero_grad(set_to_none=True)
+        (ref(x).square().mean() * 3).backward()
+        total = torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm)
+        opt.step(max_grad_norm=max_norm)
+        ropt.step()
+        assert abs(opt.last_grad_norm().item() - total.item()) <= 1e-5 * total.item(), it
+        opt.lr *= 0.9                                   # ExponentialLR(gamma=0.9)
+        for g in ropt.param_groups:
+            g["lr"] *= 0.9
+    for p1, p2 in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-4, atol=1e-6), (p1 - p2).abs().max().item()
