@@ -268,6 +268,32 @@ NPF_API int npf_adam_step_clipped(float* param, const float* grad, float* exp_av
                   float max_norm, npf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Context / target split on the device -- the step BEFORE the path (npf/utils/datasplit.py).
+ * Index / byte work: results are bit-exact against oracle/datasplit_oracle.py (same Philox-4x32-10 draws).
+ *
+ * npf_random_subset   GetRandomIndcs.__call__ (datasplit.py:108-145, is_batch_share=False) for a given count n:
+ *                     indcs[b, 0..n) (int32) = the first n entries of an independent uniformly random permutation of
+ *                     0..N-1 per row b (partial Fisher-Yates; draw i of row b = word i&3 of
+ *                     Philox4x32-10(counter {i>>2, b, 0, 0}, key {seed lo, seed hi}), j = i + mulhi(draw, N-i)).
+ *                     N <= 12288.  The count itself (random.randint(a, b) upstream) stays a host decision.
+ * npf_random_mask     RandomMasker.__call__ (datasplit.py:259-278): mask[b, p] (bytes, 0/1) = 1 at the same n positions
+ *                     npf_random_subset would return for (B, P, n, seed); every other byte of the row is cleared.
+ * npf_select_points   CntxtTrgtGetter.select (datasplit.py:246-255): Xo[b,i,:] = X[b, indcs[b,i], :] (xd features),
+ *                     Yo[b,i,:] = Y[b, indcs[b,i], :] (yd values); indices must lie in [0, N).
+ * npf_grid_select     GridCntxtTrgtGetter.select (datasplit.py:423-452): for each row the masked grid points in
+ *                     row-major order (the order of mask.nonzero()): Xo[b,k,:] = grid coordinates normalised to
+ *                     [-1, 1] * upscale (n_grid_dim = 2: (row, col) of an H x W grid; 1: H == 1), Yo[b,k,:] = img[b,p,:].
+ *                     At most n points per row are written; counts[b] (int32, may be NULL) receives the number of
+ *                     masked points so the caller can verify "same count in every row" without a sync in the hot loop.
+ * ------------------------------------------------------------------------------------------------ */
+NPF_API int npf_random_subset(int32_t* indcs, int B, int N, int n, unsigned long long seed, npf_stream_t stream);
+NPF_API int npf_random_mask(uint8_t* mask, int B, int P, int n, unsigned long long seed, npf_stream_t stream);
+NPF_API int npf_select_points(const float* X, const float* Y, const int32_t* indcs, float* Xo, float* Yo, int B, int N, int n,
+                  int xd, int yd, npf_stream_t stream);
+NPF_API int npf_grid_select(const uint8_t* mask, const float* img, float* Xo, float* Yo, int32_t* counts, int B, int H, int W,
+                  int n_grid_dim, int yd, int n, float upscale, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Input validation without a host sync  (NeuralProcessFamily._validate_inputs npf/neuralproc/base.py:241-247,
  * isin_range npf/utils/helpers.py:55-57): flag[0] |= 1 if any x outside [lo, hi]  (flag is device int32)
  * ------------------------------------------------------------------------------------------------ */

@@ -54,6 +54,10 @@ SIGNATURES = {
     "npf_sqnorm": [P, L, P, P],
     "npf_adam_step_clipped": [P, P, P, P, L, I, F, F, F, F, F, F, P, F, P],
     "npf_range_check": [P, L, F, F, P, P],
+    "npf_random_subset": [P, I, I, I, c_ulonglong, P],
+    "npf_random_mask": [P, I, I, I, c_ulonglong, P],
+    "npf_select_points": [P, P, P, P, P, I, I, I, I, I, P],
+    "npf_grid_select": [P, P, P, P, P, I, I, I, I, I, I, F, P],
 }
 BOOKKEEPING = {
     "npf_abi_version": (c_int, []),
