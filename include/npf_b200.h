@@ -294,6 +294,22 @@ NPF_API int npf_grid_select(const uint8_t* mask, const float* img, float* Xo, fl
                   int n_grid_dim, int yd, int n, float upscale, npf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Gaussian-process prior sampler -- the synthetic-task generator in front of the path (GPDataset._sample_targets,
+ * utils/data/gaussian_process.py:201-231: sklearn GaussianProcessRegressor.sample_y of the un-fitted regressor, i.e.
+ * y ~ N(0, k(X, X)); kernels of utils/ntbks_helpers.py:76-108).
+ *   X [B, N] point positions (raw scale, e.g. [-2, 2]), eps [B, S, N] standard-normal draws, Y [B, S, N] samples:
+ *   S samples share the positions of task b (upstream's n_same_samples).
+ *   kernel: 0 = RBF(length_scale), 1 = Matern(length_scale, nu = 1.5), 2 = ExpSineSquared(length_scale, periodicity);
+ *   noise_level > 0 adds WhiteKernel(noise_level) (on the diagonal).
+ *   Method: diagonally pivoted Cholesky K = L L^T + E stopped when every residual variance is <= tol (these matrices are
+ *   numerically rank-deficient), y_s = L eps_s with eps indexed by factorisation step.  Optional outputs (may be NULL):
+ *   L [B, N, N] row-major (columns beyond the rank are zero; rows in the original point order), rank [B] (int32).
+ *   N <= 232 (the factor lives in one CTA's shared memory).
+ * ------------------------------------------------------------------------------------------------ */
+NPF_API int npf_gp_sample(const float* X, const float* eps, float* Y, float* L, int32_t* rank, int B, int N, int S, int kernel,
+                  float length_scale, float periodicity, float noise_level, float tol, npf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Input validation without a host sync  (NeuralProcessFamily._validate_inputs npf/neuralproc/base.py:241-247,
  * isin_range npf/utils/helpers.py:55-57): flag[0] |= 1 if any x outside [lo, hi]  (flag is device int32)
  * ------------------------------------------------------------------------------------------------ */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "npf_random_mask": [P, I, I, I, c_ulonglong, P],
     "npf_select_points": [P, P, P, P, P, I, I, I, I, I, P],
     "npf_grid_select": [P, P, P, P, P, I, I, I, I, I, I, F, P],
+    "npf_gp_sample": [P, P, P, P, P, I, I, I, I, F, F, F, F, P],
 }
 BOOKKEEPING = {
     "npf_abi_version": (c_int, []),
