@@ -35,12 +35,20 @@ class _PreNorm:
             raise NotImplementedError("npf_b200: Normalization must be nn.Identity or nn.BatchNorm{1,2}d")
         if norm.training or not norm.track_running_stats:
             mean, var = ops.channel_moments(x)
+            n = x.numel() // x.shape[-1]
+            sync = getattr(norm, "_npf_sync_group", None)
+            if sync is not None and norm.training:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size(sync[0]) > 1:
+                    from ..parallel import sync_moments
+                    mean, var, n = sync_moments(mean, var, n, sync[0])   # statistics of the global meta-batch
+                    n = n.detach()                                       # total count stays a device scalar: no host sync
             if norm.track_running_stats:
                 with torch.no_grad():
-                    n = x.numel() // x.shape[-1]
                     mom = norm.momentum if norm.momentum is not None else 0.1
                     norm.running_mean.mul_(1 - mom).add_(mean.detach(), alpha=mom)
-                    norm.running_var.mul_(1 - mom).add_(var.detach() * (n / max(n - 1, 1)), alpha=mom)
+                    unbias = n / (n - 1).clamp(min=1) if torch.is_tensor(n) else n / max(n - 1, 1)
+                    norm.running_var.mul_(1 - mom).add_(var.detach() * unbias, alpha=mom)
                     norm.num_batches_tracked += 1
         else:
             mean, var = norm.running_mean, norm.running_var

@@ -36,6 +36,9 @@ class _Entry:
 class GraphedStep:
     def __init__(self, model, criterion, flat=None, n_warmup=2, max_graphs=8):
         self.model, self.criterion = model, criterion
+        if any(getattr(m, "_npf_sync_group", None) is not None for m in model.modules()):
+            raise NotImplementedError("GraphedStep: synchronised BatchNorm (parallel.sync_batchnorm_) issues collectives inside "
+                                      "forward and backward; run that configuration eagerly")
         self.flat = flat if flat is not None else FlatGradients(model)
         self.n_warmup, self.max_graphs = n_warmup, max_graphs
         self._graphs = OrderedDict()

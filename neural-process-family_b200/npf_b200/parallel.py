@@ -7,7 +7,7 @@ NVSwitch).  Works with any ``torch.distributed`` backend (``gloo`` on CPU for th
 import torch
 import torch.distributed as dist
 
-__all__ = ["FlatGradients", "FlatAdam", "shard_tasks"]
+__all__ = ["FlatGradients", "FlatAdam", "shard_tasks", "sync_batchnorm_", "sync_moments"]
 
 
 class FlatGradients:
@@ -111,6 +111,47 @@ class FlatAdam:
         self.step_count, self.lr = int(sd["step"]), float(sd["lr"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+
+
+class _AllReduceSum(torch.autograd.Function):
+    """Differentiable sum-all-reduce: the gradient of a sum over ranks is the sum over ranks of the gradients."""
+
+    @staticmethod
+    def forward(ctx, t, group):
+        ctx.group = group
+        out = t.detach().clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def sync_moments(mean, var, n_local, group=None):
+    """Per-rank batch statistics (mean, biased var over ``n_local`` positions) -> statistics of the GLOBAL batch, by ONE
+    all-reduce of the 2C + 1 numbers (sum x, sum x^2, count) per BatchNorm layer in forward and one of their gradients in
+    backward (SURVEY.md section 8e caveat).  Returns (mean, var, n_total); differentiable."""
+    C = mean.numel()
+    packed = torch.cat([mean * n_local, (var + mean * mean) * n_local, mean.new_full((1,), float(n_local))])
+    tot = _AllReduceSum.apply(packed, group)
+    n = tot[2 * C]
+    g_mean = tot[:C] / n
+    g_var = tot[C:2 * C] / n - g_mean * g_mean
+    return g_mean, g_var, n
+
+
+def sync_batchnorm_(module, group=None):
+    """Mark every BatchNorm of ``module`` (the ``Normalization=nn.BatchNorm*`` CNNs of the notebooks) as synchronised over
+    ``group``: in train mode the folded pre-activation affine then uses the statistics of the global meta-batch, which
+    makes an N-rank run equal to the single-process reference on the same global batch (without it every rank normalises
+    with its own shard: "replicas with local BN").  In place; returns the module.  Eval mode is unaffected."""
+    for m in module.modules():
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m._npf_sync_group = (group,)
+    return module
 
 
 def shard_tasks(batch, rank, world_size):

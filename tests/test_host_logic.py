@@ -108,3 +108,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
+
+
+def test_sync_batchnorm_marks_modules_and_graphed_step_refuses():
+    import torch.nn as nn
+    from functools import partial
+    import npf_b200
+    from npf_b200.architectures import CNN, ResConvBlock
+    from npf_b200.parallel import sync_batchnorm_
+    cnn = partial(CNN, ConvBlock=ResConvBlock, Conv=nn.Conv1d, Normalization=nn.BatchNorm1d, n_blocks=2, kernel_size=5,
+                  is_chan_last=True, n_conv_layers=2)
+    m = npf_b200.ConvCNP(1, 1, CNN=cnn)
+    assert not any(hasattr(b, "_npf_sync_group") for b in m.modules())
+    sync_batchnorm_(m)
+    bns = [b for b in m.modules() if isinstance(b, nn.BatchNorm1d)]
+    assert len(bns) == 4 and all(b._npf_sync_group == (None,) for b in bns)
+    with pytest.raises(NotImplementedError):
+        npf_b200.GraphedStep(m, npf_b200.CNPFLoss())
