@@ -1,0 +1,2 @@
+"""Helpers either side of the hot path: ``helpers`` / ``initialization`` (shape and init utilities of the models),
+``datasplit`` (context / target split on the device), ``gp`` (synthetic GP tasks on the device)."""
