@@ -107,6 +107,46 @@ class FlatAdam:
     def state_dict(self):
         return dict(step=self.step_count, lr=self.lr, exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone())
 
+    # ---- interchange with torch.optim.Adam (the ``optimizer.pt`` upstream's skorch Checkpoint writes next to ``params.pt``)
+    def torch_state_dict(self):
+        """The state in ``torch.optim.Adam.state_dict()`` layout (per-parameter moments, index keys, one param group)."""
+        state = {}
+        for i, (p, off) in enumerate(zip(self.flat.params, self.flat.offsets)):
+            sl = slice(off, off + p.numel())
+            state[i] = dict(step=torch.tensor(float(self.step_count)), exp_avg=self.exp_avg[sl].view_as(p).detach().cpu().clone(),
+                            exp_avg_sq=self.exp_avg_sq[sl].view_as(p).detach().cpu().clone())
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
+                     params=list(range(len(self.flat.params))))
+        return dict(state=state, param_groups=[group])
+
+    def load_torch_state_dict(self, sd):
+        """Resume from a ``torch.optim.Adam`` state dict -- current index-keyed layout or the legacy id-keyed one of the
+        upstream checkpoints: the i-th entry of ``param_groups[0]['params']`` belongs to the i-th parameter."""
+        groups = sd["param_groups"]
+        if len(groups) != 1:
+            raise ValueError("FlatAdam.load_torch_state_dict: exactly one param group expected")
+        g, keys = groups[0], groups[0]["params"]
+        if len(keys) != len(self.flat.params):
+            raise ValueError(f"optimizer state has {len(keys)} parameters, the model {len(self.flat.params)}")
+        if g.get("amsgrad", False):
+            raise NotImplementedError("FlatAdam: amsgrad state is not supported")
+        steps = set()
+        for key, p, off in zip(keys, self.flat.params, self.flat.offsets):
+            st = sd["state"].get(key)
+            if st is None:        # parameter never stepped
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state shape {tuple(st['exp_avg'].shape)} does not match parameter {tuple(p.shape)}")
+            sl = slice(off, off + p.numel())
+            self.exp_avg[sl].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise ValueError(f"FlatAdam keeps one step count for all parameters, the state has {sorted(steps)}")
+        self.step_count = steps.pop() if steps else 0
+        self.lr, self.betas = float(g["lr"]), tuple(g["betas"])
+        self.eps, self.weight_decay = float(g["eps"]), float(g["weight_decay"])
+
     def load_state_dict(self, sd):
         self.step_count, self.lr = int(sd["step"]), float(sd["lr"])
         self.exp_avg.copy_(sd["exp_avg"])

@@ -125,3 +125,46 @@ def test_sync_batchnorm_marks_modules_and_graphed_step_refuses():
     assert len(bns) == 4 and all(b._npf_sync_group == (None,) for b in bns)
     with pytest.raises(NotImplementedError):
         npf_b200.GraphedStep(m, npf_b200.CNPFLoss())
+
+
+def test_checkpoint_roundtrip_and_torch_adam_interchange(tmp_path):
+    """Upstream's checkpoint layout (params.pt / optimizer.pt / history.json / eval.csv): save -> load reproduces model,
+    moments, step and lr; the optimizer file is a torch.optim.Adam state dict in both directions, including the legacy
+    id-keyed layout of upstream's own files."""
+    import copy
+    import numpy as np
+    from npf_b200.parallel import FlatAdam, FlatGradients
+    from npf_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 2))
+    ref = copy.deepcopy(net)
+    ropt = torch.optim.Adam(ref.parameters(), lr=3e-3, betas=(0.8, 0.95), eps=1e-7, weight_decay=0.01)
+    for _ in range(3):
+        ropt.zero_grad()
+        ref(torch.randn(4, 5)).square().sum().backward()
+        ropt.step()
+    opt = FlatAdam(FlatGradients(net), lr=1.0)
+    net.load_state_dict(ref.state_dict())
+    opt.load_torch_state_dict(ropt.state_dict())                       # torch -> flat
+    assert opt.step_count == 3 and opt.lr == 3e-3 and opt.betas == (0.8, 0.95) and opt.eps == 1e-7 and opt.weight_decay == 0.01
+    save_checkpoint(tmp_path, net, opt, history=[dict(epoch=1, train_loss=0.5)], eval_loglik=torch.tensor([1.5, -2.25]))
+    assert sorted(os.listdir(tmp_path)) == ["eval.csv", "history.json", "model_summary.txt", "optimizer.pt", "params.pt"]
+    assert np.allclose(np.loadtxt(os.path.join(tmp_path, "eval.csv")), [1.5, -2.25])
+    net2 = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 2))
+    opt2 = FlatAdam(FlatGradients(net2), lr=9.0)
+    hist = load_checkpoint(tmp_path, net2, opt2)
+    assert hist == [dict(epoch=1, train_loss=0.5)] and opt2.step_count == 3 and opt2.lr == 3e-3
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+    assert all(torch.equal(a, b) for a, b in zip(net2.state_dict().values(), ref.state_dict().values()))
+    ropt2 = torch.optim.Adam(net2.parameters())
+    ropt2.load_state_dict(torch.load(os.path.join(tmp_path, "optimizer.pt"), weights_only=False))   # flat -> torch
+    for a, b in zip(ropt2.state_dict()["state"].values(), ropt.state_dict()["state"].values()):
+        assert torch.equal(a["exp_avg"], b["exp_avg"]) and torch.equal(a["exp_avg_sq"], b["exp_avg_sq"]) and int(a["step"]) == 3
+    legacy = ropt.state_dict()                                          # upstream's files key the state by id(param)
+    ids = [1000 + 7 * i for i in range(len(legacy["param_groups"][0]["params"]))]
+    legacy = dict(state={ids[i]: v for i, v in legacy["state"].items()}, param_groups=[dict(legacy["param_groups"][0], params=ids)])
+    opt3 = FlatAdam(FlatGradients(copy.deepcopy(net)), lr=9.0)
+    opt3.load_torch_state_dict(legacy)
+    assert torch.equal(opt3.exp_avg, opt.exp_avg) and opt3.step_count == 3
+    with pytest.raises(ValueError):
+        opt3.load_torch_state_dict(dict(state={}, param_groups=[dict(legacy["param_groups"][0], params=ids[:-1])]))
