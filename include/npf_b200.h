@@ -11,7 +11,9 @@
  *   - every pointer is a CALLER-OWNED DEVICE pointer to contiguous fp32 unless stated otherwise;
  *     leading dimensions (ld*) are in elements.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  No allocation, no
- *     synchronisation and no global mutable state inside => re-entrant per stream.
+ *     synchronisation and no global mutable state inside => re-entrant per stream.  (Kernel function attributes --
+ *     the opt-in to > 48 KB of dynamic shared memory -- are configured once per process on first use: the library
+ *     follows the one-process-per-GPU model of the data-parallel design.)
  *   - returns 0 on success, a negative NPF_E* code otherwise; npf_last_error() gives the text
  *     (thread-local).  Kernel launch errors are reported via cudaGetLastError() after the launch.
  *   - "accumulate" outputs (weight / bias / theta gradients) are ADDED to: zero them first.
