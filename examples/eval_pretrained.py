@@ -46,8 +46,7 @@ def main(n_tasks=10200, batch=50):
         with torch.no_grad():
             for i in range(0, n_tasks, batch):
                 n = (i // batch) % 51
-                idx = torch.empty(batch, n, dtype=torch.int32, device="cuda")
-                getter = ds.CntxtTrgtGetter(contexts_getter=ds.GetRandomIndcs(a=n, b=n) if n > 0 else (lambda B, N, device=None: idx))
+                getter = ds.CntxtTrgtGetter(contexts_getter=ds.GetRandomIndcs(a=n, b=n))     # exactly n context points
                 Xc, Yc, Xt, Yt = getter(X[i:i + batch], Y[i:i + batch])
                 ll.append(-crit(model(Xc, Yc, Xt, Yt), Yt))
         ll = torch.cat(ll).double().cpu().numpy()
