@@ -49,11 +49,19 @@ class GraphedStep:
         self.flat.zero_()
         out = self.model(xc, yc, xt, yt)
         loss = self.criterion(out, yt)
-        loss.backward()
+        if self.model.training:        # an eval-mode signature replays forward + loss only
+            loss.backward()
         return loss.detach()
 
     def _signature(self, tensors):
-        return (self.model.training,) + tuple((tuple(t.shape), t.dtype) for t in tensors)
+        """Everything a recorded graph froze: mode, input shapes, the induced grid (``set_extrapolation`` changes its
+        length), the number of latent samples, the arithmetic mode, and the parameter / gradient storage the kernels
+        were given pointers to (``FlatAdam`` re-points ``p.data``; a replay after that would train stale storage)."""
+        m = self.model
+        xi = getattr(m, "X_induced", None)
+        extra = (None if xi is None else (xi.data_ptr(), tuple(xi.shape)), getattr(m, "n_z_samples_train", None), getattr(m, "n_z_samples_test", None),
+                 ops.get_precision(), hash(tuple(p.data_ptr() for p in self.flat.params)), self.flat.flat.data_ptr())
+        return (m.training,) + tuple((tuple(t.shape), t.dtype) for t in tensors) + extra
 
     def _capture(self, sig, tensors):
         dev = next(self.model.parameters()).device
@@ -94,6 +102,8 @@ class GraphedStep:
         sig = self._signature(tensors)
         e = self._graphs.get(sig)
         if e is None:
+            if hasattr(self.model, "validate_now"):
+                self.model.validate_now()        # a new signature: surface the previous step's range check first
             e = self._capture(sig, tensors)
         else:
             self._graphs.move_to_end(sig)

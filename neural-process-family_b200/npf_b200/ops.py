@@ -57,10 +57,21 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _shape(cond, msg):
+    """The kernels take raw pointers + sizes: every Function checks its operands' shapes on the host first (a mismatch
+    that upstream would surface as a broadcast error must not become an out-of-bounds device read)."""
+    if not cond:
+        raise ValueError("npf_b200: " + msg)
+
+
 # ------------------------------------------------------------------------------------------------------
 # Direct gradient accumulation: every weight-gradient kernel ADDS into its output, so when a parameter already has a
 # contiguous fp32 ``.grad`` (e.g. a view into ``parallel.FlatGradients``' bucket) the kernel can write there directly
 # and the Function returns ``None`` for it -- no zeros_like fill, no autograd accumulate kernel per parameter.
+# Scope: only parameters tagged by ``parallel.FlatGradients`` (``p._npf_direct_grad``) take this path -- for every other
+# parameter the Functions return the gradient to autograd as usual, so hooks (``register_hook``, DDP reducers,
+# post-accumulate hooks) and ``torch.autograd.grad`` keep working.  ``set_direct_grad_accumulation(True)`` forces it for
+# every parameter that has a ``.grad`` (process-wide; off by default).
 # ------------------------------------------------------------------------------------------------------
 _direct_grads = False
 
@@ -74,8 +85,8 @@ def _gbuf(p):
     """(buffer to accumulate the gradient of ``p`` into, value to return to autograd for it)."""
     if p is None:
         return None, None
-    if _direct_grads and p.is_leaf and p.requires_grad and p.grad is not None and p.grad.is_contiguous() \
-            and p.grad.dtype == torch.float32 and p.grad.shape == p.shape and p.is_contiguous():
+    if (_direct_grads or getattr(p, "_npf_direct_grad", False)) and p.is_leaf and p.requires_grad and p.grad is not None \
+            and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.shape == p.shape and p.is_contiguous():
         return p.grad, None
     g = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return g, g
@@ -223,8 +234,15 @@ class _SetConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, keys, queries, values, theta, W, b, keys_regular):
         _chk(keys, queries, values, theta, W, b)
+        _shape(values.dim() == 3, f"setconv: values must be [B,K,C], got {tuple(values.shape)}")
         B, K, C = values.shape
         Q = queries.shape[-1]  # queries: [B,Q] per task or [Q] shared; keys likewise
+        _shape(keys.dim() in (1, 2) and keys.shape[-1] == K and (keys.dim() == 1 or keys.shape[0] == B),
+               f"setconv: keys {tuple(keys.shape)} do not match values {tuple(values.shape)}")
+        _shape(queries.dim() in (1, 2) and (queries.dim() == 1 or queries.shape[0] == B),
+               f"setconv: queries {tuple(queries.shape)} do not match batch {B}")
+        _shape(W.dim() == 2 and W.shape[1] == C + 1 and theta.numel() == 1 and (b is None or b.numel() == W.shape[0]),
+               f"setconv: resizer weight {tuple(W.shape)} must be [N, {C + 1}]")
         keys, queries, values = _c(keys), _c(queries), _c(values)
         key_bs = 0 if keys.dim() == 1 else K
         qry_bs = 0 if queries.dim() == 1 else Q
@@ -303,7 +321,13 @@ class _DWConv(torch.autograd.Function):
     def forward(ctx, x, Wt, bias, res, relu_in, scale, shift):
         _chk(x, Wt, bias, res, scale, shift)
         x = _c(x)
+        _shape(x.dim() in (3, 4), f"dwconv: x must be [B,L,C] or [B,H,W,C], got {tuple(x.shape)}")
         B, C = x.shape[0], x.shape[-1]
+        _shape(Wt.dim() == x.dim() and Wt.shape[0] == C and Wt.shape[1] == 1, f"dwconv: weight {tuple(Wt.shape)} does not match {C} channels")
+        _shape(res is None or res.shape == x.shape, "dwconv: residual must have the shape of x")
+        _shape(bias is None or bias.numel() == C, "dwconv: bias must have one entry per channel")
+        _shape((scale is None) == (shift is None) and (scale is None or (scale.numel() == C and shift.numel() == C)),
+               "dwconv: scale/shift must both be given with one entry per channel")
         if x.dim() == 3:
             H, Wd = 1, x.shape[1]
             kh, kw = 1, Wt.shape[-1]
@@ -391,8 +415,11 @@ class _MergeRelu(torch.autograd.Function):
     def forward(ctx, x1, x2, x2_has_t):
         _chk(x1, x2)
         x1, x2 = _c(x1), _c(x2)
+        _shape(x1.dim() == 3 and x2.dim() == 4, f"merge_relu: x1 must be [B,T,C] and x2 [Z,B,T|1,C], got {tuple(x1.shape)}, {tuple(x2.shape)}")
         B, T, C = x1.shape
         Z = x2.shape[0]
+        _shape(x2.shape[1] == B and x2.shape[3] == C and x2.shape[2] == (T if x2_has_t else 1),
+               f"merge_relu: x2 {tuple(x2.shape)} does not broadcast against x1 {tuple(x1.shape)}")
         out = torch.empty(Z, B, T, C, device=x1.device, dtype=torch.float32)
         call("npf_merge_relu_fwd", _p(x1), _p(x2), _p(out), Z, B, T, C, int(x2_has_t), _stream())
         ctx.save_for_backward(out)
@@ -415,7 +442,9 @@ def merge_relu(x1, x2):
     squeeze = x2.dim() == 3
     if squeeze:
         x2 = x2.unsqueeze(0)
-    has_t = x2.shape[2] == x1.shape[1] and not (x2.shape[2] == 1 and x1.shape[1] != 1)
+    _shape(x1.dim() == 3 and x2.dim() == 4 and x2.shape[2] in (1, x1.shape[1]),
+           f"merge_relu: x2 {tuple(x2.shape)} must have the {x1.shape[1]} targets of x1 or a singleton target axis")
+    has_t = x2.shape[2] == x1.shape[1]
     out = _MergeRelu.apply(x1, x2, has_t)
     return out.squeeze(0) if squeeze else out
 
@@ -425,6 +454,7 @@ class _MeanPool(torch.autograd.Function):
     def forward(ctx, x):
         _chk(x)
         x = _c(x)
+        _shape(x.dim() == 3, f"mean_pool: x must be [B,N,C], got {tuple(x.shape)}")
         B, N, C = x.shape
         r = torch.empty(B, 1, C, device=x.device, dtype=torch.float32)
         call("npf_mean_pool_fwd", _p(x), _p(r), B, N, C, _stream())
@@ -450,6 +480,8 @@ class _AddLayerNorm(torch.autograd.Function):
         _chk(a, b, gamma, beta)
         a, b = _c(a), _c(b)
         C = a.shape[-1]
+        _shape(a.shape == b.shape and gamma.numel() == C and beta.numel() == C,
+               f"add_layernorm: a {tuple(a.shape)}, b {tuple(b.shape)}, gamma/beta [{gamma.numel()}]/[{beta.numel()}] do not agree")
         M = a.numel() // C
         y = torch.empty_like(a)
         rstat = torch.empty(M, 2, device=a.device, dtype=torch.float32)
@@ -484,6 +516,10 @@ class _XAttn(torch.autograd.Function):
     def forward(ctx, q, k, v, n_heads, scale):
         _chk(q, k, v)
         q, k, v = _c(q), _c(k), _c(v)
+        _shape(q.dim() == 3 and k.dim() == 3 and v.dim() == 3, "xattn: q, k, v must be [B,T,E]")
+        _shape(k.shape[0] == q.shape[0] and v.shape[0] == q.shape[0] and k.shape[1] == v.shape[1] and k.shape[2] == q.shape[2],
+               f"xattn: q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)} do not agree (k/v share B and Tk; q/k share E)")
+        _shape(q.shape[2] % n_heads == 0 and v.shape[2] % n_heads == 0, f"xattn: {n_heads} heads do not divide E={q.shape[2]} / Ev={v.shape[2]}")
         B, Tq, E = q.shape
         Tk = k.shape[1]
         Ev = v.shape[2]
@@ -519,6 +555,7 @@ class _GaussHead(torch.autograd.Function):
     def forward(ctx, suff, min_scale):
         _chk(suff)
         suff = _c(suff)
+        _shape(suff.shape[-1] % 2 == 0 and suff.shape[-1] > 0, f"gauss_head: last dim {suff.shape[-1]} must be 2*y_dim")
         y = suff.shape[-1] // 2
         M = suff.numel() // (2 * y)
         loc = torch.empty(*suff.shape[:-1], y, device=suff.device, dtype=torch.float32)
@@ -548,6 +585,8 @@ class _GaussSLP(torch.autograd.Function):
     def forward(ctx, loc, scale, Y):
         _chk(loc, scale, Y)
         loc, scale, Y = _c(loc), _c(scale), _c(Y)
+        _shape(loc.dim() >= 3 and loc.shape == scale.shape, f"gauss_sum_log_prob: loc {tuple(loc.shape)} / scale {tuple(scale.shape)} must be equal [Z,B,*,y]")
+        _shape(tuple(Y.shape) == tuple(loc.shape[1:]), f"gauss_sum_log_prob: Y {tuple(Y.shape)} must be {tuple(loc.shape[1:])} (targets of loc/scale)")
         Z, B = loc.shape[0], loc.shape[1]
         n = loc.numel() // max(Z * B, 1) if Z * B > 0 else 0
         slp = torch.empty(Z, B, device=loc.device, dtype=torch.float32)
@@ -578,6 +617,9 @@ class _LatentSample(torch.autograd.Function):
     def forward(ctx, suff, eps):
         _chk(suff, eps)
         suff, eps = _c(suff), _c(eps)
+        _shape(suff.shape[-1] % 2 == 0 and eps.dim() == suff.dim() + 1 and tuple(eps.shape[1:-1]) == tuple(suff.shape[:-1])
+               and eps.shape[-1] == suff.shape[-1] // 2,
+               f"latent_sample: eps {tuple(eps.shape)} must be [S, *{tuple(suff.shape[:-1])}, {suff.shape[-1] // 2}]")
         zd = suff.shape[-1] // 2
         M = suff.numel() // (2 * zd)
         S = eps.shape[0]
@@ -610,6 +652,7 @@ class _GlobalLatent(torch.autograd.Function):
     def forward(ctx, z):
         _chk(z)
         z = _c(z)
+        _shape(z.dim() >= 3 and z.shape[-1] % 2 == 0, f"global_latent: z must be [N, *spatial, C] with even C, got {tuple(z.shape)}")
         N, C = z.shape[0], z.shape[-1]
         P = z.numel() // (N * C)
         out = torch.empty_like(z)
@@ -640,6 +683,10 @@ class _GridConvIn(torch.autograd.Function):
         _chk(img, mask_u8, Wt)
         img, mask_u8 = _c(img), _c(mask_u8)
         assert Wt.is_contiguous()
+        _shape(img.dim() == 4 and mask_u8.dim() == 4 and mask_u8.shape[:3] == img.shape[:3] and mask_u8.shape[3] in (1, img.shape[3]),
+               f"gridconv_in: image {tuple(img.shape)} (channel-last [B,H,W,y]) and mask {tuple(mask_u8.shape)} do not agree")
+        _shape(Wt.dim() == 4 and Wt.shape[0] == img.shape[3] and Wt.shape[1] == 1 and Wt.shape[2] == Wt.shape[3] and Wt.shape[2] % 2 == 1,
+               f"gridconv_in: weight {tuple(Wt.shape)} must be [y,1,k,k] with odd k")
         B, H, Wd, y = img.shape
         k = Wt.shape[-1]
         feat = torch.empty(B, H, Wd, 2 * y, device=img.device, dtype=torch.float32)

@@ -22,20 +22,30 @@ class FlatGradients:
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self._attach()
-        if dev.type == "cuda":
-            from . import ops
-            ops.set_direct_grad_accumulation(True)   # weight-gradient kernels add straight into the bucket
 
     def _attach(self):
+        base = self.flat.data_ptr()
         for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off: off + p.numel()].view_as(p)
+            # the weight-gradient kernels add straight into the bucket for THESE parameters only (ops._gbuf)
+            p._npf_direct_grad = p.is_cuda
+        self._grad_ptrs = [base + 4 * off for off in self.offsets]
+
+    def detach(self):
+        """Give the parameters back to plain autograd accumulation (drops the views into the bucket)."""
+        for p in self.params:
+            p._npf_direct_grad = False
+            p.grad = None
 
     def zero_(self):
-        """Zero the bucket (one memset) and re-attach the views if an optimizer dropped them."""
+        """Zero the bucket (one memset) and re-attach the views if anything dropped or replaced one of them
+        (``optimizer.zero_grad(set_to_none=True)``, ``model.zero_grad()``, a ``.to()`` of the module)."""
         self.flat.zero_()
-        if any(p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or
-               p.grad.data_ptr() >= self.flat.data_ptr() + 4 * max(self.flat.numel(), 1) for p in self.params[:1]):
-            self._attach()
+        for p, ptr in zip(self.params, self._grad_ptrs):
+            g = p.grad
+            if g is None or g.data_ptr() != ptr:
+                self._attach()
+                break
 
     @property
     def world_size(self):

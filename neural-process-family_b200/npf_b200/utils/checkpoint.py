@@ -31,14 +31,17 @@ def save_checkpoint(dirname, model, optimizer=None, history=None, eval_loglik=No
         f.write(str(model))
 
 
-def load_checkpoint(dirname, model, optimizer=None, strict=True):
+def load_checkpoint(dirname, model, optimizer=None, strict=True, trust=False):
     """Load ``params.pt`` into ``model`` (and ``optimizer.pt`` into ``optimizer`` when given and present); returns the
-    stored history (``[]`` if none).  Works on upstream's own checkpoint directories."""
-    sd = torch.load(os.path.join(dirname, "params.pt"), map_location="cpu")
+    stored history (``[]`` if none).  Works on upstream's own checkpoint directories.
+    Both files are read with the restricted unpickler (``weights_only=True``: tensors, dicts, lists, numbers -- all a
+    state dict holds), so a downloaded checkpoint directory cannot execute code; ``trust=True`` falls back to the full
+    unpickler for files that need it."""
+    sd = torch.load(os.path.join(dirname, "params.pt"), map_location="cpu", weights_only=not trust)
     model.load_state_dict(sd, strict=strict)
     opt_file = os.path.join(dirname, "optimizer.pt")
     if optimizer is not None and os.path.exists(opt_file):
-        osd = torch.load(opt_file, map_location="cpu", weights_only=False)
+        osd = torch.load(opt_file, map_location="cpu", weights_only=not trust)
         if hasattr(optimizer, "load_torch_state_dict"):
             optimizer.load_torch_state_dict(osd)
         else:

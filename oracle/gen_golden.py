@@ -48,8 +48,14 @@ _EPS_LOG = []
 _orig_std_normal = _tdn._standard_normal
 
 
+_EPS_SEED = [None]   # when set: eps = randn(shape, Generator(seed)) so that a large eps need not be stored in the fixture
+
+
 def _recording_standard_normal(shape, dtype, device):
-    e = _orig_std_normal(shape, dtype, device)
+    if _EPS_SEED[0] is not None:
+        e = torch.randn(tuple(shape), generator=torch.Generator().manual_seed(_EPS_SEED[0]), dtype=dtype)
+    else:
+        e = _orig_std_normal(shape, dtype, device)
     _EPS_LOG.append(e.detach().clone())
     return e
 
@@ -147,7 +153,8 @@ def grad_projection(g):
     return torch.stack(out)
 
 
-def run_case(model, cfg, name, training, inputs, loss_name, with_grads, extrap=None, seed=0):
+def run_case(model, cfg, name, training, inputs, loss_name, with_grads, extrap=None, seed=0, eps_seed=None):
+    _EPS_SEED[0] = eps_seed
     model.train(training)
     if extrap is not None:
         model.set_extrapolation(extrap)
@@ -171,7 +178,12 @@ def run_case(model, cfg, name, training, inputs, loss_name, with_grads, extrap=N
         case["q_loc"] = q_c.base_dist.loc.detach().clone()
         case["q_scale"] = q_c.base_dist.scale.detach().clone()
         assert len(_EPS_LOG) == 1
-        case["eps"] = _EPS_LOG[0]
+        if eps_seed is None:
+            case["eps"] = _EPS_LOG[0]
+        else:   # tests/_util.py::load_fixture regenerates it and verifies the checksum
+            e = _EPS_LOG[0]
+            case["eps_seed"], case["eps_shape"] = eps_seed, tuple(e.shape)
+            case["eps_check"] = torch.stack([e.double().sum(), e.double().abs().sum(), e.reshape(-1)[:: max(1, e.numel() // 7)].double().sum()])
         if q_ct is not None:
             case["q_ct_loc"] = q_ct.base_dist.loc.detach().clone()
             case["q_ct_scale"] = q_ct.base_dist.scale.detach().clone()
@@ -369,6 +381,44 @@ def main_attn_family():
     ])
 
 
+def main_baseline_shapes():
+    """Fixtures at the shapes of BASELINE.json's configs (the sizes bench.py measures), from the real reference:
+    python oracle/gen_golden.py baseline"""
+    os.makedirs(OUT, exist_ok=True)
+    # configs[1]: ConvCNP default ctor, C = T = 128 (8 of the 256 tasks; tests/test_gpu_baseline_shapes.py also runs B = 256)
+    cfg = dict(family="ConvCNP", x_dim=1, y_dim=1)
+    m = build(cfg)
+    dump("baseline_convcnp_b8_c128_t128", cfg, m, [
+        run_case(m, cfg, "train_b8_c128_t128", True, bench_offgrid(8, 128, 128, 101), "cnpf", True),
+    ])
+    # configs[2]: AttnCNP transformer attention (notebook cfg, 252 738 params), C = T = 512
+    cfg = dict(family="AttnCNP", x_dim=1, y_dim=1, notebook=True, xy_hidden=128, attention="transformer", init_seed=21)
+    m = build(cfg)
+    dump("baseline_attncnp_b2_c512_t512", cfg, m, [
+        run_case(m, cfg, "train_b2_c512_t512", True, bench_offgrid(2, 512, 512, 102), "cnpf", True),
+        run_case(m, cfg, "eval_b2_c512_t512", False, offgrid_inputs(2, 512, 512, 1, 103), "cnpf", False),
+    ])
+    # configs[3]: GridConvCNP(1, 3) default ctor, 32x32, 30 % context
+    cfg = dict(family="GridConvCNP", x_dim=1, y_dim=3, init_seed=22)
+    m = build(cfg)
+    dump("baseline_gridconvcnp_b4_32x32", cfg, m, [
+        run_case(m, cfg, "train_b4_32x32", True, grid_inputs(4, 32, 32, 3, 0.3, 104), "cnpf", True),
+    ])
+    # configs[4]: GridConvLNP(1, 3, n_z_samples_train=16), 32x32 (eps regenerated from its seed: 16.8 MB otherwise)
+    cfg = dict(family="GridConvLNP", x_dim=1, y_dim=3, n_z_samples_train=16, n_z_samples_test=4, is_q_zCct=False, init_seed=23)
+    m = build(cfg)
+    dump("baseline_gridconvlnp_b2_32x32_nz16", cfg, m, [
+        run_case(m, cfg, "train_b2_32x32_nz16", True, grid_inputs(2, 32, 32, 3, 0.3, 105), "nll", True, eps_seed=9001),
+    ])
+
+
+def bench_offgrid(B, C, T, seed):
+    """bench.py's synthetic inputs: X ~ U(-1, 1) unsorted, Y ~ N(0, 1)."""
+    g = torch.Generator().manual_seed(seed)
+    return dict(X_cntxt=torch.rand(B, C, 1, generator=g) * 2 - 1, Y_cntxt=torch.randn(B, C, 1, generator=g),
+                X_trgt=torch.rand(B, T, 1, generator=g) * 2 - 1, Y_trgt=torch.randn(B, T, 1, generator=g))
+
+
 def _xy2(B, C, T, y_dim, seed, unit=False):
     g = torch.Generator().manual_seed(seed)
     x = torch.rand(B, C + T, 2, generator=g) * 2 - 1
@@ -382,7 +432,10 @@ def _xy2(B, C, T, y_dim, seed, unit=False):
 if __name__ == "__main__":
     if sys.argv[1:] == ["attn"]:
         main_attn_family()
+    elif sys.argv[1:] == ["baseline"]:
+        main_baseline_shapes()
     else:
         main()
         main_attn_family()
+        main_baseline_shapes()
     os.system(f"du -sh {OUT}")
