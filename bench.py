@@ -8,8 +8,9 @@ k=11), meta-batch 256 tasks PER GPU, 128 context / 128 target points, fp32 stora
 weights under seed 0, X ~ U(-1,1), Y ~ N(0,1)).  Weak scaling: every rank processes its own 256 tasks; for N > 1 the
 flat gradient is all-reduced (NCCL) inside the timed region.  One JSON line on stdout (rank 0).
 
-`--impl reference` times the reference algorithm's CPU path (the oracle port, torch CPU ops on all host threads) on a
-bounded sample of the same workload.
+`--impl reference` times the reference's own CPU path (the unmodified upstream package installed under baseline/_ref by
+baseline/install_ref.sh; the oracle port only if that directory did not travel) on a bounded sample of the same workload.
+The default run also carries short runs of the other BASELINE configs as `other_workloads`.
 """
 import argparse
 import json
@@ -20,7 +21,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "neural-process-family_b200"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "neural-process-family_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -183,44 +184,88 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")          # the unmodified reference, installed by baseline/install_ref.sh
+# tasks per CPU step (a bounded sample of the workload: the reference materialises [B,T,I,128] / [B,H,T,C] tensors)
+CPU_SAMPLE_TASKS = {"ConvCNP": 8, "CNP": 16, "AttnCNP": 4, "GridConvCNP": 8, "GridConvLNP": 2}
+
+
+def _reference_model(fam):
+    """The reference's own model for the workload (npf.* from baseline/_ref), or None when it did not travel."""
+    if not os.path.isdir(os.path.join(REF_DIR, "npf")):
+        return None, None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import warnings
+        warnings.filterwarnings("ignore")
+        import npf
+        from functools import partial
+        from npf.architectures import MLP, merge_flat_input
+    except Exception as e:                                                        # noqa: BLE001
+        print(f"bench: reference import failed ({e}); falling back to the oracle port", file=sys.stderr)
+        return None, None
+    torch.manual_seed(0)
+    if fam == "ConvCNP":
+        m = npf.ConvCNP(1, 1)
+    elif fam == "CNP":
+        m = npf.CNP(1, 1)
+    elif fam == "AttnCNP":
+        m = npf.AttnCNP(1, 1, attention="transformer", XYEncoder=merge_flat_input(
+            partial(MLP, n_hidden_layers=2, hidden_size=128), is_sum_merge=True))
+    elif fam == "GridConvCNP":
+        m = npf.GridConvCNP(1, 3)
+    elif fam == "GridConvLNP":
+        m = npf.GridConvLNP(1, 3, n_z_samples_train=16, is_q_zCct=False)
+    else:
+        raise ValueError(fam)
+    return m.train(), npf
+
+
 def cpu_reference_timing(wl, steps, warmup, budget_s=25.0):
-    """The reference algorithm on host cores: oracle port (torch CPU, all threads), fwd + loss + bwd, bounded sample."""
-    from oracle import npf_oracle as O
-    import _util
+    """The reference's CPU path on the host cores: fwd + loss + bwd of a bounded sample of the workload (Bc tasks per step,
+    same C / T / image size as the GPU workload).  kind="reference": the unmodified upstream package (baseline/_ref, through
+    its own public API: npf.<Model>(...)(X_cntxt, Y_cntxt, X_trgt, Y_trgt) -> npf.<Loss> -> backward); kind="port": the
+    oracle's torch-CPU restatement, only when baseline/_ref did not travel."""
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     fam = wl["family"]
-    model = make_model(fam)
-    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
-    Bc = {"ConvCNP": 8, "CNP": wl["B"], "AttnCNP": 4, "GridConvCNP": 8, "GridConvLNP": 2}[fam]
+    Bc = min(CPU_SAMPLE_TASKS[fam], wl["B"])
     inp = make_inputs(wl, Bc, seed=1)
-    cfg = dict(family=fam, attention="transformer")
-    eps = None
-    if fam == "GridConvLNP":
-        eps = torch.randn(16, Bc, 32, 32, 128)
-    case = dict(inputs=inp, training=True, loss_name=wl["loss"], eps=eps)
+    Xc, Yc, Xt, Yt = inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"]
+    ref_model, npf_ref = _reference_model(fam)
+    if ref_model is not None:
+        kind = "reference"
+        crit = (npf_ref.CNPFLoss if wl["loss"] == "cnpf" else npf_ref.NLLLossLNPF)().train()
 
+        def step():
+            ref_model.zero_grad(set_to_none=True)
+            crit(ref_model(Xc, Yc, Xt, Yt), Yt).backward()
+        what = "unmodified reference package (baseline/_ref/npf), public API"
+    else:
+        kind = "port"
+        from oracle import npf_oracle as O          # the one place bench.py may execute oracle/: the CPU arm
+        model = make_model(fam)
+        sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+        eps = torch.randn(16, Bc, 32, 32, 128) if fam == "GridConvLNP" else None
+
+        def step():
+            for v in sd.values():
+                v.grad = None
+            if fam == "ConvCNP":
+                loc, scale = O.convcnp_forward(sd, Xc, Yc, Xt)
+            elif fam == "CNP":
+                loc, scale = O.cnp_forward(sd, Xc, Yc, Xt)
+            elif fam == "AttnCNP":
+                loc, scale = O.attncnp_forward(sd, Xc, Yc, Xt, attention="transformer")
+            elif fam == "GridConvCNP":
+                loc, scale = O.gridconvcnp_forward(sd, Xc, Yc)
+            else:
+                loc, scale, *_ = O.gridconvlnp_forward(sd, Xc, Yc, eps)
+            (O.cnpf_loss(loc, scale, Yt) if wl["loss"] == "cnpf" else O.nll_lnpf_loss(loc, scale, Yt)).backward()
+        what = "oracle/npf_oracle.py (torch-CPU restatement of the reference op sequence; baseline/_ref absent)"
+
+    # all host threads are offered; ATen's broadcast-heavy kernels are not always fastest with all of them, so the thread
+    # count is the best of {8 (the notebooks' N_THREADS), 16, 32, 64, all} on one step each -- the reference's best case
     t_cal = time.perf_counter()
-
-    def step():
-        for v in sd.values():
-            v.grad = None
-        sdd = {k: v for k, v in sd.items()}
-        Xc, Yc, Xt, Yt = inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"]
-        if fam == "ConvCNP":
-            loc, scale = O.convcnp_forward(sdd, Xc, Yc, Xt)
-        elif fam == "CNP":
-            loc, scale = O.cnp_forward(sdd, Xc, Yc, Xt)
-        elif fam == "AttnCNP":
-            loc, scale = O.attncnp_forward(sdd, Xc, Yc, Xt, attention="transformer")
-        elif fam == "GridConvCNP":
-            loc, scale = O.gridconvcnp_forward(sdd, Xc, Yc)
-        else:
-            loc, scale, *_ = O.gridconvlnp_forward(sdd, Xc, Yc, eps)
-        loss = O.cnpf_loss(loc, scale, Yt) if wl["loss"] == "cnpf" else O.nll_lnpf_loss(loc, scale, Yt)
-        loss.backward()
-
-    # use the host thread count that is fastest for this op mix (all threads is not always best for ATen's
-    # broadcast-heavy kernels): calibrate once over {8, 16, 32, 64, all}
     best = None
     for nt in sorted({n for n in (8, 16, 32, 64, avail) if n <= avail}):
         torch.set_num_threads(nt)
@@ -242,67 +287,34 @@ def cpu_reference_timing(wl, steps, warmup, budget_s=25.0):
     for _ in range(k):
         step()
     dt = (time.perf_counter() - t0) / k
-    return dict(value=Bc / dt, unit="tasks/s", cores=torch.get_num_threads(), host_cpus=avail, kind="port",
-                sample=f"{k} steps of {Bc} tasks ({fam}, same C/T as the GPU workload) in {dt * k:.1f}s; oracle/npf_oracle.py "
-                       f"(torch CPU restatement of the reference op sequence)"), dt * 1e3, k, w
+    return dict(value=Bc / dt, unit="tasks/s", cores=torch.get_num_threads(), host_cpus=avail, kind=kind, tasks_per_step=Bc,
+                sample=f"{k} steps of {Bc} tasks ({fam}, same C/T/image size as the GPU workload) in {dt * k:.1f}s; {what}; "
+                       f"thread count = fastest of {{8,16,32,64,all}}"), dt * 1e3, k, w
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="convcnp1d_b256_c128_t128", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16", "bf16x3"],
-                    help="bf16x3 (default): tcgen05 linear layers with 3-term split-bf16 operands, fp32 accumulate -- meets the fp32 parity bar (1e-4); "
-                         "fp32: FFMA GEMMs; bf16: single-pass bf16 operands (1e-2 bar)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay of the step (npf_b200.GraphedStep)")
-    ap.add_argument("--kernel-times", action="store_true", help="print the per-kernel CUDA-event breakdown to stderr")
-    args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = dict(workload=args.workload, description=wl["desc"], tasks_per_gpu=wl["B"], global_batch=wl["B"] * max(world, 1),
-               n_cntxt=wl["C"], n_trgt=wl["T"], parallelism=f"dp{max(world, 1)} (tasks sharded, flat-gradient all-reduce)",
-               l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)",
-               launch="eager" if args.no_graph else "cuda graph replay (npf_b200.GraphedStep)")
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        cb, ms, k, w = cpu_reference_timing(wl, args.steps, args.warmup)
-        line = dict(impl="reference", metric="tasks/sec (meta-batch fwd+bwd)", value=cb["value"], unit="tasks/s",
-                    n_gpus=args.gpus, steps=k, warmup=w, ms_per_step=ms, higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="f32", data="synthetic", config=cfg, cpu_baseline=cb,
-                    e2e=dict(value=cb["value"], unit="tasks/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(line))
-        return
-
+def make_loss(name, reduction="mean"):
     import npf_b200
-    from npf_b200 import ops
-    from npf_b200.parallel import FlatGradients
-    from _cfg import loss_for
+    return dict(cnpf=npf_b200.CNPFLoss, nll=npf_b200.NLLLossLNPF, elbo=npf_b200.ELBOLossLNPF)[name](reduction=reduction)
 
-    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU; there is no CPU fallback"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+
+def run_ours(wl_name, args, ctx, steps, warmup, full):
+    """One workload through the public API (GraphedStep): device-timed region with resident inputs, the end-to-end region
+    from pinned host buffers, and the per-kernel breakdown.  `full` adds the fp32-path timing."""
+    import npf_b200
+    from npf_b200 import _cabi, ops
+    from npf_b200.parallel import FlatGradients
+    wl = WORKLOADS[wl_name]
+    rank, world, dev, dist = ctx["rank"], ctx["world"], ctx["dev"], ctx["dist"]
     npf_b200.set_precision(args.precision)
     model = make_model(wl["family"]).to(dev).train()
-    crit = loss_for(wl["loss"], reduction="mean").train()
+    crit = make_loss(wl["loss"]).train()
     flat = FlatGradients(model, process_group=None if world == 1 else dist.group.WORLD)
     B = wl["B"]
     n_sets = 4
     dev_inputs = [make_inputs(wl, B, seed=100 * rank + i, device=dev) for i in range(n_sets)]
     host_inputs = [make_inputs(wl, B, seed=100 * rank + i, pin=True) for i in range(n_sets)]
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    flush = ctx["flush"]
 
     def eager_step(inp):
         flat.zero_()
@@ -325,19 +337,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    warm = max(warmup, 3)
+    for i in range(warm):
         step(dev_inputs[i % n_sets])
     barrier()
 
     # ---- timed region 1: inputs resident in HBM, CUDA events around every step, L2 flushed between steps ------------
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(ctx["local_rank"])
     if rank == 0:
         sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     n0 = ops.launch_count()
     barrier()
     t_wall = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(float(i))
         evs[i][0].record()
         step(dev_inputs[i % n_sets])
@@ -346,7 +359,7 @@ def main():
             sampler.sample_now()            # under load: the GPU is several replays behind the host here
     barrier()
     t_wall = time.perf_counter() - t_wall
-    launches = ops.launch_count() - n0 if gstep is None else gstep.last_launches * args.steps   # replays launch the recorded kernels
+    launches = ops.launch_count() - n0 if gstep is None else gstep.last_launches * steps   # replays launch the recorded kernels
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -357,7 +370,7 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         inp = {k: v.to(dev, non_blocking=True) for k, v in host_inputs[i % n_sets].items()}
         float(step(inp).item())  # device -> host read of the step's loss
     ev1.record()
@@ -366,15 +379,14 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host_inputs[0].values())
 
     # ---- per-kernel CUDA-event breakdown (separate instrumented steps; events on the launching stream) --------------
-    from npf_b200 import _cabi
+    n_prof = min(steps, 10 if full else 4)
     _cabi.enable_timing(True)
-    for i in range(min(args.steps, 10)):
+    for i in range(n_prof):
         flush.fill_(0.0)
         eager_step(dev_inputs[i % n_sets])
     torch.cuda.synchronize()
     shaped = _cabi.collect_timing(by_shape=True)   # (name, bytes/call, flops/call) -> (total_ms, calls)
     _cabi.enable_timing(False)
-    n_prof = min(args.steps, 10)
     ktimes = {}
     for (name, nb, fl), (ms, n) in shaped.items():
         t = ktimes.get(name, (0.0, 0, 0, 0))
@@ -382,14 +394,14 @@ def main():
 
     # ---- the fp32 (FFMA) path of the same step, for reference next to the default precision -------------------------
     fp32_path = None
-    if args.precision != "fp32":
+    if full and args.precision != "fp32":
         npf_b200.set_precision("fp32")
         g32 = None if args.no_graph else npf_b200.GraphedStep(model, crit, flat=flat)
         step32 = (lambda inp: eager_step(inp)) if g32 is None else (lambda inp: g32(inp["X_cntxt"], inp["Y_cntxt"], inp["X_trgt"], inp["Y_trgt"]))
         for i in range(3):
             step32(dev_inputs[i % n_sets])
         barrier()
-        n32 = max(5, args.steps // 3)
+        n32 = max(5, steps // 3)
         ev32 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n32)]
         for i in range(n32):
             flush.fill_(float(i))
@@ -400,31 +412,110 @@ def main():
         ms32 = sum(a.elapsed_time(b) for a, b in ev32) / n32
         fp32_path = dict(ms_per_step=ms32, value=B * world / (ms32 * 1e-3), unit="tasks/s", steps=n32, note="same step with precision=fp32 (FFMA GEMMs), rank-local time")
         npf_b200.set_precision(args.precision)
+        del g32
 
     tot = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(tot[0]), float(tot[1])
+    flat.detach()
+    del gstep, model, flat, dev_inputs, host_inputs
+    torch.cuda.empty_cache()
+    tasks = B * world * steps
+    return dict(wl=wl, B=B, steps=steps, warmup=warm, value=tasks / (dev_ms * 1e-3), ms_per_step=dev_ms / steps,
+                e2e=dict(value=tasks / (e2e_ms * 1e-3), unit="tasks/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+                launches=launches, wall_ms_per_step=t_wall * 1e3 / steps, clocks=clocks, ktimes=ktimes, shaped=shaped, n_prof=n_prof,
+                fp32_path=fp32_path)
+
+
+def workload_config(name, world, no_graph):
+    wl = WORKLOADS[name]
+    return dict(workload=name, description=wl["desc"], tasks_per_gpu=wl["B"], global_batch=wl["B"] * max(world, 1),
+                n_cntxt=wl["C"], n_trgt=wl["T"], parallelism=f"dp{max(world, 1)} (tasks sharded, flat-gradient all-reduce)",
+                l2="flushed between timed steps (256 MiB write, outside the per-step event pairs)",
+                launch="eager" if no_graph else "cuda graph replay (npf_b200.GraphedStep)")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="convcnp1d_b256_c128_t128", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16", "bf16x3"],
+                    help="bf16x3 (default): tcgen05 linear layers with 3-term split-bf16 operands, fp32 accumulate -- meets the fp32 parity bar (1e-4); "
+                         "fp32: FFMA GEMMs; bf16: single-pass bf16 operands (1e-2 bar)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE workloads (`other_workloads`)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay of the step (npf_b200.GraphedStep)")
+    ap.add_argument("--kernel-times", action="store_true", help="print the per-kernel CUDA-event breakdown to stderr")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, ms, k, w = cpu_reference_timing(wl, args.steps, args.warmup)
+        cfg = dict(workload=args.workload, description=wl["desc"], tasks_per_gpu=wl["B"], global_batch=wl["B"] * max(args.gpus, 1),
+                   n_cntxt=wl["C"], n_trgt=wl["T"], cpu_sample_tasks_per_step=cb["tasks_per_step"],
+                   note=f"CPU arm: each step is a bounded sample of {cb['tasks_per_step']} tasks of the workload (the GPU arm runs {wl['B']} per GPU); "
+                        "tasks/s is per-task cost and extrapolates linearly in the batch")
+        line = dict(impl="reference", metric="tasks/sec (meta-batch fwd+bwd)", value=cb["value"], unit="tasks/s",
+                    n_gpus=args.gpus, steps=k, warmup=w, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic", config=cfg, cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit="tasks/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import npf_b200  # noqa: F401
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = dict(rank=rank, world=world, local_rank=local_rank, dev=dev, dist=dist,
+               flush=torch.empty(256 * 1024 * 1024 // 4, device=dev))
+    peaks = measured_peaks()
+
+    r = run_ours(args.workload, args, ctx, args.steps, args.warmup, full=True)
+    # short runs of the other BASELINE workloads, so that one driver-run line shows every config (same protocol, fewer steps)
+    others = {}
+    if not args.no_others and args.workload == "convcnp1d_b256_c128_t128":
+        for name in ("cnp_b16_c32_t64", "attncnp_b64_c512_t512", "gridconvcnp_b128_32x32", "gridconvlnp_b64_32x32_nz16"):
+            o = run_ours(name, args, ctx, steps=max(5, min(args.steps, 20) // 2), warmup=3, full=False)
+            if rank == 0:
+                roof_o, _ = roofline(o["wl"], o["ktimes"], o["n_prof"], o["B"], peaks, o["shaped"])
+                others[name] = dict(value=o["value"], unit="tasks/s", ms_per_step=o["ms_per_step"], steps=o["steps"], warmup=o["warmup"],
+                                    e2e=o["e2e"], gpu_launches=o["launches"], config=workload_config(name, world, args.no_graph),
+                                    roofline=roof_o,
+                                    kernel_ms_per_step={k: round(v[0] / o["n_prof"], 4) for k, v in sorted(o["ktimes"].items(), key=lambda kv: -kv[1][0])[:8]})
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    tasks = B * world * args.steps
-    value = tasks / (dev_ms * 1e-3)
-    peaks = measured_peaks()
-    roof, roof_table = roofline(wl, ktimes, n_prof, B, peaks, shaped)
-    line = dict(metric="tasks/sec (meta-batch fwd+bwd)", value=value, unit="tasks/s", n_gpus=world, steps=args.steps,
-                warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
+    ktimes, n_prof = r["ktimes"], r["n_prof"]
+    roof, roof_table = roofline(wl, ktimes, n_prof, r["B"], peaks, r["shaped"])
+    line = dict(metric="tasks/sec (meta-batch fwd+bwd)", value=r["value"], unit="tasks/s", n_gpus=world, steps=args.steps,
+                warmup=r["warmup"], ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype={"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (fp32-equivalent)"}[args.precision],
-                data="synthetic", config=cfg, clocks=clocks,
-                e2e=dict(value=tasks / (e2e_ms * 1e-3), unit="tasks/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
-                gpu_launches=launches, wall_ms_per_step=t_wall * 1e3 / args.steps, roofline=roof, kernel_rooflines=roof_table,
+                data="synthetic", config=workload_config(args.workload, world, args.no_graph), clocks=r["clocks"],
+                e2e=r["e2e"], gpu_launches=r["launches"], wall_ms_per_step=r["wall_ms_per_step"], roofline=roof, kernel_rooflines=roof_table,
                 kernel_ms_per_step={k: round(v[0] / n_prof, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
                 kernel_timing="per-call CUDA events on the launching stream in 10 instrumented eager steps after the timed region "
                               "(the timed region itself replays a CUDA graph: no per-kernel events inside it)")
-    if fp32_path is not None:
-        line["fp32_path"] = fp32_path
+    if r["fp32_path"] is not None:
+        line["fp32_path"] = r["fp32_path"]
+    if others:
+        line["other_workloads"] = others
     if not args.no_cpu_baseline:
         cb, _, _, _ = cpu_reference_timing(wl, 200, 2, budget_s=15.0)
         line["cpu_baseline"] = cb
