@@ -869,6 +869,298 @@ __global__ void __launch_bounds__(kTcThreads, 1) setconv_tc_fwd_kernel(const flo
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core BACKWARD for the induced -> target direction (C == 128, regular shared key grid, Q <= 128):
+//     dV[b]     = P^T  . dF[b]              P[q,k]  = exp(a_qk - m_q) / s_q                       (value gradient)
+//     d theta  ~= sum_{k,c} V[k,c] . dV2[k,c],   dV2 = E2^T . dF,   E2[q,k] = P[q,k] ((a_qk - m_q) - A1_q),
+//                 A1_q = sum_k P[q,k] (a_qk - m_q)        (the softmax part of d theta: sum_q T_q - G_q A1_q of the SIMT kernels,
+//                 with G_q = dF_q . feat_q folded in through A1 -- feat is not read at all)
+//               + sum_{q,k} ddens_q exp(a_qk) a_qk        (the density part, accumulated by the threads that evaluate exp)
+// Both products are [128 keys x Q queries] x [Q x 128 channels] GEMMs that share the B operand: the task's dF tile is staged
+// ONCE (bf16 hi + lo, row-major = MN-major B) and the two generated left operands (P^T, E2^T: never stored anywhere) are
+// written by the producer warps straight into SWIZZLE_128B K-major images, 64 queries per stage, 2-stage ring; the MMA
+// warp accumulates hi.hi + hi.lo + lo.hi of both into two TMEM accumulators (double-buffered across key tiles: 512
+// columns); the epilogue writes the dV tile as coalesced rows and reduces dV2 against the V rows it reads from HBM exactly
+// once (V is an epilogue operand here, not an MMA operand).  HBM traffic per task: dF + V read once, dV written once
+// (the SIMT pair read V + dF + feat and dF again).  Replaces setconv_task_kernel<1> + setconv_task_dv_kernel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBwProd = 16;                                   // producer warps (A-operand generation, dF staging)
+constexpr int kBwMmaWarp = kBwProd;
+constexpr int kBwEpiWarp0 = kBwProd + 1;
+constexpr int kBwEpi = 8;
+constexpr int kBwThreads = (kBwEpiWarp0 + kBwEpi) * 32;      // 800
+constexpr uint32_t kBwImg = 128u * 64u * 2u;                  // one bf16 image of a [128 x 64] operand tile: 16 KB
+constexpr uint32_t kBwStage = 4u * kBwImg;                    // P hi, P lo, E2 hi, E2 lo: 64 KB
+constexpr uint32_t kBwF = 4u * kBwImg;                        // dF: (hi, lo) x 2 query chunks: 64 KB
+
+__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBwProd * 32) : "memory"); }
+
+__global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const float* __restrict__ keys, const float* __restrict__ queries, long qry_bs,
+                                                                      const float* __restrict__ values, const float* __restrict__ theta,
+                                                                      const float* __restrict__ mstat, const float* __restrict__ dfeat,
+                                                                      const float* __restrict__ ddens, float* __restrict__ dvalues,
+                                                                      float* __restrict__ dtheta, int B, int K, int Q) {
+    constexpr int C = 128;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_afull[2], bar_aempty[2], bar_ffull, bar_fempty, bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_keys[kMaxChunks * kChunkRows];
+    __shared__ __align__(16) float4 s_qa[128];                // (x_q, m_q log2 e, 1 / s_q, A1_q)
+    __shared__ __align__(16) float2 s_qb[128];                // (ddens_q exp(m_q), m_q)
+    __shared__ float s_part[kBwThreads / 32];
+
+    uint8_t* sA = smem_raw;                                   // 2 stages x 64 KB
+    uint8_t* sF = smem_raw + 2 * kBwStage;                    // dF images: [chunk][hi 16K | ...]: hi(c0) hi(c1) lo(c0) lo(c1)
+    float* scratch_all = reinterpret_cast<float*>(smem_raw + 2 * kBwStage + kBwF);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_afull[i], kBwProd * 32);
+            mbar_init(&bar_aempty[i], 1);
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kBwEpi * 32);
+        }
+        mbar_init(&bar_ffull, kBwProd * 32);
+        mbar_init(&bar_fempty, 1);
+    }
+    const float th = __ldg(theta);
+    const float sigma = 1e-5f + softplus_f(th);
+    const float inv_sigma = 1.f / sigma;
+    const int n_kt = (K + 127) >> 7;                          // key tiles per task
+    const int n_qc = (Q + 63) >> 6;                           // 64-query chunks per task (1 or 2)
+    const int n_tiles = B * n_kt;
+    const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int g0 = min(n_tiles, (int)blockIdx.x * per), g1 = min(n_tiles, g0 + per);
+    pdl_trigger();
+    for (int i = tid; i < K; i += kBwThreads) s_keys[i] = __ldg(keys + i);     // the grid is an input of the step
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    pdl_wait();
+
+    float part = 0.f;                                         // this thread's share of the d theta sum
+
+    if (warp < kBwProd) {
+        // ------------------------------------------------------------------ producers
+        const int r = tid & 127, quarter = tid >> 7;           // key row of the tile; queries [16 quarter, 16 quarter + 16) of a chunk
+        const float is2 = inv_sigma * 1.2011224087864498f;     // exp(a - m) = exp2(-(d is2)^2 - m log2 e)
+        const int fw = warp & 7, fc = warp >> 3;               // dF staging: rows 8 fw .. 8 fw + 7 of query chunk fc
+        const uint32_t vchunk = (uint32_t)(lane >> 1) & 7u;
+        const uint32_t voff = (uint32_t)fc * kBwImg + (uint32_t)(lane >> 4) * 8192u + (uint32_t)(fw * 8) * 128u + (uint32_t)(lane & 1) * 8u;
+        int ga = 0, ntask = 0, cur_b = -1;
+        for (int g = g0; g < g1; ++g) {
+            const int b = g / n_kt, kt = g - b * n_kt;
+            {   // pull the tile's value rows (epilogue operand) into L2 ahead of the epilogue
+                const int rows = min(128, K - kt * 128);
+                const char* vbase = reinterpret_cast<const char*>(values + ((long)b * K + kt * 128) * C);
+                for (int l = tid; l < rows * 4; l += kBwProd * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + ((long)l << 7)));
+            }
+            if (b != cur_b) {
+                cur_b = b;
+                prod_sync();                                   // everyone is done with the previous task's query records
+                float4 f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int q = fc * 64 + fw * 8 + i;
+                    f[i] = q < Q ? __ldg(reinterpret_cast<const float4*>(dfeat + ((long)b * Q + q) * C) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (tid < 128) {
+                    const int q = tid;
+                    float xq = s_keys[0], m = 0.f, invs = 0.f, dd = 0.f;       // padding queries: every generated weight is exactly 0
+                    if (q < Q) {
+                        const long oq = (long)b * Q + q;
+                        xq = __ldg(queries + (long)b * qry_bs + q);
+                        m = __ldg(mstat + oq * 2);
+                        invs = 1.f / __ldg(mstat + oq * 2 + 1);
+                        dd = __ldg(ddens + oq) * expf(m);
+                    }
+                    s_qa[q] = make_float4(xq, m * 1.4426950408889634f, invs, 0.f);
+                    s_qb[q] = make_float2(dd, m);
+                }
+                prod_sync();
+                {   // A1_q = sum_k P_qk (a_qk - m_q) over the query's sigma-window: 4 threads per query
+                    const int q = tid >> 2, kp = tid & 3;
+                    const float4 qa = s_qa[q];
+                    int lo, hi;
+                    window_t(s_keys, K, qa.x, sigma, lo, hi);
+                    float a1 = 0.f;
+                    for (int k = lo + kp; k <= hi; k += 4) {
+                        const float t = (s_keys[k] - qa.x) * is2;
+                        const float l2 = fmaf(-t, t, -qa.y);
+                        float e;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l2));
+                        a1 = fmaf(e, l2, a1);
+                    }
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+                    if (kp == 0) s_qa[q].w = (q < Q) ? a1 * qa.z * 0.6931471805599453f : 0.f;
+                }
+                if (ntask >= 1) mbar_wait(&bar_fempty, (uint32_t)(ntask - 1) & 1u);      // the previous task's MMAs no longer read the dF images
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t off = voff + (uint32_t)i * 128u + ((vchunk ^ (uint32_t)i) << 4);
+                    const uint32_t h01 = pack_bf16(f[i].x, f[i].y), h23 = pack_bf16(f[i].z, f[i].w);
+                    *reinterpret_cast<uint2*>(sF + off) = make_uint2(h01, h23);
+                    *reinterpret_cast<uint2*>(sF + 2 * kBwImg + off) =
+                        make_uint2(pack_bf16(f[i].x - __uint_as_float(h01 << 16), f[i].y - __uint_as_float(h01 & 0xFFFF0000u)),
+                                   pack_bf16(f[i].z - __uint_as_float(h23 << 16), f[i].w - __uint_as_float(h23 & 0xFFFF0000u)));
+                }
+                fence_async_smem();
+                mbar_arrive(&bar_ffull);
+                ++ntask;
+                prod_sync();                                   // A1 visible to every producer
+            }
+            const int key = kt * 128 + r;
+            const bool kok = key < K;
+            const float xk = s_keys[kok ? key : 0];
+            for (int c = 0; c < n_qc; ++c, ++ga) {
+                const int s = ga & 1;
+                if (ga >= 2) mbar_wait(&bar_aempty[s], (uint32_t)((ga >> 1) - 1) & 1u);
+                uint8_t* st_base = sA + (uint32_t)s * kBwStage;
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = quarter * 2 + jj;            // 16-byte chunk of the row = 8 queries
+                    float pv[8], ev[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int q = c * 64 + j * 8 + i;
+                        const float4 qa = s_qa[q];             // broadcast: every lane of the warp reads the same query record
+                        const float2 qb = s_qb[q];
+                        const float t = (xk - qa.x) * is2;
+                        const float l2 = fmaf(-t, t, -qa.y);
+                        float e;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l2));
+                        e = kok ? e : 0.f;
+                        const float am = l2 * 0.6931471805599453f;     // a - m
+                        const float p = e * qa.z;
+                        pv[i] = p;
+                        ev[i] = p * (am - qa.w);
+                        part = fmaf((am + qb.y) * e, qb.x, part);      // ddens_q exp(a_qk) a_qk
+                    }
+                    const uint32_t off = (uint32_t)r * 128u + (((uint32_t)j ^ (uint32_t)(r & 7)) << 4);
+                    split_store8(pv, st_base, st_base + kBwImg, off);
+                    split_store8(ev, st_base + 2 * kBwImg, st_base + 3 * kBwImg, off);
+                }
+                fence_async_smem();
+                mbar_arrive(&bar_afull[s]);
+            }
+        }
+    } else if (warp == kBwMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 128, 0, 1);     // A = generated tile (K-major), B = dF rows (MN-major view)
+            const uint32_t sf = smem_u32(sF);
+            int ga = 0, tc = 0, ntask = 0, cur_b = -1;
+            for (int g = g0; g < g1; ++g, ++tc) {
+                const int b = g / n_kt;
+                if (b != cur_b) {
+                    cur_b = b;
+                    mbar_wait(&bar_ffull, (uint32_t)ntask & 1u);
+                    ++ntask;
+                }
+                const int t = tc & 1;
+                mbar_wait(&bar_tempty[t], (uint32_t)((tc >> 1) & 1) ^ 1u);
+                const uint32_t d_v = tmem + (uint32_t)t * 256u, d_e = d_v + 128u;
+                for (int c = 0; c < n_qc; ++c, ++ga) {
+                    const int s = ga & 1;
+                    mbar_wait(&bar_afull[s], (uint32_t)(ga >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(sA + (uint32_t)s * kBwStage);
+                    const uint32_t f_hi = sf + (uint32_t)c * kBwImg, f_lo = f_hi + 2 * kBwImg;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t b_h = make_desc_sw128_t(f_hi + ks * 2048u, 8192, 1024), b_l = make_desc_sw128_t(f_lo + ks * 2048u, 8192, 1024);
+                        const uint64_t p_h = make_desc_sw128_t(sa + ks * 32u, 16, 1024), p_l = make_desc_sw128_t(sa + kBwImg + ks * 32u, 16, 1024);
+                        const uint64_t e_h = make_desc_sw128_t(sa + 2 * kBwImg + ks * 32u, 16, 1024), e_l = make_desc_sw128_t(sa + 3 * kBwImg + ks * 32u, 16, 1024);
+                        const uint32_t acc = (c | ks) ? 1u : 0u;
+                        umma_bf16(d_v, p_h, b_h, idesc, acc);
+                        umma_bf16(d_v, p_h, b_l, idesc, 1);
+                        umma_bf16(d_v, p_l, b_h, idesc, 1);
+                        umma_bf16(d_e, e_h, b_h, idesc, acc);
+                        umma_bf16(d_e, e_h, b_l, idesc, 1);
+                        umma_bf16(d_e, e_l, b_h, idesc, 1);
+                    }
+                    umma_commit(&bar_aempty[s]);
+                }
+                umma_commit(&bar_tfull[t]);
+                if (g + 1 == g1 || (g + 1) / n_kt != b) umma_commit(&bar_fempty);      // last tile of the task: the dF images may be replaced
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: dV rows out, dV2 . V reduced into d theta
+        const int e = warp - kBwEpiWarp0;
+        const int lane_base = 32 * (warp & 3);
+        const int col_base = (e >> 2) * 64;
+        float* scratch = scratch_all + e * (32 * kTcScratchLd);
+        const int r_in = lane >> 2, c4 = (lane & 3) * 4;
+        int tc = 0;
+        for (int g = g0; g < g1; ++g, ++tc) {
+            const int t = tc & 1;
+            const int b = g / n_kt, kt = g - b * n_kt;
+            const long row0 = (long)b * K + kt * 128 + lane_base;          // global row of this warp's TMEM lane 0
+            const int rows_ok = K - (kt * 128 + lane_base);                // rows [0, rows_ok) of the warp's 32 exist
+            mbar_wait(&bar_tfull[t], (uint32_t)(tc >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int c0 = col_base + ch * 16;
+                float4 vv[4];                                               // the V pieces this thread will meet after the transpose
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = j * 8 + r_in;
+                    vv[j] = rr < rows_ok ? __ldg(reinterpret_cast<const float4*>(values + (row0 + rr) * C + c0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 256 + c0), v);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(scratch + lane * kTcScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = j * 8 + r_in;
+                    if (rr < rows_ok)
+                        *reinterpret_cast<float4*>(dvalues + (row0 + rr) * C + c0 + c4) = *reinterpret_cast<const float4*>(scratch + rr * kTcScratchLd + c4);
+                }
+                __syncwarp();
+                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 256 + 128 + c0), v);
+                if (ch == 3) {
+                    tc_fence_before();
+                    mbar_arrive(&bar_tempty[t]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(scratch + lane * kTcScratchLd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = j * 8 + r_in;
+                    const float4 d2 = *reinterpret_cast<const float4*>(scratch + rr * kTcScratchLd + c4);
+                    part = fmaf(d2.x, vv[j].x, part); part = fmaf(d2.y, vv[j].y, part);
+                    part = fmaf(d2.z, vv[j].z, part); part = fmaf(d2.w, vv[j].w, part);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    part = warp_sum(part);
+    if (lane == 0) s_part[warp] = part;
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < kBwThreads / 32; ++i) tot += s_part[i];
+        atomicAdd(dtheta, tot * (-2.f / sigma) * sigmoid_f(th));
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static bool tc_bwd_ok(int K, int Q, int C, long key_bs) {
+    static const bool on = [] { const char* e = getenv("NPF_SETCONV_TC_BWD"); return !(e && e[0] == '0'); }();
+    return on && C == 128 && key_bs == 0 && K >= 3 && K <= kMaxChunks * kChunkRows && Q >= 1 && Q <= 128;
+}
+
 static bool tc_fwd_ok(int K, int Q, int C, long key_bs) {
     static const bool on = [] { const char* e = getenv("NPF_SETCONV_TC"); return !(e && e[0] == '0'); }();
     (void)Q;
@@ -932,6 +1224,16 @@ int setconv_tile_bwd(const float* keys, long key_bs, const float* queries, long 
     if (!tile_ok(K, Q, C, values) || (reinterpret_cast<uintptr_t>(dfeat) & 15) || (reinterpret_cast<uintptr_t>(feat) & 15) ||
         (dvalues && (reinterpret_cast<uintptr_t>(dvalues) & 15)))
         return NPF_ENOTSUP;
+    if (dvalues && tc_bwd_ok(K, Q, C, key_bs)) {
+        const size_t smem = 2 * kBwStage + kBwF + (size_t)kBwEpi * 32 * kTcScratchLd * sizeof(float);
+        static bool battr = false;
+        if (!battr) { cudaFuncSetAttribute(setconv_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); battr = true; }
+        const int n_tiles = B * ((K + 127) / 128);
+        launch_pdl(setconv_tc_bwd_kernel, dim3(n_tiles < kNumSMs ? n_tiles : kNumSMs), dim3(kBwThreads), smem, st, keys, queries, qry_bs, values, theta, mstat, dfeat,
+                   ddens, dvalues, dtheta, B, K, Q);
+        count_launch();
+        return check_launch("setconv_tc_bwd_kernel");
+    }
     if (task_ok(K, Q, C)) {
         static bool tattr = false;
         if (!tattr) {

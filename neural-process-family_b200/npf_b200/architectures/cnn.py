@@ -45,11 +45,16 @@ class _PreNorm:
                     n = n.detach()                                       # total count stays a device scalar: no host sync
             if norm.track_running_stats:
                 with torch.no_grad():
-                    mom = norm.momentum if norm.momentum is not None else 0.1
-                    norm.running_mean.mul_(1 - mom).add_(mean.detach(), alpha=mom)
-                    unbias = n / (n - 1).clamp(min=1) if torch.is_tensor(n) else n / max(n - 1, 1)
-                    norm.running_var.mul_(1 - mom).add_(var.detach() * unbias, alpha=mom)
                     norm.num_batches_tracked += 1
+                    unbias = n / (n - 1).clamp(min=1) if torch.is_tensor(n) else n / max(n - 1, 1)
+                    if norm.momentum is None:      # torch semantics: cumulative moving average, factor 1 / num_batches_tracked
+                        mom = 1.0 / norm.num_batches_tracked.to(torch.float32)        # device scalar: no host sync
+                        norm.running_mean.lerp_(mean.detach(), mom)
+                        norm.running_var.lerp_(var.detach() * unbias, mom)
+                    else:
+                        mom = norm.momentum
+                        norm.running_mean.mul_(1 - mom).add_(mean.detach(), alpha=mom)
+                        norm.running_var.mul_(1 - mom).add_(var.detach() * unbias, alpha=mom)
         else:
             mean, var = norm.running_mean, norm.running_var
         rstd = torch.rsqrt(var + norm.eps)

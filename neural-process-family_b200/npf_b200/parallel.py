@@ -59,8 +59,11 @@ class FlatGradients:
         w = self.world_size
         if w == 1:
             return self.flat
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.mul_(1.0 / w)
+        if self.flat.is_cuda:      # NCCL averages inside the collective: no separate 1/G kernel
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:                      # gloo (CPU host-logic tests) has no AVG
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / w)
         return self.flat
 
 

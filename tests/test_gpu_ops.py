@@ -130,6 +130,38 @@ def test_setconv(ops, B, K, Q, C, N, regular, sigma):
     _check_grads(cu_in, ref_in, yc, yr, ["values", "theta", "W", "b"])
 
 
+@pytest.mark.parametrize("B,K,Q,C,sigma,mode", [
+    (3, 128, 384, 1, 0.012, "dup"),       # duplicated context positions, queries sitting exactly on keys
+    (2, 700, 257, 3, 0.012, "rand"),      # K > block size: strided sort, y_dim 3
+    (2, 40, 384, 1, 0.012, "cluster"),    # all keys clustered far from most queries: windows of the far queries hold every key
+    (260, 128, 384, 1, 0.012, "rand"),    # config-2 geometry, more tasks than SMs
+    (2, 128, 384, 2, 3.0, "rand"),        # sigma >> key spacing: the window is the whole key set
+])
+def test_setconv_sorted_small(ops, B, K, Q, C, sigma, mode):
+    """The sorted-key few-channel kernel (context -> induced) in the interleaved [feat | dens] layout the model uses
+    (values without gradient), against the dense fp64 formula."""
+    gen = torch.Generator().manual_seed(K * 3 + Q + C)
+    keys_r = torch.rand(B, K, 1, generator=gen, dtype=torch.float64) * 2 - 1
+    if mode == "dup":
+        keys_r[:, 1::2] = keys_r[:, 0::2]
+    if mode == "cluster":
+        keys_r = keys_r * 0.01 + 0.8
+    grid = torch.linspace(-1.5, 1.5, Q).double()
+    if mode == "dup":
+        grid[5], grid[100] = keys_r[0, 0, 0], keys_r[0, 2, 0]
+    queries = grid.view(1, Q, 1).expand(B, Q, 1).contiguous()
+    values = _g(B, K, C, seed=3)
+    theta = torch.tensor([math.log(math.expm1(sigma))], dtype=torch.float64)
+    N = 128
+    W, b = _g(N, C + 1, seed=4, scale=(C + 1) ** -0.5), _g(N, seed=5)
+    ref_in = [theta.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)]
+    cu_in = [_cu(t, True) for t in (theta, W, b)]
+    yr = _setconv_ref(keys_r, queries, values, *ref_in)
+    yc = ops.setconv(keys_r.float().cuda(), grid.float().cuda(), values.float().cuda(), *cu_in, keys_regular=False)
+    assert rel_err(yc, yr) < TOL, rel_err(yc, yr)
+    _check_grads(cu_in, ref_in, yc, yr, ["theta", "W", "b"])
+
+
 def _dw_ref(x, W, b, res, relu_in, scale, shift):
     nd = x.dim()
     xs = x

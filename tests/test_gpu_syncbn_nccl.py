@@ -54,7 +54,17 @@ def _worker(rank, world, port, ret):
     sd, sd_ref = m.state_dict(), ref.state_dict()
     e_bn = max(((sd[k].float() - sd_ref[k].float()).abs().max() / sd_ref[k].float().abs().max().clamp_min(1e-12)).item()
                for k in sd if "running_" in k)
-    ret[rank] = (e_loc, e_grad, e_bn)
+    # the same sharded step through GraphedStep: the BatchNorm moment all-reduces AND the flat-gradient all-reduce (ncclAvg) are
+    # recorded into the CUDA graph; two replays must reproduce the eager gradient (running statistics advance per replay)
+    m2 = sync_batchnorm_(build_model(fx["cfg"])); m2.load_state_dict(fx["state_dict"]); m2.cuda().train()
+    flat2 = FlatGradients(m2, process_group=dist.group.WORLD)
+    gstep = npf_b200.GraphedStep(m2, crit, flat=flat2)
+    shard = shard_tasks(inputs, rank, world)
+    for _ in range(2):
+        gstep(shard["X_cntxt"], shard["Y_cntxt"], shard["X_trgt"], shard["Y_trgt"])
+    torch.cuda.synchronize()
+    e_graph = ((flat2.flat - flat_ref.flat).norm() / flat_ref.flat.norm()).item()
+    ret[rank] = (e_loc, e_grad, e_bn, e_graph)
     dist.destroy_process_group()
 
 
@@ -65,5 +75,5 @@ def test_sync_batchnorm_nccl_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     for r in range(2):
-        e_loc, e_grad, e_bn = ret[r]
-        assert e_loc < 1e-4 and e_grad < 1e-3 and e_bn < 1e-4, ret[r]
+        e_loc, e_grad, e_bn, e_graph = ret[r]
+        assert e_loc < 1e-4 and e_grad < 1e-3 and e_bn < 1e-4 and e_graph < 1e-3, ret[r]
