@@ -893,6 +893,27 @@ constexpr uint32_t kBwImg = 128u * 64u * 2u;                  // one bf16 image 
 constexpr uint32_t kBwStage = 4u * kBwImg;                    // P hi, P lo, E2 hi, E2 lo: 64 KB
 constexpr uint32_t kBwF = 4u * kBwImg;                        // dF: (hi, lo) x 2 query chunks: 64 KB
 
+// window_t() for a key grid that lives in SHARED memory (plain loads; __ldg is a global-space load)
+__device__ __forceinline__ void window_s(const float* sk, int K, float xq, float sigma, int& lo_o, int& hi_o) {
+    lo_o = 0; hi_o = K - 1;
+    if (K < 3) return;
+    const float x0 = sk[0], x1 = sk[K - 1];
+    const float dx = (x1 - x0) / (float)(K - 1);
+    if (!(dx > 0.f)) return;
+    float pos = (xq - x0) / dx;
+    pos = fminf(fmaxf(pos, 0.f), (float)(K - 1));
+    const int n0 = (int)rintf(pos);
+    const float dn = xq - sk[n0];
+    const float D = sqrtf(dn * dn + kWindowLogT * sigma * sigma);
+    float lo = floorf((xq - D - x0) / dx) - 1.f;
+    float hi = ceilf((xq + D - x0) / dx) + 1.f;
+    if (!(lo == lo) || !(hi == hi)) return;
+    lo = fminf(fmaxf(lo, 0.f), (float)(K - 1));
+    hi = fminf(fmaxf(hi, 0.f), (float)(K - 1));
+    lo_o = min((int)lo, n0);
+    hi_o = max((int)hi, n0);
+}
+
 __device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBwProd * 32) : "memory"); }
 
 __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const float* __restrict__ keys, const float* __restrict__ queries, long qry_bs,
@@ -985,7 +1006,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
                     const int q = tid >> 2, kp = tid & 3;
                     const float4 qa = s_qa[q];
                     int lo, hi;
-                    window_t(s_keys, K, qa.x, sigma, lo, hi);
+                    window_s(s_keys, K, qa.x, sigma, lo, hi);
                     float a1 = 0.f;
                     for (int k = lo + kp; k <= hi; k += 4) {
                         const float t = (s_keys[k] - qa.x) * is2;

@@ -105,6 +105,8 @@ def _setconv_ref(keys, queries, values, theta, W, b):
     (3, 296, 128, 128, 128, True, 0.012),  # task-resident path (V in shared memory via TMA bulk copies), bench geometry
     (2, 296, 40, 128, 128, True, 0.2),    # task-resident, windows spanning several 32-row chunks
     (149, 296, 9, 128, 128, True, 0.012),  # more tasks than SMs: the persistent CTA loop re-arms its barriers
+    (160, 384, 128, 128, 128, True, 0.012),  # bench geometry, 480 key tiles over 148 CTAs: tcgen05 backward, dF restaged per task
+    (5, 500, 100, 128, 128, True, 0.03),   # 4 key tiles with a 116-row tail, 2 query chunks with a 36-query tail
 ])
 def test_setconv(ops, B, K, Q, C, N, regular, sigma):
     gen = torch.Generator().manual_seed(K * 7 + Q)
