@@ -101,6 +101,17 @@ NPF_API int npf_linear_bwd(const float* dY, int lddy, const float* X, int ldx, c
 NPF_API int npf_mlp_chain_fwd(const float* X, int ldx, const float* const* W, const float* const* b, float* const* Y, int L, int M,
                       int width, int relu_in, unsigned relu_mask, int precision, npf_stream_t stream);
 
+/* Whole backward of the same L square layers (replaces L npf_linear_bwd calls; upstream mlp.py:95-109 through autograd):
+ *     dZ_{L-1} = dY  (gradient w.r.t. the PRE-activation output of the last layer);  for l = L-1 .. 0:
+ *     dW_l += dZ_l^T . X_l ,  db_l += colsum(dZ_l) ,  dZ_{l-1} = (dZ_l . W_l) (.) (X_l > 0)
+ * with X_l the saved INPUT of layer l (X_0 = chain input, X_l = Y_{l-1} of npf_mlp_chain_fwd: post-ReLU, so every
+ * intermediate layer is masked); dX (optional) = dZ_{-1}, masked with X_0 > 0 only if flags has NPF_MASK_X.
+ * X / W / dW / db are HOST arrays of L device pointers (db may be NULL or hold NULL entries), all [.,width] contiguous.
+ * The gradient stays on chip between layers: HBM sees dY and every X_l once and dX once.  Covered: width 128, tensor-core
+ * precisions, M >= 64; returns NPF_ENOTSUP otherwise (no scratch memory is owned here: call npf_linear_bwd per layer). */
+NPF_API int npf_mlp_chain_bwd(const float* dY, int lddy, const float* const* X, const float* const* W, float* dX, int lddx,
+                      float* const* dW, float* const* db, int L, int M, int width, int flags, int precision, npf_stream_t stream);
+
 /* dW[N,K] += dY[M,N]^T . act_in(X)[M,K] ;  db[N] += sum_m dY[m,:] ;  dw2[N*ldw2] += sum_m dY[m,:] u[m]
  * db, u/dw2 optional. */
 NPF_API int npf_linear_bwd_weight(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db,

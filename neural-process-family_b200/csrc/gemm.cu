@@ -253,6 +253,8 @@ int thin128_out_bwd(const float* dY, long lddy, const float* X, long ldx, const 
                     float* db, long M, int J, int relu_in, int use_mask, cudaStream_t st);
 int mlp_chain_fwd_tc(const float* X, int ldx, const float* const* W, const int* ldw, const float* const* b, float* const* Y, const int* ldy, int L, int M,
                      int relu_in, unsigned relu_mask, int precision, cudaStream_t st);
+int mlp_chain_bwd_tc(const float* dY, int lddy, const float* const* X, const float* const* W, float* dX, int lddx, float* const* dW, float* const* db,
+                     int L, int M, int mask0, int precision, cudaStream_t st);
 int linear_bwd_fused_tc(const float* dY, int lddy, const float* X, int ldx, const float* W, int ldw, float* dX, int lddx, float* dW,
                         int lddw, float* db, int M, int K, int N, int flags, int precision, cudaStream_t st);
 int linear_bwd_weight_tc(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int* db_done, int M,
@@ -454,6 +456,22 @@ extern "C" int npf_linear_bwd(const float* dY, int lddy, const float* X, int ldx
     int rc = npf_linear_bwd_weight(dY, lddy, X, ldx, dW, lddw, db, M, K, N, flags & NPF_RELU_IN, nullptr, nullptr, 0, precision, stream);
     if (rc != NPF_OK || !dX) return rc;
     return npf_linear_bwd_data(dY, lddy, W, ldw, dX, lddx, M, K, N, (flags & NPF_MASK_X) ? X : nullptr, ldx, 0, precision, stream);
+}
+
+extern "C" int npf_mlp_chain_bwd(const float* dY, int lddy, const float* const* X, const float* const* W, float* dX, int lddx, float* const* dW,
+                                 float* const* db, int L, int M, int width, int flags, int precision, npf_stream_t stream) {
+    if (M == 0) return NPF_OK;
+    NPF_REQUIRE(dY && X && W && dW && L >= 1 && L <= 8, "npf_mlp_chain_bwd: null pointer or bad layer count");
+    NPF_REQUIRE(M >= 0 && width >= 1 && lddy >= width && (!dX || lddx >= width), "npf_mlp_chain_bwd: bad shape");
+    for (int l = 0; l < L; ++l) NPF_REQUIRE(X[l] && W[l] && dW[l], "npf_mlp_chain_bwd: null layer pointer");
+    if (width == 128) {
+        const int rc = npf::mlp_chain_bwd_tc(dY, lddy, X, W, dX, lddx, dW, db, L, M, (flags & NPF_MASK_X) ? 1 : 0, precision, npf::as_stream(stream));
+        if (rc != NPF_ENOTSUP) return rc;
+    }
+    // layer by layer: needs a scratch gradient per intermediate layer, which this allocation-free entry point does not own
+    npf::set_error("npf_mlp_chain_bwd: shape / precision not covered by the on-chip chain (width 128, tensor-core precision, M >= 64, "
+                   "16-byte aligned rows); call npf_linear_bwd per layer");
+    return NPF_ENOTSUP;
 }
 
 extern "C" int npf_mlp_chain_fwd(const float* X, int ldx, const float* const* W, const float* const* b, float* const* Y, int L, int M, int width,

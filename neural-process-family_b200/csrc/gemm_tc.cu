@@ -1611,6 +1611,349 @@ int linear_bwd_fused_tc(const float* dY, int lddy, const float* X, int ldx, cons
     return precision == NPF_PREC_BF16X3 ? launch_fused<3>(p, st) : launch_fused<1>(p, st);
 }
 
+// ------------------------------------------------------------------------------------------------ MLP chain BACKWARD (128-wide)
+// Whole backward of L consecutive Linear(128 -> 128) + ReLU layers with the pre-activation gradient kept ON CHIP between layers
+// (the mirror of mlp_chain_fwd_kernel).  A CTA owns a row group of up to 256 rows = four 64-row blocks whose gradient images
+// dZ_l (bf16 hi / lo, SWIZZLE_128B, row-major) stay resident in shared memory; layers are walked from the last to the first:
+//     dA^T[k, m] = sum_n W_l[n, k] dZ_l[m, n]          (A = W_l^T: MN-major view of the row-staged W_l,  B = dZ block, K-major, N = 64)
+//     dW_l[n, k] += sum_m dZ_l[m, n] X_l[m, k]         (A = dZ_l^T, B = X_l block: MN-major views; TMEM accumulator over the CTA's blocks,
+//                                                       one flush of float4 atomics per layer, double-buffered across layers)
+//     dZ_{l-1} = dA (.) (X_l > 0)                      written by the epilogue straight back into the block's image (thread = column k),
+//     db_{l-1} = colsum(dZ_{l-1})                      summed in the epilogue's registers (exact fp32)
+// so per layer HBM sees only the saved input X_l (read once: wgrad operand AND relu mask) -- dY is read once for the whole
+// chain and only the first layer's dX is written.  Against L x npf_linear_bwd this removes L - 1 writes and L - 1 reads of an
+// [M, 128] gradient (250 MB -> 117 MB for the 4-layer decoder at M = 32 768) and L - 1 launches with their fill / drain.
+// Roles as in linear_bwd_fused64_kernel: 16 producer warps (dY blocks once, then W_l and the X_l blocks), 1 MMA warp, 8 epilogue
+// warps.  Shared memory: 4 x 32 KB gradient images + 32 KB X stage + 64 KB weights = 224 KB (x3).
+constexpr int kCbBlocks = 4;
+struct ChainBwdParams {
+    const float* dY; long lddy;
+    const float* X[kChainMaxLayers]; long ldx[kChainMaxLayers];      // input of layer l (post-relu output of layer l - 1)
+    const float* W[kChainMaxLayers]; long ldw[kChainMaxLayers];
+    float* dW[kChainMaxLayers]; long lddw[kChainMaxLayers];
+    float* db[kChainMaxLayers];                                       // null entries allowed
+    float* dX; long lddx;                                             // gradient w.r.t. X[0]; null to skip
+    int L, M, rows_per_grp, n_groups, mask0, w_vec, dw_vec;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_wfull, bar_wfree, bar_xfull, bar_dwdone, bar_mask, bar_z0[kCbBlocks], bar_z[kCbBlocks], bar_tfull[2],
+        bar_tempty[2], bar_dwfull[2], bar_dwflushed[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_db[128];
+
+    constexpr uint32_t kHalf = 64u * 128u * 2u;                    // one bf16 64 x 128 image: 16 KB
+    constexpr uint32_t kOp = (NSPLIT == 3 ? 2u : 1u) * kHalf;      // hi [+ lo]
+    constexpr uint32_t kWTile = 128u * 128u * 2u;
+    uint8_t* x_hi = smem_raw + kCbBlocks * kOp;
+    uint8_t* w_hi = x_hi + kOp;
+    uint8_t* w_lo = w_hi + kWTile;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (tid == 32) {
+        mbar_init(&bar_wfull, kFbProdWarps * 32);
+        mbar_init(&bar_wfree, 1);
+        mbar_init(&bar_xfull, kFbProdWarps * 32);
+        mbar_init(&bar_dwdone, 1);
+        mbar_init(&bar_mask, kWsEpiWarps * 32);
+        for (int i = 0; i < kCbBlocks; ++i) {
+            mbar_init(&bar_z0[i], kFbProdWarps * 32);
+            mbar_init(&bar_z[i], kWsEpiWarps * 32);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kWsEpiWarps * 32);
+            mbar_init(&bar_dwfull[i], 1);
+            mbar_init(&bar_dwflushed[i], kWsEpiWarps * 32);
+        }
+    }
+    if (tid < 128) s_db[tid] = 0.f;
+    const int L = p.L;
+    const bool need_dx = p.dX != nullptr;
+    const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < kFbProdWarps) {
+        // ------------------------------------------------------------------ producers
+        const uint32_t woff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
+        const int prow = warp * 4;                                     // rows 4 w .. 4 w + 3 of a 64-row block
+        const uint32_t psoff = (uint32_t)(lane >> 4) * 8192u + (uint32_t)prow * 128u + (uint32_t)(lane & 1) * 8u;
+        const uint32_t rsw = (uint32_t)(prow & 7);
+        float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
+        int li = 0, bi = 0;
+        for (int grp = blockIdx.x, gi = 0; grp < p.n_groups; grp += gridDim.x, ++gi) {
+            const int r_begin = grp * p.rows_per_grp, r_end = min(p.M, r_begin + p.rows_per_grp);
+            const int n_blk = (r_end - r_begin + kF64Rows - 1) / kF64Rows;
+            // weights of the last layer: parameters, may be fetched before the predecessor kernel has finished
+            float4 wv[8];
+            auto load_w = [&](int l) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float* g = p.W[l] + (long)(warp * 8 + i) * p.ldw[l] + lane * 4;
+                    if (p.w_vec) wv[i] = __ldg(reinterpret_cast<const float4*>(g));
+                    else wv[i] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), __ldg(g + 3));
+                }
+            };
+            auto store_w = [&]() {
+                if (li > 0) mbar_wait(&bar_wfree, (uint32_t)(li - 1) & 1u);          // the previous layer's MMAs have read the weight buffer
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cvt_store<NSPLIT>(wv[i], w_hi, w_lo, woff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4), 0);
+                fence_async_smem();
+                mbar_arrive(&bar_wfull);
+            };
+            load_w(L - 1);
+            if (gi == 0) pdl_wait();
+            if (bi > 0) mbar_wait(&bar_dwdone, (uint32_t)(bi - 1) & 1u);            // previous group: every MMA has read its images
+            for (int j = 0; j < n_blk; ++j) {                                        // the chain's incoming gradient -> resident images
+                const int row0 = r_begin + j * kF64Rows, rv = min(kF64Rows, r_end - row0);
+                float4 yy[4];
+                f64_load_rows(yy, p.dY + ((long)row0 + prow) * p.lddy + lane * 4, p.lddy, prow, rv);
+                uint8_t* z_hi = smem_raw + (uint32_t)j * kOp;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    dbs.x += yy[i].x; dbs.y += yy[i].y; dbs.z += yy[i].z; dbs.w += yy[i].w;
+                    cvt_store<NSPLIT>(yy[i], z_hi, z_hi + kHalf, psoff + (uint32_t)i * 128u + ((pchunk ^ (rsw + (uint32_t)i)) << 4), 0);
+                }
+                fence_async_smem();
+                mbar_arrive(&bar_z0[j]);
+            }
+            for (int l = L - 1; l >= 0; --l, ++li) {
+                if (l < L - 1) load_w(l);
+                float4 xx[4];
+                f64_load_rows(xx, p.X[l] + ((long)r_begin + prow) * p.ldx[l] + lane * 4, p.ldx[l], prow, min(kF64Rows, r_end - r_begin));
+                store_w();
+                for (int j = 0; j < n_blk; ++j, ++bi) {
+                    if (bi > 0) {
+                        mbar_wait(&bar_dwdone, (uint32_t)(bi - 1) & 1u);             // the wgrad MMAs of the previous block have read the X stage
+                        mbar_wait(&bar_mask, (uint32_t)(bi - 1) & 1u);               // and the epilogue has taken its relu mask
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        cvt_store<NSPLIT>(xx[i], x_hi, x_hi + kHalf, psoff + (uint32_t)i * 128u + ((pchunk ^ (rsw + (uint32_t)i)) << 4), 0);
+                    fence_async_smem();
+                    mbar_arrive(&bar_xfull);
+                    if (j + 1 < n_blk) {
+                        const int row0 = r_begin + (j + 1) * kF64Rows;
+                        f64_load_rows(xx, p.X[l] + ((long)row0 + prow) * p.ldx[l] + lane * 4, p.ldx[l], prow, min(kF64Rows, r_end - row0));
+                    }
+                }
+            }
+        }
+        if (p.db[L - 1]) {
+            atomicAdd(&s_db[lane * 4 + 0], dbs.x); atomicAdd(&s_db[lane * 4 + 1], dbs.y);
+            atomicAdd(&s_db[lane * 4 + 2], dbs.z); atomicAdd(&s_db[lane * 4 + 3], dbs.w);
+            asm volatile("bar.sync 1, %0;" ::"n"(kFbProdWarps * 32) : "memory");
+            if (tid < 128) atomicAdd(p.db[L - 1] + tid, s_db[tid]);
+        }
+    } else if (warp == kFbProdWarps) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_dx = make_idesc(128, 64, 1, 0);
+            const uint32_t idesc_dw = make_idesc(128, 128, 1, 1);
+            const uint32_t sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
+            const uint32_t sx_hi = smem_u32(x_hi), sx_lo = sx_hi + kHalf;
+            int li = 0, bi = 0, ti = 0;
+            for (int grp = blockIdx.x, gi = 0; grp < p.n_groups; grp += gridDim.x, ++gi) {
+                const int r_begin = grp * p.rows_per_grp, r_end = min(p.M, r_begin + p.rows_per_grp);
+                const int n_blk = (r_end - r_begin + kF64Rows - 1) / kF64Rows;
+                for (int l = L - 1; l >= 0; --l, ++li) {
+                    const int d = li & 1;
+                    const uint32_t d_dw = tmem + 128u + (uint32_t)d * 128u;
+                    mbar_wait(&bar_wfull, (uint32_t)li & 1u);
+                    if (li >= 2) mbar_wait(&bar_dwflushed[d], (uint32_t)((li >> 1) - 1) & 1u);
+                    for (int j = 0; j < n_blk; ++j, ++bi) {
+                        mbar_wait(&bar_xfull, (uint32_t)bi & 1u);
+                        if (l == L - 1) mbar_wait(&bar_z0[j], (uint32_t)gi & 1u);
+                        else mbar_wait(&bar_z[j], (uint32_t)(gi * (L - 1) + (L - 2 - l)) & 1u);
+                        tc_fence_after();
+                        const uint32_t sz_hi = smem_u32(smem_raw + (uint32_t)j * kOp), sz_lo = sz_hi + kHalf;
+                        if (l > 0 || need_dx) {
+                            const int a = ti & 1;
+                            mbar_wait(&bar_tempty[a], (uint32_t)((ti >> 1) & 1) ^ 1u);
+                            tc_fence_after();
+                            const uint32_t d_dx = tmem + (uint32_t)a * 64u;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) {
+                                const uint32_t bo = (uint32_t)(ks >> 2) * 8192u + (uint32_t)(ks & 3) * 32u;
+                                const uint64_t a_h = make_desc_sw128(sw_hi + ks * 2048u, 16384, 1024), b_h = make_desc_sw128(sz_hi + bo, 16, 1024);
+                                umma_bf16(d_dx, a_h, b_h, idesc_dx, ks ? 1u : 0u);
+                                if (NSPLIT == 3) {
+                                    umma_bf16(d_dx, a_h, make_desc_sw128(sz_lo + bo, 16, 1024), idesc_dx, 1);
+                                    umma_bf16(d_dx, make_desc_sw128(sw_lo + ks * 2048u, 16384, 1024), b_h, idesc_dx, 1);
+                                }
+                            }
+                            umma_commit(&bar_tfull[a]);
+                            ++ti;
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t acc = (j | ks) ? 1u : 0u;
+                            const uint64_t a_h = make_desc_sw128(sz_hi + ks * 2048u, 8192, 1024), b_h = make_desc_sw128(sx_hi + ks * 2048u, 8192, 1024);
+                            umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
+                            if (NSPLIT == 3) {
+                                umma_bf16(d_dw, a_h, make_desc_sw128(sx_lo + ks * 2048u, 8192, 1024), idesc_dw, 1);
+                                umma_bf16(d_dw, make_desc_sw128(sz_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
+                            }
+                        }
+                        umma_commit(&bar_dwdone);
+                    }
+                    umma_commit(&bar_wfree);
+                    umma_commit(&bar_dwfull[d]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: thread = column k, 32 rows of a block
+        const int e = warp - kFbEpiWarp0;
+        const int lane_base = 32 * (warp & 3);
+        const int k = lane_base + lane;
+        const int mh = (e >> 2) * 32;
+        const int col_base = (e >> 2) * 64;
+        const uint32_t xk_off = (uint32_t)(k >> 6) * 8192u + (uint32_t)(k & 7) * 2u, xk_chunk = (uint32_t)(k & 63) >> 3;
+        pdl_wait();
+        int li = 0, bi = 0, ti = 0;
+        for (int grp = blockIdx.x, gi = 0; grp < p.n_groups; grp += gridDim.x, ++gi) {
+            const int r_begin = grp * p.rows_per_grp, r_end = min(p.M, r_begin + p.rows_per_grp);
+            const int n_blk = (r_end - r_begin + kF64Rows - 1) / kF64Rows;
+            for (int l = L - 1; l >= 0; --l, ++li) {
+                const int d = li & 1;
+                const bool masked = l > 0 || p.mask0;
+                float dbacc = 0.f;
+                for (int j = 0; j < n_blk; ++j, ++bi) {
+                    // Every block iteration waits for the block's wgrad MMAs (bar_dwdone) BEFORE it releases the X stage (bar_mask):
+                    // the producers need both to stage the next block, so neither barrier can run two phases ahead of a waiter.
+                    if (!(l > 0 || need_dx)) { mbar_wait(&bar_dwdone, (uint32_t)bi & 1u); mbar_arrive(&bar_mask); continue; }
+                    const int a = ti & 1;
+                    mbar_wait(&bar_tfull[a], (uint32_t)(ti >> 1) & 1u);
+                    tc_fence_after();
+                    uint32_t mbits = 0xFFFFFFFFu;
+                    if (masked) {                  // relu mask of column k for the 32 rows, from the staged X_l block: bf16 > 0 <=> int16 > 0
+                        mbits = 0u;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t m = (uint32_t)(mh + i);
+                            const short xb = *reinterpret_cast<const short*>(x_hi + xk_off + m * 128u + ((xk_chunk ^ (m & 7u)) << 4));
+                            mbits |= (xb > 0 ? 1u : 0u) << i;
+                        }
+                    }
+                    float v[32];
+                    {
+                        float v0[16], v1[16];
+                        tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(a * 64 + mh), v0);
+                        tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(a * 64 + mh + 16), v1);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { v[i] = v0[i]; v[16 + i] = v1[i]; }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&bar_tempty[a]);
+                    ++ti;
+                    mbar_wait(&bar_dwdone, (uint32_t)bi & 1u);           // the wgrad MMAs of this block have read image j and the X stage
+                    mbar_arrive(&bar_mask);
+                    if (l > 0) {
+                        uint8_t* z_hi = smem_raw + (uint32_t)j * kOp;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t m = (uint32_t)(mh + i);
+                            const float val = ((mbits >> i) & 1u) ? v[i] : 0.f;
+                            dbacc += val;
+                            const uint32_t off = xk_off + m * 128u + ((xk_chunk ^ (m & 7u)) << 4);
+                            const __nv_bfloat16 h = __float2bfloat16_rn(val);
+                            *reinterpret_cast<__nv_bfloat16*>(z_hi + off) = h;
+                            if (NSPLIT == 3) *reinterpret_cast<__nv_bfloat16*>(z_hi + kHalf + off) = __float2bfloat16_rn(val - __bfloat162float(h));
+                        }
+                        fence_async_smem();
+                        mbar_arrive(&bar_z[j]);
+                    } else {
+                        const int row0 = r_begin + j * kF64Rows + mh;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int row = row0 + i;
+                            if (row < r_end) p.dX[(long)row * p.lddx + k] = ((mbits >> i) & 1u) ? v[i] : 0.f;
+                        }
+                    }
+                }
+                if (l > 0 && p.db[l - 1]) atomicAdd(p.db[l - 1] + k, dbacc);
+                // ---- flush of this layer's weight gradient: thread = row n of dW, 64 columns per warp
+                mbar_wait(&bar_dwfull[d], (uint32_t)(li >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int c0 = col_base + ch * 16;
+                    float v[16];
+                    tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(128 + d * 128 + c0), v);
+                    float* dst = p.dW[l] + (long)k * p.lddw[l] + c0;
+                    if (p.dw_vec) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) atomicAdd(dst + i, v[i]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bar_dwflushed[d]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int NSPLIT>
+static int launch_chain_bwd(ChainBwdParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)(NSPLIT == 3 ? 2 : 1) * (kCbBlocks + 1) * 16384 + 65536;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(mlp_chain_bwd_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return NPF_ENOTSUP;
+        }
+        attr = true;
+    }
+    const int max_rows = kCbBlocks * kF64Rows;
+    int grid = (int)cdiv(p.M, max_rows);
+    if (grid <= kNumSMs) {                       // one balanced row group per CTA
+        long want = cdiv(p.M, kF64Rows);          // at least one full 64-row block per group
+        if (want > kNumSMs) want = kNumSMs;
+        p.rows_per_grp = (int)(cdiv(cdiv(p.M, want), 8) * 8);
+        if (p.rows_per_grp > max_rows) p.rows_per_grp = max_rows;
+        p.n_groups = (int)cdiv(p.M, p.rows_per_grp);
+        grid = p.n_groups;
+    } else {                                     // persistent CTAs walk 256-row groups
+        p.rows_per_grp = max_rows;
+        p.n_groups = grid;
+        grid = kNumSMs;
+    }
+    launch_pdl(mlp_chain_bwd_kernel<NSPLIT>, dim3(grid), dim3(kFbThreads), smem, st, p);
+    count_launch();
+    return check_launch("mlp_chain_bwd_kernel");
+}
+
+// Backward of L consecutive Linear(128 -> 128) layers (ReLU between them); NPF_ENOTSUP for other shapes / alignments / fp32.
+int mlp_chain_bwd_tc(const float* dY, int lddy, const float* const* X, const float* const* W, float* dX, int lddx, float* const* dW, float* const* db,
+                     int L, int M, int mask0, int precision, cudaStream_t st) {
+    if (L < 2 || L > kChainMaxLayers || M < 64 || precision == NPF_PREC_FP32) return NPF_ENOTSUP;
+    if (lddy % 4 != 0 || !aligned16(dY) || (dX && (lddx % 4 != 0 || !aligned16(dX)))) return NPF_ENOTSUP;
+    ChainBwdParams p{};
+    p.dY = dY; p.lddy = lddy; p.dX = dX; p.lddx = lddx; p.L = L; p.M = M; p.mask0 = mask0;
+    p.w_vec = 1; p.dw_vec = 1;
+    for (int l = 0; l < L; ++l) {
+        if (!aligned16(X[l])) return NPF_ENOTSUP;
+        p.X[l] = X[l]; p.ldx[l] = 128; p.W[l] = W[l]; p.ldw[l] = 128; p.dW[l] = dW[l]; p.lddw[l] = 128; p.db[l] = db ? db[l] : nullptr;
+        if (!aligned16(W[l])) p.w_vec = 0;
+        if (!aligned16(dW[l])) p.dw_vec = 0;
+    }
+    return precision == NPF_PREC_BF16X3 ? launch_chain_bwd<3>(p, st) : launch_chain_bwd<1>(p, st);
+}
+
 // Chain of L Linear(128 -> 128) layers with bias / ReLU epilogues, all outputs stored (saved activations).  NPF_ENOTSUP unless
 // every layer is 128 x 128, rows are 16-byte aligned and M fits one wave of 256-row CTAs.
 template <int NSPLIT>

@@ -974,9 +974,10 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
         int ga = 0, ntask = 0, cur_b = -1;
         for (int g = g0; g < g1; ++g) {
             const int b = g / n_kt, kt = g - b * n_kt;
-            {   // pull the tile's value rows (epilogue operand) into L2 ahead of the epilogue
-                const int rows = min(128, K - kt * 128);
-                const char* vbase = reinterpret_cast<const char*>(values + ((long)b * K + kt * 128) * C);
+            for (int gp = (g == g0 ? g : g + 1); gp <= g + 1 && gp < g1; ++gp) {   // the value rows of the NEXT tile (epilogue operand) -> L2, one tile ahead
+                const int bp = gp / n_kt, ktp = gp - bp * n_kt;
+                const int rows = min(128, K - ktp * 128);
+                const char* vbase = reinterpret_cast<const char*>(values + ((long)bp * K + ktp * 128) * C);
                 for (int l = tid; l < rows * 4; l += kBwProd * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + ((long)l << 7)));
             }
             if (b != cur_b) {
@@ -1118,6 +1119,20 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
         float* scratch = scratch_all + e * (32 * kTcScratchLd);
         const int r_in = lane >> 2, c4 = (lane & 3) * 4;
         int tc = 0;
+        // the V pieces this thread meets after the transpose, fetched ONE (tile, column chunk) step ahead of their use: the
+        // loads of step i + 1 are in flight while step i waits for the tensor core, drains TMEM and stores dV
+        auto vload = [&](int g, int ch, float4 (&dst)[4]) {
+            const int b = g / n_kt, kt = g - b * n_kt;
+            const long row0 = (long)b * K + kt * 128 + lane_base;
+            const int rows_ok = K - (kt * 128 + lane_base);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int rr = j * 8 + r_in;
+                dst[j] = rr < rows_ok ? __ldg(reinterpret_cast<const float4*>(values + (row0 + rr) * C + col_base + ch * 16 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 vn[4];
+        if (g0 < g1) vload(g0, 0, vn);
         for (int g = g0; g < g1; ++g, ++tc) {
             const int t = tc & 1;
             const int b = g / n_kt, kt = g - b * n_kt;
@@ -1128,12 +1143,11 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 const int c0 = col_base + ch * 16;
-                float4 vv[4];                                               // the V pieces this thread will meet after the transpose
+                float4 vv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rr = j * 8 + r_in;
-                    vv[j] = rr < rows_ok ? __ldg(reinterpret_cast<const float4*>(values + (row0 + rr) * C + c0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int j = 0; j < 4; ++j) vv[j] = vn[j];
+                if (ch < 3) vload(g, ch + 1, vn);
+                else if (g + 1 < g1) vload(g + 1, 0, vn);
                 float v[16];
                 tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 256 + c0), v);
 #pragma unroll

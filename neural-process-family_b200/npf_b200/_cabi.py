@@ -25,6 +25,7 @@ SIGNATURES = {
     "npf_linear_bwd_weight": [P, I, P, I, P, I, P, I, I, I, I, P, P, I, I, P],
     "npf_linear_bwd": [P, I, P, I, P, I, P, I, P, I, P, I, I, I, I, I, P],
     "npf_mlp_chain_fwd": [P, I, P, P, P, I, I, I, I, I, I, P],
+    "npf_mlp_chain_bwd": [P, I, P, P, P, I, P, P, I, I, I, I, I, P],
     "npf_relu_bwd": [P, P, P, L, P],
     "npf_setconv_fwd": [P, L, P, L, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "npf_setconv_bwd": [P, L, P, L, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
@@ -112,6 +113,8 @@ ALGO = {
     # X read once, every layer output written once (no intermediate read back)
     "npf_mlp_chain_fwd": lambda a: (4 * a[6] * a[7] * (a[5] + 1) + 4 * a[5] * a[7] * a[7], 2 * a[6] * a[7] * a[7] * a[5]),
     # keys/queries + values + feat (+ dens/stat): B*(K*C + Q*C)*4 dominates
+    # dY read once, every layer input once, dX written once
+    "npf_mlp_chain_bwd": lambda a: (4 * a[9] * a[10] * (a[8] + 1 + (1 if a[4] else 0)) + 4 * a[8] * a[10] * a[10], 4 * a[9] * a[10] * a[10] * a[8]),
     "npf_setconv_fwd": lambda a: (4 * a[9] * (a[10] * a[12] + a[11] * a[12] + 3 * a[11] + a[10]), 2 * a[9] * a[11] * a[10] * a[12]),
     "npf_setconv_bwd": lambda a: (4 * a[13] * (2 * a[14] * a[16] + 2 * a[15] * a[16] + 4 * a[15] + a[14]), 6 * a[13] * a[15] * a[14] * a[16]),
     "npf_dwconv_fwd": lambda a: (4 * a[5] * a[6] * a[7] * a[8] * (3 if a[3] else 2), 2 * a[5] * a[6] * a[7] * a[8] * a[9] * a[10]),

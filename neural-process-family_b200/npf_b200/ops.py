@@ -191,7 +191,47 @@ class _MLPChain(torch.autograd.Function):
             dz = dzm
         dWs, dbs = [None] * n, [None] * n
         dx = None
-        for i in range(n - 1, -1, -1):
+        p_eff = _precision if ctx.prec is None else ctx.prec
+        i = n - 1
+        while i >= 0:
+            # run of consecutive square 128-wide layers i0 .. i: ONE kernel keeps the gradient on chip between the layers
+            # (npf_mlp_chain_bwd: dY and every saved input read once, only the run's dX written)
+            i0 = i
+            if p_eff != _PRECISION["fp32"] and M >= 64 and dz.shape[1] == 128 and dz.is_contiguous():
+                while i0 >= 0 and Ws[i0].shape[0] == 128 and Ws[i0].numel() == 128 * 128 and Ws[i0].is_contiguous() \
+                        and (bs[i0] is None or bs[i0].is_contiguous()):
+                    i0 -= 1
+                i0 += 1
+            if i - i0 + 1 >= 2:
+                Lr = i - i0 + 1
+                need_dx = i0 > 0 or ctx.needs_input_grad[0]
+                bufs = [(_gbuf(Ws[l]), _gbuf(bs[l])) for l in range(i0, i + 1)]
+                for l, ((dW, rW), (db, rb)) in zip(range(i0, i + 1), bufs):
+                    dWs[l], dbs[l] = rW, rb
+                dxr = torch.empty(M, 128, device=dz.device, dtype=torch.float32) if need_dx else None
+                Xp = (ctypes.c_void_p * Lr)(*[acts[l].data_ptr() for l in range(i0, i + 1)])
+                Wp = (ctypes.c_void_p * Lr)(*[Ws[l].data_ptr() for l in range(i0, i + 1)])
+                dWp = (ctypes.c_void_p * Lr)(*[b_[0][0].data_ptr() for b_ in bufs])
+                dbp = (ctypes.c_void_p * Lr)(*[(b_[1][0].data_ptr() if b_[1][0] is not None else None) for b_ in bufs])
+                call("npf_mlp_chain_bwd", _p(dz), 128, Xp, Wp, _p(dxr), 128, dWp, dbp, Lr, M, 128, MASK_X if i0 > 0 else 0, p_eff, _stream())
+                dz = dxr
+                if i0 == 0 and need_dx:
+                    dx = dz.reshape(ctx.x_shape)
+                i = i0 - 1
+                continue
+            i = _MLPChain._one_layer_bwd(ctx, i, dz, acts, Ws, bs, dWs, dbs, M)
+            dz, dx_i = i[1], i[2]
+            if dx_i is not None:
+                dx = dx_i
+            i = i[0]
+        grads = tuple(dWs) + (tuple(dbs) if ctx.has_bias else ())
+        return (dx, None, None, None) + grads
+
+    @staticmethod
+    def _one_layer_bwd(ctx, i, dz, acts, Ws, bs, dWs, dbs, M):
+        """backward of layer i alone; returns (next layer index, gradient for it, dx or None)"""
+        dx = None
+        if True:
             W = _c(Ws[i])
             N = W.shape[0]
             K = W.numel() // N
@@ -206,8 +246,7 @@ class _MLPChain(torch.autograd.Function):
                 dz = torch.empty(0, K, device=dz.device, dtype=torch.float32)
             if i == 0 and need_dx:
                 dx = dz.reshape(ctx.x_shape)
-        grads = tuple(dWs) + (tuple(dbs) if ctx.has_bias else ())
-        return (dx, None, None, None) + grads
+        return i - 1, dz, dx
 
 
 def mlp_chain(x, weights, biases, final_relu=False, precision=None):

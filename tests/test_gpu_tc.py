@@ -130,6 +130,58 @@ def test_tc_mlp_chain_entry(npf, prec, L, M, relu_mask, relu_in):
 
 
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("L,M,need_dx,mask0", [(2, 64, True, False), (4, 100, True, True), (5, 257, False, False), (4, 1024, True, False),
+                                               (4, 32768, True, False), (3, 40000, True, True), (8, 4099, True, False)])
+def test_tc_mlp_chain_bwd_entry(npf, prec, L, M, need_dx, mask0):
+    """npf_mlp_chain_bwd (gradient kept on chip between the layers) against fp64: dX, every dW (accumulated into a non-zero
+    buffer) and db (one entry NULL), partial 64-row blocks, one and several row groups per CTA, with / without dX and input mask."""
+    import ctypes
+    from npf_b200 import _cabi
+    pr = {"bf16": 1, "bf16x3": 2}[prec]
+    _, gtol = BARS[prec]
+    st = torch.cuda.current_stream().cuda_stream
+    Ws = [_g(128, 128, seed=10 + l, scale=128 ** -0.5) for l in range(L)]
+    X0 = _g(M, 128, seed=1)
+    if mask0:
+        X0 = torch.relu(X0)
+    Xs = [X0]
+    for l in range(L - 1):                                           # saved inputs: post-ReLU outputs of the previous layer
+        Xs.append(torch.relu(Xs[-1] @ Ws[l].t() + 0.1 * _g(128, seed=40 + l)))
+    dY = _g(M, 128, seed=2)
+    dW0 = [_g(128, 128, seed=60 + l) for l in range(L)]
+    db0 = [_g(128, seed=80 + l) for l in range(L)]
+    # fp64 reference
+    dz, dWr, dbr = dY, [None] * L, [None] * L
+    for l in range(L - 1, -1, -1):
+        dWr[l] = dz.t() @ Xs[l]
+        dbr[l] = dz.sum(0)
+        dz = dz @ Ws[l]
+        if l > 0 or mask0:
+            dz = dz * (Xs[l] > 0)
+    c = lambda t: t.float().cuda().contiguous()
+    Xc, Wc, dWc, dbc, dYc = [c(x) for x in Xs], [c(w) for w in Ws], [c(w) for w in dW0], [c(b) for b in db0], c(dY)
+    skip_db = 1 if L > 2 else -1
+    dXc = torch.full((M, 128), float("nan"), device="cuda") if need_dx else None
+    arr = lambda ts: (ctypes.c_void_p * L)(*[None if t is None else t.data_ptr() for t in ts])
+    _cabi.call("npf_mlp_chain_bwd", dYc.data_ptr(), 128, arr(Xc), arr(Wc), None if dXc is None else dXc.data_ptr(), 128, arr(dWc),
+               arr([None if l == skip_db else dbc[l] for l in range(L)]), L, M, 128, 16 if mask0 else 0, pr, st)
+    torch.cuda.synchronize()
+    if need_dx:
+        assert torch.isfinite(dXc).all()
+        assert l2_rel(dXc, dz) < gtol * L, ("dX", l2_rel(dXc, dz))
+        if mask0:
+            assert (dXc[Xc[0] <= 0] == 0).all()
+    for l in range(L):
+        e = l2_rel(dWc[l] - c(dW0[l]), dWr[l])
+        assert e < gtol * (L - l), (f"dW{l}", e)
+        if l == skip_db:
+            assert torch.equal(dbc[l], c(db0[l]))
+        else:
+            e = l2_rel(dbc[l] - c(db0[l]), dbr[l])
+            assert e < gtol * (L - l), (f"db{l}", e)
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
 def test_tc_model_parity_convcnp(npf, prec):
     """Whole ConvCNP (pointwise convs, SetConv resizer with the rank-1 density column, decoder MLP) on tensor cores."""
     npf.set_precision(prec)
