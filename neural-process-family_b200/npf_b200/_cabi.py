@@ -117,8 +117,10 @@ ALGO = {
     "npf_mlp_chain_bwd": lambda a: (4 * a[9] * a[10] * (a[8] + 1 + (1 if a[4] else 0)) + 4 * a[8] * a[10] * a[10], 4 * a[9] * a[10] * a[10] * a[8]),
     "npf_setconv_fwd": lambda a: (4 * a[9] * (a[10] * a[12] + a[11] * a[12] + 3 * a[11] + a[10]), 2 * a[9] * a[11] * a[10] * a[12]),
     "npf_setconv_bwd": lambda a: (4 * a[13] * (2 * a[14] * a[16] + 2 * a[15] * a[16] + 4 * a[15] + a[14]), 6 * a[13] * a[15] * a[14] * a[16]),
-    "npf_dwconv_fwd": lambda a: (4 * a[5] * a[6] * a[7] * a[8] * (3 if a[3] else 2), 2 * a[5] * a[6] * a[7] * a[8] * a[9] * a[10]),
-    "npf_dwconv_bwd": lambda a: (4 * a[6] * a[7] * a[8] * a[9] * 4, 4 * a[6] * a[7] * a[8] * a[9] * a[10] * a[11]),
+    # x read + y written (+ the residual only when it is a different tensor from x: in a one-conv ResConvBlock res IS x)
+    "npf_dwconv_fwd": lambda a: (4 * a[5] * a[6] * a[7] * a[8] * (3 if (a[3] and a[3] != a[0]) else 2), 2 * a[5] * a[6] * a[7] * a[8] * a[9] * a[10]),
+    # dy + x read, dx written
+    "npf_dwconv_bwd": lambda a: (4 * a[6] * a[7] * a[8] * a[9] * 3, 4 * a[6] * a[7] * a[8] * a[9] * a[10] * a[11]),
     "npf_xattn_fwd": lambda a: (4 * a[5] * a[8] * (2 * a[6] * a[9] + a[7] * a[9] + a[7] * a[10] + a[6]), 2 * a[5] * a[8] * a[6] * a[7] * (a[9] + a[10])),
     "npf_xattn_bwd": lambda a: (4 * a[9] * a[12] * (4 * a[10] * a[13] + 2 * a[11] * a[13] + 2 * a[11] * a[14]), 5 * a[9] * a[12] * a[10] * a[11] * (a[13] + a[14])),
 }

@@ -167,3 +167,63 @@ def test_checkpoint_roundtrip_and_torch_adam_interchange(tmp_path):
     assert torch.equal(opt3.exp_avg, opt.exp_avg) and opt3.step_count == 3
     with pytest.raises(ValueError):
         opt3.load_torch_state_dict(dict(state={}, param_groups=[dict(legacy["param_groups"][0], params=ids[:-1])]))
+
+
+def test_train_models_signature_layout_and_eval_csv(tmp_path):
+    """npf_b200.utils.train.train_models / eval_loglike (upstream utils/train.py:34-305, utils/evaluate.py:9-28) on the CPU
+    with a toy module: loop nest, checkpoint directory layout, best-epoch reload, lr decay, eval.csv in dataset order,
+    load-only mode reproducing the stored evaluation."""
+    import json
+    import numpy as np
+    import torch.nn as nn
+    from torch.utils.data import TensorDataset
+    from npf_b200.utils.train import eval_loglike, train_models
+
+    class Toy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = nn.Linear(1, 1)
+
+        def forward(self, X_cntxt, Y_cntxt, X_trgt, Y_trgt=None):
+            return (self.lin(X_trgt) + Y_cntxt.mean(1, keepdim=True), None, None, None)
+
+    class ToyLoss(nn.Module):
+        def __init__(self, reduction="mean"):
+            super().__init__()
+            self.reduction = reduction
+
+        def forward(self, pred, Y):
+            per_task = ((pred[0] - Y) ** 2).sum((1, 2))
+            return per_task if self.reduction is None else per_task.mean(0)
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(40, 8, 1, generator=g) * 2 - 1
+    y = 3 * x + 0.5
+    train, test = TensorDataset(x[:32], y[:32]), TensorDataset(x[32:], y[32:])
+
+    def collate(batch):
+        X, Y = torch.stack([b[0] for b in batch]), torch.stack([b[1] for b in batch])
+        return dict(X_cntxt=X[:, :3], Y_cntxt=Y[:, :3], X_trgt=X[:, 3:], Y_trgt=Y[:, 3:]), Y[:, 3:]
+
+    kw = dict(criterion=ToyLoss, chckpnt_dirname=str(tmp_path) + "/", device="cpu", max_epochs=6, batch_size=8, lr=5e-2, decay_lr=10, seed=123,
+              test_datasets={"toy": test}, train_split=0.25, iterator_train__collate_fn=collate, iterator_valid__collate_fn=collate)
+    trainers = train_models({"toy": train}, {"M": Toy}, is_retrain=True, runs=2, **kw)
+    assert set(trainers) == {"toy/M/run_0", "toy/M/run_1"}
+    t0 = trainers["toy/M/run_0"]
+    run_dir = tmp_path / "toy" / "M" / "run_0"
+    assert {"params.pt", "optimizer.pt", "history.json", "eval.csv", "model_summary.txt"} <= {p.name for p in run_dir.iterdir()}
+    hist = json.load(open(run_dir / "history.json"))
+    assert len(hist) == 6 and hist[-1]["train_loss"] < hist[0]["train_loss"]
+    assert abs(hist[-1]["lr"] / hist[0]["lr"] - 10 ** (-5 / 6)) < 1e-6               # exponential decay by a total factor 10 over 6 epochs
+    assert any(r["valid_loss_best"] for r in hist) and next(p for p in t0.module_.parameters()).device.type == "cpu"
+    ev = np.loadtxt(run_dir / "eval.csv", delimiter=",")
+    assert ev.shape == (8,)
+    ll = eval_loglike(t0, test)                                                        # same numbers, dataset order
+    assert np.allclose(ll, ev, rtol=1e-5, atol=1e-6)
+    # load-only mode: the stored best checkpoint and eval.csv are returned without training
+    loaded = train_models({"toy": train}, {"M": Toy}, is_retrain=False, runs=1, **kw)["toy/M/run_0"]
+    for a, b in zip(loaded.module_.parameters(), t0.module_.parameters()):
+        assert torch.equal(a, b)
+    assert len(loaded.history) == 6
+    with pytest.raises(FileNotFoundError):
+        train_models({"toy": train}, {"Other": Toy}, is_retrain=False, **kw)
