@@ -1708,8 +1708,16 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                 fence_async_smem();
                 mbar_arrive(&bar_wfull);
             };
+            // the group's rows of a saved layer input -> L2, issued one whole layer ahead of their use (the X blocks are then
+            // fetched from L2 while the previous block is multiplied instead of exposing a DRAM round trip per block)
+            auto prefetch_x = [&](int l) {
+                const char* base = reinterpret_cast<const char*>(p.X[l] + (long)r_begin * p.ldx[l]);
+                const int lines = (r_end - r_begin) * 4;                                // 512 bytes per row
+                for (int i = tid; i < lines; i += kFbProdWarps * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((long)(i >> 2) * p.ldx[l] * 4 + (i & 3) * 128)));
+            };
             load_w(L - 1);
             if (gi == 0) pdl_wait();
+            prefetch_x(L - 1);
             if (bi > 0) mbar_wait(&bar_dwdone, (uint32_t)(bi - 1) & 1u);            // previous group: every MMA has read its images
             for (int j = 0; j < n_blk; ++j) {                                        // the chain's incoming gradient -> resident images
                 const int row0 = r_begin + j * kF64Rows, rv = min(kF64Rows, r_end - row0);
@@ -1726,6 +1734,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
             }
             for (int l = L - 1; l >= 0; --l, ++li) {
                 if (l < L - 1) load_w(l);
+                if (l > 0) prefetch_x(l - 1);
                 float4 xx[4];
                 f64_load_rows(xx, p.X[l] + ((long)r_begin + prow) * p.ldx[l] + lane * 4, p.ldx[l], prow, min(kF64Rows, r_end - r_begin));
                 store_w();

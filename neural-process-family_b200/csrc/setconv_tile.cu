@@ -952,8 +952,9 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
     const int n_kt = (K + 127) >> 7;                          // key tiles per task
     const int n_qc = (Q + 63) >> 6;                           // 64-query chunks per task (1 or 2)
     const int n_tiles = B * n_kt;
-    const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int g0 = min(n_tiles, (int)blockIdx.x * per), g1 = min(n_tiles, g0 + per);
+    // contiguous, balanced tile ranges: the first n_tiles % grid CTAs take one tile more
+    const int per = n_tiles / (int)gridDim.x, rem = n_tiles - per * (int)gridDim.x;
+    const int g0 = (int)blockIdx.x * per + min((int)blockIdx.x, rem), g1 = g0 + per + ((int)blockIdx.x < rem ? 1 : 0);
     pdl_trigger();
     for (int i = tid; i < K; i += kBwThreads) s_keys[i] = __ldg(keys + i);     // the grid is an input of the step
     tc_fence_before();
@@ -972,6 +973,17 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
         const uint32_t vchunk = (uint32_t)(lane >> 1) & 7u;
         const uint32_t voff = (uint32_t)fc * kBwImg + (uint32_t)(lane >> 4) * 8192u + (uint32_t)(fw * 8) * 128u + (uint32_t)(lane & 1) * 8u;
         int ga = 0, ntask = 0, cur_b = -1;
+        float nq_x = 0.f, nq_m = 0.f, nq_s = 1.f, nq_d = 0.f;       // query record of the next task (threads 0..127: one query each)
+        auto load_qrec = [&](int bb) {
+            if (tid < 128 && tid < Q) {
+                const long oq = (long)bb * Q + tid;
+                nq_x = __ldg(queries + (long)bb * qry_bs + tid);
+                nq_m = __ldg(mstat + oq * 2);
+                nq_s = __ldg(mstat + oq * 2 + 1);
+                nq_d = __ldg(ddens + oq);
+            }
+        };
+        if (g0 < g1) load_qrec(g0 / n_kt);
         for (int g = g0; g < g1; ++g) {
             const int b = g / n_kt, kt = g - b * n_kt;
             for (int gp = (g == g0 ? g : g + 1); gp <= g + 1 && gp < g1; ++gp) {   // the value rows of the NEXT tile (epilogue operand) -> L2, one tile ahead
@@ -992,15 +1004,18 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
                 if (tid < 128) {
                     const int q = tid;
                     float xq = s_keys[0], m = 0.f, invs = 0.f, dd = 0.f;       // padding queries: every generated weight is exactly 0
-                    if (q < Q) {
-                        const long oq = (long)b * Q + q;
-                        xq = __ldg(queries + (long)b * qry_bs + q);
-                        m = __ldg(mstat + oq * 2);
-                        invs = 1.f / __ldg(mstat + oq * 2 + 1);
-                        dd = __ldg(ddens + oq) * expf(m);
+                    if (q < Q) {                                                // fetched one task ahead (nq_*): no load latency here
+                        xq = nq_x; m = nq_m;
+                        invs = 1.f / nq_s;
+                        dd = nq_d * expf(m);
                     }
                     s_qa[q] = make_float4(xq, m * 1.4426950408889634f, invs, 0.f);
                     s_qb[q] = make_float2(dd, m);
+                }
+                if ((b + 1) * n_kt < g1) {                                      // the NEXT task of this CTA: query records -> registers, dF rows -> L2
+                    load_qrec(b + 1);
+                    const char* fbase = reinterpret_cast<const char*>(dfeat + (long)(b + 1) * Q * C);
+                    for (int l = tid; l < Q * 4; l += kBwProd * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(fbase + ((long)l << 7)));
                 }
                 prod_sync();
                 {   // A1_q = sum_k P_qk (a_qk - m_q) over the query's sigma-window: 4 threads per query
@@ -1119,8 +1134,9 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
         float* scratch = scratch_all + e * (32 * kTcScratchLd);
         const int r_in = lane >> 2, c4 = (lane & 3) * 4;
         int tc = 0;
-        // the V pieces this thread meets after the transpose, fetched ONE (tile, column chunk) step ahead of their use: the
-        // loads of step i + 1 are in flight while step i waits for the tensor core, drains TMEM and stores dV
+        // The V pieces this thread meets after the transpose are fetched FAR ahead of their use: two column chunks are always in
+        // flight in registers, issued before the tile's dV half (4 TMEM drains + stores) or two dV2 chunks earlier, so an L2 /
+        // DRAM round trip (~1-2.5 k cycles under load) is covered by several hundred-cycle epilogue steps instead of one.
         auto vload = [&](int g, int ch, float4 (&dst)[4]) {
             const int b = g / n_kt, kt = g - b * n_kt;
             const long row0 = (long)b * K + kt * 128 + lane_base;
@@ -1131,8 +1147,8 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
                 dst[j] = rr < rows_ok ? __ldg(reinterpret_cast<const float4*>(values + (row0 + rr) * C + col_base + ch * 16 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        float4 vn[4];
-        if (g0 < g1) vload(g0, 0, vn);
+        float4 va[4], vb[4];
+        if (g0 < g1) { vload(g0, 0, va); vload(g0, 1, vb); }
         for (int g = g0; g < g1; ++g, ++tc) {
             const int t = tc & 1;
             const int b = g / n_kt, kt = g - b * n_kt;
@@ -1140,14 +1156,10 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
             const int rows_ok = K - (kt * 128 + lane_base);                // rows [0, rows_ok) of the warp's 32 exist
             mbar_wait(&bar_tfull[t], (uint32_t)(tc >> 1) & 1u);
             tc_fence_after();
+            // ---- value gradient: TMEM -> per-warp transpose -> coalesced rows of dV
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 const int c0 = col_base + ch * 16;
-                float4 vv[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) vv[j] = vn[j];
-                if (ch < 3) vload(g, ch + 1, vn);
-                else if (g + 1 < g1) vload(g + 1, 0, vn);
                 float v[16];
                 tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 256 + c0), v);
 #pragma unroll
@@ -1160,8 +1172,12 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
                         *reinterpret_cast<float4*>(dvalues + (row0 + rr) * C + c0 + c4) = *reinterpret_cast<const float4*>(scratch + rr * kTcScratchLd + c4);
                 }
                 __syncwarp();
-                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 256 + 128 + c0), v);
-                if (ch == 3) {
+            }
+            // ---- d theta: sum of dV2 (.) V over the tile
+            auto dot_chunk = [&](int ch, const float4 (&vv)[4], bool last) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(t * 256 + 128 + col_base + ch * 16), v);
+                if (last) {                                                 // both accumulators of buffer t are drained
                     tc_fence_before();
                     mbar_arrive(&bar_tempty[t]);
                 }
@@ -1176,7 +1192,15 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
                     part = fmaf(d2.z, vv[j].z, part); part = fmaf(d2.w, vv[j].w, part);
                 }
                 __syncwarp();
-            }
+            };
+            dot_chunk(0, va, false);
+            vload(g, 2, va);
+            dot_chunk(1, vb, false);
+            vload(g, 3, vb);
+            dot_chunk(2, va, false);
+            if (g + 1 < g1) vload(g + 1, 0, va);
+            dot_chunk(3, vb, true);
+            if (g + 1 < g1) vload(g + 1, 1, vb);
         }
     }
     part = warp_sum(part);
