@@ -60,6 +60,9 @@ typedef void* npf_stream_t;
 #define NPF_API
 #endif
 
+/* Diagnostics only: device buffer (>= 4096 uint64, zeroed by the caller) into which CTA 0 of the kernels that support it
+ * (npf_mlp_chain_bwd, npf_setconv_bwd tensor-core path) writes per-role (event, SM clock) records; NULL disables. */
+NPF_API int npf_debug_set_trace(unsigned long long* device_buffer);
 NPF_API int npf_abi_version(void);
 NPF_API const char* npf_last_error(void);
 /* number of kernels launched by this library in the calling process so far (monotonic; for bench.py) */
@@ -165,6 +168,16 @@ NPF_API int npf_dwconv_fwd(const float* X, const float* Wt, const float* bias, c
 NPF_API int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, float* dX, float* dWt, float* dbias, int B,
                    int H, int Wd, int C, int kh, int kw, int flags, const float* pre_scale,
                    const float* pre_shift, float* dpre_scale, float* dpre_shift, npf_stream_t stream);
+
+/* The whole 1-D pre-activation residual block of the ConvCNP CNN in ONE kernel (upstream cnn.py:204-215 with
+ * n_conv_layers = 1 and Normalization = Identity, helpers.py:354-403):
+ *     O = depthwise_k(relu(X)) + bdw + X        Y = O . wpw^T + bpw
+ * X, O, Y [B,L,128] channel-last contiguous; wdw [128,k] (the Conv1d weight [128,1,k]), wpw [128,128] (the 1x1 Conv1d
+ * weight); O = NULL skips the write of the intermediate (a backward that recomputes it does not need it).
+ * Raw rows reach shared memory by TMA bulk copies; O never makes a round trip through HBM.
+ * Covered: C = 128, k = 11, NPF_PREC_BF16X3; NPF_ENOTSUP otherwise (run npf_dwconv_fwd + npf_linear_fwd). */
+NPF_API int npf_resblock1d_fwd(const float* X, const float* wdw, const float* bdw, const float* wpw, const float* bpw, float* O,
+                       float* Y, int B, int L, int C, int k, int precision, npf_stream_t stream);
 
 /* per-channel batch statistics of a channel-last tensor X[M,C] (train-mode BatchNorm of the notebook CNN
  * configs, two-pass like ATen: first the mean, then the centred second moment):

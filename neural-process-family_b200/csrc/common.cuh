@@ -10,6 +10,19 @@ namespace npf {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+unsigned long long* trace_buffer();     // diagnostics (npf_debug_set_trace); nullptr unless set
+
+// timeline record of CTA 0: slot `role` (0..15) holds up to 255 (event, clock) records after a counter
+__device__ __forceinline__ void trace_ev(unsigned long long* tr, int role, int event) {
+    if (tr == nullptr || blockIdx.x != 0) return;
+    unsigned long long* slot = tr + role * 256;
+    const unsigned long long n = slot[0];
+    if (n < 255) {
+        const unsigned long long t = (unsigned long long)clock64();      // SM cycle counter: every role of the CTA shares it
+        slot[1 + n] = ((unsigned long long)event << 56) | (t & 0x00FFFFFFFFFFFFFFull);
+        slot[0] = n + 1;
+    }
+}
 
 // returns NPF_OK or NPF_ECUDA after a kernel launch (no sync)
 int check_launch(const char* what);

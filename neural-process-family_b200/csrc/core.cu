@@ -26,6 +26,9 @@ bool pdl_enabled() {
     return on;
 }
 
+static unsigned long long* g_trace = nullptr;
+unsigned long long* trace_buffer() { return g_trace; }
+
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -37,6 +40,9 @@ int check_launch(const char* what) {
 
 }  // namespace npf
 
+// diagnostics: a device buffer of >= 4096 u64 into which CTA 0 of the warp-specialised kernels that support it writes
+// (role, event, clock64) records -- profiles/microbench/trace_timeline.py; NULL (the default) disables it
+extern "C" int npf_debug_set_trace(unsigned long long* device_buffer) { npf::g_trace = device_buffer; return NPF_OK; }
 extern "C" int npf_abi_version(void) { return NPF_ABI_VERSION; }
 extern "C" const char* npf_last_error(void) { return npf::g_err; }
 extern "C" unsigned long long npf_launch_count(void) { return npf::g_launches.load(std::memory_order_relaxed); }

@@ -1634,6 +1634,7 @@ struct ChainBwdParams {
     float* db[kChainMaxLayers];                                       // null entries allowed
     float* dX; long lddx;                                             // gradient w.r.t. X[0]; null to skip
     int L, M, rows_per_grp, n_groups, mask0, w_vec, dw_vec;
+    unsigned long long* trace;                                        // diagnostics (npf_debug_set_trace)
 };
 
 template <int NSPLIT>
@@ -1739,15 +1740,18 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                 f64_load_rows(xx, p.X[l] + ((long)r_begin + prow) * p.ldx[l] + lane * 4, p.ldx[l], prow, min(kF64Rows, r_end - r_begin));
                 store_w();
                 for (int j = 0; j < n_blk; ++j, ++bi) {
+                    if (tid == 0) trace_ev(p.trace, 0, 1);
                     if (bi > 0) {
                         mbar_wait(&bar_dwdone, (uint32_t)(bi - 1) & 1u);             // the wgrad MMAs of the previous block have read the X stage
                         mbar_wait(&bar_mask, (uint32_t)(bi - 1) & 1u);               // and the epilogue has taken its relu mask
                     }
+                    if (tid == 0) trace_ev(p.trace, 0, 2);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         cvt_store<NSPLIT>(xx[i], x_hi, x_hi + kHalf, psoff + (uint32_t)i * 128u + ((pchunk ^ (rsw + (uint32_t)i)) << 4), 0);
                     fence_async_smem();
                     mbar_arrive(&bar_xfull);
+                    if (tid == 0) trace_ev(p.trace, 0, 3);
                     if (j + 1 < n_blk) {
                         const int row0 = r_begin + (j + 1) * kF64Rows;
                         f64_load_rows(xx, p.X[l] + ((long)row0 + prow) * p.ldx[l] + lane * 4, p.ldx[l], prow, min(kF64Rows, r_end - row0));
@@ -1778,7 +1782,9 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                     mbar_wait(&bar_wfull, (uint32_t)li & 1u);
                     if (li >= 2) mbar_wait(&bar_dwflushed[d], (uint32_t)((li >> 1) - 1) & 1u);
                     for (int j = 0; j < n_blk; ++j, ++bi) {
+                        trace_ev(p.trace, 1, 1);
                         mbar_wait(&bar_xfull, (uint32_t)bi & 1u);
+                        trace_ev(p.trace, 1, 2);
                         if (l == L - 1) mbar_wait(&bar_z0[j], (uint32_t)gi & 1u);
                         else mbar_wait(&bar_z[j], (uint32_t)(gi * (L - 1) + (L - 2 - l)) & 1u);
                         tc_fence_after();
@@ -1812,6 +1818,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                             }
                         }
                         umma_commit(&bar_dwdone);
+                        trace_ev(p.trace, 1, 3);
                     }
                     umma_commit(&bar_wfree);
                     umma_commit(&bar_dwfull[d]);
@@ -1840,8 +1847,10 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                     // the producers need both to stage the next block, so neither barrier can run two phases ahead of a waiter.
                     if (!(l > 0 || need_dx)) { mbar_wait(&bar_dwdone, (uint32_t)bi & 1u); mbar_arrive(&bar_mask); continue; }
                     const int a = ti & 1;
+                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 1);
                     mbar_wait(&bar_tfull[a], (uint32_t)(ti >> 1) & 1u);
                     tc_fence_after();
+                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 2);
                     uint32_t mbits = 0xFFFFFFFFu;
                     if (masked) {                  // relu mask of column k for the 32 rows, from the staged X_l block: bf16 > 0 <=> int16 > 0
                         mbits = 0u;
@@ -1863,8 +1872,10 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                     tc_fence_before();
                     mbar_arrive(&bar_tempty[a]);
                     ++ti;
+                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 3);
                     mbar_wait(&bar_dwdone, (uint32_t)bi & 1u);           // the wgrad MMAs of this block have read image j and the X stage
                     mbar_arrive(&bar_mask);
+                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 4);
                     if (l > 0) {
                         uint8_t* z_hi = smem_raw + (uint32_t)j * kOp;
 #pragma unroll
@@ -1879,6 +1890,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                         }
                         fence_async_smem();
                         mbar_arrive(&bar_z[j]);
+                        if (e == 0 && lane == 0) trace_ev(p.trace, 2, 5);
                     } else {
                         const int row0 = r_begin + j * kF64Rows + mh;
 #pragma unroll
@@ -1954,6 +1966,7 @@ int mlp_chain_bwd_tc(const float* dY, int lddy, const float* const* X, const flo
     ChainBwdParams p{};
     p.dY = dY; p.lddy = lddy; p.dX = dX; p.lddx = lddx; p.L = L; p.M = M; p.mask0 = mask0;
     p.w_vec = 1; p.dw_vec = 1;
+    p.trace = trace_buffer();
     for (int l = 0; l < L; ++l) {
         if (!aligned16(X[l])) return NPF_ENOTSUP;
         p.X[l] = X[l]; p.ldx[l] = 128; p.W[l] = W[l]; p.ldw[l] = 128; p.dW[l] = dW[l]; p.lddw[l] = 128; p.db[l] = db ? db[l] : nullptr;

@@ -98,6 +98,11 @@ class ResConvBlock(nn.Module):
     def forward(self, X):
         """X channel-last: [B, L, C] or [B, H, W, C]."""
         h = X
+        if self.n_conv_layers == 1 and isinstance(self.norm2, nn.Identity) and self.conv2_depthwise.bias is not None \
+                and self.conv2_pointwise.bias is not None and ops.resblock1d_supported(X, self.conv2_depthwise.weight, self.conv2_pointwise.weight) \
+                and self.conv2_depthwise.weight.is_contiguous() and self.conv2_pointwise.weight.is_contiguous():
+            # the ConvCNP default block: one kernel (depthwise out of a TMA-staged raw tile, pointwise on the tensor core)
+            return ops.resblock1d(X, self.conv2_depthwise.weight, self.conv2_depthwise.bias, self.conv2_pointwise.weight, self.conv2_pointwise.bias)
         if self.n_conv_layers == 2:
             sc, sh = _PreNorm.affine(self.norm1, X)
             h = ops.dwconv(X, self.conv1.depthwise.weight, self.conv1.depthwise.bias, None, True, sc, sh)

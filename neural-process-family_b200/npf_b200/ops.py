@@ -12,7 +12,7 @@ from . import _cabi
 from ._cabi import ACCUM, ADD_DY, MASK_X, RELU_IN, RELU_OUT, call
 
 __all__ = [
-    "set_precision", "get_precision", "linear", "mlp_chain", "setconv", "dwconv", "channel_moments",
+    "set_precision", "get_precision", "linear", "mlp_chain", "setconv", "dwconv", "resblock1d", "resblock1d_supported", "channel_moments",
     "merge_relu", "mean_pool", "add_layernorm", "xattn", "gauss_head", "gauss_sum_log_prob", "latent_sample",
     "global_latent", "gridconv_in", "range_flag", "launch_count", "set_direct_grad_accumulation",
 ]
@@ -408,6 +408,54 @@ class _DWConv(torch.autograd.Function):
 def dwconv(x, weight, bias=None, res=None, relu_in=False, scale=None, shift=None):
     """Channel-last depthwise conv.  x [B,L,C] (1-D) or [B,H,W,C] (2-D); weight [C,1,k] / [C,1,k,k]."""
     return _DWConv.apply(x, weight, bias, res, relu_in, scale, shift)
+
+
+class _ResBlock1d(torch.autograd.Function):
+    """y = pw(dw_k(relu(x)) + b_dw + x) + b_pw for [B,L,128] signals: one fused forward kernel (npf_resblock1d_fwd: raw rows by
+    TMA, depthwise in the producers, pointwise on tcgen05).  The intermediate O is saved for the backward, which runs the
+    pointwise and depthwise gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, x, wdw, bdw, wpw, bpw):
+        _chk(x, wdw, bdw, wpw, bpw)
+        x = _c(x)
+        B, L, C = x.shape
+        k = wdw.shape[-1]
+        o = torch.empty_like(x)
+        y = torch.empty_like(x)
+        call("npf_resblock1d_fwd", _p(x), _p(wdw), _p(bdw), _p(wpw), _p(bpw), _p(o), _p(y), B, L, C, k, _precision, _stream())
+        ctx.save_for_backward(x, o, wdw, wpw)
+        ctx.refs = (bdw, bpw)
+        ctx.cfg = (B, L, C, k)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, o, wdw, wpw = ctx.saved_tensors
+        bdw, bpw = ctx.refs
+        B, L, C, k = ctx.cfg
+        M = B * L
+        dy2 = _c(dy).reshape(M, C)
+        dWp, rWp = _gbuf(wpw)
+        dbp, rbp = _gbuf(bpw)
+        do = _lin_bwd(dy2, o.reshape(M, C), _p(wpw), C, _p(dWp), C, dbp, M, C, C, mask=False)
+        dWd, rWd = _gbuf(wdw)
+        dbd, rbd = _gbuf(bdw)
+        dx = torch.empty_like(x)
+        call("npf_dwconv_bwd", _p(do), _p(x), _p(wdw), _p(dx), _p(dWd), _p(dbd), B, 1, L, C, 1, k, RELU_IN | ADD_DY, None, None, None, None,
+             _stream())
+        return dx, rWd, rbd, rWp, rbp
+
+
+def resblock1d_supported(x, dw_weight, pw_weight):
+    """The fused block kernel covers the ConvCNP default: [B,L,128] signals, kernel size 11, the bf16x3 arithmetic mode."""
+    return (x.dim() == 3 and x.shape[-1] == 128 and dw_weight.shape[-1] == 11 and dw_weight.shape[0] == 128 and pw_weight.shape[0] == 128
+            and pw_weight.numel() == 128 * 128 and _precision == _PRECISION["bf16x3"] and x.is_cuda and x.shape[0] > 0)
+
+
+def resblock1d(x, dw_weight, dw_bias, pw_weight, pw_bias):
+    """Fused pre-activation residual block (depthwise k + residual + pointwise); x [B,L,128] channel-last."""
+    return _ResBlock1d.apply(x, dw_weight, dw_bias, pw_weight, pw_bias)
 
 
 class _ChannelMoments(torch.autograd.Function):

@@ -179,6 +179,31 @@ def _dw_ref(x, W, b, res, relu_in, scale, shift):
     return y + res if res is not None else y
 
 
+@pytest.mark.parametrize("B,L", [(2, 384), (3, 100), (1, 7), (2, 128), (1, 129), (52, 384), (3, 1000)])
+def test_resblock1d_fused(ops, B, L):
+    """npf_resblock1d_fwd (depthwise 11 taps + residual + pointwise in one kernel, raw rows by TMA) against the fp64 composite:
+    task edges (zero padding inside the halo), row tails, one and several tiles per task, more tiles than CTAs; gradients
+    through the autograd Function."""
+    import npf_b200
+    npf_b200.set_precision("bf16x3")
+    try:
+        x = _g(B, L, 128, seed=1)
+        wd, bd = _g(128, 1, 11, seed=2, scale=0.3), _g(128, seed=3)
+        wp, bp = _g(128, 128, 1, seed=4, scale=128 ** -0.5), _g(128, seed=5)
+        ref_in = [t.clone().requires_grad_(True) for t in (x, wd, bd, wp, bp)]
+        cu_in = [_cu(t, True) for t in (x, wd, bd, wp, bp)]
+        xr = ref_in[0]
+        o = F.conv1d(torch.relu(xr).transpose(1, 2), ref_in[1], ref_in[2], padding=5, groups=128).transpose(1, 2) + xr
+        yr = o @ ref_in[3].view(128, 128).t() + ref_in[4]
+        assert ops.resblock1d_supported(cu_in[0], cu_in[1], cu_in[3])
+        yc = ops.resblock1d(*cu_in)
+        assert torch.isfinite(yc).all()
+        assert rel_err(yc, yr) < TOL, rel_err(yc, yr)
+        _check_grads(cu_in, ref_in, yc, yr, ["x", "w_dw", "b_dw", "w_pw", "b_pw"])
+    finally:
+        npf_b200.set_precision("fp32")
+
+
 @pytest.mark.parametrize("shape,k,relu_in,affine,res", [
     ((2, 384, 128), 11, True, False, True),
     ((3, 100, 128), 19, True, True, True),
