@@ -179,6 +179,13 @@ NPF_API int npf_dwconv_bwd(const float* dY, const float* X, const float* Wt, flo
 NPF_API int npf_resblock1d_fwd(const float* X, const float* wdw, const float* bdw, const float* wpw, const float* bpw, float* O,
                        float* Y, int B, int L, int C, int k, int precision, npf_stream_t stream);
 
+/* Backward of npf_resblock1d_fwd in ONE kernel with O recomputed from X (so the forward may pass O = NULL):
+ *     dX (overwritten) , dWdw [128,k] += , dbdw [128] += (optional) , dWpw [128,128] += , dbpw [128] += (optional)
+ * HBM sees dY and X once and dX once; neither dO nor O exists in memory.  Same coverage as the forward. */
+NPF_API int npf_resblock1d_bwd(const float* dY, const float* X, const float* wdw, const float* bdw, const float* wpw, float* dX,
+                       float* dWdw, float* dbdw, float* dWpw, float* dbpw, int B, int L, int C, int k, int precision,
+                       npf_stream_t stream);
+
 /* per-channel batch statistics of a channel-last tensor X[M,C] (train-mode BatchNorm of the notebook CNN
  * configs, two-pass like ATen: first the mean, then the centred second moment):
  *   sum[C] += sum_m (x - center[c]) ;  sumsq[C] += sum_m (x - center[c])^2      center optional (NULL = 0)

@@ -259,6 +259,338 @@ static int launch_rb_fwd(RbFwdParams& p, cudaStream_t st) {
     return check_launch("resblock1d_fwd_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of the same block in ONE kernel, with O RECOMPUTED (the forward then never writes it):
+//     dO = dY . Wpw          dWpw += dY^T . O        dbpw += colsum(dY)
+//     dX[m] = dO[m] + relu'(X[m]) sum_j wdw[j] dO[m - j + p]      dwdw[j] += sum_l dO[l] relu(X[l + j - p])      dbdw += colsum(dO)
+// against npf_linear_bwd + npf_dwconv_bwd: dO (50 MB written + read at config 2) and the saved O (50 MB read, and its write
+// in the forward) disappear; HBM sees dY and X once (+ halo re-reads out of L2) and dX once.
+// Tiles of 64 rows of one task = 48 interior rows + the +-p halo the transposed depthwise conv needs.  As in
+// linear_bwd_fused64_kernel the data gradient is computed TRANSPOSED,  dO^T[k, m] = sum_n Wpw[n, k] dY[m, n]  (A = Wpw^T: MN-major
+// view of the row-staged weights, B = dY tile K-major, N = 64), so an epilogue thread owns ONE channel k and the tile's rows sit
+// in its registers: the depthwise transposed conv, the filter gradient and the relu mask are register arithmetic along the row
+// axis with X read from the raw tile in shared memory -- no exchange between threads.  dWpw accumulates in TMEM over the CTA's
+// tiles (A = dY^T, B = O: MN-major views; O rows outside the interior are zero so that every row counts once).
+// Roles: loader warp (TMA bulk copies of the raw dY / X tiles, zero fill outside the task), 16 producer warps (dY raw -> image;
+// O recomputed from raw X -> image), 1 MMA warp, 8 epilogue warps.  Raw X is double-buffered (the epilogue of tile i still reads
+// it while tile i + 1 is prepared).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kRwRows = 64;
+constexpr int kRwInt = 48;                                      // interior rows per tile (k = 11: 48 + 2 * 5 = 58 <= 64)
+constexpr int kRwLoadWarp = kRbEpiWarp0 + kRbEpi;               // warp 25
+constexpr int kRwThreads = (kRwLoadWarp + 1) * 32;              // 832
+constexpr uint32_t kRwHalf = 64u * 128u * 2u;                   // one bf16 64 x 128 image: 16 KB
+
+struct RbBwdParams {
+    const float* dY; const float* X; const float* wdw; const float* bdw; const float* wpw;
+    float* dX; float* dWdw; float* dbdw; float* dWpw; float* dbpw;
+    int B, L, n_lt, n_tiles;
+};
+
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// byte offset of element (row m, col c) of a [64 x 128] bf16 SWIZZLE_128B image (two 64-column atoms of 8 KB)
+__device__ __forceinline__ uint32_t rw_img_off(uint32_t m, uint32_t c) {
+    return (c >> 6) * 8192u + m * 128u + ((((c & 63u) >> 3) ^ (m & 7u)) << 4) + (c & 7u) * 2u;
+}
+
+template <int KW>
+__global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdParams p) {
+    constexpr int P = KW / 2;
+    static_assert(kRwInt + 2 * P <= kRwRows, "tile too small for the halo");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_y, bar_yfree, bar_x[2], bar_xfree[2], bar_afull, bar_aempty, bar_tfull[2], bar_tempty[2], bar_dwfull;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_db[128];
+
+    uint8_t* y_hi = smem_raw;                                   // dY image: hi 16 KB | lo 16 KB
+    uint8_t* o_hi = smem_raw + 2 * kRwHalf;                     // O image
+    uint8_t* w_hi = smem_raw + 4 * kRwHalf;                     // Wpw: hi 32 KB | lo 32 KB
+    uint8_t* w_lo = w_hi + kRbTile;
+    float* rawY = reinterpret_cast<float*>(smem_raw + 4 * kRwHalf + 2 * kRbTile);          // [64][128]
+    float* rawX = rawY + kRwRows * 128;                                                       // 2 x [64][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (tid == 32) {
+        mbar_init(&bar_y, 1);
+        mbar_init(&bar_yfree, kRbProd * 32);
+        mbar_init(&bar_afull, kRbProd * 32);
+        mbar_init(&bar_aempty, 1);
+        mbar_init(&bar_dwfull, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_x[i], 1);
+            mbar_init(&bar_xfree[i], kRbProd * 32 + kRbEpi * 32);
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], kRbEpi * 32);
+        }
+    }
+    if (tid < 128) s_db[tid] = 0.f;
+    const int per = p.n_tiles / (int)gridDim.x, rem = p.n_tiles - per * (int)gridDim.x;
+    const int g0 = (int)blockIdx.x * per + min((int)blockIdx.x, rem), g1 = g0 + per + ((int)blockIdx.x < rem ? 1 : 0);
+    pdl_trigger();
+    if (warp < kRbProd) {          // pointwise weights: warp w stages rows 8 w .. 8 w + 7 of Wpw[n][k] (two 64-column atoms of 16 KB)
+        const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
+        const uint32_t woff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.wpw + (long)(warp * 8 + i) * 128) + lane);
+            const uint32_t off = woff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4);
+            const uint32_t h01 = pack_bf16(v.x, v.y), h23 = pack_bf16(v.z, v.w);
+            *reinterpret_cast<uint2*>(w_hi + off) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2*>(w_lo + off) = make_uint2(pack_bf16(v.x - __uint_as_float(h01 << 16), v.y - __uint_as_float(h01 & 0xFFFF0000u)),
+                                                                 pack_bf16(v.z - __uint_as_float(h23 << 16), v.w - __uint_as_float(h23 & 0xFFFF0000u)));
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    pdl_wait();
+
+    if (warp == kRwLoadWarp) {
+        // ------------------------------------------------------------------ loader: raw tiles by TMA, zero rows outside the task
+        auto fetch = [&](const float* src, float* dst, uint64_t* bar, int g) {
+            const int b = g / p.n_lt, pos0 = (g - b * p.n_lt) * kRwInt - P;          // position of tile row 0
+            const int s0 = max(0, pos0), e0 = min(p.L, pos0 + kRwRows);
+            const int d0 = s0 - pos0, n = max(0, e0 - s0);
+            for (int i = lane; i < (kRwRows - n) * 32; i += 32) {
+                const int r = i >> 5, rr = r < d0 ? r : d0 + n + (r - d0);
+                reinterpret_cast<float4*>(dst + rr * 128)[i & 31] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                fence_async_smem();
+                const uint32_t bytes = (uint32_t)n * 512u;
+                mbar_expect_tx(bar, bytes);
+                if (bytes) bulk_g2s(dst + d0 * 128, src + ((long)b * p.L + s0) * 128, bytes, bar);
+            }
+            __syncwarp();
+        };
+        const int nt = g1 - g0;
+        if (nt > 0) { fetch(p.X, rawX, &bar_x[0], g0); fetch(p.dY, rawY, &bar_y, g0); }
+        if (nt > 1) fetch(p.X, rawX + kRwRows * 128, &bar_x[1], g0 + 1);
+        for (int it = 0; it < nt; ++it) {
+            if (it + 1 < nt) {                                   // raw dY of tile it consumed by the producers -> next tile's dY
+                mbar_wait(&bar_yfree, (uint32_t)it & 1u);
+                fetch(p.dY, rawY, &bar_y, g0 + it + 1);
+            }
+            if (it + 2 < nt) {                                   // raw X buffer of tile it released by producers AND epilogue -> tile it + 2
+                mbar_wait(&bar_xfree[it & 1], (uint32_t)(it >> 1) & 1u);
+                fetch(p.X, rawX + (it & 1) * kRwRows * 128, &bar_x[it & 1], g0 + it + 2);
+            }
+        }
+    } else if (warp < kRbProd) {
+        // ------------------------------------------------------------------ producers
+        const int cp = lane + 32 * (warp & 1);                   // O: channels 2 cp, 2 cp + 1 ...
+        const int rg = warp >> 1;                                // ... rows 8 rg .. 8 rg + 7
+        float w0[KW], w1[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) { w0[j] = __ldg(p.wdw + (2 * cp) * KW + j); w1[j] = __ldg(p.wdw + (2 * cp + 1) * KW + j); }
+        const float bd0 = p.bdw ? __ldg(p.bdw + 2 * cp) : 0.f, bd1 = p.bdw ? __ldg(p.bdw + 2 * cp + 1) : 0.f;
+        const int prow = warp * 4;                               // dY: rows 4 w .. 4 w + 3, float4 column lane
+        const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
+        const uint32_t psoff = (uint32_t)(lane >> 4) * 8192u + (uint32_t)prow * 128u + (uint32_t)(lane & 1) * 8u;
+        const uint32_t rsw = (uint32_t)(prow & 7);
+        float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
+        int it = 0;
+        for (int g = g0; g < g1; ++g, ++it) {
+            const int s = it & 1;
+            const float* rx = rawX + s * kRwRows * 128;
+            // ---- O rows 8 rg .. 8 rg + 7 of channels 2 cp, 2 cp + 1 from the raw X tile (registers only)
+            mbar_wait(&bar_x[s], (uint32_t)(it >> 1) & 1u);
+            float a0[8], a1[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) { a0[o] = bd0; a1[o] = bd1; }
+#pragma unroll
+            for (int i = 0; i < 8 + 2 * P; ++i) {
+                const int rr = 8 * rg - P + i;                   // tile row feeding outputs o = i - j
+                float2 v = make_float2(0.f, 0.f);
+                if (rr >= 0 && rr < kRwRows) v = *reinterpret_cast<const float2*>(rx + rr * 128 + 2 * cp);
+                const float r0 = fmaxf(v.x, 0.f), r1 = fmaxf(v.y, 0.f);
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                    const int o = i - j;
+                    if (o >= 0 && o < 8) { a0[o] = fmaf(w0[j], r0, a0[o]); a1[o] = fmaf(w1[j], r1, a1[o]); }
+                }
+                if (i - P >= 0 && i - P < 8) { a0[i - P] += v.x; a1[i - P] += v.y; }
+            }
+            mbar_arrive(&bar_xfree[s]);                          // the producers' reads of this raw X buffer are done
+            // ---- images: wait for the previous tile's MMAs, then dY raw -> image and O -> image
+            mbar_wait(&bar_y, (uint32_t)it & 1u);
+            if (it > 0) mbar_wait(&bar_aempty, (uint32_t)(it - 1) & 1u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = prow + i;
+                const float4 v = *reinterpret_cast<const float4*>(rawY + r * 128 + lane * 4);
+                if (r >= P && r < P + kRwInt) { dbs.x += v.x; dbs.y += v.y; dbs.z += v.z; dbs.w += v.w; }
+                const uint32_t off = psoff + (uint32_t)i * 128u + ((pchunk ^ (rsw + (uint32_t)i)) << 4);
+                const uint32_t h01 = pack_bf16(v.x, v.y), h23 = pack_bf16(v.z, v.w);
+                *reinterpret_cast<uint2*>(y_hi + off) = make_uint2(h01, h23);
+                *reinterpret_cast<uint2*>(y_hi + kRwHalf + off) =
+                    make_uint2(pack_bf16(v.x - __uint_as_float(h01 << 16), v.y - __uint_as_float(h01 & 0xFFFF0000u)),
+                               pack_bf16(v.z - __uint_as_float(h23 << 16), v.w - __uint_as_float(h23 & 0xFFFF0000u)));
+            }
+            mbar_arrive(&bar_yfree);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const uint32_t row = (uint32_t)(8 * rg + o);
+                const bool interior = row >= (uint32_t)P && row < (uint32_t)(P + kRwInt);
+                const float v0 = interior ? a0[o] : 0.f, v1 = interior ? a1[o] : 0.f;
+                const uint32_t off = rw_img_off(row, (uint32_t)(2 * cp));
+                const uint32_t h = pack_bf16(v0, v1);
+                *reinterpret_cast<uint32_t*>(o_hi + off) = h;
+                *reinterpret_cast<uint32_t*>(o_hi + kRwHalf + off) = pack_bf16(v0 - __uint_as_float(h << 16), v1 - __uint_as_float(h & 0xFFFF0000u));
+            }
+            fence_async_smem();
+            mbar_arrive(&bar_afull);
+        }
+        if (p.dbpw) {
+            atomicAdd(&s_db[lane * 4 + 0], dbs.x); atomicAdd(&s_db[lane * 4 + 1], dbs.y);
+            atomicAdd(&s_db[lane * 4 + 2], dbs.z); atomicAdd(&s_db[lane * 4 + 3], dbs.w);
+            rb_prod_sync();
+            if (tid < 128) atomicAdd(p.dbpw + tid, s_db[tid]);
+        }
+    } else if (warp == kRbMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_dx = make_idesc(128, 64, 1, 0);      // A = Wpw^T (MN-major view), B = dY tile (K-major), D = dO^T [k x m]
+            const uint32_t idesc_dw = make_idesc(128, 128, 1, 1);     // A = dY^T, B = O: MN-major views (reduction over the tile's rows)
+            const uint32_t sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
+            const uint32_t sy_hi = smem_u32(y_hi), sy_lo = sy_hi + kRwHalf, so_hi = smem_u32(o_hi), so_lo = so_hi + kRwHalf;
+            const uint32_t d_dw = tmem + 128u;
+            int it = 0;
+            for (int g = g0; g < g1; ++g, ++it) {
+                const int a = it & 1;
+                mbar_wait(&bar_afull, (uint32_t)it & 1u);
+                mbar_wait(&bar_tempty[a], (uint32_t)((it >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_dx = tmem + (uint32_t)a * 64u;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t bo = (uint32_t)(ks >> 2) * 8192u + (uint32_t)(ks & 3) * 32u;
+                    const uint64_t a_h = rb_desc_sw128(sw_hi + ks * 2048u, 16384, 1024), b_h = rb_desc_sw128(sy_hi + bo, 16, 1024);
+                    umma_bf16(d_dx, a_h, b_h, idesc_dx, ks ? 1u : 0u);
+                    umma_bf16(d_dx, a_h, rb_desc_sw128(sy_lo + bo, 16, 1024), idesc_dx, 1);
+                    umma_bf16(d_dx, rb_desc_sw128(sw_lo + ks * 2048u, 16384, 1024), b_h, idesc_dx, 1);
+                }
+                umma_commit(&bar_tfull[a]);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t acc = (it | ks) ? 1u : 0u;
+                    const uint64_t a_h = rb_desc_sw128(sy_hi + ks * 2048u, 8192, 1024), b_h = rb_desc_sw128(so_hi + ks * 2048u, 8192, 1024);
+                    umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
+                    umma_bf16(d_dw, a_h, rb_desc_sw128(so_lo + ks * 2048u, 8192, 1024), idesc_dw, 1);
+                    umma_bf16(d_dw, rb_desc_sw128(sy_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
+                }
+                umma_commit(&bar_aempty);
+            }
+            umma_commit(&bar_dwfull);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: thread = channel k, half of the interior rows
+        const int e = warp - kRbEpiWarp0;
+        const int lane_base = 32 * (warp & 3);
+        const int k = lane_base + lane;
+        const int h = e >> 2;                                     // interior rows [P + 24 h, P + 24 h + 24)
+        float wk[KW], acc[KW];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) { wk[j] = __ldg(p.wdw + k * KW + j); acc[j] = 0.f; }
+        float dbacc = 0.f;
+        int it = 0;
+        for (int g = g0; g < g1; ++g, ++it) {
+            const int a = it & 1, s = it & 1;
+            const int b = g / p.n_lt, l0 = (g - b * p.n_lt) * kRwInt;
+            const float* rx = rawX + s * kRwRows * 128 + k;
+            mbar_wait(&bar_x[s], (uint32_t)(it >> 1) & 1u);       // the raw X tile (async-proxy writes) is visible to this thread too
+            mbar_wait(&bar_tfull[a], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int sp = 0; sp < 2; ++sp) {                     // two sub-passes of 12 interior rows: dO window of 12 + 2 P = 22 rows
+                const int c = (kRwInt / 2) * h + 12 * sp;        // first tile row (= accumulator column) of the window: 0, 12, 24, 36
+                const int cs = c - 4 * sp;                        // ... fetched from the 8-aligned column below it: the window starts at d[4 sp]
+                float d[32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float d8[8];
+                    tmem_ld8(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(a * 64 + cs + 8 * q), d8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[8 * q + i] = d8[i];
+                }
+                if (sp == 1) {                                    // accumulator a fully read by this thread
+                    tc_fence_before();
+                    mbar_arrive(&bar_tempty[a]);
+                }
+                float* dxp = p.dX + ((long)b * p.L + l0 + c) * 128 + k;    // interior row t of the window <-> position l0 + c + t
+#pragma unroll
+                for (int i = 0; i < 12 + 2 * P; ++i) {            // X row of the window: tile row c + i
+                    const float x = rx[(c + i) * 128];
+                    const float rxv = fmaxf(x, 0.f);
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) {                // filter gradient: interior row t = i - j meets X row i through tap j
+                        const int t = i - j;
+                        if (t >= 0 && t < 12) acc[j] = fmaf(d[4 * sp + P + t], rxv, acc[j]);
+                    }
+                    const int t = i - P;                          // this X row is interior row t: its data gradient
+                    if (t >= 0 && t < 12) {
+                        float conv = 0.f;
+#pragma unroll
+                        for (int j = 0; j < KW; ++j) conv = fmaf(wk[j], d[4 * sp + 2 * P + t - j], conv);
+                        dbacc += d[4 * sp + P + t];
+                        if (l0 + c + t < p.L) dxp[(long)t * 128] = d[4 * sp + P + t] + (x > 0.f ? conv : 0.f);
+                    }
+                }
+            }
+            mbar_arrive(&bar_xfree[s]);                           // the epilogue's reads of this raw X buffer are done
+        }
+#pragma unroll
+        for (int j = 0; j < KW; ++j) atomicAdd(p.dWdw + k * KW + j, acc[j]);
+        if (p.dbdw) atomicAdd(p.dbdw + k, dbacc);
+        // ---- flush of the CTA's pointwise weight gradient: thread = row n of dWpw, 64 columns per warp
+        mbar_wait(&bar_dwfull, 0);
+        tc_fence_after();
+        const int col_base = (e >> 2) * 64;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            const int c0 = col_base + ch * 16;
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(128 + c0), v);
+            float* dst = p.dWpw + (long)k * 128 + c0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+template <int KW>
+static int launch_rb_bwd(RbBwdParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)4 * kRwHalf + 2 * kRbTile + (size_t)3 * kRwRows * 512;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(resblock1d_bwd_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return NPF_ENOTSUP;
+        }
+        attr = true;
+    }
+    const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+    launch_pdl(resblock1d_bwd_kernel<KW>, dim3(grid), dim3(kRwThreads), smem, st, p);
+    count_launch();
+    return check_launch("resblock1d_bwd_kernel");
+}
+
 static inline bool rb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace npf
@@ -280,4 +612,23 @@ extern "C" int npf_resblock1d_fwd(const float* X, const float* wdw, const float*
     p.n_lt = (L + 127) / 128;
     p.n_tiles = B * p.n_lt;
     return launch_rb_fwd<11>(p, as_stream(stream));
+}
+
+extern "C" int npf_resblock1d_bwd(const float* dY, const float* X, const float* wdw, const float* bdw, const float* wpw, float* dX, float* dWdw,
+                                  float* dbdw, float* dWpw, float* dbpw, int B, int L, int C, int k, int precision, npf_stream_t stream) {
+    NPF_REQUIRE(dY && X && wdw && wpw && dX && dWdw && dWpw, "npf_resblock1d_bwd: null pointer");
+    NPF_REQUIRE(B >= 0 && L >= 1 && k >= 1 && (k & 1), "npf_resblock1d_bwd: bad shape (odd kernel size)");
+    if (B == 0) return NPF_OK;
+    static const bool on = [] { const char* e = getenv("NPF_RESBLOCK_FUSED"); return !(e && e[0] == '0'); }();
+    if (!on || C != 128 || precision != NPF_PREC_BF16X3 || k != 11 || !rb_aligned16(dY) || !rb_aligned16(X) || !rb_aligned16(dX) || !rb_aligned16(wpw) ||
+        !rb_aligned16(dWpw)) {
+        set_error("npf_resblock1d_bwd: covered: 128 channels, kernel size 11, precision bf16x3, 16-byte aligned tensors; run npf_linear_bwd + npf_dwconv_bwd otherwise");
+        return NPF_ENOTSUP;
+    }
+    RbBwdParams p{};
+    p.dY = dY; p.X = X; p.wdw = wdw; p.bdw = bdw; p.wpw = wpw; p.dX = dX; p.dWdw = dWdw; p.dbdw = dbdw; p.dWpw = dWpw; p.dbpw = dbpw;
+    p.B = B; p.L = L;
+    p.n_lt = (L + kRwInt - 1) / kRwInt;
+    p.n_tiles = B * p.n_lt;
+    return launch_rb_bwd<11>(p, as_stream(stream));
 }

@@ -33,6 +33,7 @@ SIGNATURES = {
     "npf_dwconv_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P],
     "npf_dwconv_bwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "npf_resblock1d_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, P],
+    "npf_resblock1d_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
     "npf_channel_stats": [P, P, P, P, L, I, P],
     "npf_channel_affine": [P, P, P, P, L, I, I, P],
     "npf_gridconv_in_fwd": [P, P, I, P, P, I, I, I, I, I, P],
@@ -125,6 +126,8 @@ ALGO = {
     "npf_dwconv_bwd": lambda a: (4 * a[6] * a[7] * a[8] * a[9] * 3, 4 * a[6] * a[7] * a[8] * a[9] * a[10] * a[11]),
     # X read, Y written (+ O written when saved): the intermediate never makes a round trip
     "npf_resblock1d_fwd": lambda a: (4 * a[7] * a[8] * a[9] * (3 if a[5] else 2) + 4 * a[9] * a[9], 2 * a[7] * a[8] * a[9] * (a[9] + a[10])),
+    # dY + X read, dX written
+    "npf_resblock1d_bwd": lambda a: (4 * a[10] * a[11] * a[12] * 3 + 4 * a[12] * a[12], 2 * a[10] * a[11] * a[12] * (3 * a[12] + 3 * a[13])),
     "npf_xattn_fwd": lambda a: (4 * a[5] * a[8] * (2 * a[6] * a[9] + a[7] * a[9] + a[7] * a[10] + a[6]), 2 * a[5] * a[8] * a[6] * a[7] * (a[9] + a[10])),
     "npf_xattn_bwd": lambda a: (4 * a[9] * a[12] * (4 * a[10] * a[13] + 2 * a[11] * a[13] + 2 * a[11] * a[14]), 5 * a[9] * a[12] * a[10] * a[11] * (a[13] + a[14])),
 }

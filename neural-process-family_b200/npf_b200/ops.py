@@ -411,9 +411,9 @@ def dwconv(x, weight, bias=None, res=None, relu_in=False, scale=None, shift=None
 
 
 class _ResBlock1d(torch.autograd.Function):
-    """y = pw(dw_k(relu(x)) + b_dw + x) + b_pw for [B,L,128] signals: one fused forward kernel (npf_resblock1d_fwd: raw rows by
-    TMA, depthwise in the producers, pointwise on tcgen05).  The intermediate O is saved for the backward, which runs the
-    pointwise and depthwise gradient kernels."""
+    """y = pw(dw_k(relu(x)) + b_dw + x) + b_pw for [B,L,128] signals: ONE kernel per direction (npf_resblock1d_fwd / _bwd: raw rows
+    by TMA, depthwise in registers out of shared memory, pointwise on tcgen05).  Only x is saved: the backward recomputes the
+    intermediate O, so neither O nor its gradient ever exists in HBM."""
 
     @staticmethod
     def forward(ctx, x, wdw, bdw, wpw, bpw):
@@ -421,28 +421,25 @@ class _ResBlock1d(torch.autograd.Function):
         x = _c(x)
         B, L, C = x.shape
         k = wdw.shape[-1]
-        o = torch.empty_like(x)
         y = torch.empty_like(x)
-        call("npf_resblock1d_fwd", _p(x), _p(wdw), _p(bdw), _p(wpw), _p(bpw), _p(o), _p(y), B, L, C, k, _precision, _stream())
-        ctx.save_for_backward(x, o, wdw, wpw)
+        call("npf_resblock1d_fwd", _p(x), _p(wdw), _p(bdw), _p(wpw), _p(bpw), None, _p(y), B, L, C, k, _precision, _stream())
+        ctx.save_for_backward(x, wdw, wpw, bdw)
         ctx.refs = (bdw, bpw)
-        ctx.cfg = (B, L, C, k)
+        ctx.cfg = (B, L, C, k, _precision)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, o, wdw, wpw = ctx.saved_tensors
+        x, wdw, wpw, bdw_saved = ctx.saved_tensors
         bdw, bpw = ctx.refs
-        B, L, C, k = ctx.cfg
-        M = B * L
-        dy2 = _c(dy).reshape(M, C)
+        B, L, C, k, prec = ctx.cfg
+        dy = _c(dy)
         dWp, rWp = _gbuf(wpw)
         dbp, rbp = _gbuf(bpw)
-        do = _lin_bwd(dy2, o.reshape(M, C), _p(wpw), C, _p(dWp), C, dbp, M, C, C, mask=False)
         dWd, rWd = _gbuf(wdw)
         dbd, rbd = _gbuf(bdw)
         dx = torch.empty_like(x)
-        call("npf_dwconv_bwd", _p(do), _p(x), _p(wdw), _p(dx), _p(dWd), _p(dbd), B, 1, L, C, 1, k, RELU_IN | ADD_DY, None, None, None, None,
+        call("npf_resblock1d_bwd", _p(dy), _p(x), _p(wdw), _p(bdw_saved), _p(wpw), _p(dx), _p(dWd), _p(dbd), _p(dWp), _p(dbp), B, L, C, k, prec,
              _stream())
         return dx, rWd, rbd, rWp, rbp
 
