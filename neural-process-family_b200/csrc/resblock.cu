@@ -39,6 +39,7 @@ struct RbFwdParams {
     float* O;            // [B, L, 128] or null
     float* Y;            // [B, L, 128]
     int B, L, n_lt, n_tiles;
+    unsigned long long* trace;      // diagnostics (npf_debug_set_trace)
 };
 
 __device__ __forceinline__ uint64_t rb_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -134,8 +135,10 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
         for (int g = g0; g < g1; ++g, ++it) {
             const int b = g / p.n_lt, l0 = (g - b * p.n_lt) * 128;
             const int rows_ok = min(128, p.L - l0);
+            if (tid == 0) trace_ev(p.trace, 0, 1);
             mbar_wait(&bar_raw, (uint32_t)it & 1u);
             rb_prod_sync();                                       // the zero-filled rows of this tile are visible to every producer
+            if (tid == 0) trace_ev(p.trace, 0, 2);
             float a0[16], a1[16];
 #pragma unroll
             for (int o = 0; o < 16; ++o) { a0[o] = bd0; a1[o] = bd1; }
@@ -151,8 +154,10 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
                 }
                 if (i - P >= 0 && i - P < 16) { a0[i - P] += v.x; a1[i - P] += v.y; }          // residual: the block input itself
             }
+            if (tid == 0) trace_ev(p.trace, 0, 3);
             rb_prod_sync();                                       // every producer has finished reading the raw tile
             if (g + 1 < g1) fetch(g + 1);
+            if (tid == 0) trace_ev(p.trace, 0, 4);
             if (p.O) {                                            // O saved for a backward pass that does not recompute it
 #pragma unroll
                 for (int o = 0; o < 16; ++o) {
@@ -161,6 +166,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
                 }
             }
             if (it > 0) mbar_wait(&bar_aempty, (uint32_t)(it - 1) & 1u);        // the MMAs of the previous tile have read the image
+            if (tid == 0) trace_ev(p.trace, 0, 5);
 #pragma unroll
             for (int o = 0; o < 16; ++o) {
                 const uint32_t row = (uint32_t)(16 * rg + o);
@@ -171,6 +177,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
             }
             fence_async_smem();
             mbar_arrive(&bar_afull);
+            if (tid == 0) trace_ev(p.trace, 0, 6);
         }
     } else if (warp == kRbMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer
@@ -180,9 +187,11 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
             int it = 0;
             for (int g = g0; g < g1; ++g, ++it) {
                 const int t = it & 1;
+                trace_ev(p.trace, 1, 1);
                 mbar_wait(&bar_afull, (uint32_t)it & 1u);
                 mbar_wait(&bar_tempty[t], (uint32_t)((it >> 1) & 1) ^ 1u);
                 tc_fence_after();
+                trace_ev(p.trace, 1, 2);
                 const uint32_t d = tmem + (uint32_t)t * 128u;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
@@ -194,6 +203,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
                 }
                 umma_commit(&bar_aempty);
                 umma_commit(&bar_tfull[t]);
+                trace_ev(p.trace, 1, 3);
             }
         }
     } else {
@@ -209,8 +219,10 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
             const int b = g / p.n_lt, l0 = (g - b * p.n_lt) * 128;
             const int rows_ok = min(128, p.L - l0) - lane_base;        // rows [0, rows_ok) of this warp's 32 exist
             float* yb = p.Y + ((long)b * p.L + l0 + lane_base) * 128;
+            if (e == 0 && lane == 0) trace_ev(p.trace, 2, 1);
             mbar_wait(&bar_tfull[t], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
+            if (e == 0 && lane == 0) trace_ev(p.trace, 2, 2);
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 const int c0 = col_base + ch * 16;
@@ -611,6 +623,7 @@ extern "C" int npf_resblock1d_fwd(const float* X, const float* wdw, const float*
     p.X = X; p.wdw = wdw; p.bdw = bdw; p.wpw = wpw; p.bpw = bpw; p.O = O; p.Y = Y; p.B = B; p.L = L;
     p.n_lt = (L + 127) / 128;
     p.n_tiles = B * p.n_lt;
+    p.trace = trace_buffer();
     return launch_rb_fwd<11>(p, as_stream(stream));
 }
 

@@ -25,14 +25,23 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy (tcgen05.commit)
 }
-// bounded spin: a lost arrival traps (error return) instead of hanging the GPU
+// Bounded wait: a lost arrival traps (error return) instead of hanging the GPU.  The try_wait carries a suspend-time hint, so a
+// waiting warp is parked by the hardware until the phase completes (or the hint expires) instead of hot-spinning: in the
+// warp-specialised kernels ~20 of the 25 warps of a CTA are waiting at any time, and with a bare try_wait loop their polling
+// took the issue slots the ONE MMA-issuing thread needs (measured with the timeline hook: 90-150 cycles per tcgen05.mma issued
+// against 33-65 cycles of tensor time; profiles/r2/trace_*).  A short nanosleep backs the loop off further if the hint is not
+// honoured.
+#ifndef NPF_MBAR_HINT_NS
+#define NPF_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok = 0;
-    for (uint32_t it = 0; it < (1u << 28); ++it) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"((uint32_t)NPF_MBAR_HINT_NS) : "memory");
         if (ok) return;
+        if (it > 2) __nanosleep(64);
     }
     __trap();
 }
