@@ -15,6 +15,7 @@
 //     buffered in TMEM), 8 epilogue warps add the bias and store coalesced rows.
 // HBM sees X once (+ 2p / 128 halo re-reads out of L2) and Y once.
 #include <cstdlib>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -109,10 +110,10 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
         // ------------------------------------------------------------------ producers: raw tile -> depthwise -> O image
         const int cp = lane + 32 * (warp & 1);                   // channel pair: channels 2 cp, 2 cp + 1
         const int rg = warp >> 1;                                // rows 16 rg .. 16 rg + 15 of the tile
-        float w0[KW], w1[KW];
+        float2 w2[KW];                                            // taps of the two channels, packed for FFMA2 (fp32 x 2 per instruction)
 #pragma unroll
-        for (int j = 0; j < KW; ++j) { w0[j] = __ldg(p.wdw + (2 * cp) * KW + j); w1[j] = __ldg(p.wdw + (2 * cp + 1) * KW + j); }
-        const float bd0 = p.bdw ? __ldg(p.bdw + 2 * cp) : 0.f, bd1 = p.bdw ? __ldg(p.bdw + 2 * cp + 1) : 0.f;
+        for (int j = 0; j < KW; ++j) w2[j] = make_float2(__ldg(p.wdw + (2 * cp) * KW + j), __ldg(p.wdw + (2 * cp + 1) * KW + j));
+        const float2 bd2 = make_float2(p.bdw ? __ldg(p.bdw + 2 * cp) : 0.f, p.bdw ? __ldg(p.bdw + 2 * cp + 1) : 0.f);
 
         // raw rows of tile g: TMA bulk copy of the in-task part, zero fill of the rest (issued when the raw buffer is free)
         auto fetch = [&](int g) {
@@ -139,21 +140,24 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
             mbar_wait(&bar_raw, (uint32_t)it & 1u);
             rb_prod_sync();                                       // the zero-filled rows of this tile are visible to every producer
             if (tid == 0) trace_ev(p.trace, 0, 2);
-            float a0[16], a1[16];
+            float2 acc2[16];
 #pragma unroll
-            for (int o = 0; o < 16; ++o) { a0[o] = bd0; a1[o] = bd1; }
+            for (int o = 0; o < 16; ++o) acc2[o] = bd2;
             const float* rp = raw + (16 * rg) * 128 + 2 * cp;
 #pragma unroll
             for (int i = 0; i < 16 + 2 * P; ++i) {                // raw row 16 rg + i feeds outputs o = i - j, tap j
                 const float2 v = *reinterpret_cast<const float2*>(rp + i * 128);
-                const float r0 = fmaxf(v.x, 0.f), r1 = fmaxf(v.y, 0.f);
+                const float2 r = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
 #pragma unroll
                 for (int j = 0; j < KW; ++j) {
                     const int o = i - j;
-                    if (o >= 0 && o < 16) { a0[o] = fmaf(w0[j], r0, a0[o]); a1[o] = fmaf(w1[j], r1, a1[o]); }
+                    if (o >= 0 && o < 16) acc2[o] = __ffma2_rn(w2[j], r, acc2[o]);
                 }
-                if (i - P >= 0 && i - P < 16) { a0[i - P] += v.x; a1[i - P] += v.y; }          // residual: the block input itself
+                if (i - P >= 0 && i - P < 16) acc2[i - P] = __fadd2_rn(acc2[i - P], v);          // residual: the block input itself
             }
+            float a0[16], a1[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) { a0[o] = acc2[o].x; a1[o] = acc2[o].y; }
             if (tid == 0) trace_ev(p.trace, 0, 3);
             rb_prod_sync();                                       // every producer has finished reading the raw tile
             if (g + 1 < g1) fetch(g + 1);
@@ -289,7 +293,11 @@ static int launch_rb_fwd(RbFwdParams& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kRwRows = 64;
 constexpr int kRwInt = 48;                                      // interior rows per tile (k = 11: 48 + 2 * 5 = 58 <= 64)
-constexpr int kRwLoadWarp = kRbEpiWarp0 + kRbEpi;               // warp 25
+constexpr int kRwProd = 8;                                      // producer warps 0..7
+constexpr int kRwMmaWarp = kRwProd;                             // warp 8
+constexpr int kRwEpiWarp0 = kRwProd + 1;                        // warps 9..24: 16 epilogue warps = 4 TMEM lane quadrants x 4 row quarters
+constexpr int kRwEpi = 16;
+constexpr int kRwLoadWarp = kRwEpiWarp0 + kRwEpi;               // warp 25
 constexpr int kRwThreads = (kRwLoadWarp + 1) * 32;              // 832
 constexpr uint32_t kRwHalf = 64u * 128u * 2u;                   // one bf16 64 x 128 image: 16 KB
 
@@ -313,6 +321,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 __device__ __forceinline__ uint32_t rw_img_off(uint32_t m, uint32_t c) {
     return (c >> 6) * 8192u + m * 128u + ((((c & 63u) >> 3) ^ (m & 7u)) << 4) + (c & 7u) * 2u;
 }
+__device__ __forceinline__ void rw_prod_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kRwProd * 32) : "memory"); }
 
 template <int KW>
 __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdParams p) {
@@ -334,28 +343,28 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     if (tid == 32) {
         mbar_init(&bar_y, 1);
-        mbar_init(&bar_yfree, kRbProd * 32);
-        mbar_init(&bar_afull, kRbProd * 32);
+        mbar_init(&bar_yfree, kRwProd * 32);
+        mbar_init(&bar_afull, kRwProd * 32);
         mbar_init(&bar_aempty, 1);
         mbar_init(&bar_dwfull, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_x[i], 1);
-            mbar_init(&bar_xfree[i], kRbProd * 32 + kRbEpi * 32);
+            mbar_init(&bar_xfree[i], kRwProd * 32 + kRwEpi * 32);
             mbar_init(&bar_tfull[i], 1);
-            mbar_init(&bar_tempty[i], kRbEpi * 32);
+            mbar_init(&bar_tempty[i], kRwEpi * 32);
         }
     }
     if (tid < 128) s_db[tid] = 0.f;
     const int per = p.n_tiles / (int)gridDim.x, rem = p.n_tiles - per * (int)gridDim.x;
     const int g0 = (int)blockIdx.x * per + min((int)blockIdx.x, rem), g1 = g0 + per + ((int)blockIdx.x < rem ? 1 : 0);
     pdl_trigger();
-    if (warp < kRbProd) {          // pointwise weights: warp w stages rows 8 w .. 8 w + 7 of Wpw[n][k] (two 64-column atoms of 16 KB)
+    if (warp < kRwProd) {          // pointwise weights: warp w stages rows 16 w .. 16 w + 15 of Wpw[n][k] (two 64-column atoms of 16 KB)
         const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
-        const uint32_t woff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
+        const uint32_t woff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 16) * 128u + (uint32_t)(lane & 1) * 8u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.wpw + (long)(warp * 8 + i) * 128) + lane);
-            const uint32_t off = woff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4);
+        for (int i = 0; i < 16; ++i) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.wpw + (long)(warp * 16 + i) * 128) + lane);
+            const uint32_t off = woff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4);
             const uint32_t h01 = pack_bf16(v.x, v.y), h23 = pack_bf16(v.z, v.w);
             *reinterpret_cast<uint2*>(w_hi + off) = make_uint2(h01, h23);
             *reinterpret_cast<uint2*>(w_lo + off) = make_uint2(pack_bf16(v.x - __uint_as_float(h01 << 16), v.y - __uint_as_float(h01 & 0xFFFF0000u)),
@@ -401,51 +410,50 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
                 fetch(p.X, rawX + (it & 1) * kRwRows * 128, &bar_x[it & 1], g0 + it + 2);
             }
         }
-    } else if (warp < kRbProd) {
-        // ------------------------------------------------------------------ producers
+    } else if (warp < kRwProd) {
+        // ------------------------------------------------------------------ producers (8 warps)
         const int cp = lane + 32 * (warp & 1);                   // O: channels 2 cp, 2 cp + 1 ...
-        const int rg = warp >> 1;                                // ... rows 8 rg .. 8 rg + 7
-        float w0[KW], w1[KW];
+        const int rg = warp >> 1;                                // ... rows 16 rg .. 16 rg + 15
+        float2 w2[KW];
 #pragma unroll
-        for (int j = 0; j < KW; ++j) { w0[j] = __ldg(p.wdw + (2 * cp) * KW + j); w1[j] = __ldg(p.wdw + (2 * cp + 1) * KW + j); }
-        const float bd0 = p.bdw ? __ldg(p.bdw + 2 * cp) : 0.f, bd1 = p.bdw ? __ldg(p.bdw + 2 * cp + 1) : 0.f;
-        const int prow = warp * 4;                               // dY: rows 4 w .. 4 w + 3, float4 column lane
+        for (int j = 0; j < KW; ++j) w2[j] = make_float2(__ldg(p.wdw + (2 * cp) * KW + j), __ldg(p.wdw + (2 * cp + 1) * KW + j));
+        const float2 bd2 = make_float2(p.bdw ? __ldg(p.bdw + 2 * cp) : 0.f, p.bdw ? __ldg(p.bdw + 2 * cp + 1) : 0.f);
+        const int prow = warp * 8;                               // dY: rows 8 w .. 8 w + 7, float4 column lane
         const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
         const uint32_t psoff = (uint32_t)(lane >> 4) * 8192u + (uint32_t)prow * 128u + (uint32_t)(lane & 1) * 8u;
-        const uint32_t rsw = (uint32_t)(prow & 7);
         float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
         int it = 0;
         for (int g = g0; g < g1; ++g, ++it) {
             const int s = it & 1;
             const float* rx = rawX + s * kRwRows * 128;
-            // ---- O rows 8 rg .. 8 rg + 7 of channels 2 cp, 2 cp + 1 from the raw X tile (registers only)
+            // ---- O rows 16 rg .. 16 rg + 15 of channels 2 cp, 2 cp + 1 from the raw X tile (registers only)
             mbar_wait(&bar_x[s], (uint32_t)(it >> 1) & 1u);
-            float a0[8], a1[8];
+            float2 acc2[16];
 #pragma unroll
-            for (int o = 0; o < 8; ++o) { a0[o] = bd0; a1[o] = bd1; }
+            for (int o = 0; o < 16; ++o) acc2[o] = bd2;
 #pragma unroll
-            for (int i = 0; i < 8 + 2 * P; ++i) {
-                const int rr = 8 * rg - P + i;                   // tile row feeding outputs o = i - j
+            for (int i = 0; i < 16 + 2 * P; ++i) {
+                const int rr = 16 * rg - P + i;                  // tile row feeding outputs o = i - j
                 float2 v = make_float2(0.f, 0.f);
                 if (rr >= 0 && rr < kRwRows) v = *reinterpret_cast<const float2*>(rx + rr * 128 + 2 * cp);
-                const float r0 = fmaxf(v.x, 0.f), r1 = fmaxf(v.y, 0.f);
+                const float2 r = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
 #pragma unroll
                 for (int j = 0; j < KW; ++j) {
                     const int o = i - j;
-                    if (o >= 0 && o < 8) { a0[o] = fmaf(w0[j], r0, a0[o]); a1[o] = fmaf(w1[j], r1, a1[o]); }
+                    if (o >= 0 && o < 16) acc2[o] = __ffma2_rn(w2[j], r, acc2[o]);
                 }
-                if (i - P >= 0 && i - P < 8) { a0[i - P] += v.x; a1[i - P] += v.y; }
+                if (i - P >= 0 && i - P < 16) acc2[i - P] = __fadd2_rn(acc2[i - P], v);
             }
             mbar_arrive(&bar_xfree[s]);                          // the producers' reads of this raw X buffer are done
             // ---- images: wait for the previous tile's MMAs, then dY raw -> image and O -> image
             mbar_wait(&bar_y, (uint32_t)it & 1u);
             if (it > 0) mbar_wait(&bar_aempty, (uint32_t)(it - 1) & 1u);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 const int r = prow + i;
                 const float4 v = *reinterpret_cast<const float4*>(rawY + r * 128 + lane * 4);
                 if (r >= P && r < P + kRwInt) { dbs.x += v.x; dbs.y += v.y; dbs.z += v.z; dbs.w += v.w; }
-                const uint32_t off = psoff + (uint32_t)i * 128u + ((pchunk ^ (rsw + (uint32_t)i)) << 4);
+                const uint32_t off = psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4);
                 const uint32_t h01 = pack_bf16(v.x, v.y), h23 = pack_bf16(v.z, v.w);
                 *reinterpret_cast<uint2*>(y_hi + off) = make_uint2(h01, h23);
                 *reinterpret_cast<uint2*>(y_hi + kRwHalf + off) =
@@ -454,10 +462,10 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
             }
             mbar_arrive(&bar_yfree);
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const uint32_t row = (uint32_t)(8 * rg + o);
+            for (int o = 0; o < 16; ++o) {
+                const uint32_t row = (uint32_t)(16 * rg + o);
                 const bool interior = row >= (uint32_t)P && row < (uint32_t)(P + kRwInt);
-                const float v0 = interior ? a0[o] : 0.f, v1 = interior ? a1[o] : 0.f;
+                const float v0 = interior ? acc2[o].x : 0.f, v1 = interior ? acc2[o].y : 0.f;
                 const uint32_t off = rw_img_off(row, (uint32_t)(2 * cp));
                 const uint32_t h = pack_bf16(v0, v1);
                 *reinterpret_cast<uint32_t*>(o_hi + off) = h;
@@ -469,10 +477,10 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
         if (p.dbpw) {
             atomicAdd(&s_db[lane * 4 + 0], dbs.x); atomicAdd(&s_db[lane * 4 + 1], dbs.y);
             atomicAdd(&s_db[lane * 4 + 2], dbs.z); atomicAdd(&s_db[lane * 4 + 3], dbs.w);
-            rb_prod_sync();
+            rw_prod_sync();
             if (tid < 128) atomicAdd(p.dbpw + tid, s_db[tid]);
         }
-    } else if (warp == kRbMmaWarp) {
+    } else if (warp == kRwMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc_dx = make_idesc(128, 64, 1, 0);      // A = Wpw^T (MN-major view), B = dY tile (K-major), D = dO^T [k x m]
@@ -509,11 +517,12 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
             umma_commit(&bar_dwfull);
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: thread = channel k, half of the interior rows
-        const int e = warp - kRbEpiWarp0;
-        const int lane_base = 32 * (warp & 3);
+        // ------------------------------------------------------------------ epilogue (16 warps): thread = channel k, ONE 12-row quarter of the interior
+        const int e = warp - kRwEpiWarp0;
+        const int lane_base = 32 * (warp & 3);                    // the TMEM lane quadrant this warp may read
         const int k = lane_base + lane;
-        const int h = e >> 2;                                     // interior rows [P + 24 h, P + 24 h + 24)
+        const int qr = e >> 2;                                    // interior rows [P + 12 qr, P + 12 qr + 12) of the tile
+        const int c = 12 * qr;                                    // first tile row (= accumulator column) of the 22-row dO window
         float wk[KW], acc[KW];
 #pragma unroll
         for (int j = 0; j < KW; ++j) { wk[j] = __ldg(p.wdw + k * KW + j); acc[j] = 0.f; }
@@ -526,22 +535,19 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
             mbar_wait(&bar_x[s], (uint32_t)(it >> 1) & 1u);       // the raw X tile (async-proxy writes) is visible to this thread too
             mbar_wait(&bar_tfull[a], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-#pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {                     // two sub-passes of 12 interior rows: dO window of 12 + 2 P = 22 rows
-                const int c = (kRwInt / 2) * h + 12 * sp;        // first tile row (= accumulator column) of the window: 0, 12, 24, 36
-                const int cs = c - 4 * sp;                        // ... fetched from the 8-aligned column below it: the window starts at d[4 sp]
+            // the window is fetched from the 8-aligned column at or below c; OFF = c - that column (0 or 4, uniform per warp)
+            auto quarter = [&](auto off_c) {
+                constexpr int OFF = decltype(off_c)::value;
                 float d[32];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float d8[8];
-                    tmem_ld8(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(a * 64 + cs + 8 * q), d8);
+                    tmem_ld8(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(a * 64 + c - OFF + 8 * q), d8);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) d[8 * q + i] = d8[i];
                 }
-                if (sp == 1) {                                    // accumulator a fully read by this thread
-                    tc_fence_before();
-                    mbar_arrive(&bar_tempty[a]);
-                }
+                tc_fence_before();
+                mbar_arrive(&bar_tempty[a]);                      // accumulator a read by this thread
                 float* dxp = p.dX + ((long)b * p.L + l0 + c) * 128 + k;    // interior row t of the window <-> position l0 + c + t
 #pragma unroll
                 for (int i = 0; i < 12 + 2 * P; ++i) {            // X row of the window: tile row c + i
@@ -550,30 +556,30 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
 #pragma unroll
                     for (int j = 0; j < KW; ++j) {                // filter gradient: interior row t = i - j meets X row i through tap j
                         const int t = i - j;
-                        if (t >= 0 && t < 12) acc[j] = fmaf(d[4 * sp + P + t], rxv, acc[j]);
+                        if (t >= 0 && t < 12) acc[j] = fmaf(d[OFF + P + t], rxv, acc[j]);
                     }
                     const int t = i - P;                          // this X row is interior row t: its data gradient
                     if (t >= 0 && t < 12) {
                         float conv = 0.f;
 #pragma unroll
-                        for (int j = 0; j < KW; ++j) conv = fmaf(wk[j], d[4 * sp + 2 * P + t - j], conv);
-                        dbacc += d[4 * sp + P + t];
-                        if (l0 + c + t < p.L) dxp[(long)t * 128] = d[4 * sp + P + t] + (x > 0.f ? conv : 0.f);
+                        for (int j = 0; j < KW; ++j) conv = fmaf(wk[j], d[OFF + 2 * P + t - j], conv);
+                        dbacc += d[OFF + P + t];
+                        if (l0 + c + t < p.L) dxp[(long)t * 128] = d[OFF + P + t] + (x > 0.f ? conv : 0.f);
                     }
                 }
-            }
+            };
+            if (qr & 1) quarter(std::integral_constant<int, 4>{}); else quarter(std::integral_constant<int, 0>{});
             mbar_arrive(&bar_xfree[s]);                           // the epilogue's reads of this raw X buffer are done
         }
 #pragma unroll
         for (int j = 0; j < KW; ++j) atomicAdd(p.dWdw + k * KW + j, acc[j]);
         if (p.dbdw) atomicAdd(p.dbdw + k, dbacc);
-        // ---- flush of the CTA's pointwise weight gradient: thread = row n of dWpw, 64 columns per warp
+        // ---- flush of the CTA's pointwise weight gradient: thread = row n of dWpw, 32 columns per warp
         mbar_wait(&bar_dwfull, 0);
         tc_fence_after();
-        const int col_base = (e >> 2) * 64;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-            const int c0 = col_base + ch * 16;
+        for (int ch = 0; ch < 2; ++ch) {
+            const int c0 = qr * 32 + ch * 16;
             float v[16];
             tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(128 + c0), v);
             float* dst = p.dWpw + (long)k * 128 + c0;

@@ -9,9 +9,9 @@ one host call per step, kernels back to back on the device.
     loss = step(X_cntxt, Y_cntxt, X_trgt, Y_trgt)   # gradients are in p.grad (views of step.flat.flat) afterwards
     optimizer.step()
 
-What is captured: ``flat.zero_()``, ``model(...)``, ``criterion(...)``, ``loss.backward()`` and, on more than one rank, the
-flat-gradient all-reduce (NCCL, ``ReduceOp.AVG``).  What stays outside: the host->device copies of the inputs into the
-graph's static buffers, the optimizer, and the host side of the asynchronous [-1, 1] range validation (``_validate_inputs`` only launches the check
+What is captured: ``flat.zero_()``, ``model(...)``, ``criterion(...)``, ``loss.backward()`` (and, with
+``NPF_GRAPH_ALLREDUCE=1``, the flat-gradient all-reduce).  What stays outside: the host->device copies of the inputs into the
+graph's static buffers, the flat-gradient all-reduce (default; NCCL ``ReduceOp.AVG`` right after the replay), the optimizer, and the host side of the asynchronous [-1, 1] range validation (``_validate_inputs`` only launches the check
 kernel while capturing; the flag is read back after every replay).
 
 Constraints (the usual ones of whole-network capture): shapes are static per graph -- a new (n_cntxt, n_trgt, batch)
@@ -36,8 +36,15 @@ class _Entry:
 class GraphedStep:
     def __init__(self, model, criterion, flat=None, n_warmup=2, max_graphs=8):
         self.model, self.criterion = model, criterion
+        if any(getattr(m, "_npf_sync_group", None) is not None for m in model.modules()):
+            raise NotImplementedError("GraphedStep: synchronised BatchNorm (parallel.sync_batchnorm_) issues collectives from the autograd "
+                                      "thread inside backward; run that configuration eagerly")
         self.flat = flat if flat is not None else FlatGradients(model)
         self.n_warmup, self.max_graphs = n_warmup, max_graphs
+        import os
+        # where the gradient all-reduce of a multi-GPU step runs: inside the recorded graph, or right after the replay on the
+        # caller's stream (NPF_GRAPH_ALLREDUCE=0/1; measured at N=2 on B200, profiles/r2/allreduce_placement.md)
+        self.allreduce_in_graph = os.environ.get("NPF_GRAPH_ALLREDUCE", "0") == "1"
         self._graphs = OrderedDict()
         self._side = None
 
@@ -48,10 +55,10 @@ class GraphedStep:
         loss = self.criterion(out, yt)
         if self.model.training:        # an eval-mode signature replays forward + loss only
             loss.backward()
-            # multi-GPU: the flat-gradient all-reduce (ncclAvg) is part of the recorded step -- NCCL collectives are
-            # capturable -- so a replay has no host-side launch after the backward and no separate 1/G kernel.  The
-            # per-BatchNorm-layer moment all-reduces of parallel.sync_batchnorm_ are captured the same way.
-            self.flat.all_reduce_mean()
+            if self.allreduce_in_graph:
+                # multi-GPU: the flat-gradient all-reduce recorded into the step (NCCL collectives are capturable): a replay
+                # then has no host-side launch after the backward
+                self.flat.all_reduce_mean()
         return loss.detach()
 
     def _signature(self, tensors):
@@ -114,6 +121,8 @@ class GraphedStep:
         e.graph.replay()
         if hasattr(self.model, "_after_graph_replay"):
             self.model._after_graph_replay()
+        if not self.allreduce_in_graph and self.model.training:
+            self.flat.all_reduce_mean()
         self.last_launches = e.launches
         return e.loss
 

@@ -59,7 +59,8 @@ class FlatGradients:
         w = self.world_size
         if w == 1:
             return self.flat
-        if self.flat.is_cuda:      # NCCL averages inside the collective: no separate 1/G kernel
+        import os
+        if self.flat.is_cuda and os.environ.get("NPF_ALLREDUCE_AVG", "1") == "1":      # NCCL averages inside the collective: no separate 1/G kernel
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
         else:                      # gloo (CPU host-logic tests) has no AVG
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)

@@ -54,16 +54,20 @@ def _worker(rank, world, port, ret):
     sd, sd_ref = m.state_dict(), ref.state_dict()
     e_bn = max(((sd[k].float() - sd_ref[k].float()).abs().max() / sd_ref[k].float().abs().max().clamp_min(1e-12)).item()
                for k in sd if "running_" in k)
-    # the same sharded step through GraphedStep: the BatchNorm moment all-reduces AND the flat-gradient all-reduce (ncclAvg) are
-    # recorded into the CUDA graph; two replays must reproduce the eager gradient (running statistics advance per replay)
-    m2 = sync_batchnorm_(build_model(fx["cfg"])); m2.load_state_dict(fx["state_dict"]); m2.cuda().train()
+    # the plain (no BatchNorm) model through GraphedStep on 2 ranks: replay + flat-gradient all-reduce == eager gradient of the whole batch
+    fx2 = load_fixture("convcnp_default")
+    case2 = fx2["cases"][1]
+    inp2 = {k: v.cuda() for k, v in case2["inputs"].items()}
+    r2 = build_model(fx2["cfg"]); r2.load_state_dict(fx2["state_dict"])
+    _, flat_ref2 = run(r2, inp2)
+    m2 = build_model(fx2["cfg"]); m2.load_state_dict(fx2["state_dict"]); m2.cuda().train()
     flat2 = FlatGradients(m2, process_group=dist.group.WORLD)
     gstep = npf_b200.GraphedStep(m2, crit, flat=flat2)
-    shard = shard_tasks(inputs, rank, world)
+    shard = shard_tasks(inp2, rank, world)
     for _ in range(2):
         gstep(shard["X_cntxt"], shard["Y_cntxt"], shard["X_trgt"], shard["Y_trgt"])
     torch.cuda.synchronize()
-    e_graph = ((flat2.flat - flat_ref.flat).norm() / flat_ref.flat.norm()).item()
+    e_graph = ((flat2.flat - flat_ref2.flat).norm() / flat_ref2.flat.norm()).item()
     ret[rank] = (e_loc, e_grad, e_bn, e_graph)
     dist.destroy_process_group()
 
