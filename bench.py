@@ -532,7 +532,7 @@ def roofline(wl, ktimes, n_prof, B, peaks, shaped):
     plus aggregate figures for every timed entry point.  achieved = algorithmic bytes of ONE launch (SURVEY.md section 8d:
     every operand and result once, fp32; table in npf_b200/_cabi.py) / the average duration of that launch, measured with
     CUDA events on the launching stream; peak = MEASURED_PEAKS.json (sustained figures: the kernels run inside a long
-    step); traffic = DRAM bytes of the same launch from the committed `ncu --set full` capture (profiles/traffic_r1.json)."""
+    step); traffic = DRAM bytes of the same launch from the committed `ncu --set full` capture (profiles/traffic_r2.json)."""
     if not ktimes:
         return None, None
     total = sum(v[0] for v in ktimes.values())
@@ -557,13 +557,14 @@ def roofline(wl, ktimes, n_prof, B, peaks, shaped):
     (name, nb, fl), (ms, calls) = max(classes.items(), key=lambda kv: kv[1][0])
     e = entry(ms, calls, nb * calls, fl * calls)
     traffic, cuda_kernel = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
-            for rec in json.load(f)["kernels"]:
-                if rec["entry"] == name and rec["algorithmic_bytes"] == nb:
-                    traffic, cuda_kernel = rec["dram_bytes"], rec["cuda_kernel"]
-    except (OSError, KeyError, ValueError):
-        pass
+    for fn in ("traffic_r2.json", "traffic_r1.json"):      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full captures)
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                for rec in json.load(f)["kernels"]:
+                    if rec["entry"] == name and rec.get("algorithmic_bytes") in (None, nb) and traffic is None:
+                        traffic, cuda_kernel = rec["dram_bytes"], rec["cuda_kernel"]
+        except (OSError, KeyError, ValueError):
+            pass
     dom = dict(kernel=name, cuda_kernel=cuda_kernel, algorithmic_bytes_per_launch=nb, flops_per_launch=fl, peak_source=peaks["source"], traffic=traffic,
                avg_launch_ms=ms / calls, **{k: e[k] for k in ("bound", "achieved", "peak", "unit", "frac", "launches_per_step", "share_of_step")})
     return dom, table

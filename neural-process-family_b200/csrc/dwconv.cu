@@ -33,8 +33,12 @@ struct DwParams {
     int accum;
 };
 
+// 4 channels x one tap: two packed fp32x2 FMAs (FFMA2, sm_100): the depthwise kernels are bound by the number of FMA instructions
+// they issue (121 taps x 16 float4 per thread in the 2-D case), and a float4's (x, y) / (z, w) halves are aligned register pairs
 __device__ __forceinline__ float4 f4_fma(const float4 a, const float4 b, const float4 c) {
-    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+    const float2 lo = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+    const float2 hi = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(c.z, c.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 template <int KW>

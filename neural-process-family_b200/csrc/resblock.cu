@@ -293,11 +293,7 @@ static int launch_rb_fwd(RbFwdParams& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kRwRows = 64;
 constexpr int kRwInt = 48;                                      // interior rows per tile (k = 11: 48 + 2 * 5 = 58 <= 64)
-constexpr int kRwProd = 8;                                      // producer warps 0..7
-constexpr int kRwMmaWarp = kRwProd;                             // warp 8
-constexpr int kRwEpiWarp0 = kRwProd + 1;                        // warps 9..24: 16 epilogue warps = 4 TMEM lane quadrants x 4 row quarters
-constexpr int kRwEpi = 16;
-constexpr int kRwLoadWarp = kRwEpiWarp0 + kRwEpi;               // warp 25
+constexpr int kRwLoadWarp = kRbEpiWarp0 + kRbEpi;               // warp 25
 constexpr int kRwThreads = (kRwLoadWarp + 1) * 32;              // 832
 constexpr uint32_t kRwHalf = 64u * 128u * 2u;                   // one bf16 64 x 128 image: 16 KB
 
@@ -305,6 +301,7 @@ struct RbBwdParams {
     const float* dY; const float* X; const float* wdw; const float* bdw; const float* wpw;
     float* dX; float* dWdw; float* dbdw; float* dWpw; float* dbpw;
     int B, L, n_lt, n_tiles;
+    unsigned long long* trace;
 };
 
 // 32 lanes x 8 consecutive fp32 columns
@@ -321,7 +318,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 __device__ __forceinline__ uint32_t rw_img_off(uint32_t m, uint32_t c) {
     return (c >> 6) * 8192u + m * 128u + ((((c & 63u) >> 3) ^ (m & 7u)) << 4) + (c & 7u) * 2u;
 }
-__device__ __forceinline__ void rw_prod_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kRwProd * 32) : "memory"); }
 
 template <int KW>
 __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdParams p) {
@@ -343,28 +339,28 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     if (tid == 32) {
         mbar_init(&bar_y, 1);
-        mbar_init(&bar_yfree, kRwProd * 32);
-        mbar_init(&bar_afull, kRwProd * 32);
+        mbar_init(&bar_yfree, kRbProd * 32);
+        mbar_init(&bar_afull, kRbProd * 32);
         mbar_init(&bar_aempty, 1);
         mbar_init(&bar_dwfull, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_x[i], 1);
-            mbar_init(&bar_xfree[i], kRwProd * 32 + kRwEpi * 32);
+            mbar_init(&bar_xfree[i], kRbProd * 32 + kRbEpi * 32);
             mbar_init(&bar_tfull[i], 1);
-            mbar_init(&bar_tempty[i], kRwEpi * 32);
+            mbar_init(&bar_tempty[i], kRbEpi * 32);
         }
     }
     if (tid < 128) s_db[tid] = 0.f;
     const int per = p.n_tiles / (int)gridDim.x, rem = p.n_tiles - per * (int)gridDim.x;
     const int g0 = (int)blockIdx.x * per + min((int)blockIdx.x, rem), g1 = g0 + per + ((int)blockIdx.x < rem ? 1 : 0);
     pdl_trigger();
-    if (warp < kRwProd) {          // pointwise weights: warp w stages rows 16 w .. 16 w + 15 of Wpw[n][k] (two 64-column atoms of 16 KB)
+    if (warp < kRbProd) {          // pointwise weights: warp w stages rows 8 w .. 8 w + 7 of Wpw[n][k] (two 64-column atoms of 16 KB)
         const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
-        const uint32_t woff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 16) * 128u + (uint32_t)(lane & 1) * 8u;
+        const uint32_t woff = (uint32_t)(lane >> 4) * 16384u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.wpw + (long)(warp * 16 + i) * 128) + lane);
-            const uint32_t off = woff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)(i & 7)) << 4);
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.wpw + (long)(warp * 8 + i) * 128) + lane);
+            const uint32_t off = woff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4);
             const uint32_t h01 = pack_bf16(v.x, v.y), h23 = pack_bf16(v.z, v.w);
             *reinterpret_cast<uint2*>(w_hi + off) = make_uint2(h01, h23);
             *reinterpret_cast<uint2*>(w_lo + off) = make_uint2(pack_bf16(v.x - __uint_as_float(h01 << 16), v.y - __uint_as_float(h01 & 0xFFFF0000u)),
@@ -410,50 +406,58 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
                 fetch(p.X, rawX + (it & 1) * kRwRows * 128, &bar_x[it & 1], g0 + it + 2);
             }
         }
-    } else if (warp < kRwProd) {
-        // ------------------------------------------------------------------ producers (8 warps)
+    } else if (warp < kRbProd) {
+        // ------------------------------------------------------------------ producers
         const int cp = lane + 32 * (warp & 1);                   // O: channels 2 cp, 2 cp + 1 ...
-        const int rg = warp >> 1;                                // ... rows 16 rg .. 16 rg + 15
+        const int rg = warp >> 1;                                // ... rows 8 rg .. 8 rg + 7
         float2 w2[KW];
 #pragma unroll
         for (int j = 0; j < KW; ++j) w2[j] = make_float2(__ldg(p.wdw + (2 * cp) * KW + j), __ldg(p.wdw + (2 * cp + 1) * KW + j));
         const float2 bd2 = make_float2(p.bdw ? __ldg(p.bdw + 2 * cp) : 0.f, p.bdw ? __ldg(p.bdw + 2 * cp + 1) : 0.f);
-        const int prow = warp * 8;                               // dY: rows 8 w .. 8 w + 7, float4 column lane
+        const int prow = warp * 4;                               // dY: rows 4 w .. 4 w + 3, float4 column lane
         const uint32_t pchunk = (uint32_t)(lane >> 1) & 7u;
         const uint32_t psoff = (uint32_t)(lane >> 4) * 8192u + (uint32_t)prow * 128u + (uint32_t)(lane & 1) * 8u;
+        const uint32_t rsw = (uint32_t)(prow & 7);
         float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
         int it = 0;
         for (int g = g0; g < g1; ++g, ++it) {
             const int s = it & 1;
             const float* rx = rawX + s * kRwRows * 128;
-            // ---- O rows 16 rg .. 16 rg + 15 of channels 2 cp, 2 cp + 1 from the raw X tile (registers only)
+            // ---- O rows 8 rg .. 8 rg + 7 of channels 2 cp, 2 cp + 1 from the raw X tile (registers only)
+            if (tid == 0) trace_ev(p.trace, 0, 1);
             mbar_wait(&bar_x[s], (uint32_t)(it >> 1) & 1u);
-            float2 acc2[16];
+            if (tid == 0) trace_ev(p.trace, 0, 2);
+            float2 acc2[8];
 #pragma unroll
-            for (int o = 0; o < 16; ++o) acc2[o] = bd2;
+            for (int o = 0; o < 8; ++o) acc2[o] = bd2;
 #pragma unroll
-            for (int i = 0; i < 16 + 2 * P; ++i) {
-                const int rr = 16 * rg - P + i;                  // tile row feeding outputs o = i - j
+            for (int i = 0; i < 8 + 2 * P; ++i) {
+                const int rr = 8 * rg - P + i;                   // tile row feeding outputs o = i - j
                 float2 v = make_float2(0.f, 0.f);
                 if (rr >= 0 && rr < kRwRows) v = *reinterpret_cast<const float2*>(rx + rr * 128 + 2 * cp);
                 const float2 r = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
 #pragma unroll
                 for (int j = 0; j < KW; ++j) {
                     const int o = i - j;
-                    if (o >= 0 && o < 16) acc2[o] = __ffma2_rn(w2[j], r, acc2[o]);
+                    if (o >= 0 && o < 8) acc2[o] = __ffma2_rn(w2[j], r, acc2[o]);
                 }
-                if (i - P >= 0 && i - P < 16) acc2[i - P] = __fadd2_rn(acc2[i - P], v);
+                if (i - P >= 0 && i - P < 8) acc2[i - P] = __fadd2_rn(acc2[i - P], v);
             }
+            float a0[8], a1[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) { a0[o] = acc2[o].x; a1[o] = acc2[o].y; }
             mbar_arrive(&bar_xfree[s]);                          // the producers' reads of this raw X buffer are done
+            if (tid == 0) trace_ev(p.trace, 0, 3);
             // ---- images: wait for the previous tile's MMAs, then dY raw -> image and O -> image
             mbar_wait(&bar_y, (uint32_t)it & 1u);
             if (it > 0) mbar_wait(&bar_aempty, (uint32_t)(it - 1) & 1u);
+            if (tid == 0) trace_ev(p.trace, 0, 4);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 const int r = prow + i;
                 const float4 v = *reinterpret_cast<const float4*>(rawY + r * 128 + lane * 4);
                 if (r >= P && r < P + kRwInt) { dbs.x += v.x; dbs.y += v.y; dbs.z += v.z; dbs.w += v.w; }
-                const uint32_t off = psoff + (uint32_t)i * 128u + ((pchunk ^ (uint32_t)i) << 4);
+                const uint32_t off = psoff + (uint32_t)i * 128u + ((pchunk ^ (rsw + (uint32_t)i)) << 4);
                 const uint32_t h01 = pack_bf16(v.x, v.y), h23 = pack_bf16(v.z, v.w);
                 *reinterpret_cast<uint2*>(y_hi + off) = make_uint2(h01, h23);
                 *reinterpret_cast<uint2*>(y_hi + kRwHalf + off) =
@@ -462,10 +466,10 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
             }
             mbar_arrive(&bar_yfree);
 #pragma unroll
-            for (int o = 0; o < 16; ++o) {
-                const uint32_t row = (uint32_t)(16 * rg + o);
+            for (int o = 0; o < 8; ++o) {
+                const uint32_t row = (uint32_t)(8 * rg + o);
                 const bool interior = row >= (uint32_t)P && row < (uint32_t)(P + kRwInt);
-                const float v0 = interior ? acc2[o].x : 0.f, v1 = interior ? acc2[o].y : 0.f;
+                const float v0 = interior ? a0[o] : 0.f, v1 = interior ? a1[o] : 0.f;
                 const uint32_t off = rw_img_off(row, (uint32_t)(2 * cp));
                 const uint32_t h = pack_bf16(v0, v1);
                 *reinterpret_cast<uint32_t*>(o_hi + off) = h;
@@ -473,14 +477,15 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
             }
             fence_async_smem();
             mbar_arrive(&bar_afull);
+            if (tid == 0) trace_ev(p.trace, 0, 5);
         }
         if (p.dbpw) {
             atomicAdd(&s_db[lane * 4 + 0], dbs.x); atomicAdd(&s_db[lane * 4 + 1], dbs.y);
             atomicAdd(&s_db[lane * 4 + 2], dbs.z); atomicAdd(&s_db[lane * 4 + 3], dbs.w);
-            rw_prod_sync();
+            rb_prod_sync();
             if (tid < 128) atomicAdd(p.dbpw + tid, s_db[tid]);
         }
-    } else if (warp == kRwMmaWarp) {
+    } else if (warp == kRbMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc_dx = make_idesc(128, 64, 1, 0);      // A = Wpw^T (MN-major view), B = dY tile (K-major), D = dO^T [k x m]
@@ -491,9 +496,12 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
             int it = 0;
             for (int g = g0; g < g1; ++g, ++it) {
                 const int a = it & 1;
+                trace_ev(p.trace, 1, 1);
                 mbar_wait(&bar_afull, (uint32_t)it & 1u);
+                trace_ev(p.trace, 1, 2);
                 mbar_wait(&bar_tempty[a], (uint32_t)((it >> 1) & 1) ^ 1u);
                 tc_fence_after();
+                trace_ev(p.trace, 1, 3);
                 const uint32_t d_dx = tmem + (uint32_t)a * 64u;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
@@ -513,16 +521,16 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
                     umma_bf16(d_dw, rb_desc_sw128(sy_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
                 }
                 umma_commit(&bar_aempty);
+                trace_ev(p.trace, 1, 4);
             }
             umma_commit(&bar_dwfull);
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (16 warps): thread = channel k, ONE 12-row quarter of the interior
-        const int e = warp - kRwEpiWarp0;
-        const int lane_base = 32 * (warp & 3);                    // the TMEM lane quadrant this warp may read
+        // ------------------------------------------------------------------ epilogue: thread = channel k, half of the interior rows
+        const int e = warp - kRbEpiWarp0;
+        const int lane_base = 32 * (warp & 3);
         const int k = lane_base + lane;
-        const int qr = e >> 2;                                    // interior rows [P + 12 qr, P + 12 qr + 12) of the tile
-        const int c = 12 * qr;                                    // first tile row (= accumulator column) of the 22-row dO window
+        const int h = e >> 2;                                     // interior rows [P + 24 h, P + 24 h + 24)
         float wk[KW], acc[KW];
 #pragma unroll
         for (int j = 0; j < KW; ++j) { wk[j] = __ldg(p.wdw + k * KW + j); acc[j] = 0.f; }
@@ -532,22 +540,27 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
             const int a = it & 1, s = it & 1;
             const int b = g / p.n_lt, l0 = (g - b * p.n_lt) * kRwInt;
             const float* rx = rawX + s * kRwRows * 128 + k;
+            if (e == 0 && lane == 0) trace_ev(p.trace, 2, 1);
             mbar_wait(&bar_x[s], (uint32_t)(it >> 1) & 1u);       // the raw X tile (async-proxy writes) is visible to this thread too
             mbar_wait(&bar_tfull[a], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            // the window is fetched from the 8-aligned column at or below c; OFF = c - that column (0 or 4, uniform per warp)
-            auto quarter = [&](auto off_c) {
-                constexpr int OFF = decltype(off_c)::value;
+            if (e == 0 && lane == 0) trace_ev(p.trace, 2, 2);
+#pragma unroll
+            for (int sp = 0; sp < 2; ++sp) {                     // two sub-passes of 12 interior rows: dO window of 12 + 2 P = 22 rows
+                const int c = (kRwInt / 2) * h + 12 * sp;        // first tile row (= accumulator column) of the window: 0, 12, 24, 36
+                const int cs = c - 4 * sp;                        // ... fetched from the 8-aligned column below it: the window starts at d[4 sp]
                 float d[32];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float d8[8];
-                    tmem_ld8(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(a * 64 + c - OFF + 8 * q), d8);
+                    tmem_ld8(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(a * 64 + cs + 8 * q), d8);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) d[8 * q + i] = d8[i];
                 }
-                tc_fence_before();
-                mbar_arrive(&bar_tempty[a]);                      // accumulator a read by this thread
+                if (sp == 1) {                                    // accumulator a fully read by this thread
+                    tc_fence_before();
+                    mbar_arrive(&bar_tempty[a]);
+                }
                 float* dxp = p.dX + ((long)b * p.L + l0 + c) * 128 + k;    // interior row t of the window <-> position l0 + c + t
 #pragma unroll
                 for (int i = 0; i < 12 + 2 * P; ++i) {            // X row of the window: tile row c + i
@@ -556,30 +569,31 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
 #pragma unroll
                     for (int j = 0; j < KW; ++j) {                // filter gradient: interior row t = i - j meets X row i through tap j
                         const int t = i - j;
-                        if (t >= 0 && t < 12) acc[j] = fmaf(d[OFF + P + t], rxv, acc[j]);
+                        if (t >= 0 && t < 12) acc[j] = fmaf(d[4 * sp + P + t], rxv, acc[j]);
                     }
                     const int t = i - P;                          // this X row is interior row t: its data gradient
                     if (t >= 0 && t < 12) {
                         float conv = 0.f;
 #pragma unroll
-                        for (int j = 0; j < KW; ++j) conv = fmaf(wk[j], d[OFF + 2 * P + t - j], conv);
-                        dbacc += d[OFF + P + t];
-                        if (l0 + c + t < p.L) dxp[(long)t * 128] = d[OFF + P + t] + (x > 0.f ? conv : 0.f);
+                        for (int j = 0; j < KW; ++j) conv = fmaf(wk[j], d[4 * sp + 2 * P + t - j], conv);
+                        dbacc += d[4 * sp + P + t];
+                        if (l0 + c + t < p.L) dxp[(long)t * 128] = d[4 * sp + P + t] + (x > 0.f ? conv : 0.f);
                     }
                 }
-            };
-            if (qr & 1) quarter(std::integral_constant<int, 4>{}); else quarter(std::integral_constant<int, 0>{});
+            }
             mbar_arrive(&bar_xfree[s]);                           // the epilogue's reads of this raw X buffer are done
+            if (e == 0 && lane == 0) trace_ev(p.trace, 2, 3);
         }
 #pragma unroll
         for (int j = 0; j < KW; ++j) atomicAdd(p.dWdw + k * KW + j, acc[j]);
         if (p.dbdw) atomicAdd(p.dbdw + k, dbacc);
-        // ---- flush of the CTA's pointwise weight gradient: thread = row n of dWpw, 32 columns per warp
+        // ---- flush of the CTA's pointwise weight gradient: thread = row n of dWpw, 64 columns per warp
         mbar_wait(&bar_dwfull, 0);
         tc_fence_after();
+        const int col_base = (e >> 2) * 64;
 #pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-            const int c0 = qr * 32 + ch * 16;
+        for (int ch = 0; ch < 4; ++ch) {
+            const int c0 = col_base + ch * 16;
             float v[16];
             tmem_ld16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(128 + c0), v);
             float* dst = p.dWpw + (long)k * 128 + c0;
@@ -649,5 +663,6 @@ extern "C" int npf_resblock1d_bwd(const float* dY, const float* X, const float* 
     p.B = B; p.L = L;
     p.n_lt = (L + kRwInt - 1) / kRwInt;
     p.n_tiles = B * p.n_lt;
+    p.trace = trace_buffer();
     return launch_rb_bwd<11>(p, as_stream(stream));
 }

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "neural-process-family_b200"))
 from npf_b200 import _cabi  # noqa: E402
 
 
-def main(B=256, L=384):
+def main(B=256, L=384, bwd=0):
     dev = "cuda"
     g = torch.Generator().manual_seed(0)
     x = torch.randn(B, L, 128, generator=g).to(dev)
@@ -21,6 +21,13 @@ def main(B=256, L=384):
     y = torch.empty_like(x)
     st = torch.cuda.current_stream().cuda_stream
     run = lambda: _cabi.call("npf_resblock1d_fwd", x.data_ptr(), wd.data_ptr(), bd.data_ptr(), wp.data_ptr(), bp.data_ptr(), None, y.data_ptr(), B, L, 128, 11, 2, st)
+    if bwd:      # backward roles: 0 producer (1 before X wait, 2 X landed, 3 O computed, 4 images free, 5 images stored), 1 MMA (1 before afull,
+        #          2 after, 3 TMEM free, 4 issued), 2 epilogue warp 0 (1 before tfull, 2 after, 3 tile done)
+        dy = torch.randn(B, L, 128, generator=g).to(dev)
+        dx = torch.empty_like(x)
+        gw = [torch.zeros_like(t) for t in (wd, bd, wp, bp)]
+        run = lambda: _cabi.call("npf_resblock1d_bwd", dy.data_ptr(), x.data_ptr(), wd.data_ptr(), bd.data_ptr(), wp.data_ptr(), dx.data_ptr(), gw[0].data_ptr(),
+                                 gw[1].data_ptr(), gw[2].data_ptr(), gw[3].data_ptr(), B, L, 128, 11, 2, st)
     for _ in range(3):
         run()
     flush = torch.empty(64 * 1024 * 1024, device=dev)
