@@ -1640,7 +1640,7 @@ struct ChainBwdParams {
 template <int NSPLIT>
 __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_wfull, bar_wfree, bar_xfull, bar_dwdone, bar_z0[kCbBlocks], bar_z[kCbBlocks], bar_tfull[2],
+    __shared__ __align__(8) uint64_t bar_wfull, bar_wfree, bar_xfull, bar_dwdone, bar_mask, bar_z0[kCbBlocks], bar_z[kCbBlocks], bar_tfull[2],
         bar_tempty[2], bar_dwfull[2], bar_dwflushed[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_db[128];
@@ -1659,6 +1659,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
         mbar_init(&bar_wfree, 1);
         mbar_init(&bar_xfull, kFbProdWarps * 32);
         mbar_init(&bar_dwdone, 1);
+        mbar_init(&bar_mask, kWsEpiWarps * 32);
         for (int i = 0; i < kCbBlocks; ++i) {
             mbar_init(&bar_z0[i], kFbProdWarps * 32);
             mbar_init(&bar_z[i], kWsEpiWarps * 32);
@@ -1745,7 +1746,10 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                 store_w();
                 for (int j = 0; j < n_blk; ++j, ++bi) {
                     if (tid == 0) trace_ev(p.trace, 0, 1);
-                    if (bi > 0) mbar_wait(&bar_dwdone, (uint32_t)(bi - 1) & 1u);      // the wgrad MMAs of the previous block have read the X stage
+                    if (bi > 0) {
+                        mbar_wait(&bar_dwdone, (uint32_t)(bi - 1) & 1u);             // the wgrad MMAs of the previous block have read the X stage
+                        mbar_wait(&bar_mask, (uint32_t)(bi - 1) & 1u);               // and the epilogue has taken its relu mask
+                    }
                     if (tid == 0) trace_ev(p.trace, 0, 2);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -1790,19 +1794,6 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                         else mbar_wait(&bar_z[j], (uint32_t)(gi * (L - 1) + (L - 2 - l)) & 1u);
                         tc_fence_after();
                         const uint32_t sz_hi = smem_u32(smem_raw + (uint32_t)j * kOp), sz_lo = sz_hi + kHalf;
-                        // wgrad first: the X stage is released (bar_dwdone) while the data-gradient MMAs of the same block still run, so the
-                        // producers stage the next block's X underneath them
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint32_t acc = (j | ks) ? 1u : 0u;
-                            const uint64_t a_h = make_desc_sw128(sz_hi + ks * 2048u, 8192, 1024), b_h = make_desc_sw128(sx_hi + ks * 2048u, 8192, 1024);
-                            umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
-                            if (NSPLIT == 3) {
-                                umma_bf16(d_dw, a_h, make_desc_sw128(sx_lo + ks * 2048u, 8192, 1024), idesc_dw, 1);
-                                umma_bf16(d_dw, make_desc_sw128(sz_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
-                            }
-                        }
-                        umma_commit(&bar_dwdone);
                         if (l > 0 || need_dx) {
                             const int a = ti & 1;
                             mbar_wait(&bar_tempty[a], (uint32_t)((ti >> 1) & 1) ^ 1u);
@@ -1818,9 +1809,20 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                                     umma_bf16(d_dx, make_desc_sw128(sw_lo + ks * 2048u, 16384, 1024), b_h, idesc_dx, 1);
                                 }
                             }
-                            umma_commit(&bar_tfull[a]);         // completes after every MMA issued before it: the wgrad MMAs of this block too
+                            umma_commit(&bar_tfull[a]);
                             ++ti;
                         }
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t acc = (j | ks) ? 1u : 0u;
+                            const uint64_t a_h = make_desc_sw128(sz_hi + ks * 2048u, 8192, 1024), b_h = make_desc_sw128(sx_hi + ks * 2048u, 8192, 1024);
+                            umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
+                            if (NSPLIT == 3) {
+                                umma_bf16(d_dw, a_h, make_desc_sw128(sx_lo + ks * 2048u, 8192, 1024), idesc_dw, 1);
+                                umma_bf16(d_dw, make_desc_sw128(sz_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
+                            }
+                        }
+                        umma_commit(&bar_dwdone);
                         trace_ev(p.trace, 1, 3);
                     }
                     umma_commit(&bar_wfree);
@@ -1846,25 +1848,24 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                 const bool masked = l > 0 || p.mask0;
                 float dbacc = 0.f;
                 for (int j = 0; j < n_blk; ++j, ++bi) {
-                    if (!(l > 0 || need_dx)) continue;
+                    // Every block iteration waits for the block's wgrad MMAs (bar_dwdone) BEFORE it releases the X stage (bar_mask):
+                    // the producers need both to stage the next block, so neither barrier can run two phases ahead of a waiter.
+                    if (!(l > 0 || need_dx)) { mbar_wait(&bar_dwdone, (uint32_t)bi & 1u); mbar_arrive(&bar_mask); continue; }
                     const int a = ti & 1;
-                    // relu mask of column k for this warp's 32 rows, read from the saved layer input in global memory (L2: the producers
-                    // stream the same rows) BEFORE waiting for the tensor core: the X stage is then held by the wgrad MMAs only
+                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 1);
+                    mbar_wait(&bar_tfull[a], (uint32_t)(ti >> 1) & 1u);
+                    tc_fence_after();
+                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 2);
                     uint32_t mbits = 0xFFFFFFFFu;
-                    if (masked) {
-                        const int row0 = r_begin + j * kF64Rows + mh;
-                        const float* xp = p.X[l] + (long)row0 * p.ldx[l] + k;
+                    if (masked) {                  // relu mask of column k for the 32 rows, from the staged X_l block: bf16 > 0 <=> int16 > 0
                         mbits = 0u;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float xv = (row0 + i < r_end) ? __ldg(xp + (long)i * p.ldx[l]) : 0.f;
-                            mbits |= (xv > 0.f ? 1u : 0u) << i;
+                            const uint32_t m = (uint32_t)(mh + i);
+                            const short xb = *reinterpret_cast<const short*>(x_hi + xk_off + m * 128u + ((xk_chunk ^ (m & 7u)) << 4));
+                            mbits |= (xb > 0 ? 1u : 0u) << i;
                         }
                     }
-                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 1);
-                    mbar_wait(&bar_tfull[a], (uint32_t)(ti >> 1) & 1u);      // implies the wgrad MMAs of this block are done: image j may be rewritten
-                    tc_fence_after();
-                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 2);
                     float v[32];
                     {
                         float v0[16], v1[16];
@@ -1877,6 +1878,9 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                     mbar_arrive(&bar_tempty[a]);
                     ++ti;
                     if (e == 0 && lane == 0) trace_ev(p.trace, 2, 3);
+                    mbar_wait(&bar_dwdone, (uint32_t)bi & 1u);           // the wgrad MMAs of this block have read image j and the X stage
+                    mbar_arrive(&bar_mask);
+                    if (e == 0 && lane == 0) trace_ev(p.trace, 2, 4);
                     if (l > 0) {
                         uint8_t* z_hi = smem_raw + (uint32_t)j * kOp;
 #pragma unroll
