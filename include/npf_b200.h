@@ -60,6 +60,22 @@ typedef void* npf_stream_t;
 #define NPF_API
 #endif
 
+/* ---- multi-GPU: one-shot mean all-reduce of the flat gradient bucket over NVLink peer memory (one process per GPU) ----------
+ * npf_p2p_alloc / _get_handle / _open / _close wrap cudaMalloc and the CUDA IPC handle calls so that the host language needs no
+ * CUDA binding of its own: every rank allocates its bucket, output-less signal block (2 * world ints) and exchanges the 64-byte
+ * handles through its own channel (torch.distributed here), then opens the peers' handles once.
+ * npf_allreduce_mean_p2p: `in` / `sig` are HOST arrays of `world` device pointers (in[rank] / sig[rank] are this rank's own
+ * allocations, the others peer mappings); out[n] = mean_r in_r[n]; `state` = 2 zero-initialised ints of local device memory.
+ * The kernel carries its own inter-rank barriers (epoch flags in the signal blocks): the peers' buckets may be read as soon as it
+ * starts and this rank's bucket may be overwritten as soon as it ends.  Same launch every step (CUDA-graph capturable). */
+NPF_API int npf_p2p_alloc(void** ptr, size_t bytes);
+NPF_API int npf_p2p_free(void* ptr);
+NPF_API int npf_p2p_get_handle(void* ptr, unsigned char* handle64);
+NPF_API int npf_p2p_open(const unsigned char* handle64, void** ptr);
+NPF_API int npf_p2p_close(void* ptr);
+NPF_API int npf_allreduce_mean_p2p(const float* const* in, int* const* sig, float* out, int* state, int rank, int world, long n,
+                           npf_stream_t stream);
+
 /* Diagnostics only: device buffer (>= 4096 uint64, zeroed by the caller) into which CTA 0 of the kernels that support it
  * (npf_mlp_chain_bwd, npf_setconv_bwd tensor-core path) writes per-role (event, SM clock) records; NULL disables. */
 NPF_API int npf_debug_set_trace(unsigned long long* device_buffer);

@@ -28,6 +28,12 @@ SIGNATURES = {
     "npf_mlp_chain_bwd": [P, I, P, P, P, I, P, P, I, I, I, I, I, P],
     "npf_relu_bwd": [P, P, P, L, P],
     "npf_debug_set_trace": [P],
+    "npf_p2p_alloc": [P, ctypes.c_size_t],
+    "npf_p2p_free": [P],
+    "npf_p2p_get_handle": [P, P],
+    "npf_p2p_open": [P, P],
+    "npf_p2p_close": [P],
+    "npf_allreduce_mean_p2p": [P, P, P, P, I, I, L, P],
     "npf_setconv_fwd": [P, L, P, L, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "npf_setconv_bwd": [P, L, P, L, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "npf_dwconv_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P],

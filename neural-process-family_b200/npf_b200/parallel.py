@@ -7,7 +7,82 @@ NVSwitch).  Works with any ``torch.distributed`` backend (``gloo`` on CPU for th
 import torch
 import torch.distributed as dist
 
-__all__ = ["FlatGradients", "FlatAdam", "shard_tasks", "sync_batchnorm_", "sync_moments"]
+__all__ = ["FlatGradients", "FlatAdam", "P2PAllReduce", "shard_tasks", "sync_batchnorm_", "sync_moments"]
+
+
+class _DevMem:
+    """A cudaMalloc allocation of the library (npf_p2p_alloc) exposed to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, numel, typestr):
+        self.ptr, self.numel = ptr, numel
+        self.__cuda_array_interface__ = dict(shape=(numel,), typestr=typestr, data=(ptr, False), version=2)
+
+
+class P2PAllReduce:
+    """One-kernel mean all-reduce of the flat gradient bucket over NVLink peer memory (csrc/p2p.cu): every rank maps the other
+    ranks' buckets (CUDA IPC, one process per GPU of one node) and reads them directly; inter-rank barriers are epoch flags in peer
+    memory inside the kernel.  ``bucket`` is the tensor the gradients are accumulated into (allocated here so that it can be shared);
+    ``reduce_()`` leaves the mean in it."""
+
+    def __init__(self, numel, device, group=None):
+        import ctypes
+        from . import _cabi
+        self.group, self.rank, self.world = group, dist.get_rank(group), dist.get_world_size(group)
+        n = (numel + 3) // 4 * 4
+        self.n = n
+        mine = []
+        for nbytes in (4 * n, 4 * n, 4 * 2 * self.world, 8):          # bucket, output, signal block, local state
+            p = ctypes.c_void_p()
+            _cabi.call("npf_p2p_alloc", ctypes.byref(p), nbytes)
+            mine.append(p.value)
+        self._mine = mine
+        torch.cuda.synchronize(device)
+        handles = []
+        for ptr in (mine[0], mine[2]):
+            h = (ctypes.c_ubyte * 64)()
+            _cabi.call("npf_p2p_get_handle", ptr, h)
+            handles.append(bytes(h))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (handles, torch.cuda.current_device()), group=group)
+        self._opened, ins, sigs = [], [], []
+        for r, (hs, _dev) in enumerate(gathered):
+            if r == self.rank:
+                ins.append(mine[0]); sigs.append(mine[2])
+                continue
+            ptrs = []
+            for hb in hs:
+                p = ctypes.c_void_p()
+                _cabi.call("npf_p2p_open", (ctypes.c_ubyte * 64).from_buffer_copy(hb), ctypes.byref(p))
+                ptrs.append(p.value)
+                self._opened.append(p.value)
+            ins.append(ptrs[0]); sigs.append(ptrs[1])
+        self._in = (ctypes.c_void_p * self.world)(*ins)
+        self._sig = (ctypes.c_void_p * self.world)(*sigs)
+        self.bucket = torch.as_tensor(_DevMem(mine[0], n, "<f4"), device=device)
+        self.out = torch.as_tensor(_DevMem(mine[1], n, "<f4"), device=device)
+        dist.barrier(group=group)                                          # every rank has opened every handle before the first launch
+
+    def reduce_(self):
+        from . import _cabi
+        _cabi.call("npf_allreduce_mean_p2p", self._in, self._sig, self._mine[1], self._mine[3], self.rank, self.world, self.n,
+                   torch.cuda.current_stream().cuda_stream)
+        self.bucket.copy_(self.out)
+        return self.bucket
+
+
+def _try_p2p(numel, device, group):
+    """P2PAllReduce if every rank of the group can set it up (same node, peer access), else None -- decided collectively."""
+    import os
+    if os.environ.get("NPF_P2P_ALLREDUCE", "1") == "0" or device.type != "cuda" or dist.get_backend(group) != "nccl":
+        return None
+    p2p, ok = None, 1
+    try:
+        p2p = P2PAllReduce(numel, device, group)
+    except Exception:                                                       # noqa: BLE001  (IPC / peer access unavailable)
+        ok = 0
+    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return p2p if int(flag.item()) == 1 else None
 
 
 class FlatGradients:
@@ -20,7 +95,10 @@ class FlatGradients:
             self.offsets.append(n)
             n += (p.numel() + 31) // 32 * 32
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.p2p = None
+        if dev.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            self.p2p = _try_p2p(n, dev, process_group)          # one-kernel all-reduce over NVLink peer memory (falls back to NCCL)
+        self.flat = self.p2p.bucket[:n] if self.p2p is not None else torch.zeros(n, dtype=torch.float32, device=dev)
         self._attach()
 
     def _attach(self):
@@ -58,6 +136,9 @@ class FlatGradients:
         batch mean for equal shards.  No-op on a single rank."""
         w = self.world_size
         if w == 1:
+            return self.flat
+        if self.p2p is not None:
+            self.p2p.reduce_()
             return self.flat
         import os
         if self.flat.is_cuda and os.environ.get("NPF_ALLREDUCE_AVG", "1") == "1":      # NCCL averages inside the collective: no separate 1/G kernel
