@@ -44,7 +44,10 @@ class GraphedStep:
         import os
         # where the gradient all-reduce of a multi-GPU step runs: inside the recorded graph, or right after the replay on the
         # caller's stream (NPF_GRAPH_ALLREDUCE=0/1; measured at N=2 on B200, profiles/r2/allreduce_placement.md)
-        self.allreduce_in_graph = os.environ.get("NPF_GRAPH_ALLREDUCE", "0") == "1"
+        # Default: the one-kernel NVLink all-reduce (parallel.P2PAllReduce) is recorded into the graph (0.758 vs 0.762 ms at N=2); the NCCL
+        # fallback runs after the replay (no difference measured either way).
+        dflt = "1" if getattr(self.flat, "p2p", None) is not None else "0"
+        self.allreduce_in_graph = os.environ.get("NPF_GRAPH_ALLREDUCE", dflt) == "1"
         self._graphs = OrderedDict()
         self._side = None
 
