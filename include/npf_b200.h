@@ -75,6 +75,10 @@ NPF_API int npf_p2p_open(const unsigned char* handle64, void** ptr);
 NPF_API int npf_p2p_close(void* ptr);
 NPF_API int npf_allreduce_mean_p2p(const float* const* in, int* const* sig, float* out, int* state, int rank, int world, long n,
                            npf_stream_t stream);
+/* Two-shot variant: rank r reduces slice r only and writes its mean into EVERY rank's output buffer (`out` = HOST array of `world`
+ * device pointers, out[rank] local); 2 (world - 1) / world bucket sizes cross NVLink per rank instead of (world - 1). */
+NPF_API int npf_allreduce_mean_p2p2(const float* const* in, int* const* sig, float* const* out, int* state, int rank, int world, long n,
+                            npf_stream_t stream);
 
 /* Diagnostics only: device buffer (>= 4096 uint64, zeroed by the caller) into which CTA 0 of the kernels that support it
  * (npf_mlp_chain_bwd, npf_setconv_bwd tensor-core path) writes per-role (event, SM clock) records; NULL disables. */

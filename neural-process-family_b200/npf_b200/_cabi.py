@@ -34,6 +34,7 @@ SIGNATURES = {
     "npf_p2p_open": [P, P],
     "npf_p2p_close": [P],
     "npf_allreduce_mean_p2p": [P, P, P, P, I, I, L, P],
+    "npf_allreduce_mean_p2p2": [P, P, P, P, I, I, L, P],
     "npf_setconv_fwd": [P, L, P, L, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "npf_setconv_bwd": [P, L, P, L, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "npf_dwconv_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, P, P, P],

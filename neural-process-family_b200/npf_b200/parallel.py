@@ -38,16 +38,16 @@ class P2PAllReduce:
         self._mine = mine
         torch.cuda.synchronize(device)
         handles = []
-        for ptr in (mine[0], mine[2]):
+        for ptr in (mine[0], mine[2], mine[1]):
             h = (ctypes.c_ubyte * 64)()
             _cabi.call("npf_p2p_get_handle", ptr, h)
             handles.append(bytes(h))
         gathered = [None] * self.world
         dist.all_gather_object(gathered, (handles, torch.cuda.current_device()), group=group)
-        self._opened, ins, sigs = [], [], []
+        self._opened, ins, sigs, outs = [], [], [], []
         for r, (hs, _dev) in enumerate(gathered):
             if r == self.rank:
-                ins.append(mine[0]); sigs.append(mine[2])
+                ins.append(mine[0]); sigs.append(mine[2]); outs.append(mine[1])
                 continue
             ptrs = []
             for hb in hs:
@@ -55,17 +55,26 @@ class P2PAllReduce:
                 _cabi.call("npf_p2p_open", (ctypes.c_ubyte * 64).from_buffer_copy(hb), ctypes.byref(p))
                 ptrs.append(p.value)
                 self._opened.append(p.value)
-            ins.append(ptrs[0]); sigs.append(ptrs[1])
+            ins.append(ptrs[0]); sigs.append(ptrs[1]); outs.append(ptrs[2])
         self._in = (ctypes.c_void_p * self.world)(*ins)
         self._sig = (ctypes.c_void_p * self.world)(*sigs)
+        self._out = (ctypes.c_void_p * self.world)(*outs)
+        import os
+        # two-shot (each rank reduces one slice and writes it to everybody) from 4 ranks up, one-shot (everybody reads everything) below:
+        # measured on B200 NVLink, profiles/r2/allreduce_placement.md
+        self.two_shot = os.environ.get("NPF_P2P_TWO_SHOT", "1" if self.world >= 4 else "0") == "1"
         self.bucket = torch.as_tensor(_DevMem(mine[0], n, "<f4"), device=device)
         self.out = torch.as_tensor(_DevMem(mine[1], n, "<f4"), device=device)
         dist.barrier(group=group)                                          # every rank has opened every handle before the first launch
 
     def reduce_(self):
         from . import _cabi
-        _cabi.call("npf_allreduce_mean_p2p", self._in, self._sig, self._mine[1], self._mine[3], self.rank, self.world, self.n,
-                   torch.cuda.current_stream().cuda_stream)
+        if self.two_shot:
+            _cabi.call("npf_allreduce_mean_p2p2", self._in, self._sig, self._out, self._mine[3], self.rank, self.world, self.n,
+                       torch.cuda.current_stream().cuda_stream)
+        else:
+            _cabi.call("npf_allreduce_mean_p2p", self._in, self._sig, self._mine[1], self._mine[3], self.rank, self.world, self.n,
+                       torch.cuda.current_stream().cuda_stream)
         self.bucket.copy_(self.out)
         return self.bucket
 

@@ -28,8 +28,9 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     worst = 0.0
-    for numel in (137476 + 60, 8):
+    for numel, two_shot in ((137476 + 60, False), (8, False), (137476 + 60, True), (12, True)):
         ar = P2PAllReduce(numel, dev)
+        ar.two_shot = two_shot
         for epoch in range(6):
             g = torch.Generator(device="cpu").manual_seed(100 * epoch + rank)
             x = torch.randn(ar.n, generator=g).to(dev) * (epoch + 1)
