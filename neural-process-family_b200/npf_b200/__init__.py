@@ -8,7 +8,7 @@ constructors, same ``forward(X_cntxt, Y_cntxt, X_trgt, Y_trgt=None)``, same ``st
 from . import ops
 from .losses import *
 from .neuralproc import *
-from .graph import GraphedStep
+from .graph import GraphedStep, PipelinedStep
 from .ops import get_precision, set_precision
 
 __version__ = "0.1.0"

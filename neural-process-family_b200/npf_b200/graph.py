@@ -26,7 +26,7 @@ import torch
 from . import ops
 from .parallel import FlatGradients
 
-__all__ = ["GraphedStep"]
+__all__ = ["GraphedStep", "PipelinedStep"]
 
 
 class _Entry:
@@ -135,3 +135,71 @@ class GraphedStep:
         sig = self._signature(tensors)
         e = self._graphs.get(sig) or self._capture(sig, tensors)
         return tuple(e.inputs)
+
+
+class PipelinedStep:
+    """Host-side input / result pipeline around a ``GraphedStep`` for batches that start in (pinned) host memory:
+
+        pipe = PipelinedStep(step)
+        for batch in loader:                       # dict(X_cntxt=, Y_cntxt=, X_trgt=, Y_trgt=) of pinned CPU tensors
+            prev_loss = pipe.submit(batch)         # float loss of the PREVIOUS step (None for the first call)
+        last_loss = pipe.drain()
+
+    Every step still does its own host->device copy of the inputs and its own device->host read of the loss; what changes is *when*:
+    the copy of step i+1 runs on a side stream into a staging buffer while step i's graph replays (a 2 us device-to-device copy
+    moves it into the graph's static inputs), and the loss of step i is read back while step i+1 runs, so the GPU never idles on
+    PCIe latency or on the host's ``.item()`` round trip.  Gradients of step i are complete when ``submit`` of step i returns in
+    stream order (run the optimizer on the same stream as usual)."""
+
+    def __init__(self, step):
+        self.step = step
+        self._copy = None
+        self._stage = [None, None]
+        self._h2d = [None, None]
+        self._used = [None, None]
+        self._loss_host = None
+        self._loss_ev = [None, None]
+        self._i = 0
+
+    def _setup(self, batch, dev):
+        self._copy = torch.cuda.Stream(device=dev)
+        for k in range(2):
+            self._stage[k] = {n: torch.empty(t.shape, dtype=t.dtype, device=dev) for n, t in batch.items()}
+            self._h2d[k], self._used[k] = torch.cuda.Event(), torch.cuda.Event()
+            self._loss_ev[k] = torch.cuda.Event()
+        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def _enqueue_copy(self, batch, k, dev):
+        with torch.cuda.stream(self._copy):
+            if self._i >= 2:
+                self._copy.wait_event(self._used[k])              # the step that last read this staging set has consumed it
+            for n, t in batch.items():
+                self._stage[k][n].copy_(t, non_blocking=True)
+            self._h2d[k].record(self._copy)
+
+    def submit(self, batch):
+        dev = next(self.step.model.parameters()).device
+        if self._copy is None:
+            self._setup(batch, dev)
+        k = self._i & 1
+        self._enqueue_copy(batch, k, dev)
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(self._h2d[k])
+        st = self._stage[k]
+        loss = self.step(st["X_cntxt"], st["Y_cntxt"], st["X_trgt"], st["Y_trgt"])     # copies into the graph's static inputs, replays
+        self._used[k].record(main)
+        self._loss_host[k:k + 1].copy_(loss.reshape(1), non_blocking=True)
+        self._loss_ev[k].record(main)
+        prev = None
+        if self._i >= 1:
+            self._loss_ev[k ^ 1].synchronize()
+            prev = float(self._loss_host[k ^ 1])
+        self._i += 1
+        return prev
+
+    def drain(self):
+        if self._i == 0:
+            return None
+        k = (self._i - 1) & 1
+        self._loss_ev[k].synchronize()
+        return float(self._loss_host[k])

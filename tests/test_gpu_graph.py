@@ -68,3 +68,30 @@ def test_graphed_step_new_shapes_and_range_error():
     step(bad, torch.zeros(4, 3, 1).cuda(), torch.zeros(4, 11, 1).cuda(), torch.zeros(4, 11, 1).cuda())
     with pytest.raises(ValueError):
         m.validate_now()
+
+
+def test_pipelined_step_matches_sequential():
+    """npf_b200.PipelinedStep: batches from pinned host memory, the copy of step i+1 and the loss read of step i-1 overlapping step i;
+    the losses it returns (one step late) must be the ones a plain sequence of GraphedStep calls on the same batches gives."""
+    import npf_b200
+    npf_b200.set_precision("fp32")
+    fx = load_fixture("convcnp_default")
+    case = fx["cases"][1]
+    crit = loss_for("cnpf", reduction="mean").train()
+    batches = []
+    for i in range(5):
+        g = torch.Generator().manual_seed(i)
+        b = {k: v.clone() for k, v in case["inputs"].items()}
+        b["Y_cntxt"] = b["Y_cntxt"] + 0.1 * torch.randn(b["Y_cntxt"].shape, generator=g)
+        b["Y_trgt"] = b["Y_trgt"] + 0.1 * torch.randn(b["Y_trgt"].shape, generator=g)
+        batches.append({k: v.float().pin_memory() for k, v in b.items()})
+    m1 = build_model(fx["cfg"]).cuda().train(); m1.load_state_dict(fx["state_dict"])
+    m2 = copy.deepcopy(m1)
+    s1 = npf_b200.GraphedStep(m1, crit)
+    ref = [float(s1(*[b[k].cuda() for k in ("X_cntxt", "Y_cntxt", "X_trgt", "Y_trgt")]).item()) for b in batches]
+    pipe = npf_b200.PipelinedStep(npf_b200.GraphedStep(m2, crit))
+    got = [pipe.submit(b) for b in batches]
+    assert got[0] is None
+    got = got[1:] + [pipe.drain()]
+    for a, b in zip(ref, got):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (ref, got)
