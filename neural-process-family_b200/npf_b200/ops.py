@@ -92,6 +92,7 @@ def _gbuf(p):
     return g, g
 
 
+_CHAIN_BWD_MAX_ROWS = 148 * 256   # npf_mlp_chain_bwd: one resident row group per SM
 _CHAIN_MAX_ROWS = 1 << 30       # npf_mlp_chain_fwd: one 256-row block per CTA up to 37 888 rows, persistent CTAs over blocks beyond
 
 
@@ -197,7 +198,9 @@ class _MLPChain(torch.autograd.Function):
             # run of consecutive square 128-wide layers i0 .. i: ONE kernel keeps the gradient on chip between the layers
             # (npf_mlp_chain_bwd: dY and every saved input read once, only the run's dX written)
             i0 = i
-            if p_eff != _PRECISION["fp32"] and M >= 64 and dz.shape[1] == 128 and dz.is_contiguous():
+            # (one row group of <= 256 rows per CTA: beyond 148 x 256 rows the kernel would re-stage the weights and flush dW with
+            # atomics once per group and layer -- measured slower than one npf_linear_bwd per layer at M = 131 072)
+            if p_eff != _PRECISION["fp32"] and 64 <= M <= _CHAIN_BWD_MAX_ROWS and dz.shape[1] == 128 and dz.is_contiguous():
                 while i0 >= 0 and Ws[i0].shape[0] == 128 and Ws[i0].numel() == 128 * 128 and Ws[i0].is_contiguous() \
                         and (bs[i0] is None or bs[i0].is_contiguous()):
                     i0 -= 1
