@@ -651,13 +651,13 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], uint8_t* hi, u
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) setconv_tc_fwd_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
+__global__ void __launch_bounds__(kTcThreads + 32, 1) setconv_tc_fwd_kernel(const float* __restrict__ keys, long key_bs, const float* __restrict__ queries,
                                                                       long qry_bs, const float* __restrict__ values, const float* __restrict__ theta,
                                                                       float* __restrict__ feat_o, float* __restrict__ dens_o, float* __restrict__ mstat_o,
                                                                       int B, int K, int Q) {
     constexpr int C = 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_vfull[2], bar_wfull[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_vfull[2], bar_wfull[2], bar_empty[2], bar_tfull[2], bar_tempty[2], bar_rfull[2], bar_rempty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_sum[2][128];
     __shared__ __align__(16) float s_keys[kMaxChunks * kChunkRows + kTcKeys];   // shared key grid, padded with +inf to whole chunks
@@ -666,6 +666,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) setconv_tc_fwd_kernel(const flo
     constexpr uint32_t kVTile = kTcKeys * 128u * 2u;            // V chunk, one bf16 image: 16 KB
     constexpr uint32_t kStage = 2u * kWTile + 2u * kVTile;      // hi + lo of both: 64 KB
     float* scratch_all = reinterpret_cast<float*>(smem_raw + 2 * kStage);
+    // raw fp32 V chunks (64 rows x 512 B), filled by TMA bulk copies from a loader warp two chunks ahead of the converting warps:
+    // the V stream no longer waits on a global-load round trip per chunk (the register-staged version kept 32 KB in flight per SM)
+    float* vraw = scratch_all + kTcEpi * 32 * kTcScratchLd;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
@@ -676,6 +679,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) setconv_tc_fwd_kernel(const flo
             mbar_init(&bar_empty[i], 1);
             mbar_init(&bar_tfull[i], 1);
             mbar_init(&bar_tempty[i], kTcEpi * 32);
+            mbar_init(&bar_rfull[i], 1);
+            mbar_init(&bar_rempty[i], kTcVProd * 32);
         }
     }
     const float sigma = 1e-5f + softplus_f(__ldg(theta));
@@ -684,14 +689,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) setconv_tc_fwd_kernel(const flo
     const int n_qt = (Q + 127) >> 7;
     const int n_units = B * n_qt;                                // (task, 128-query tile)
     pdl_trigger();
-    for (int i = tid; i < n_chunks * kTcKeys; i += kTcThreads) s_keys[i] = i < K ? __ldg(keys + i) : INFINITY;   // the grid is an input of the step
+    for (int i = tid; i < n_chunks * kTcKeys; i += kTcThreads + 32) s_keys[i] = i < K ? __ldg(keys + i) : INFINITY;   // the grid is an input of the step
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     pdl_wait();
 
-    if (warp < kTcVProd) {
+    if (warp == kTcThreads / 32) {
+        // ------------------------------------------------------------------ loader: raw V chunks by TMA bulk copies, 2-deep ring
+        int gr = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const float* vb = values + (long)(u / n_qt) * K * C;
+            for (int c = 0; c < n_chunks; ++c, ++gr) {
+                const int r = gr & 1;
+                if (gr >= 2) mbar_wait(&bar_rempty[r], (uint32_t)((gr >> 1) - 1) & 1u);
+                float* dst = vraw + r * (kTcKeys * C);
+                const int rows = min(kTcKeys, K - c * kTcKeys);
+                for (int i = lane; i < (kTcKeys - rows) * 32; i += 32) reinterpret_cast<float4*>(dst + rows * C)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                if (lane == 0) {
+                    fence_async_smem();
+                    const uint32_t bytes = (uint32_t)rows * C * sizeof(float);
+                    mbar_expect_tx(&bar_rfull[r], bytes);
+                    bulk_g2s(dst, vb + (long)c * kTcKeys * C, bytes, &bar_rfull[r]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < kTcVProd) {
         // ------------------------------------------------------------------ V producers: warp w owns rows 8 w .. 8 w + 7 of a 64-key chunk
         const uint32_t vchunk = (uint32_t)(lane >> 1) & 7u;
         const uint32_t voff = (uint32_t)(lane >> 4) * 8192u + (uint32_t)(warp * 8) * 128u + (uint32_t)(lane & 1) * 8u;
@@ -712,11 +738,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) setconv_tc_fwd_kernel(const flo
             for (int c = 0; c < n_chunks; ++c, ++g) {
                 const int s = g & 1;
                 float4 v[8];
+                const int r = g & 1;
+                mbar_wait(&bar_rfull[r], (uint32_t)(g >> 1) & 1u);
+                const float* src = vraw + r * (kTcKeys * C) + (warp * 8) * C + lane * 4;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = c * kTcKeys + warp * 8 + i;
-                    v[i] = row < K ? __ldg(reinterpret_cast<const float4*>(vb + (long)row * C) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(src + i * C);
+                mbar_arrive(&bar_rempty[r]);                       // the raw chunk is in registers: the loader may refill the slot
                 if (g >= 2) mbar_wait(&bar_empty[s], ((g >> 1) - 1) & 1);
                 uint8_t* v_hi = smem_raw + s * kStage + 2 * kWTile;
 #pragma unroll
@@ -1252,10 +1279,10 @@ int setconv_tile_fwd(const float* keys, long key_bs, const float* queries, long 
     if (!tile_ok(K, Q, C, values) || (reinterpret_cast<uintptr_t>(feat) & 15)) return NPF_ENOTSUP;
     if (tc_fwd_ok(K, Q, C, key_bs)) {
         static bool cattr = false;
-        if (!cattr) { cudaFuncSetAttribute(setconv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); cattr = true; }
+        if (!cattr) { cudaFuncSetAttribute(setconv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); cattr = true; }
         const int units = B * ((Q + 127) / 128);
-        const size_t smem = 2 * 65536 + (size_t)kTcEpi * 32 * kTcScratchLd * sizeof(float);
-        launch_pdl(setconv_tc_fwd_kernel, dim3(units < kNumSMs ? units : kNumSMs), dim3(kTcThreads), smem, st, keys, key_bs, queries, qry_bs, values, theta, feat, dens,
+        const size_t smem = 2 * 65536 + (size_t)kTcEpi * 32 * kTcScratchLd * sizeof(float) + 2 * (size_t)kTcKeys * 128 * sizeof(float);
+        launch_pdl(setconv_tc_fwd_kernel, dim3(units < kNumSMs ? units : kNumSMs), dim3(kTcThreads + 32), smem, st, keys, key_bs, queries, qry_bs, values, theta, feat, dens,
                    mstat, B, K, Q);
         count_launch();
         return check_launch("setconv_tc_fwd_kernel");
