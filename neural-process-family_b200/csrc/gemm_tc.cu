@@ -455,20 +455,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_ws_kernel(TcLinParams p)
                 tc_fence_after();
                 const uint32_t sa_hi = smem_u32(smem_raw + s * kStage), sa_lo = sa_hi + kTile;
                 const uint32_t d = tmem + (uint32_t)s * 128u;
+                const uint64_t da_h = make_desc_sw128(sa_hi, 16, 1024), da_l = make_desc_sw128(sa_lo, 16, 1024);
+                const uint64_t db_h = p.transposed_w ? make_desc_sw128(sb_hi, 16384, 1024) : make_desc_sw128(sb_hi, 16, 1024);
+                const uint64_t db_l = p.transposed_w ? make_desc_sw128(sb_lo, 16384, 1024) : make_desc_sw128(sb_lo, 16, 1024);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     uint64_t a_h, a_l, b_h, b_l;
                     if (SW) {
                         const uint32_t ao = (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u;
-                        a_h = make_desc_sw128(sa_hi + ao, 16, 1024);
-                        a_l = make_desc_sw128(sa_lo + ao, 16, 1024);
-                        if (p.transposed_w) {
-                            b_h = make_desc_sw128(sb_hi + ks * 2048u, 16384, 1024);
-                            b_l = make_desc_sw128(sb_lo + ks * 2048u, 16384, 1024);
-                        } else {
-                            b_h = make_desc_sw128(sb_hi + ao, 16, 1024);
-                            b_l = make_desc_sw128(sb_lo + ao, 16, 1024);
-                        }
+                        a_h = desc_adv(da_h, ao);
+                        a_l = desc_adv(da_l, ao);
+                        b_h = desc_adv(db_h, p.transposed_w ? ks * 2048u : ao);
+                        b_l = desc_adv(db_l, p.transposed_w ? ks * 2048u : ao);
                     } else {
                         a_h = make_desc(sa_hi + ks * 4096u, 2048, 128);
                         a_l = make_desc(sa_lo + ks * 4096u, 2048, 128);
@@ -673,15 +671,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) mlp_chain_fwd_kernel(ChainParam
                         }
                         tc_fence_after();
                         const uint32_t sa_hi = smem_u32(smem_raw + t * kImg), sa_lo = sa_hi + kTile;
+                        const uint64_t da_h = make_desc_sw128(sa_hi, 16, 1024), da_l = make_desc_sw128(sa_lo, 16, 1024);
+                        const uint64_t db_h = make_desc_sw128(sb_hi, 16, 1024), db_l = make_desc_sw128(sb_lo, 16, 1024);
                         const uint32_t d = tmem + (uint32_t)t * 128u;
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
                             const uint32_t ao = (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u;
-                            const uint64_t a_h = make_desc_sw128(sa_hi + ao, 16, 1024), b_h = make_desc_sw128(sb_hi + ao, 16, 1024);
+                            const uint64_t a_h = desc_adv(da_h, ao), b_h = desc_adv(db_h, ao);
                             umma_bf16(d, a_h, b_h, idesc, ks ? 1u : 0u);
                             if (NSPLIT == 3) {
-                                umma_bf16(d, a_h, make_desc_sw128(sb_lo + ao, 16, 1024), idesc, 1);
-                                umma_bf16(d, make_desc_sw128(sa_lo + ao, 16, 1024), b_h, idesc, 1);
+                                umma_bf16(d, a_h, desc_adv(db_l, ao), idesc, 1);
+                                umma_bf16(d, desc_adv(da_l, ao), b_h, idesc, 1);
                             }
                         }
                         umma_commit(&bar_mma[t]);
@@ -1468,25 +1468,30 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused64_kernel(TcFus
                 tc_fence_after();
                 const uint32_t sy_hi = smem_u32(smem_raw + s * kStage), sy_lo = sy_hi + kHalf, sx_hi = sy_hi + kOp, sx_lo = sx_hi + kHalf;
                 const uint32_t d_dx = tmem + (uint32_t)s * 64u;
+                // base descriptors once per tile, one add per k-slice (desc_adv): the issuing thread's instruction count is what paces the MMAs
+                const uint64_t dwt_h = make_desc_sw128(sw_hi, 16384, 1024), dwt_l = make_desc_sw128(sw_lo, 16384, 1024);
+                const uint64_t dyk_h = make_desc_sw128(sy_hi, 16, 1024), dyk_l = make_desc_sw128(sy_lo, 16, 1024);
+                const uint64_t dym_h = make_desc_sw128(sy_hi, 8192, 1024), dym_l = make_desc_sw128(sy_lo, 8192, 1024);
+                const uint64_t dxm_h = make_desc_sw128(sx_hi, 8192, 1024), dxm_l = make_desc_sw128(sx_lo, 8192, 1024);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {                     // reduction over n (16 per step)
                     const uint32_t bo = (uint32_t)(ks >> 2) * 8192u + (uint32_t)(ks & 3) * 32u;
-                    const uint64_t a_h = make_desc_sw128(sw_hi + ks * 2048u, 16384, 1024), b_h = make_desc_sw128(sy_hi + bo, 16, 1024);
+                    const uint64_t a_h = desc_adv(dwt_h, ks * 2048u), b_h = desc_adv(dyk_h, bo);
                     umma_bf16(d_dx, a_h, b_h, idesc_dx, ks ? 1u : 0u);
                     if (NSPLIT == 3) {
-                        umma_bf16(d_dx, a_h, make_desc_sw128(sy_lo + bo, 16, 1024), idesc_dx, 1);
-                        umma_bf16(d_dx, make_desc_sw128(sw_lo + ks * 2048u, 16384, 1024), b_h, idesc_dx, 1);
+                        umma_bf16(d_dx, a_h, desc_adv(dyk_l, bo), idesc_dx, 1);
+                        umma_bf16(d_dx, desc_adv(dwt_l, ks * 2048u), b_h, idesc_dx, 1);
                     }
                 }
                 umma_commit(&bar_tfull[s]);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {                     // reduction over the 64 rows of the tile
                     const uint32_t acc = (it | ks) ? 1u : 0u;
-                    const uint64_t a_h = make_desc_sw128(sy_hi + ks * 2048u, 8192, 1024), b_h = make_desc_sw128(sx_hi + ks * 2048u, 8192, 1024);
+                    const uint64_t a_h = desc_adv(dym_h, ks * 2048u), b_h = desc_adv(dxm_h, ks * 2048u);
                     umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
                     if (NSPLIT == 3) {
-                        umma_bf16(d_dw, a_h, make_desc_sw128(sx_lo + ks * 2048u, 8192, 1024), idesc_dw, 1);
-                        umma_bf16(d_dw, make_desc_sw128(sy_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
+                        umma_bf16(d_dw, a_h, desc_adv(dxm_l, ks * 2048u), idesc_dw, 1);
+                        umma_bf16(d_dw, desc_adv(dym_l, ks * 2048u), b_h, idesc_dw, 1);
                     }
                 }
                 umma_commit(&bar_empty[s]);
@@ -1777,6 +1782,9 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
             const uint32_t idesc_dw = make_idesc(128, 128, 1, 1);
             const uint32_t sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
             const uint32_t sx_hi = smem_u32(x_hi), sx_lo = sx_hi + kHalf;
+            // base descriptors built once (desc_adv steps through the k-slices): W^T MN-major view, X block MN-major
+            const uint64_t dwt_h = make_desc_sw128(sw_hi, 16384, 1024), dwt_l = make_desc_sw128(sw_lo, 16384, 1024);
+            const uint64_t dxm_h = make_desc_sw128(sx_hi, 8192, 1024), dxm_l = make_desc_sw128(sx_lo, 8192, 1024);
             int li = 0, bi = 0, ti = 0;
             for (int grp = blockIdx.x, gi = 0; grp < p.n_groups; grp += gridDim.x, ++gi) {
                 const int r_begin = grp * p.rows_per_grp, r_end = min(p.M, r_begin + p.rows_per_grp);
@@ -1794,6 +1802,8 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
                         else mbar_wait(&bar_z[j], (uint32_t)(gi * (L - 1) + (L - 2 - l)) & 1u);
                         tc_fence_after();
                         const uint32_t sz_hi = smem_u32(smem_raw + (uint32_t)j * kOp), sz_lo = sz_hi + kHalf;
+                        const uint64_t dzk_h = make_desc_sw128(sz_hi, 16, 1024), dzk_l = make_desc_sw128(sz_lo, 16, 1024);          // K-major (data gradient)
+                        const uint64_t dzm_h = make_desc_sw128(sz_hi, 8192, 1024), dzm_l = make_desc_sw128(sz_lo, 8192, 1024);      // MN-major (weight gradient)
                         if (l > 0 || need_dx) {
                             const int a = ti & 1;
                             mbar_wait(&bar_tempty[a], (uint32_t)((ti >> 1) & 1) ^ 1u);
@@ -1802,11 +1812,11 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks) {
                                 const uint32_t bo = (uint32_t)(ks >> 2) * 8192u + (uint32_t)(ks & 3) * 32u;
-                                const uint64_t a_h = make_desc_sw128(sw_hi + ks * 2048u, 16384, 1024), b_h = make_desc_sw128(sz_hi + bo, 16, 1024);
+                                const uint64_t a_h = desc_adv(dwt_h, ks * 2048u), b_h = desc_adv(dzk_h, bo);
                                 umma_bf16(d_dx, a_h, b_h, idesc_dx, ks ? 1u : 0u);
                                 if (NSPLIT == 3) {
-                                    umma_bf16(d_dx, a_h, make_desc_sw128(sz_lo + bo, 16, 1024), idesc_dx, 1);
-                                    umma_bf16(d_dx, make_desc_sw128(sw_lo + ks * 2048u, 16384, 1024), b_h, idesc_dx, 1);
+                                    umma_bf16(d_dx, a_h, desc_adv(dzk_l, bo), idesc_dx, 1);
+                                    umma_bf16(d_dx, desc_adv(dwt_l, ks * 2048u), b_h, idesc_dx, 1);
                                 }
                             }
                             umma_commit(&bar_tfull[a]);
@@ -1815,11 +1825,11 @@ __global__ void __launch_bounds__(kFbThreads, 1) mlp_chain_bwd_kernel(ChainBwdPa
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t acc = (j | ks) ? 1u : 0u;
-                            const uint64_t a_h = make_desc_sw128(sz_hi + ks * 2048u, 8192, 1024), b_h = make_desc_sw128(sx_hi + ks * 2048u, 8192, 1024);
+                            const uint64_t a_h = desc_adv(dzm_h, ks * 2048u), b_h = desc_adv(dxm_h, ks * 2048u);
                             umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
                             if (NSPLIT == 3) {
-                                umma_bf16(d_dw, a_h, make_desc_sw128(sx_lo + ks * 2048u, 8192, 1024), idesc_dw, 1);
-                                umma_bf16(d_dw, make_desc_sw128(sz_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
+                                umma_bf16(d_dw, a_h, desc_adv(dxm_l, ks * 2048u), idesc_dw, 1);
+                                umma_bf16(d_dw, desc_adv(dzm_l, ks * 2048u), b_h, idesc_dw, 1);
                             }
                         }
                         umma_commit(&bar_dwdone);

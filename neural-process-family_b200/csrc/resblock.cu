@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, 128, 0, 0);
-            const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+            const uint64_t da_h = rb_desc_sw128(smem_u32(a_hi), 16, 1024), da_l = rb_desc_sw128(smem_u32(a_lo), 16, 1024);
+            const uint64_t db_h = rb_desc_sw128(smem_u32(b_hi), 16, 1024), db_l = rb_desc_sw128(smem_u32(b_lo), 16, 1024);
             int it = 0;
             for (int g = g0; g < g1; ++g, ++it) {
                 const int t = it & 1;
@@ -200,10 +201,10 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock1d_fwd_kernel(RbFwdPara
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint32_t ao = (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u;
-                    const uint64_t a_h = rb_desc_sw128(sa_hi + ao, 16, 1024), b_h = rb_desc_sw128(sb_hi + ao, 16, 1024);
+                    const uint64_t a_h = desc_adv(da_h, ao), b_h = desc_adv(db_h, ao);
                     umma_bf16(d, a_h, b_h, idesc, ks ? 1u : 0u);
-                    umma_bf16(d, a_h, rb_desc_sw128(sb_lo + ao, 16, 1024), idesc, 1);
-                    umma_bf16(d, rb_desc_sw128(sa_lo + ao, 16, 1024), b_h, idesc, 1);
+                    umma_bf16(d, a_h, desc_adv(db_l, ao), idesc, 1);
+                    umma_bf16(d, desc_adv(da_l, ao), b_h, idesc, 1);
                 }
                 umma_commit(&bar_aempty);
                 umma_commit(&bar_tfull[t]);
@@ -492,6 +493,11 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
             const uint32_t idesc_dw = make_idesc(128, 128, 1, 1);     // A = dY^T, B = O: MN-major views (reduction over the tile's rows)
             const uint32_t sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
             const uint32_t sy_hi = smem_u32(y_hi), sy_lo = sy_hi + kRwHalf, so_hi = smem_u32(o_hi), so_lo = so_hi + kRwHalf;
+            // base descriptors, built once: W^T (MN-major view), dY K-major (data gradient), dY^T / O MN-major (weight gradient)
+            const uint64_t dw_h = rb_desc_sw128(sw_hi, 16384, 1024), dw_l = rb_desc_sw128(sw_lo, 16384, 1024);
+            const uint64_t dyk_h = rb_desc_sw128(sy_hi, 16, 1024), dyk_l = rb_desc_sw128(sy_lo, 16, 1024);
+            const uint64_t dym_h = rb_desc_sw128(sy_hi, 8192, 1024), dym_l = rb_desc_sw128(sy_lo, 8192, 1024);
+            const uint64_t dom_h = rb_desc_sw128(so_hi, 8192, 1024), dom_l = rb_desc_sw128(so_lo, 8192, 1024);
             const uint32_t d_dw = tmem + 128u;
             int it = 0;
             for (int g = g0; g < g1; ++g, ++it) {
@@ -506,19 +512,19 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint32_t bo = (uint32_t)(ks >> 2) * 8192u + (uint32_t)(ks & 3) * 32u;
-                    const uint64_t a_h = rb_desc_sw128(sw_hi + ks * 2048u, 16384, 1024), b_h = rb_desc_sw128(sy_hi + bo, 16, 1024);
+                    const uint64_t a_h = desc_adv(dw_h, ks * 2048u), b_h = desc_adv(dyk_h, bo);
                     umma_bf16(d_dx, a_h, b_h, idesc_dx, ks ? 1u : 0u);
-                    umma_bf16(d_dx, a_h, rb_desc_sw128(sy_lo + bo, 16, 1024), idesc_dx, 1);
-                    umma_bf16(d_dx, rb_desc_sw128(sw_lo + ks * 2048u, 16384, 1024), b_h, idesc_dx, 1);
+                    umma_bf16(d_dx, a_h, desc_adv(dyk_l, bo), idesc_dx, 1);
+                    umma_bf16(d_dx, desc_adv(dw_l, ks * 2048u), b_h, idesc_dx, 1);
                 }
                 umma_commit(&bar_tfull[a]);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t acc = (it | ks) ? 1u : 0u;
-                    const uint64_t a_h = rb_desc_sw128(sy_hi + ks * 2048u, 8192, 1024), b_h = rb_desc_sw128(so_hi + ks * 2048u, 8192, 1024);
+                    const uint64_t a_h = desc_adv(dym_h, ks * 2048u), b_h = desc_adv(dom_h, ks * 2048u);
                     umma_bf16(d_dw, a_h, b_h, idesc_dw, acc);
-                    umma_bf16(d_dw, a_h, rb_desc_sw128(so_lo + ks * 2048u, 8192, 1024), idesc_dw, 1);
-                    umma_bf16(d_dw, rb_desc_sw128(sy_lo + ks * 2048u, 8192, 1024), b_h, idesc_dw, 1);
+                    umma_bf16(d_dw, a_h, desc_adv(dom_l, ks * 2048u), idesc_dw, 1);
+                    umma_bf16(d_dw, desc_adv(dym_l, ks * 2048u), b_h, idesc_dw, 1);
                 }
                 umma_commit(&bar_aempty);
                 trace_ev(p.trace, 1, 4);

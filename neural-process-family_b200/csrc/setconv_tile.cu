@@ -841,12 +841,14 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) setconv_tc_fwd_kernel(cons
                     mbar_wait(&bar_wfull[s], par);
                     tc_fence_after();
                     const uint32_t sw_hi = smem_u32(smem_raw + s * kStage), sw_lo = sw_hi + kWTile, sv_hi = sw_hi + 2 * kWTile, sv_lo = sv_hi + kVTile;
+                    const uint64_t de_h = make_desc_sw128_t(sw_hi, 16, 1024), de_l = make_desc_sw128_t(sw_lo, 16, 1024);
+                    const uint64_t dv_h = make_desc_sw128_t(sv_hi, 8192, 1024), dv_l = make_desc_sw128_t(sv_lo, 8192, 1024);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t a_h = make_desc_sw128_t(sw_hi + ks * 32u, 16, 1024), b_h = make_desc_sw128_t(sv_hi + ks * 2048u, 8192, 1024);
+                        const uint64_t a_h = desc_adv(de_h, ks * 32u), b_h = desc_adv(dv_h, ks * 2048u);
                         umma_bf16(d, a_h, b_h, idesc, (c | ks) ? 1u : 0u);
-                        umma_bf16(d, a_h, make_desc_sw128_t(sv_lo + ks * 2048u, 8192, 1024), idesc, 1);
-                        umma_bf16(d, make_desc_sw128_t(sw_lo + ks * 32u, 16, 1024), b_h, idesc, 1);
+                        umma_bf16(d, a_h, desc_adv(dv_l, ks * 2048u), idesc, 1);
+                        umma_bf16(d, desc_adv(de_l, ks * 32u), b_h, idesc, 1);
                     }
                     umma_commit(&bar_empty[s]);
                 }
@@ -1134,11 +1136,14 @@ __global__ void __launch_bounds__(kBwThreads, 1) setconv_tc_bwd_kernel(const flo
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + (uint32_t)s * kBwStage);
                     const uint32_t f_hi = sf + (uint32_t)c * kBwImg, f_lo = f_hi + 2 * kBwImg;
+                    const uint64_t db_h = make_desc_sw128_t(f_hi, 8192, 1024), db_l = make_desc_sw128_t(f_lo, 8192, 1024);
+                    const uint64_t dp_h = make_desc_sw128_t(sa, 16, 1024), dp_l = make_desc_sw128_t(sa + kBwImg, 16, 1024);
+                    const uint64_t de_h = make_desc_sw128_t(sa + 2 * kBwImg, 16, 1024), de_l = make_desc_sw128_t(sa + 3 * kBwImg, 16, 1024);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t b_h = make_desc_sw128_t(f_hi + ks * 2048u, 8192, 1024), b_l = make_desc_sw128_t(f_lo + ks * 2048u, 8192, 1024);
-                        const uint64_t p_h = make_desc_sw128_t(sa + ks * 32u, 16, 1024), p_l = make_desc_sw128_t(sa + kBwImg + ks * 32u, 16, 1024);
-                        const uint64_t e_h = make_desc_sw128_t(sa + 2 * kBwImg + ks * 32u, 16, 1024), e_l = make_desc_sw128_t(sa + 3 * kBwImg + ks * 32u, 16, 1024);
+                        const uint64_t b_h = desc_adv(db_h, ks * 2048u), b_l = desc_adv(db_l, ks * 2048u);
+                        const uint64_t p_h = desc_adv(dp_h, ks * 32u), p_l = desc_adv(dp_l, ks * 32u);
+                        const uint64_t e_h = desc_adv(de_h, ks * 32u), e_l = desc_adv(de_l, ks * 32u);
                         const uint32_t acc = (c | ks) ? 1u : 0u;
                         umma_bf16(d_v, p_h, b_h, idesc, acc);
                         umma_bf16(d_v, p_h, b_l, idesc, 1);

@@ -89,6 +89,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// A descriptor whose start address is `bytes` further on (bytes % 16 == 0; the 14-bit address field cannot overflow: shared memory is
+// < 256 KB).  The MMA loops build each operand's base descriptor ONCE and step through the k-slices with this single add: the
+// issuing thread is one lane competing with 24 other warps for issue slots, and re-deriving every descriptor (mask, shift, three ORs
+// in 64 bit) cost it more than the tensor core needed for the MMA.
+__device__ __forceinline__ uint64_t desc_adv(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
 // Instruction descriptor, kind::f16: c_format f32 (1 @ bit 4), a/b format bf16 (1 @ bits 7, 10), a_major @ 15,
 // b_major @ 16 (1 = MN-major), N >> 3 @ bits [17,23), M >> 4 @ bits [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
