@@ -2,7 +2,7 @@
 test log-likelihood per task next to the published number.  The weights travel with the repo as
 the ``state_dict`` of the golden fixtures (tests/golden/*_pretrained.pt, written from results/pretrained/RBF_Kernel/*).
 
-NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent): first GPU call of the next round.
+Run on a B200 in round 2 (profiles/r2/eval_pretrained_r2c1.jsonl).
     python examples/eval_pretrained.py [n_tasks]
 The context size is cycled through 0..50 (the expectation of upstream's per-batch draw without its variance: upstream's
 own mean is over 156 batches that share one drawn size each, s.e. ~22 for ConvCNP); quantiles are printed as well."""
@@ -14,10 +14,9 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [os.path.join(ROOT, "neural-process-family_b200"), os.path.join(ROOT, "tests")]
+sys.path[:0] = [os.path.join(ROOT, "neural-process-family_b200")]
 import npf_b200  # noqa: E402
-from _cfg import build_model, loss_for  # noqa: E402
-from _util import load_fixture  # noqa: E402
+from npf_b200.utils.configs import build_model, loss_for  # noqa: E402
 from npf_b200.utils import datasplit as ds  # noqa: E402
 from npf_b200.utils.gp import GPSampler  # noqa: E402
 
@@ -35,7 +34,7 @@ def main(n_tasks=10200, batch=50):
     sampler = GPSampler(dict(kind="rbf", length_scale=0.2), min_max=(-2, 2), n_points=128, n_same_samples=20)
     X, Y = sampler.get_samples(n_tasks)
     for name, (loss_name, published) in PUBLISHED.items():
-        fx = load_fixture(name)
+        fx = torch.load(os.path.join(ROOT, "tests", "golden", name + ".pt"), map_location="cpu", weights_only=False)   # cfg + upstream weights (data only)
         model = build_model(fx["cfg"])
         model.load_state_dict(fx["state_dict"])
         model.cuda().eval()
