@@ -67,6 +67,21 @@ class P2PAllReduce:
         self.out = torch.as_tensor(_DevMem(mine[1], n, "<f4"), device=device)
         dist.barrier(group=group)                                          # every rank has opened every handle before the first launch
 
+    def close(self):
+        """Unmap the peers' allocations and free this rank's (collective: every rank calls it; nobody may still be inside an all-reduce)."""
+        from . import _cabi
+        if self._mine is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for ptr in self._opened:
+            _cabi.call("npf_p2p_close", ptr)
+        dist.barrier(group=self.group)                  # every peer has unmapped before the owner frees
+        self.bucket = self.out = None
+        for ptr in self._mine:
+            _cabi.call("npf_p2p_free", ptr)
+        self._mine, self._opened = None, []
+
     def reduce_(self):
         from . import _cabi
         if self.two_shot:
@@ -119,10 +134,15 @@ class FlatGradients:
         self._grad_ptrs = [base + 4 * off for off in self.offsets]
 
     def detach(self):
-        """Give the parameters back to plain autograd accumulation (drops the views into the bucket)."""
+        """Give the parameters back to plain autograd accumulation (drops the views into the bucket) and release the peer-memory
+        all-reduce, if any (collective on more than one rank)."""
         for p in self.params:
             p._npf_direct_grad = False
             p.grad = None
+        if self.p2p is not None:
+            self.flat = None
+            self.p2p.close()
+            self.p2p = None
 
     def zero_(self):
         """Zero the bucket (one memset) and re-attach the views if anything dropped or replaced one of them
