@@ -579,11 +579,14 @@ __global__ void __launch_bounds__(kRwThreads, 1) resblock1d_bwd_kernel(RbBwdPara
                     }
                     const int t = i - P;                          // this X row is interior row t: its data gradient
                     if (t >= 0 && t < 12) {
-                        float conv = 0.f;
+                        float conv0 = 0.f, conv1 = 0.f, conv2 = 0.f;     // three partial sums: a third of the dependent-FMA chain
 #pragma unroll
-                        for (int j = 0; j < KW; ++j) conv = fmaf(wk[j], d[4 * sp + 2 * P + t - j], conv);
+                        for (int j = 0; j < KW; ++j) {
+                            const float dv = d[4 * sp + 2 * P + t - j];
+                            if (j % 3 == 0) conv0 = fmaf(wk[j], dv, conv0); else if (j % 3 == 1) conv1 = fmaf(wk[j], dv, conv1); else conv2 = fmaf(wk[j], dv, conv2);
+                        }
                         dbacc += d[4 * sp + P + t];
-                        if (l0 + c + t < p.L) dxp[(long)t * 128] = d[4 * sp + P + t] + (x > 0.f ? conv : 0.f);
+                        if (l0 + c + t < p.L) dxp[(long)t * 128] = d[4 * sp + P + t] + (x > 0.f ? (conv0 + conv1) + conv2 : 0.f);
                     }
                 }
             }
