@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..utils.helpers import make_depth_sep_conv
+from ..utils.helpers import conv_padding, make_depth_sep_conv
 
 __all__ = ["ResConvBlock", "CNN"]
 
@@ -19,7 +19,20 @@ __all__ = ["ResConvBlock", "CNN"]
 def _check_conv(conv, what):
     if not isinstance(conv, (nn.Conv1d, nn.Conv2d)) or conv.padding_mode != "zeros" or any(s != 1 for s in conv.stride) \
             or any(d != 1 for d in conv.dilation):
-        raise NotImplementedError(f"npf_b200: {what} must be a plain zero-padded, stride-1 nn.Conv1d / nn.Conv2d")
+        raise NotImplementedError(f"npf_b200: {what} must be a stride-1 nn.Conv1d / nn.Conv2d, zero-padded or wrapped by "
+                                  "make_padded_conv(Conv, CircularPad2d)")
+    conv_padding(conv)   # 'same' padding, zero or circular
+
+
+def _depthwise(x, conv, res, sc, sh):
+    """relu(sc * x + sh) -> depthwise conv (+ res).  With a circular padder (upstream helpers.py:334-351, 406-414) the
+    signal is extended by wrap-around, run through the same zero-padded kernel and cropped: on the original grid every tap
+    then reads a wrapped sample, never the kernel's own zero padding."""
+    padder, p = conv_padding(conv)
+    if padder is None:
+        return ops.dwconv(x, conv.weight, conv.bias, res, True, sc, sh)
+    y = ops.dwconv(padder(x).contiguous(), conv.weight, conv.bias, None, True, sc, sh)[:, p:-p, p:-p, :]
+    return y + res if res is not None else y.contiguous()
 
 
 class _PreNorm:
@@ -99,16 +112,17 @@ class ResConvBlock(nn.Module):
         """X channel-last: [B, L, C] or [B, H, W, C]."""
         h = X
         if self.n_conv_layers == 1 and isinstance(self.norm2, nn.Identity) and self.conv2_depthwise.bias is not None \
+                and getattr(self.conv2_depthwise, "padder", None) is None \
                 and self.conv2_pointwise.bias is not None and ops.resblock1d_supported(X, self.conv2_depthwise.weight, self.conv2_pointwise.weight) \
                 and self.conv2_depthwise.weight.is_contiguous() and self.conv2_pointwise.weight.is_contiguous():
             # the ConvCNP default block: one kernel (depthwise out of a TMA-staged raw tile, pointwise on the tensor core)
             return ops.resblock1d(X, self.conv2_depthwise.weight, self.conv2_depthwise.bias, self.conv2_pointwise.weight, self.conv2_pointwise.bias)
         if self.n_conv_layers == 2:
             sc, sh = _PreNorm.affine(self.norm1, X)
-            h = ops.dwconv(X, self.conv1.depthwise.weight, self.conv1.depthwise.bias, None, True, sc, sh)
+            h = _depthwise(X, self.conv1.depthwise, None, sc, sh)
             h = self._pointwise(h, self.conv1.pointwise)
         sc, sh = _PreNorm.affine(self.norm2, h)
-        h = ops.dwconv(h, self.conv2_depthwise.weight, self.conv2_depthwise.bias, X, True, sc, sh)
+        h = _depthwise(h, self.conv2_depthwise, X, sc, sh)
         return self._pointwise(h, self.conv2_pointwise)
 
 

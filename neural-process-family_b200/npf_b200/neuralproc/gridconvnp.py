@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..architectures import CNN, ResConvBlock
-from ..utils.helpers import make_abs_conv
+from ..utils.helpers import conv_padding, make_abs_conv
 from .base import LatentNeuralProcessFamily, NeuralProcessFamily
 from .convnp import ConvCNP, ConvLNP
 from .helpers import collapse_z_samples_batch
@@ -39,11 +39,11 @@ class GridConvCNP(NeuralProcessFamily):
         self.conv = Conv(y_dim)
         c = self.conv
         ok = (isinstance(c, nn.Conv2d) and getattr(c, "_npf_abs", False) and c.groups == y_dim and c.bias is None
-              and c.kernel_size[0] == c.kernel_size[1] and c.padding[0] == c.kernel_size[0] // 2
-              and c.padding_mode == "zeros")
+              and c.kernel_size[0] == c.kernel_size[1] and c.padding_mode == "zeros")
         if not ok:
-            raise NotImplementedError("npf_b200.GridConvCNP: `Conv` must be a zero-padded, bias-free depthwise "
-                                      "`make_abs_conv(nn.Conv2d)` (the upstream default)")
+            raise NotImplementedError("npf_b200.GridConvCNP: `Conv` must be a bias-free depthwise `make_abs_conv(nn.Conv2d)` "
+                                      "(the upstream default), zero-padded or wrapped by make_padded_conv(.., CircularPad2d)")
+        conv_padding(c)
         self.resizer = nn.Linear(self.y_dim * 2, self.r_dim)  # signal + confidence channels
         self.induced_to_induced = CNN(self.r_dim)
 
@@ -51,7 +51,11 @@ class GridConvCNP(NeuralProcessFamily):
 
     def cntxt_to_induced(self, mask_cntxt, X):
         """[signal / max(density, 1e-5) ; density] of the masked image under the |w| filter, resized to r_dim."""
-        feat = ops.gridconv_in(X, mask_cntxt, self.conv.weight)
+        padder, p = conv_padding(self.conv)
+        if padder is None:
+            feat = ops.gridconv_in(X, mask_cntxt, self.conv.weight)
+        else:   # wrap-around first layer of `model_2d_extrap`: extend image and mask, same kernel, crop
+            feat = ops.gridconv_in(padder(X).contiguous(), padder(mask_cntxt).contiguous(), self.conv.weight)[:, p:-p, p:-p, :].contiguous()
         return ops.linear(feat, self.resizer.weight, self.resizer.bias)
 
     def encode_globally(self, mask_cntxt, X):

@@ -7,6 +7,7 @@ import torch.nn as nn
 
 from .. import CNP, LNP, AttnCNP, AttnLNP, ConvCNP, ConvLNP, GridConvCNP, GridConvLNP, CNPFLoss, ELBOLossLNPF, NLLLossLNPF
 from ..architectures import CNN, MLP, ResConvBlock, SetConv, discard_ith_arg, merge_flat_input
+from .helpers import CircularPad2d, make_abs_conv, make_padded_conv
 
 __all__ = ["build_model", "loss_for"]
 
@@ -36,6 +37,12 @@ def build_model(cfg):
         c = cfg["cnn"]
         Conv = nn.Conv1d if c["dim"] == 1 else nn.Conv2d
         Norm = {None: nn.Identity, "bn": nn.BatchNorm1d if c["dim"] == 1 else nn.BatchNorm2d}[c.get("norm")]
+        if "bn_eps" in c:
+            Norm = partial(Norm, eps=c["bn_eps"])
+        if cfg.get("circular"):  # `model_2d_extrap` of ConvCNP.ipynb / ConvLNP.ipynb: wrap-around padding everywhere
+            Conv = make_padded_conv(Conv, CircularPad2d)
+            kw["Conv"] = lambda y_dim: make_padded_conv(make_abs_conv(nn.Conv2d), CircularPad2d)(
+                y_dim, y_dim, groups=y_dim, kernel_size=11, padding=11 // 2, bias=False)
         kw["CNN"] = partial(CNN, ConvBlock=ResConvBlock, Conv=Conv, Normalization=Norm, n_blocks=c["n_blocks"],
                             kernel_size=c["kernel_size"], is_chan_last=True, n_conv_layers=c["n_conv_layers"])
     for k in ("density_induced", "attention", "n_z_samples_train", "n_z_samples_test", "is_global", "encoded_path",

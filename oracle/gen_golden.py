@@ -89,6 +89,13 @@ def build(cfg):
         c = cfg["cnn"]
         Conv = nn.Conv1d if c["dim"] == 1 else nn.Conv2d
         Norm = {None: nn.Identity, "bn": nn.BatchNorm1d if c["dim"] == 1 else nn.BatchNorm2d}[c.get("norm")]
+        if "bn_eps" in c:
+            Norm = partial(Norm, eps=c["bn_eps"])
+        if cfg.get("circular"):  # `model_2d_extrap` of ConvCNP.ipynb / ConvLNP.ipynb: wrap-around padding everywhere
+            from npf.utils.helpers import CircularPad2d, make_abs_conv, make_padded_conv
+            Conv = make_padded_conv(Conv, CircularPad2d)
+            kw["Conv"] = lambda y_dim: make_padded_conv(make_abs_conv(nn.Conv2d), CircularPad2d)(
+                y_dim, y_dim, groups=y_dim, kernel_size=11, padding=11 // 2, bias=False)
         kw["CNN"] = partial(CNN, ConvBlock=ResConvBlock, Conv=Conv, Normalization=Norm, n_blocks=c["n_blocks"],
                             kernel_size=c["kernel_size"], is_chan_last=True, n_conv_layers=c["n_conv_layers"])
     for k in ("density_induced", "attention", "n_z_samples_train", "n_z_samples_test", "is_global", "encoded_path",
@@ -429,13 +436,43 @@ def _xy2(B, C, T, y_dim, seed, unit=False):
                 Y_trgt=y[:, C:].contiguous())
 
 
+def main_circular():
+    """`model_2d_extrap` (wrap-around padding, upstream helpers.py:334-351, 406-414) with the upstream zsmms checkpoints, and the
+    12-block `model_2d_XL` celeba128 checkpoint:  python oracle/gen_golden.py circular"""
+    os.makedirs(OUT, exist_ok=True)
+    cnn = dict(dim=2, norm="bn", bn_eps=1e-2, n_blocks=5, kernel_size=9, n_conv_layers=2)
+    cfg = dict(family="GridConvCNP", x_dim=1, y_dim=1, notebook=True, circular=True, pretrained="zsmms/ConvCNP", cnn=cnn)
+    m = build(cfg)
+    dump("gridconvcnp_extrap_pretrained", cfg, m, [
+        run_case(m, cfg, "eval_b2_40x40", False, grid_inputs(2, 40, 40, 1, 0.2, 70), "cnpf", False),
+        run_case(m, cfg, "train_b2_28x20", True, grid_inputs(2, 28, 20, 1, 0.3, 71), "cnpf", True),
+    ])
+    cfg = dict(family="GridConvLNP", x_dim=1, y_dim=1, notebook=True, circular=True, is_global=False, pretrained="zsmms/ConvLNP",
+               n_z_samples_train=3, n_z_samples_test=2, cnn=dict(cnn, n_blocks=4))
+    m = build(cfg)
+    dump("gridconvlnp_extrap_pretrained", cfg, m, [
+        run_case(m, cfg, "train_b2_24x24_nz3", True, grid_inputs(2, 24, 24, 1, 0.3, 72), "nll", True, eps_seed=720),
+        run_case(m, cfg, "eval_b1_32x32_nz2", False, grid_inputs(1, 32, 32, 1, 0.1, 73), "nll", False, eps_seed=730),
+    ])
+    cfg = dict(family="GridConvCNP", x_dim=1, y_dim=3, notebook=True, pretrained="celeba128/ConvCNPXL",
+               cnn=dict(dim=2, norm="bn", n_blocks=12, kernel_size=9, n_conv_layers=2))
+    m = build(cfg)
+    dump("gridconvcnp_xl_pretrained", cfg, m, [
+        run_case(m, cfg, "eval_b1_48x48", False, grid_inputs(1, 48, 48, 3, 0.15, 74), "cnpf", False),
+        run_case(m, cfg, "train_b2_24x24", True, grid_inputs(2, 24, 24, 3, 0.3, 75), "cnpf", True),
+    ])
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["attn"]:
         main_attn_family()
+    elif sys.argv[1:] == ["circular"]:
+        main_circular()
     elif sys.argv[1:] == ["baseline"]:
         main_baseline_shapes()
     else:
         main()
         main_attn_family()
         main_baseline_shapes()
+        main_circular()
     os.system(f"du -sh {OUT}")

@@ -122,16 +122,18 @@ def _norm(sd, prefix, X, training, bn_eps=1e-5):
     )
 
 
-def _conv(sd, prefix, X, groups):
+def _conv(sd, prefix, X, groups, circular=False):
     w = sd[prefix + "weight"]
     b = sd.get(prefix + "bias")
     pad = w.shape[-1] // 2
+    if circular and pad > 0:  # make_padded_conv(Conv, CircularPad2d), npf/utils/helpers.py:334-351, 406-414
+        return F.conv2d(F.pad(X, (pad,) * 4, mode="circular"), w, b, padding=0, groups=groups)
     if w.dim() == 3:
         return F.conv1d(X, w, b, padding=pad, groups=groups)
     return F.conv2d(X, w, b, padding=pad, groups=groups)
 
 
-def res_conv_cnn(sd, prefix, X, training=True):
+def res_conv_cnn(sd, prefix, X, training=True, circular=False, bn_eps=1e-5):
     """CNN.forward (is_chan_last=True) over ResConvBlocks, npf/architectures/cnn.py:363-380, 204-215;
     depth-separable conv of npf/utils/helpers.py:354-403.
 
@@ -146,11 +148,11 @@ def res_conv_cnn(sd, prefix, X, training=True):
     while (prefix + f"conv_blocks.{i}.conv2_depthwise.weight") in sd:
         p = prefix + f"conv_blocks.{i}."
         if (p + "conv1.depthwise.weight") in sd:
-            h = _conv(sd, p + "conv1.depthwise.", torch.relu(_norm(sd, p + "norm1.", X, training)), C)
+            h = _conv(sd, p + "conv1.depthwise.", torch.relu(_norm(sd, p + "norm1.", X, training, bn_eps)), C, circular)
             h = _conv(sd, p + "conv1.pointwise.", h, 1)
         else:
             h = X
-        h = _conv(sd, p + "conv2_depthwise.", torch.relu(_norm(sd, p + "norm2.", h, training)), C)
+        h = _conv(sd, p + "conv2_depthwise.", torch.relu(_norm(sd, p + "norm2.", h, training, bn_eps)), C, circular)
         h = h + X
         X = _conv(sd, p + "conv2_pointwise.", h.contiguous(), 1)
         i += 1
@@ -305,7 +307,7 @@ def convcnp_forward(sd, X_cntxt, Y_cntxt, X_trgt, X_induced=None, training=True)
     return _decode(sd, X_trgt, R_trgt.unsqueeze(0), y_dim)
 
 
-def _grid_cntxt_to_induced(sd, mask_cntxt, Y):
+def _grid_cntxt_to_induced(sd, mask_cntxt, Y, circular=False):
     """GridConvCNP.cntxt_to_induced, npf/neuralproc/gridconvnp.py:136-162; abs-weight depthwise conv
     of npf/utils/helpers.py:316-331 (no bias, one filter per y channel)."""
     X = Y.permute(0, 3, 1, 2)
@@ -313,17 +315,23 @@ def _grid_cntxt_to_induced(sd, mask_cntxt, Y):
     w = sd["conv.weight"].abs()
     y_dim = X.shape[1]
     pad = w.shape[-1] // 2
-    signal = F.conv2d(X * m, w, None, padding=pad, groups=y_dim)
-    density = F.conv2d(m.expand_as(X), w, None, padding=pad, groups=y_dim)
+    if circular:  # the padded first layer of `model_2d_extrap` (helpers.py:334-351): wrap-around, then an unpadded conv
+        wrap = lambda t: F.pad(t, (pad,) * 4, mode="circular")
+        signal = F.conv2d(wrap(X * m), w, None, padding=0, groups=y_dim)
+        density = F.conv2d(wrap(m.expand_as(X)), w, None, padding=0, groups=y_dim)
+    else:
+        signal = F.conv2d(X * m, w, None, padding=pad, groups=y_dim)
+        density = F.conv2d(m.expand_as(X), w, None, padding=pad, groups=y_dim)
     out = signal / torch.clamp(density, min=1e-5)
     out = torch.cat([out, density], dim=1).permute(0, 2, 3, 1)
     return _lin(sd, "resizer.", out)
 
 
-def gridconvcnp_forward(sd, mask_cntxt, Y, mask_trgt=None, training=True):
-    """GridConvCNP, npf/neuralproc/gridconvnp.py:136-175.  mask_cntxt bool [B,H,W,1], Y [B,H,W,y]."""
+def gridconvcnp_forward(sd, mask_cntxt, Y, mask_trgt=None, training=True, circular=False, bn_eps=1e-5):
+    """GridConvCNP, npf/neuralproc/gridconvnp.py:136-175.  mask_cntxt bool [B,H,W,1], Y [B,H,W,y].  ``circular``: every
+    convolution wraps around (`model_2d_extrap` of the notebooks)."""
     y_dim = Y.shape[-1]
-    R = res_conv_cnn(sd, "induced_to_induced.", _grid_cntxt_to_induced(sd, mask_cntxt, Y), training)
+    R = res_conv_cnn(sd, "induced_to_induced.", _grid_cntxt_to_induced(sd, mask_cntxt, Y, circular), training, circular, bn_eps)
     return _decode(sd, None, R.unsqueeze(0), y_dim)
 
 
@@ -437,11 +445,11 @@ def convlnp_forward(sd, X_cntxt, Y_cntxt, X_trgt, eps, X_induced=None, is_global
     return loc, scale, z, q_loc, q_scale
 
 
-def gridconvlnp_forward(sd, mask_cntxt, Y, eps, is_global=False, training=True):
+def gridconvlnp_forward(sd, mask_cntxt, Y, eps, is_global=False, training=True, circular=False, bn_eps=1e-5):
     """GridConvLNP (encoded_path="latent"), npf/neuralproc/gridconvnp.py:244-289: latent per pixel,
     (global pooling BEFORE the post-sampling CNN), CNN on the (n_z*B) collapsed batch."""
     y_dim = Y.shape[-1]
-    R = res_conv_cnn(sd, "induced_to_induced.", _grid_cntxt_to_induced(sd, mask_cntxt, Y), training)
+    R = res_conv_cnn(sd, "induced_to_induced.", _grid_cntxt_to_induced(sd, mask_cntxt, Y, circular), training, circular, bn_eps)
     z_dim = sd["latent_encoder.out.weight"].shape[0] // 2
     q_loc, q_scale = _latent_dist(sd, R, z_dim)
     z = q_loc.unsqueeze(0) + q_scale.unsqueeze(0) * eps  # [n_z,B,H,W,z]
@@ -451,7 +459,7 @@ def gridconvlnp_forward(sd, mask_cntxt, Y, eps, is_global=False, training=True):
         zc = _add_global_latent(zc)
     if "reshaper_z.weight" in sd:
         zc = _lin(sd, "reshaper_z.", zc)
-    R_trgt = res_conv_cnn(sd, "induced_to_induced_post_sampling.", zc, training)
+    R_trgt = res_conv_cnn(sd, "induced_to_induced_post_sampling.", zc, training, circular, bn_eps)
     R_trgt = R_trgt.view(n_z, B, *R_trgt.shape[1:])
     loc, scale = _decode(sd, None, R_trgt, y_dim)
     return loc, scale, z, q_loc, q_scale

@@ -83,7 +83,7 @@ def oracle_run(cfg, state_dict, case, dtype=torch.float32, with_grads=False):
         Xi = _induced(cfg, case, dtype)
         loc, scale = O.convcnp_forward(sd, Xc, Yc, Xt, X_induced=Xi, training=training)
     elif fam == "GridConvCNP":
-        loc, scale = O.gridconvcnp_forward(sd, Xc, Yc, Xt, training=training)
+        loc, scale = O.gridconvcnp_forward(sd, Xc, Yc, Xt, training=training, **_conv_opts(cfg))
     elif fam == "LNP":
         eps = cast(case["eps"])
         if cfg.get("is_q_zCct") and training:
@@ -100,7 +100,7 @@ def oracle_run(cfg, state_dict, case, dtype=torch.float32, with_grads=False):
         extra.update(q_loc=q_loc, q_scale=q_scale)
     elif fam == "GridConvLNP":
         loc, scale, z, q_loc, q_scale = O.gridconvlnp_forward(
-            sd, Xc, Yc, cast(case["eps"]), is_global=cfg.get("is_global", False), training=training)
+            sd, Xc, Yc, cast(case["eps"]), is_global=cfg.get("is_global", False), training=training, **_conv_opts(cfg))
         extra.update(q_loc=q_loc, q_scale=q_scale)
     else:
         raise ValueError(fam)
@@ -120,6 +120,10 @@ def oracle_run(cfg, state_dict, case, dtype=torch.float32, with_grads=False):
         loss.backward()
         out["grads"] = {k: v.grad.detach() for k, v in sd.items() if v.is_floating_point() and v.grad is not None}
     return out
+
+
+def _conv_opts(cfg):
+    return dict(circular=bool(cfg.get("circular", False)), bn_eps=cfg.get("cnn", {}).get("bn_eps", 1e-5))
 
 
 def _induced(cfg, case, dtype):

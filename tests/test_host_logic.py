@@ -228,3 +228,59 @@ def test_train_models_signature_layout_and_eval_csv(tmp_path):
     assert len(loaded.history) == 6
     with pytest.raises(FileNotFoundError):
         train_models({"toy": train}, {"Other": Toy}, is_retrain=False, **kw)
+
+
+def test_circular_padding_host_logic(monkeypatch):
+    """`make_padded_conv(Conv, CircularPad2d)` (upstream helpers.py:334-351, 406-414): wrap-around extension -> the zero-padded
+    kernel -> crop must equal a wrap-around convolution.  The CUDA kernels are replaced by torch stand-ins (CPU test of the host logic;
+    the kernels themselves run the `*_extrap_pretrained` fixtures in the gpu tests)."""
+    import torch.nn.functional as F
+    from npf_b200 import ops
+    from npf_b200.architectures import cnn as cnn_mod
+    from npf_b200.utils.helpers import CircularPad2d, conv_padding, make_abs_conv, make_padded_conv
+
+    def to2nd(t):
+        return t.permute(0, 3, 1, 2)
+
+    def fake_dwconv(x, w, b, res, relu_in, sc, sh):
+        h = x if sc is None else x * sc + sh
+        h = torch.relu(h) if relu_in else h
+        y = F.conv2d(to2nd(h), w, b, padding=w.shape[-1] // 2, groups=w.shape[0]).permute(0, 2, 3, 1)
+        return y + res if res is not None else y
+
+    def fake_gridconv_in(img, mask, w):
+        w = w.abs()
+        m = to2nd(mask).to(img.dtype).expand(-1, img.shape[-1], -1, -1)
+        pad = w.shape[-1] // 2
+        sig = F.conv2d(to2nd(img) * m, w, None, padding=pad, groups=w.shape[0])
+        den = F.conv2d(m, w, None, padding=pad, groups=w.shape[0])
+        return torch.cat([sig / den.clamp(min=1e-5), den], 1).permute(0, 2, 3, 1)
+
+    monkeypatch.setattr(ops, "dwconv", fake_dwconv)
+    monkeypatch.setattr(ops, "gridconv_in", fake_gridconv_in)
+    monkeypatch.setattr(ops, "linear", lambda x, w, b: F.linear(x, w, b))
+    torch.manual_seed(0)
+    conv = make_padded_conv(nn.Conv2d, CircularPad2d)(6, 6, 5, padding=2, groups=6)
+    assert conv.padding == (0, 0) and conv_padding(conv)[1] == 2 and isinstance(conv.padder, CircularPad2d)
+    x, res = torch.randn(2, 7, 9, 6), torch.randn(2, 7, 9, 6)
+    sc, sh = torch.rand(6) + 0.5, torch.randn(6)
+    got = cnn_mod._depthwise(x, conv, res, sc, sh)
+    want = F.conv2d(F.pad(to2nd(torch.relu(x * sc + sh)), (2,) * 4, mode="circular"), conv.weight, conv.bias, groups=6).permute(0, 2, 3, 1) + res
+    assert torch.allclose(got, want, atol=1e-5)
+    # pointwise convs built through the same factory carry CircularPad2d(0): plain path
+    assert conv_padding(make_padded_conv(nn.Conv2d, CircularPad2d)(6, 4, 1))[0] is None
+    # Padder=None keeps the zero padding (upstream :339-342)
+    assert make_padded_conv(nn.Conv2d, None)(6, 6, 5, padding=2).padding == (2, 2)
+
+    first = lambda y: make_padded_conv(make_abs_conv(nn.Conv2d), CircularPad2d)(y, y, groups=y, kernel_size=11, padding=5, bias=False)
+    m = npf_b200.GridConvCNP(1, 2, Conv=first)
+    img, mask = torch.rand(2, 12, 14, 2), torch.rand(2, 12, 14, 1) < 0.3
+    got = m.cntxt_to_induced(mask, img)
+    w = m.conv.weight.abs()
+    mm = to2nd(mask).float().expand(-1, 2, -1, -1)
+    wrap = lambda t: F.pad(t, (5,) * 4, mode="circular")
+    sig, den = F.conv2d(wrap(to2nd(img) * mm), w, groups=2), F.conv2d(wrap(mm), w, groups=2)
+    want = F.linear(torch.cat([sig / den.clamp(min=1e-5), den], 1).permute(0, 2, 3, 1), m.resizer.weight, m.resizer.bias)
+    assert torch.allclose(got, want, atol=1e-5)
+    with pytest.raises(NotImplementedError):   # a padder the kernels cannot reproduce
+        npf_b200.architectures.ResConvBlock(4, 4, make_padded_conv(nn.Conv2d, nn.ReflectionPad2d), kernel_size=3)
