@@ -361,6 +361,11 @@ NPF_API int npf_grid_select(const uint8_t* mask, const float* img, float* Xo, fl
  * ------------------------------------------------------------------------------------------------ */
 NPF_API int npf_gp_sample(const float* X, const float* eps, float* Y, float* L, int32_t* rank, int B, int N, int S, int kernel,
                   float length_scale, float periodicity, float noise_level, float tol, npf_stream_t stream);
+/* Same with PER-TASK hyper-parameters (GPDataset(is_vary_kernel_hyp=True), utils/data/gaussian_process.py:206-207, 233-242: every group
+ * of n_same_samples functions is drawn from a kernel whose hyper-parameters were sampled uniformly in their bounds):
+ * hyp [B, 3] device = (length_scale, periodicity, noise_level) of task b; the caller draws them. */
+NPF_API int npf_gp_sample_hyp(const float* X, const float* eps, float* Y, float* L, int32_t* rank, const float* hyp, int B, int N, int S,
+                      int kernel, float tol, npf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Input validation without a host sync  (NeuralProcessFamily._validate_inputs npf/neuralproc/base.py:241-247,

@@ -1012,8 +1012,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused_kernel(TcFused
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
             } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) atomicAdd(d + j, v[j]);
+                atomic_add16(d, v);
             }
         }
     }
@@ -1207,8 +1206,7 @@ __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(TcWgParams p) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(d + j, v[j]);
+                    atomic_add16(d, v);
                 }
             }
         }
@@ -1551,8 +1549,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) linear_bwd_fused64_kernel(TcFus
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
             } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) atomicAdd(d + j, v[j]);
+                atomic_add16(d, v);
             }
         }
     }

@@ -46,7 +46,7 @@ __device__ __forceinline__ float gp_cov(const GpKernel& g, float xi, float xj) {
 // K[:, p] - L[:, :k] L[p, :k]^T; d_i -= L[i, k]^2.
 __global__ void __launch_bounds__(kGpThreads, 1)
 gp_sample_kernel(const float* __restrict__ X, const float* __restrict__ eps, float* __restrict__ Y, float* __restrict__ Lout,
-                 int32_t* __restrict__ rank_out, int N, int S, GpKernel g, float tol) {
+                 int32_t* __restrict__ rank_out, int N, int S, GpKernel g, const float* __restrict__ hyp, float tol) {
     extern __shared__ float gp_smem[];
     float* Lc = gp_smem;                 // [N][N]
     float* xs = Lc + (size_t)N * N;      // [N]
@@ -58,6 +58,11 @@ gp_sample_kernel(const float* __restrict__ X, const float* __restrict__ eps, flo
 
     const int b = blockIdx.x, i = threadIdx.x, lane = i & 31, warp = i >> 5;
     const bool active = i < N;
+    if (hyp) {      // per-task hyper-parameters (upstream `is_vary_kernel_hyp`): (length_scale, periodicity, noise_level) of task b
+        g.length_scale = __ldg(hyp + 3 * (long)b);
+        g.periodicity = __ldg(hyp + 3 * (long)b + 1);
+        g.noise = __ldg(hyp + 3 * (long)b + 2);
+    }
     if (active) xs[i] = X[(long)b * N + i];
     __syncthreads();
     const float xi = active ? xs[i] : 0.f;
@@ -125,12 +130,8 @@ gp_sample_kernel(const float* __restrict__ X, const float* __restrict__ eps, flo
 
 using namespace npf;
 
-extern "C" int npf_gp_sample(const float* X, const float* eps, float* Y, float* L, int32_t* rank, int B, int N, int S, int kernel,
-                             float length_scale, float periodicity, float noise_level, float tol, npf_stream_t stream) {
-    NPF_REQUIRE(B >= 0 && N >= 1 && S >= 0, "npf_gp_sample: bad shape");
-    NPF_REQUIRE(kernel >= 0 && kernel <= 2, "npf_gp_sample: kernel must be 0 (RBF), 1 (Matern-1.5) or 2 (ExpSineSquared)");
-    NPF_REQUIRE(length_scale > 0.f && (kernel != 2 || periodicity > 0.f) && noise_level >= 0.f && tol >= 0.f,
-                "npf_gp_sample: bad hyper-parameter");
+static int gp_launch(const float* X, const float* eps, float* Y, float* L, int32_t* rank, const float* hyp, int B, int N, int S, GpKernel g,
+                     float tol, npf_stream_t stream) {
     if (N > kGpMaxN) {
         set_error("npf_gp_sample: N=%d exceeds the %d points whose factor fits one CTA's shared memory", N, kGpMaxN);
         return NPF_ENOTSUP;
@@ -144,8 +145,24 @@ extern "C" int npf_gp_sample(const float* X, const float* eps, float* Y, float* 
             return check_launch("npf_gp_sample: cudaFuncSetAttribute");
         configured = smem;
     }
-    GpKernel g{kernel, length_scale, periodicity, noise_level};
-    gp_sample_kernel<<<B, kGpThreads, smem, as_stream(stream)>>>(X, eps, Y, L, rank, N, S, g, tol);
+    gp_sample_kernel<<<B, kGpThreads, smem, as_stream(stream)>>>(X, eps, Y, L, rank, N, S, g, hyp, tol);
     count_launch();
     return check_launch("gp_sample_kernel");
+}
+
+extern "C" int npf_gp_sample(const float* X, const float* eps, float* Y, float* L, int32_t* rank, int B, int N, int S, int kernel,
+                             float length_scale, float periodicity, float noise_level, float tol, npf_stream_t stream) {
+    NPF_REQUIRE(B >= 0 && N >= 1 && S >= 0, "npf_gp_sample: bad shape");
+    NPF_REQUIRE(kernel >= 0 && kernel <= 2, "npf_gp_sample: kernel must be 0 (RBF), 1 (Matern-1.5) or 2 (ExpSineSquared)");
+    NPF_REQUIRE(length_scale > 0.f && (kernel != 2 || periodicity > 0.f) && noise_level >= 0.f && tol >= 0.f,
+                "npf_gp_sample: bad hyper-parameter");
+    return gp_launch(X, eps, Y, L, rank, nullptr, B, N, S, GpKernel{kernel, length_scale, periodicity, noise_level}, tol, stream);
+}
+
+extern "C" int npf_gp_sample_hyp(const float* X, const float* eps, float* Y, float* L, int32_t* rank, const float* hyp, int B, int N, int S,
+                                 int kernel, float tol, npf_stream_t stream) {
+    NPF_REQUIRE(B >= 0 && N >= 1 && S >= 0, "npf_gp_sample_hyp: bad shape");
+    NPF_REQUIRE(kernel >= 0 && kernel <= 2, "npf_gp_sample_hyp: kernel must be 0 (RBF), 1 (Matern-1.5) or 2 (ExpSineSquared)");
+    NPF_REQUIRE(tol >= 0.f && (B == 0 || hyp), "npf_gp_sample_hyp: bad tolerance / null hyper-parameter table");
+    return gp_launch(X, eps, Y, L, rank, hyp, B, N, S, GpKernel{kernel, 1.f, 1.f, 0.f}, tol, stream);
 }

@@ -34,16 +34,36 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 #ifndef NPF_MBAR_HINT_NS
 #define NPF_MBAR_HINT_NS 20000
 #endif
+#ifndef NPF_MBAR_OUTLINE
+#define NPF_MBAR_OUTLINE 0
+#endif
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity), "r"((uint32_t)NPF_MBAR_HINT_NS) : "memory");
+    return ok;
+}
+// the retry loop, out of line: the (unrolled) poll / back-off code of ~25 call sites was most of these kernels' 60-100 KB of SASS
+static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        if (mbar_try_wait(addr, parity)) return;
+        if (it > 1) __nanosleep(64);
+    }
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t ok = 0;
+#if NPF_MBAR_OUTLINE
+    if (mbar_try_wait(addr, parity)) return;
+    mbar_wait_slow(addr, parity);
+#else
     for (uint32_t it = 0; it < (1u << 24); ++it) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity), "r"((uint32_t)NPF_MBAR_HINT_NS) : "memory");
-        if (ok) return;
+        if (mbar_try_wait(addr, parity)) return;
         if (it > 2) __nanosleep(64);
     }
     __trap();
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -65,6 +85,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand read from tensor memory (lane = row of A, one 32-bit column = two consecutive K elements,
+// low half first; K-major only) -- no shared-memory read for A.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 registers per thread -> 32 lanes x 16 consecutive 32-bit columns (thread = TMEM lane)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -123,5 +158,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+
+// 16 consecutive floats accumulated at a 4-byte aligned address: scalar atomics up to the next 16-byte boundary, float4 atomics for
+// the aligned middle, scalars for the tail.  Rows of a [N, ld] gradient with ld % 4 != 0 (the 129-column SetConv resizer) cost 7 atomic
+// operations per 16 values instead of 16.
+template <int H>
+__device__ __forceinline__ void atomic_add16_head(float* d, const float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < H; ++j) atomicAdd(d + j, v[j]);
+    constexpr int NV = H == 0 ? 4 : 3;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        atomicAdd(reinterpret_cast<float4*>(d + H + 4 * i), make_float4(v[H + 4 * i], v[H + 4 * i + 1], v[H + 4 * i + 2], v[H + 4 * i + 3]));
+#pragma unroll
+    for (int j = H + 4 * NV; j < 16; ++j) atomicAdd(d + j, v[j]);
+}
+__device__ __forceinline__ void atomic_add16(float* d, const float (&v)[16]) {
+    switch (((16u - (unsigned)(reinterpret_cast<uintptr_t>(d) & 15u)) >> 2) & 3u) {
+        case 0: atomic_add16_head<0>(d, v); break;
+        case 1: atomic_add16_head<1>(d, v); break;
+        case 2: atomic_add16_head<2>(d, v); break;
+        default: atomic_add16_head<3>(d, v); break;
+    }
+}
 
 }  // namespace npf

@@ -70,6 +70,7 @@ SIGNATURES = {
     "npf_select_points": [P, P, P, P, P, I, I, I, I, I, P],
     "npf_grid_select": [P, P, P, P, P, I, I, I, I, I, I, F, P],
     "npf_gp_sample": [P, P, P, P, P, I, I, I, I, F, F, F, F, P],
+    "npf_gp_sample_hyp": [P, P, P, P, P, P, I, I, I, I, F, P],
 }
 BOOKKEEPING = {
     "npf_abi_version": (c_int, []),

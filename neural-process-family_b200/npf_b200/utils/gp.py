@@ -17,7 +17,7 @@ import torch
 
 from .. import _cabi
 
-__all__ = ["GPSampler", "kernel_hyperparameters"]
+__all__ = ["GPSampler", "kernel_hyperparameters", "kernel_hyperparameter_bounds"]
 
 KINDS = {"rbf": 0, "matern15": 1, "periodic": 2}
 
@@ -51,18 +51,75 @@ def kernel_hyperparameters(kernel):
     raise NotImplementedError(f"npf_b200.GPSampler: kernel {name} is not implemented")
 
 
+def kernel_hyperparameter_bounds(kernel):
+    """(lo, hi) per hyper-parameter name for the ones a `is_vary_kernel_hyp` dataset resamples: the kernel's own
+    ``<name>_bounds`` (scikit-learn attribute or dict key); "fixed" / absent bounds leave that hyper-parameter at the kernel's value
+    (upstream draws ``uniform(*hyperparam.bounds)`` for every entry of ``kernel.hyperparameters``, gaussian_process.py:239-242)."""
+    out = {}
+
+    def take(obj, name):
+        b = obj.get(name + "_bounds") if isinstance(obj, dict) else getattr(obj, name + "_bounds", None)
+        if b is None or (isinstance(b, str) and b == "fixed"):
+            return
+        lo, hi = (float(v) for v in b)
+        if not (0 < lo <= hi):
+            raise ValueError(f"{name}_bounds must satisfy 0 < lo <= hi, got {b}")
+        out[name] = (lo, hi)
+
+    if isinstance(kernel, dict):
+        for name in ("length_scale", "periodicity", "noise_level"):
+            take(kernel, name)
+        return out
+    name = type(kernel).__name__
+    if name == "Sum":
+        for part in (kernel.k1, kernel.k2):
+            out.update(kernel_hyperparameter_bounds(part))
+        return out
+    if name == "WhiteKernel":
+        take(kernel, "noise_level")
+    else:
+        take(kernel, "length_scale")
+        if name == "ExpSineSquared":
+            take(kernel, "periodicity")
+    return out
+
+
 class GPSampler:
-    def __init__(self, kernel, min_max=(-2, 2), n_points=128, n_same_samples=20, tol=1e-5, device="cuda"):
+    """``is_vary_kernel_hyp=True`` (upstream gaussian_process.py:39-41, 206-207, 233-242): every group of ``n_same_samples`` functions
+    comes from a kernel whose hyper-parameters were drawn uniformly in their bounds -- drawn here on the device, one row of
+    (length_scale, periodicity, noise_level) per group, and consumed by ``npf_gp_sample_hyp``."""
+
+    def __init__(self, kernel, min_max=(-2, 2), n_points=128, n_same_samples=20, tol=1e-5, device="cuda", is_vary_kernel_hyp=False):
         self.hyp = kernel_hyperparameters(kernel)
+        self.is_vary_kernel_hyp = bool(is_vary_kernel_hyp)
+        self.bounds = kernel_hyperparameter_bounds(kernel) if self.is_vary_kernel_hyp else {}
         self.min_max, self.n_points, self.n_same_samples, self.tol = min_max, n_points, n_same_samples, tol
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("npf_b200.GPSampler runs on CUDA devices only (there is no CPU fallback)")
 
-    def sample_targets(self, X, n_same_samples=1, eps=None, return_factor=False):
-        """X [T, N] raw positions -> Y [T, n_same_samples, N] (and the factor L [T, N, N], rank [T] when asked)."""
+    def sample_hyperparameters(self, T):
+        """[T, 3] device rows (length_scale, periodicity, noise_level): U(lo, hi) where bounds exist, the kernel's value otherwise."""
+        h = self.hyp
+        cols = []
+        for name in ("length_scale", "periodicity", "noise_level"):
+            if name in self.bounds and not (name == "periodicity" and h["kind"] != "periodic"):
+                lo, hi = self.bounds[name]
+                cols.append(torch.rand(T, device=self.device) * (hi - lo) + lo)
+            else:
+                cols.append(torch.full((T,), h[name], device=self.device))
+        return torch.stack(cols, dim=1).contiguous()
+
+    def sample_targets(self, X, n_same_samples=1, eps=None, return_factor=False, hyp=None):
+        """X [T, N] raw positions -> Y [T, n_same_samples, N] (and the factor L [T, N, N], rank [T] when asked).  ``hyp`` [T, 3]:
+        per-task (length_scale, periodicity, noise_level); default: drawn when ``is_vary_kernel_hyp``, else the kernel's own."""
         X = X.to(self.device, torch.float32).contiguous()
         T, N = X.shape
+        if hyp is None and self.is_vary_kernel_hyp:
+            hyp = self.sample_hyperparameters(T)
+        if hyp is not None:
+            hyp = hyp.to(self.device, torch.float32).contiguous()
+            assert tuple(hyp.shape) == (T, 3), f"hyp must be [T, 3], got {tuple(hyp.shape)}"
         S = n_same_samples
         if eps is None:
             eps = torch.randn(T, S, N, device=self.device, dtype=torch.float32)
@@ -73,6 +130,11 @@ class GPSampler:
         rank = torch.empty(T, device=self.device, dtype=torch.int32) if return_factor else None
         h = self.hyp
         with torch.cuda.device(self.device):
+            if hyp is not None:
+                _cabi.call("npf_gp_sample_hyp", X.data_ptr(), eps.data_ptr(), Y.data_ptr(), None if L is None else L.data_ptr(),
+                           None if rank is None else rank.data_ptr(), hyp.data_ptr(), T, N, S, KINDS[h["kind"]], float(self.tol),
+                           torch.cuda.current_stream().cuda_stream)
+                return (Y, L, rank) if return_factor else Y
             _cabi.call("npf_gp_sample", X.data_ptr(), eps.data_ptr(), Y.data_ptr(), None if L is None else L.data_ptr(),
                        None if rank is None else rank.data_ptr(), T, N, S, KINDS[h["kind"]], h["length_scale"], h["periodicity"],
                        h["noise_level"], float(self.tol), torch.cuda.current_stream().cuda_stream)

@@ -145,6 +145,24 @@ def grid_inputs(B, H, W, y_dim, frac, seed):
     return dict(X_cntxt=mask, Y_cntxt=img, X_trgt=torch.ones(B, H, W, 1, dtype=torch.bool), Y_trgt=img.clone())
 
 
+def blob_inputs(B, H, W, frac, seed):
+    """Digit-like single-channel images (a few soft strokes on a black background, values in [0, 1]) for the checkpoints trained on
+    MNIST-type data: uniform noise drives those models to sigma = 0.01 everywhere and NLLs of 1e5-1e6, whose gradients are sums of huge
+    cancelling terms (nothing a fp32 implementation can be pinned on to 1e-3)."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    img = torch.zeros(B, H, W)
+    for b in range(B):
+        for _ in range(4):
+            cy, cx = torch.rand(2, generator=g) * torch.tensor([H - 1.0, W - 1.0])
+            s = 1.2 + 1.8 * torch.rand(1, generator=g)
+            img[b] += torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * s * s))
+    img = img.clamp(0, 1).unsqueeze(-1)
+    out = grid_inputs(B, H, W, 1, frac, seed + 1)
+    out["Y_cntxt"], out["Y_trgt"] = img, img.clone()
+    return out
+
+
 N_PROJ = 8
 
 
@@ -444,15 +462,18 @@ def main_circular():
     cfg = dict(family="GridConvCNP", x_dim=1, y_dim=1, notebook=True, circular=True, pretrained="zsmms/ConvCNP", cnn=cnn)
     m = build(cfg)
     dump("gridconvcnp_extrap_pretrained", cfg, m, [
-        run_case(m, cfg, "eval_b2_40x40", False, grid_inputs(2, 40, 40, 1, 0.2, 70), "cnpf", False),
-        run_case(m, cfg, "train_b2_28x20", True, grid_inputs(2, 28, 20, 1, 0.3, 71), "cnpf", True),
+        run_case(m, cfg, "eval_b2_40x40", False, blob_inputs(2, 40, 40, 0.2, 70), "cnpf", False),
+        run_case(m, cfg, "eval_b1_28x20", False, blob_inputs(1, 28, 20, 0.3, 71), "cnpf", False),
     ])
+    # (no train case here: train-mode batch statistics of these MNIST-trained weights on a 2-image batch make the reference's own fp32
+    # gradients differ from its fp64 ones by 3e-3 -- nothing to pin a 1e-3 bar on; gradients through the wrap-around path are pinned by
+    # the GridConvLNP fixture below, whose fp32 / fp64 gradients agree to 3e-5)
     cfg = dict(family="GridConvLNP", x_dim=1, y_dim=1, notebook=True, circular=True, is_global=False, pretrained="zsmms/ConvLNP",
                n_z_samples_train=3, n_z_samples_test=2, cnn=dict(cnn, n_blocks=4))
     m = build(cfg)
     dump("gridconvlnp_extrap_pretrained", cfg, m, [
-        run_case(m, cfg, "train_b2_24x24_nz3", True, grid_inputs(2, 24, 24, 1, 0.3, 72), "nll", True, eps_seed=720),
-        run_case(m, cfg, "eval_b1_32x32_nz2", False, grid_inputs(1, 32, 32, 1, 0.1, 73), "nll", False, eps_seed=730),
+        run_case(m, cfg, "train_b2_24x24_nz3", True, blob_inputs(2, 24, 24, 0.3, 72), "nll", True, eps_seed=720),
+        run_case(m, cfg, "eval_b1_32x32_nz2", False, blob_inputs(1, 32, 32, 0.1, 73), "nll", False, eps_seed=730),
     ])
     cfg = dict(family="GridConvCNP", x_dim=1, y_dim=3, notebook=True, pretrained="celeba128/ConvCNPXL",
                cnn=dict(dim=2, norm="bn", n_blocks=12, kernel_size=9, n_conv_layers=2))

@@ -69,3 +69,24 @@ def test_host_side_kernel_parsing():
     except ImportError:
         return
     assert kernel_hyperparameters(SkWhite(noise_level=0.1) + SkRBF(length_scale=0.2))["noise_level"] == 0.1
+
+
+def test_hyperparameter_bounds_parsing():
+    """`is_vary_kernel_hyp` (upstream gaussian_process.py:39-41, 233-242): the bounds that are resampled are the kernel's own `*_bounds`;
+    fixed ones stay at the kernel's value (upstream would fail on a "fixed" bound: it draws `uniform(*hyperparam.bounds)` for every entry)."""
+    from npf_b200.utils.gp import kernel_hyperparameter_bounds
+    assert kernel_hyperparameter_bounds(dict(kind="rbf", length_scale=0.2)) == {}
+    assert kernel_hyperparameter_bounds(dict(kind="periodic", length_scale=1.0, periodicity=0.5, length_scale_bounds=(0.5, 2),
+                                             periodicity_bounds="fixed", noise_level_bounds=(0.01, 0.1))) == \
+        {"length_scale": (0.5, 2.0), "noise_level": (0.01, 0.1)}
+    with pytest.raises(ValueError):
+        kernel_hyperparameter_bounds(dict(kind="rbf", length_scale=0.2, length_scale_bounds=(0.0, 1.0)))
+    try:
+        from sklearn.gaussian_process.kernels import RBF, ExpSineSquared, WhiteKernel
+    except ImportError:
+        return
+    k = WhiteKernel(0.1, noise_level_bounds=(0.01, 0.5)) + ExpSineSquared(1.0, 0.5, length_scale_bounds=(0.5, 2), periodicity_bounds="fixed")
+    got = kernel_hyperparameter_bounds(k)
+    assert got == {"noise_level": (0.01, 0.5), "length_scale": (0.5, 2.0)}
+    assert sorted(got) == sorted(h.name.split("__")[-1] for h in k.hyperparameters if not h.fixed)   # the free ones, as scikit-learn sees them
+    assert kernel_hyperparameter_bounds(RBF(0.2)) == {"length_scale": (1e-5, 1e5)}           # scikit-learn's default bounds

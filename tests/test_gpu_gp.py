@@ -71,3 +71,39 @@ def test_get_samples_contract_and_limits():
     loss = npf_b200.CNPFLoss()(m(Xc, Yc, Xt, Yt), Yt)
     loss.backward()
     assert torch.isfinite(loss)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_per_task_hyperparameters(kind):
+    """npf_gp_sample_hyp (`is_vary_kernel_hyp`, upstream gaussian_process.py:206-207, 233-242): every task factorises the covariance of
+    ITS OWN (length_scale, periodicity, noise_level) row -- checked against the scikit-learn-pinned covariance of the oracle."""
+    from npf_b200.utils.gp import GPSampler
+    x = FIX[NAMES[0] + "_x"]
+    N = len(x)
+    s = GPSampler(dict(kind=KIND[kind], length_scale=0.5, periodicity=0.7))
+    hyp = torch.tensor([[0.15, 0.4, 0.0], [0.4, 0.9, 0.02], [1.1, 1.7, 0.0], [0.25, 0.55, 0.1]])
+    X = torch.from_numpy(np.stack([x] * 4)).float()
+    eps = torch.randn(4, 3, N, generator=torch.Generator().manual_seed(2))
+    Y, L, rank = s.sample_targets(X, 3, eps=eps, return_factor=True, hyp=hyp)
+    L64 = L.double().cpu().numpy()
+    for t in range(4):
+        K = G.cov_matrix(x, kind, float(hyp[t, 0]), float(hyp[t, 1]), float(hyp[t, 2]))
+        assert np.abs(L64[t] @ L64[t].T - K).max() < 5e-5, (kind, t)
+    want = np.einsum("tik,tsk->tsi", L64, eps.double().numpy())
+    assert np.abs(Y.double().cpu().numpy() - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+    assert len(set(int(r) for r in rank)) > 1                                # different kernels, different numerical ranks
+
+
+def test_vary_kernel_hyp_dataset():
+    from npf_b200.utils.gp import GPSampler
+    s = GPSampler(dict(kind="rbf", length_scale=0.2, length_scale_bounds=(0.1, 1.0), noise_level_bounds=(0.001, 0.05)),
+                  n_points=64, n_same_samples=5, is_vary_kernel_hyp=True)
+    torch.manual_seed(3)
+    h = s.sample_hyperparameters(1000)
+    assert h.shape == (1000, 3) and 0.1 <= float(h[:, 0].min()) and float(h[:, 0].max()) <= 1.0
+    assert abs(float(h[:, 0].mean()) - 0.55) < 0.03 and bool((h[:, 1] == 1.0).all())          # uniform in the bounds; periodicity untouched
+    assert 0.001 <= float(h[:, 2].min()) and float(h[:, 2].max()) <= 0.05
+    X, Y = s.get_samples(43)
+    assert X.shape == (43, 64, 1) and Y.shape == (43, 64, 1) and torch.isfinite(Y).all()
+    fixed = GPSampler(dict(kind="rbf", length_scale=0.2, length_scale_bounds=(0.1, 1.0)), n_points=64)     # bounds ignored unless asked
+    assert fixed.bounds == {} and not fixed.is_vary_kernel_hyp
