@@ -14,6 +14,8 @@
 //   Q, K   K-major over d :  (d/8)*LBO + (row/8)*128 + (row%8)*16 + (d%8)*2,   LBO = rows*16
 //   P      K-major over key: (key/8)*2048 + (q/8)*128 + (q%8)*16 + (key%8)*2
 //   V      MN-major (N = channel c, K = key): (key/8)*LBO + (c/8)*128 + (key%8)*16 + (c%8)*2,  LBO = (Dv/8)*128
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace npf {
@@ -84,6 +86,20 @@ __device__ __forceinline__ void mma_logits(uint32_t d, uint32_t a_h, uint32_t a_
     }
 }
 
+// the same product with different leading-dimension offsets for the two operands (tiles with different row counts)
+template <int NSPLIT>
+__device__ __forceinline__ void mma_logits2(uint32_t d, uint32_t a_h, uint32_t a_m, uint32_t a_l, uint32_t a_lbo, uint32_t b_h, uint32_t b_m, uint32_t b_l,
+                                            uint32_t b_lbo, uint32_t idesc, uint32_t acc) {
+    umma_bf16(d, make_desc(a_h, a_lbo, 128), make_desc(b_h, b_lbo, 128), idesc, acc);
+    if (NSPLIT == 3) {
+        umma_bf16(d, make_desc(a_h, a_lbo, 128), make_desc(b_m, b_lbo, 128), idesc, 1);
+        umma_bf16(d, make_desc(a_m, a_lbo, 128), make_desc(b_h, b_lbo, 128), idesc, 1);
+        umma_bf16(d, make_desc(a_m, a_lbo, 128), make_desc(b_m, b_lbo, 128), idesc, 1);
+        umma_bf16(d, make_desc(a_h, a_lbo, 128), make_desc(b_l, b_lbo, 128), idesc, 1);
+        umma_bf16(d, make_desc(a_l, a_lbo, 128), make_desc(b_h, b_lbo, 128), idesc, 1);
+    }
+}
+
 // V chunk as MN-major B operand (N = channel, K = key): thread = key row.
 template <int NSPLIT>
 __device__ __forceinline__ void stage_rows_mnmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, long ld, int row, bool valid, int width) {
@@ -106,13 +122,15 @@ __device__ __forceinline__ void stage_rows_mnmajor(uint8_t* hi, uint8_t* lo, con
     }
 }
 
-template <int NSPLIT, int DV>
+// KC keys per chunk: 128, or 64 -- half the logits / probability tile, 55 KB of shared memory and 128 TMEM columns per CTA, so that FOUR
+// CTAs share an SM instead of two (every phase of a CTA is serial: stage -> MMA -> softmax -> MMA; the overlap comes from the neighbours).
+template <int NSPLIT, int DV, int KC>
 __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_s, bar_o;
     __shared__ uint32_t tmem_slot;
     const int D = p.D;
-    const uint32_t q_bytes = kQB * D * 2u, k_bytes = kKC * D * 2u, v_bytes = kKC * DV * 2u, p_bytes = kQB * kKC * 2u;
+    const uint32_t q_bytes = kQB * D * 2u, k_bytes = KC * D * 2u, v_bytes = KC * DV * 2u, p_bytes = kQB * KC * 2u;
     uint8_t* q_hi = smem_raw;
     uint8_t* k_hi = q_hi + q_bytes;
     uint8_t* v_hi = k_hi + k_bytes;
@@ -130,7 +148,7 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
     const float* Kb = p.K + ((long)b * p.Tk) * ldq + h * D;
     const float* Vb = p.V + ((long)b * p.Tk) * ldv + h * DV;
 
-    constexpr uint32_t kCols = 256;   // S: [0,128), O chunk: [128, 128 + DV)
+    constexpr uint32_t kCols = KC == 128 ? 256 : 128;   // S: [0, KC), O chunk: [KC, KC + DV)
     if (warp == 0) tmem_alloc(&tmem_slot, kCols);
     if (tid == 0) { mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); }
     stage_rows_kmajor<NSPLIT>(q_hi, q_lo, Qb + (long)qb * kQB * ldq, ldq, tid, q_ok, D, kQB, NSPLIT == 3 ? q_l2 : nullptr);   // tile row tid <- query row
@@ -139,10 +157,10 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t t_s = tmem + ((uint32_t)(32 * warp) << 16);
-    const uint32_t t_o = t_s + 128u;
-    const uint32_t idesc_s = make_idesc(128, kKC, 0, 0);
+    const uint32_t t_o = t_s + (uint32_t)KC;
+    const uint32_t idesc_s = make_idesc(128, KC, 0, 0);
     const uint32_t idesc_o = make_idesc(128, DV, 0, 1);
-    const uint32_t q_lbo = kQB * 16u, k_lbo = kKC * 16u, p_lbo = kQB * 16u, v_lbo = (uint32_t)(DV >> 3) * 128u;
+    const uint32_t q_lbo = kQB * 16u, k_lbo = KC * 16u, p_lbo = kQB * 16u, v_lbo = (uint32_t)(DV >> 3) * 128u;
 
     const float sl2 = p.scale * 1.4426950408889634f;      // logits in log2 units: exp(x) = exp2(x * log2 e)
     float m_run = -INFINITY, l_run = 0.f;
@@ -151,21 +169,27 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
     for (int c = 0; c < DV; ++c) o_run[c] = 0.f;
 
     uint32_t ph = 0;
-    for (int k0 = 0; k0 < p.Tk; k0 += kKC) {
+    for (int k0 = 0; k0 < p.Tk; k0 += KC) {
         // stage this chunk of K and V (thread = key row); the previous chunk's MMAs have completed (bar_o waited below)
-        const int key = k0 + tid;
-        const bool k_ok = key < p.Tk;
-        stage_rows_kmajor<NSPLIT>(k_hi, k_lo, Kb + (long)k0 * ldq, ldq, tid, k_ok, D, kKC, NSPLIT == 3 ? k_l2 : nullptr);
-        stage_rows_mnmajor<NSPLIT>(v_hi, v_lo, Vb + (long)k0 * ldv, ldv, tid, k_ok, DV);
+        if (KC == 128) {
+            const bool k_ok = k0 + tid < p.Tk;
+            stage_rows_kmajor<NSPLIT>(k_hi, k_lo, Kb + (long)k0 * ldq, ldq, tid, k_ok, D, KC, NSPLIT == 3 ? k_l2 : nullptr);
+            stage_rows_mnmajor<NSPLIT>(v_hi, v_lo, Vb + (long)k0 * ldv, ldv, tid, k_ok, DV);
+        } else {                                   // 64 keys: threads 0..63 stage the K rows, threads 64..127 the V rows
+            const int row = tid & 63;
+            const bool k_ok = k0 + row < p.Tk;
+            if (tid < 64) stage_rows_kmajor<NSPLIT>(k_hi, k_lo, Kb + (long)k0 * ldq, ldq, row, k_ok, D, KC, NSPLIT == 3 ? k_l2 : nullptr);
+            else stage_rows_mnmajor<NSPLIT>(v_hi, v_lo, Vb + (long)k0 * ldv, ldv, row, k_ok, DV);
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
             for (int ks = 0; ks < D / 16; ++ks) {
-                const uint32_t o = (uint32_t)ks * 2u * q_lbo;      // q_lbo == k_lbo (both tiles have 128 rows)
-                mma_logits<NSPLIT>(tmem, smem_u32(q_hi) + o, smem_u32(q_lo) + o, smem_u32(q_l2) + o, smem_u32(k_hi) + o, smem_u32(k_lo) + o,
-                                   smem_u32(k_l2) + o, q_lbo, idesc_s, ks > 0);
+                const uint32_t oq = (uint32_t)ks * 2u * q_lbo, ok = (uint32_t)ks * 2u * k_lbo;
+                mma_logits2<NSPLIT>(tmem, smem_u32(q_hi) + oq, smem_u32(q_lo) + oq, smem_u32(q_l2) + oq, q_lbo, smem_u32(k_hi) + ok, smem_u32(k_lo) + ok,
+                                    smem_u32(k_l2) + ok, k_lbo, idesc_s, ks > 0);
             }
             umma_commit(&bar_s);
         }
@@ -173,10 +197,10 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
         tc_fence_after();
 
         // ---- online softmax over this chunk's 128 logits of row `tid` ----
-        const int n_valid = min(kKC, p.Tk - k0);
+        const int n_valid = min(KC, p.Tk - k0);
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kKC; c0 += 32) {
+        for (int c0 = 0; c0 < KC; c0 += 32) {
             float v[32];
             tmem_ld32(t_s + (uint32_t)c0, v);
 #pragma unroll
@@ -187,7 +211,7 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
         const float alpha = exp2f(m_run - m_new);           // first chunk: exp2(-inf) = 0
         float lsum = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kKC; c0 += 32) {
+        for (int c0 = 0; c0 < KC; c0 += 32) {
             float v[32];
             tmem_ld32(t_s + (uint32_t)c0, v);
 #pragma unroll
@@ -219,13 +243,13 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
         if (tid == 0) {
             tc_fence_after();
             uint32_t acc = 0;
-            for (int ks = 0; ks < kKC / 16; ++ks) {
+            for (int ks = 0; ks < KC / 16; ++ks) {
                 const uint32_t po = (uint32_t)ks * 2u * p_lbo, vo = (uint32_t)ks * 2u * v_lbo;
-                umma_bf16(tmem + 128u, make_desc(smem_u32(p_hi) + po, p_lbo, 128), make_desc(smem_u32(v_hi) + vo, v_lbo, 128), idesc_o, acc);
+                umma_bf16(tmem + (uint32_t)KC, make_desc(smem_u32(p_hi) + po, p_lbo, 128), make_desc(smem_u32(v_hi) + vo, v_lbo, 128), idesc_o, acc);
                 acc = 1;
                 if (NSPLIT == 3) {
-                    umma_bf16(tmem + 128u, make_desc(smem_u32(p_hi) + po, p_lbo, 128), make_desc(smem_u32(v_lo) + vo, v_lbo, 128), idesc_o, 1);
-                    umma_bf16(tmem + 128u, make_desc(smem_u32(p_lo) + po, p_lbo, 128), make_desc(smem_u32(v_hi) + vo, v_lbo, 128), idesc_o, 1);
+                    umma_bf16(tmem + (uint32_t)KC, make_desc(smem_u32(p_hi) + po, p_lbo, 128), make_desc(smem_u32(v_lo) + vo, v_lbo, 128), idesc_o, 1);
+                    umma_bf16(tmem + (uint32_t)KC, make_desc(smem_u32(p_lo) + po, p_lbo, 128), make_desc(smem_u32(v_hi) + vo, v_lbo, 128), idesc_o, 1);
                 }
             }
             umma_commit(&bar_o);
@@ -255,22 +279,30 @@ __global__ void __launch_bounds__(128) xattn_fwd_tc_kernel(AttnTcParams p) {
     if (warp == 0) tmem_dealloc(tmem, kCols);
 }
 
-template <int NSPLIT, int DV>
-static int launch_fwd(AttnTcParams& p, int B, cudaStream_t st) {
-    const size_t half = (size_t)(kQB * p.D + kKC * p.D + kKC * DV + kQB * kKC) * 2;
-    const size_t smem = half * (NSPLIT == 3 ? 2 : 1) + (NSPLIT == 3 ? (size_t)(kQB + kKC) * p.D * 2 : 0);
+template <int NSPLIT, int DV, int KC>
+static int launch_fwd_kc(AttnTcParams& p, int B, cudaStream_t st) {
+    const size_t half = (size_t)(kQB * p.D + KC * p.D + KC * DV + kQB * KC) * 2;
+    const size_t smem = half * (NSPLIT == 3 ? 2 : 1) + (NSPLIT == 3 ? (size_t)(kQB + KC) * p.D * 2 : 0);
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(xattn_fwd_tc_kernel<NSPLIT, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(xattn_fwd_tc_kernel<NSPLIT, DV, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return NPF_ENOTSUP;
         }
         attr = true;
     }
     dim3 grid((unsigned)cdiv(p.Tq, kQB), (unsigned)p.H, (unsigned)B);
-    xattn_fwd_tc_kernel<NSPLIT, DV><<<grid, 128, smem, st>>>(p);
+    xattn_fwd_tc_kernel<NSPLIT, DV, KC><<<grid, 128, smem, st>>>(p);
     count_launch();
     return check_launch("xattn_fwd_tc_kernel");
+}
+template <int NSPLIT, int DV>
+static int launch_fwd(AttnTcParams& p, int B, cudaStream_t st) {
+    static const int kc = [] { const char* e = getenv("NPF_XATTN_KC"); return e && atoi(e) == 128 ? 128 : (e && atoi(e) == 64 ? 64 : 0); }();
+    // 64-key chunks when there are enough CTAs to fill four per SM and more than one chunk of keys anyway
+    const long ctas = (long)cdiv(p.Tq, kQB) * p.H * B;
+    const bool small = kc == 64 || (kc == 0 && p.Tk > 64 && ctas >= 2L * kNumSMs);
+    return small ? launch_fwd_kc<NSPLIT, DV, 64>(p, B, st) : launch_fwd_kc<NSPLIT, DV, 128>(p, B, st);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
