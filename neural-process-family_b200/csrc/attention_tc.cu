@@ -504,6 +504,192 @@ __global__ void __launch_bounds__(256, 1) xattn_bwd_tc_kernel(AttnTcParams p) {
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Backward, second arrangement: 64-query blocks and the score tile TRANSPOSED (TMEM lane = key), so that two CTAs fit an SM.
+// The kernel above holds P and dS for 128 x 128 scores as bf16 hi / lo images (128 KB) and 352 TMEM columns: one CTA per SM, and
+// its phases (stage -> MMA -> exp -> MMA -> atomics) are strictly serial, so the SM idles through every hand-off.  Here, per 64-query block:
+//   S^T = K Q^T, dP^T = V dO^T                 (M = 128 keys, N = 64 queries, K = D | Dv: every operand in its natural row-major staging)
+//   thread (key r, query half) : P^T = exp2(S^T scale - lse[q]), dS^T = P^T (dP^T - Di[q]) scale      -> [128 keys x 64 q] bf16 hi / lo images
+//   dV += P^T dO,  dK += dS^T Q                (A = the images as stored, K-major over q; B = dO / Q read through the transposed view)
+//   dQ_blk = dS K                               (A = transposed view of the dS^T image: its M extent is the 64 queries; the MMA runs with
+//                                                M = 128 and the upper 64 accumulator rows, fed by whatever follows the image, are never read)
+// 94 KB of shared memory (head dim 16) and 224 TMEM columns per CTA.
+// ----------------------------------------------------------------------------------------------------------------
+template <int NSPLIT>
+__global__ void __launch_bounds__(256, 2) xattn_bwd_tc_q64_kernel(AttnTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar1, bar2;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_lse2[64], s_di[64];
+    const int D = p.D, DV = p.Dv;
+    constexpr uint32_t CHK = 2048u, CHQ = 1024u;                 // column-chunk strides of the 128-row and the 64-row tiles
+    constexpr int QB = 64;
+    const uint32_t kt_b = (uint32_t)(D >> 3) * CHK, vt_b = (uint32_t)(DV >> 3) * CHK, qt_b = (uint32_t)(D >> 3) * CHQ, dot_b = (uint32_t)(DV >> 3) * CHQ;
+    constexpr uint32_t pt_b = (QB / 8) * CHK;                    // 16 KB
+    uint8_t* kt = smem_raw;
+    uint8_t* vt = kt + kt_b;
+    uint8_t* qt = vt + vt_b;
+    uint8_t* dot_ = qt + qt_b;
+    uint8_t* dst = dot_ + dot_b;                                  // dS^T, then P^T: the M = 128 read of the transposed dS view runs on into P^T
+    uint8_t* pt = dst + pt_b;
+    const uint32_t half = kt_b + vt_b + qt_b + dot_b + 2u * pt_b;
+    const uint32_t LO = half;                                     // byte offset of the "lo" copies (NSPLIT == 3)
+    uint8_t* kt_l2 = smem_raw + 2 * half; uint8_t* qt_l2 = kt_l2 + kt_b;     // third bf16 term of K and Q (logits only)
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & 127, qh = tid >> 7;
+    const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const long ldq = (long)p.H * D, ldv = (long)p.H * DV;
+    const float* Qb = p.Q + ((long)b * p.Tq) * ldq + h * D;
+    const float* Kb = p.K + ((long)b * p.Tk) * ldq + h * D;
+    const float* Vb = p.V + ((long)b * p.Tk) * ldv + h * DV;
+    const float* Ob = p.O + ((long)b * p.Tq) * ldv + h * DV;
+    const float* Gb = p.dO + ((long)b * p.Tq) * ldv + h * DV;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); }
+    const int key0 = kb * 128;
+    const bool key_ok = key0 + r < p.Tk;
+    if (qh == 0) stage_rows_kmajor<NSPLIT>(kt, kt + LO, Kb + (long)key0 * ldq, ldq, r, key_ok, D, 128, NSPLIT == 3 ? kt_l2 : nullptr);
+    else stage_rows_kmajor<NSPLIT>(vt, vt + LO, Vb + (long)key0 * ldv, ldv, r, key_ok, DV, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    const uint32_t T_S = 0, T_DP = 64, T_DQ = 128, T_DK = 160, T_DV = 192;
+    const uint32_t idesc_sp = make_idesc(128, QB, 0, 0);
+    const uint32_t idesc_dv = make_idesc(128, DV, 0, 1), idesc_dk = make_idesc(128, D, 0, 1), idesc_dq = make_idesc(128, D, 1, 1);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const uint32_t s_kt = smem_u32(kt), s_vt = smem_u32(vt), s_qt = smem_u32(qt), s_dot = smem_u32(dot_), s_pt = smem_u32(pt), s_dst = smem_u32(dst);
+
+    uint32_t ph = 0, acc_kv = 0;
+    for (int q0 = 0; q0 < p.Tq; q0 += QB) {
+        // stage this query block: Q rows (threads 0..63), dO rows (64..127), per-row lse and Di = dO . O (128..191)
+        if (tid < 64) {
+            stage_rows_kmajor<NSPLIT>(qt, qt + LO, Qb + (long)q0 * ldq, ldq, tid, q0 + tid < p.Tq, D, QB, NSPLIT == 3 ? qt_l2 : nullptr);
+        } else if (tid < 128) {
+            stage_rows_kmajor<NSPLIT>(dot_, dot_ + LO, Gb + (long)q0 * ldv, ldv, tid - 64, q0 + tid - 64 < p.Tq, DV, QB);
+        } else if (tid < 192) {
+            const int q = q0 + tid - 128;
+            float di = 0.f;
+            if (q < p.Tq)
+                for (int c = 0; c < DV; c += 4) {
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(Gb + (long)q * ldv + c)), o4 = __ldg(reinterpret_cast<const float4*>(Ob + (long)q * ldv + c));
+                    di = fmaf(g4.x, o4.x, fmaf(g4.y, o4.y, fmaf(g4.z, o4.z, fmaf(g4.w, o4.w, di))));
+                }
+            s_di[tid - 128] = di;
+            s_lse2[tid - 128] = q < p.Tq ? __ldg(p.LSE + ((long)b * p.H + h) * p.Tq + q) * 1.4426950408889634f : INFINITY;   // +inf -> P = 0
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < D / 16; ++ks)      // S^T = K Q^T : both K-major over d, fp32-level product
+                mma_logits2<NSPLIT>(tmem + T_S, s_kt + ks * 2 * CHK, s_kt + LO + ks * 2 * CHK, smem_u32(kt_l2) + ks * 2 * CHK, CHK, s_qt + ks * 2 * CHQ,
+                                    s_qt + LO + ks * 2 * CHQ, smem_u32(qt_l2) + ks * 2 * CHQ, CHQ, idesc_sp, ks > 0);
+            for (int ks = 0; ks < DV / 16; ++ks)     // dP^T = V dO^T
+                mma3<NSPLIT>(tmem + T_DP, s_vt + ks * 2 * CHK, s_vt + LO + ks * 2 * CHK, CHK, 128, s_dot + ks * 2 * CHQ, s_dot + LO + ks * 2 * CHQ, CHQ, 128,
+                             idesc_sp, ks > 0);
+            umma_commit(&bar1);
+        }
+        mbar_wait(&bar1, ph);
+        tc_fence_after();
+        {   // P^T and dS^T of key row r, queries [32 qh, 32 qh + 32) of the block
+            const int c0 = 32 * qh;
+            float sv[32], dv[32];
+            tmem_ld32(tmem + lane_addr + T_S + (uint32_t)c0, sv);
+            tmem_ld32(tmem + lane_addr + T_DP + (uint32_t)c0, dv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float pj = key_ok ? exp2f(fmaf(sv[j], sl2, -s_lse2[c0 + j])) : 0.f;
+                sv[j] = pj;
+                dv[j] = pj * (dv[j] - s_di[c0 + j]) * p.scale;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float a8[8], b8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { a8[i] = sv[g * 8 + i]; b8[i] = dv[g * 8 + i]; }
+                const uint32_t off = (uint32_t)((c0 >> 3) + g) * CHK + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+                *reinterpret_cast<uint4*>(pt + off) = pack8(a8);
+                *reinterpret_cast<uint4*>(dst + off) = pack8(b8);
+                if (NSPLIT == 3) {
+                    float l8[8];
+                    split8(a8, l8);
+                    *reinterpret_cast<uint4*>(pt + LO + off) = pack8(l8);
+                    split8(b8, l8);
+                    *reinterpret_cast<uint4*>(dst + LO + off) = pack8(l8);
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < QB / 16; ++ks) {   // reduction over the block's 64 queries, 16 per step
+                // dV += P^T dO : A = the P^T image (K-major over q), B = dO through the transposed view (N = channel)
+                mma3<NSPLIT>(tmem + T_DV, s_pt + ks * 2 * CHK, s_pt + LO + ks * 2 * CHK, CHK, 128, s_dot + ks * 256, s_dot + LO + ks * 256, 128, CHQ, idesc_dv,
+                             acc_kv | (uint32_t)(ks > 0));
+                // dK += dS^T Q
+                mma3<NSPLIT>(tmem + T_DK, s_dst + ks * 2 * CHK, s_dst + LO + ks * 2 * CHK, CHK, 128, s_qt + ks * 256, s_qt + LO + ks * 256, 128, CHQ, idesc_dk,
+                             acc_kv | (uint32_t)(ks > 0));
+            }
+            for (int ks = 0; ks < 8; ++ks)           // dQ_blk = dS K : reduction over the 128 keys; A = transposed view of dS^T (rows 64..127 of D: unused)
+                mma3<NSPLIT>(tmem + T_DQ, s_dst + ks * 256, s_dst + LO + ks * 256, 128, CHK, s_kt + ks * 256, s_kt + LO + ks * 256, 128, CHK, idesc_dq, ks > 0);
+            umma_commit(&bar2);
+        }
+        acc_kv = 1;
+        mbar_wait(&bar2, ph);
+        ph ^= 1;
+        tc_fence_after();
+        if (tid < QB) {                              // lanes 0..63 of the dQ accumulator = the block's queries
+            const int q = q0 + tid;
+            for (int c0 = 0; c0 < D; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + lane_addr + T_DQ + (uint32_t)c0, v);
+                if (q < p.Tq) {
+                    float* d = p.dQ + ((long)b * p.Tq + q) * ldq + h * D + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (acc_kv) {
+        tc_fence_after();
+        const int key = key0 + r;
+        if (qh == 0) {
+            for (int c0 = 0; c0 < D; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + lane_addr + T_DK + (uint32_t)c0, v);
+                if (key < p.Tk) {
+                    float* d = p.dK + ((long)b * p.Tk + key) * ldq + h * D + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        } else {
+            for (int c0 = 0; c0 < DV; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + lane_addr + T_DV + (uint32_t)c0, v);
+                if (key < p.Tk) {
+                    float* d = p.dV + ((long)b * p.Tk + key) * ldv + h * DV + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 static bool attn_tc_ok(const AttnTcParams& p) {
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     return (p.D == 16 || p.D == 32) && (p.Dv == 16 || p.Dv == 32) && al(p.Q) && al(p.K) && al(p.V) && p.Tk >= 1;
@@ -526,8 +712,30 @@ int xattn_bwd_tc(const float* Q, const float* K, const float* V, const float* O,
     p.Tq = Tq; p.Tk = Tk; p.H = H; p.D = D; p.Dv = Dv; p.scale = scale;
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!attn_tc_ok(p) || !al(O) || !al(dO) || !al(dQ) || !al(dK) || !al(dV) || Tq < 1) return NPF_ENOTSUP;
-    const size_t half = (size_t)(2 * (D >> 3) + 2 * (Dv >> 3) + 32) * 2048;
     const bool x3 = precision == NPF_PREC_BF16X3;
+    {   // 64-query arrangement (two CTAs per SM) unless switched off
+        static const bool q64 = [] { const char* e = getenv("NPF_XATTN_BWD_Q64"); return !(e && e[0] == '0'); }();
+        const size_t half64 = (size_t)(D >> 3) * 2048 + (size_t)(Dv >> 3) * 2048 + (size_t)(D >> 3) * 1024 + (size_t)(Dv >> 3) * 1024 + 2 * 16384;
+        const size_t smem64 = half64 * (x3 ? 2 : 1) + (x3 ? (size_t)(D >> 3) * (2048 + 1024) : 0);
+        if (q64 && smem64 <= 200 * 1024) {
+            static bool attr64 = false;
+            if (!attr64) {
+                if (cudaFuncSetAttribute(xattn_bwd_tc_q64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+                    cudaFuncSetAttribute(xattn_bwd_tc_q64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+                    cudaGetLastError();
+                    return NPF_ENOTSUP;
+                }
+                attr64 = true;
+            }
+            cudaMemsetAsync(dQ, 0, sizeof(float) * (size_t)B * Tq * H * D, st);   // dQ is accumulated over key blocks with atomics
+            dim3 grid((unsigned)cdiv(Tk, 128), (unsigned)H, (unsigned)B);
+            if (x3) xattn_bwd_tc_q64_kernel<3><<<grid, 256, smem64, st>>>(p);
+            else xattn_bwd_tc_q64_kernel<1><<<grid, 256, smem64, st>>>(p);
+            count_launch();
+            return check_launch("xattn_bwd_tc_q64_kernel");
+        }
+    }
+    const size_t half = (size_t)(2 * (D >> 3) + 2 * (Dv >> 3) + 32) * 2048;
     const size_t smem = half * (x3 ? 2 : 1) + (x3 ? (size_t)2 * (D >> 3) * 2048 : 0);
     static bool attr = false;
     if (!attr) {
