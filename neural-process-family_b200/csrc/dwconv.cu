@@ -9,6 +9,8 @@
 // staged float4 is read once per filter row instead of once per tap.  The same kernel with flipped filters and a
 // relu-mask epilogue is the data gradient; the filter gradient kernel uses the mirrored register scheme.
 // KW is a compile-time (padded) filter width in {9, 11, 19}; narrower filters are centred and zero-padded.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace npf {
@@ -780,10 +782,204 @@ __global__ void __launch_bounds__(128) dwconv2d_wgrad_kernel(DwParams p, const f
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// 2-D path, second arrangement (round 2): a WARP owns one channel pair.  The kernel above keeps 4 channels x 8 columns x 2 rows per
+// thread and reads both the input window and the filter taps with LDS.128 from four different channel quads per warp: 40 shared-memory
+// wavefront groups per 176 float4 FMAs -- the shared-memory pipe (not the FMA pipe) is what saturates, at 30 % FMA utilisation.
+// Here every lane of a warp works on the SAME two channels (packed fp32x2: one FFMA2 per tap and pixel), so
+//   * a filter tap is one address for the whole warp: LDS.128 broadcasts (two taps each, one wavefront);
+//   * a lane owns 8 rows x 4 columns of the 32 x 32 output tile (64 float2 accumulators); an input row segment (4 + KW - 1 pixels, 7
+//     LDS.128) is loaded ONCE and feeds every (output row, tap row) combination it belongs to: 44 FFMA2 per combination;
+//   * the tile is stored plane by plane (pair, row, column) with a 16-byte shift on every other 8-row block, which makes the 32-byte
+//     lane stride of the window loads conflict-free across the four row blocks of a warp.
+// Per warp and tile: 3 872 FFMA2 against ~1 030 shared-memory wavefronts: FMA-bound.  CTA = one image tile x 8 channels (4 warps),
+// 63 KB of shared memory: three CTAs per SM.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int V2T = 32;          // output tile edge
+constexpr int V2P = 4;           // channel pairs (warps) per CTA
+
+template <int KW>
+__global__ void __launch_bounds__(V2P * 32, 3) dwconv2d_v2_kernel(DwParams p) {
+    constexpr int ROWS = V2T + KW - 1, COLS = V2T + KW - 1;
+    constexpr int PITCH = COLS * 8 + 16;                 // bytes per staged row (float2 per pixel) + room for the 16-byte shift
+    constexpr int PLANE = ROWS * PITCH;
+    constexpr int WP = KW + 1;                           // taps per filter row, padded to an even count (LDS.128 = two taps)
+    constexpr int XC = 4 + KW - 1;                       // input pixels per lane and row
+    static_assert(PITCH % 16 == 0 && XC % 2 == 0 && WP % 2 == 0, "layout");
+    extern __shared__ __align__(16) uint8_t smem_v2[];
+    uint8_t* xs = smem_v2;                                // [V2P][ROWS][PITCH]
+    float2* ws = reinterpret_cast<float2*>(smem_v2 + V2P * PLANE);     // [V2P][KW][WP]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int h0 = (tile / p.tiles_w) * V2T, w0 = (tile % p.tiles_w) * V2T;
+    const int c0 = blockIdx.y * (2 * V2P);
+    const int b = blockIdx.z;
+    const int ph = KW / 2, joff = (KW - p.kw) / 2;        // kh == kw (<= KW); narrower filters are centred in the padded one
+    const long img = (long)b * p.H * p.Wd;
+
+    // ---- filters: ws[pair][i][j] = (W[c0 + 2 pair][i][j], W[c0 + 2 pair + 1][i][j]), flipped for the data gradient, zero padding
+    for (int idx = tid; idx < V2P * KW * WP; idx += V2P * 32) {
+        const int j = idx % WP, i = (idx / WP) % KW, pr = idx / (WP * KW);
+        float2 v = make_float2(0.f, 0.f);
+        const int ir = i - joff, jr = j - joff;
+        if (ir >= 0 && ir < p.kh && jr >= 0 && jr < p.kw) {
+            const int ii = p.flip ? p.kh - 1 - ir : ir, jj = p.flip ? p.kw - 1 - jr : jr;
+            const float* w = p.Wt + ((long)(c0 + 2 * pr) * p.kh + ii) * p.kw + jj;
+            v = make_float2(__ldg(w), __ldg(w + (long)p.kh * p.kw));
+        }
+        ws[idx] = v;
+    }
+    // ---- input tile with halo: thread = (pixel, half of the 8 channels); activation only on real pixels (the padding stays exactly 0)
+    {
+        const bool affine = p.relu_in && p.scale != nullptr;
+        const int half = tid & 1;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (affine) { sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4 * half)); sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4 * half)); }
+        for (int base = 0; base < ROWS * COLS; base += 4 * (V2P * 16)) {
+            float4 v[4];
+            int pix[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pix[u] = base + u * (V2P * 16) + (tid >> 1);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pix[u] < ROWS * COLS) {
+                    const int rr = pix[u] / COLS, cc = pix[u] - rr * COLS;
+                    const int gh = h0 + rr - ph, gw = w0 + cc - ph;
+                    if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.Wd) {
+                        v[u] = __ldg(reinterpret_cast<const float4*>(p.X + (img + (long)gh * p.Wd + gw) * p.C + c0 + 4 * half));
+                        if (p.relu_in) v[u] = act4(v[u], affine, sc, sh);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pix[u] >= ROWS * COLS) continue;
+                const int rr = pix[u] / COLS, cc = pix[u] - rr * COLS;
+                uint8_t* d = xs + (2 * half) * PLANE + rr * PITCH + ((rr >> 3) & 1) * 16 + cc * 8;
+                *reinterpret_cast<float2*>(d) = make_float2(v[u].x, v[u].y);
+                *reinterpret_cast<float2*>(d + PLANE) = make_float2(v[u].z, v[u].w);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- main loop: lane = (column quad cq, row block rb) of the warp's channel pair
+    const int cq = lane & 7, rb = lane >> 3;
+    const uint8_t* plane = xs + warp * PLANE + (4 * cq) * 8;
+    const float2* wp = ws + warp * (KW * WP);
+    float2 acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int rr = 0; rr < 8 + KW - 1; ++rr) {            // tile row 8 rb + rr feeds output row r through tap row i = rr - r
+        const int trow = 8 * rb + rr;
+        const uint8_t* rowp = plane + trow * PITCH + ((trow >> 3) & 1) * 16;
+        float2 x[XC];
+#pragma unroll
+        for (int k = 0; k < XC / 2; ++k) {
+            const float4 t = *reinterpret_cast<const float4*>(rowp + 16 * k);
+            x[2 * k] = make_float2(t.x, t.y);
+            x[2 * k + 1] = make_float2(t.z, t.w);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = rr - r;
+            if (i < 0 || i >= KW) continue;                // uniform over the warp
+            float2 w[WP];
+#pragma unroll
+            for (int k = 0; k < WP / 2; ++k) {
+                const float4 t = *reinterpret_cast<const float4*>(wp + i * WP + 2 * k);      // one address per warp: broadcast
+                w[2 * k] = make_float2(t.x, t.y);
+                w[2 * k + 1] = make_float2(t.z, t.w);
+            }
+#pragma unroll
+            for (int j = 0; j < KW; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = __ffma2_rn(w[j], x[c + j], acc[r][c]);
+        }
+    }
+
+    // ---- epilogue.  The accumulators go through shared memory (the input planes are dead) so that global memory is touched the way the
+    // staging touches it: thread = (pixel, half of the 8 channels), 16-byte accesses, 32 contiguous bytes per pixel.  Written straight
+    // from the accumulator layout (lane = 4 columns of ONE channel pair) every store / mask load / residual load instruction would
+    // touch 32 different cache lines for 8 bytes each: four times the LSU wavefronts, and it was those that bounded the kernel.
+    __syncthreads();
+    {
+        float2* op = reinterpret_cast<float2*>(xs) + warp * (V2T * V2T);          // [pair][32 rows][32 cols]
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; c += 2)
+                *reinterpret_cast<float4*>(op + (8 * rb + r) * V2T + 4 * cq + c) = make_float4(acc[r][c].x, acc[r][c].y, acc[r][c + 1].x, acc[r][c + 1].y);
+    }
+    __syncthreads();
+    {
+        const int half = tid & 1;
+        const int ch = c0 + 4 * half;
+        const float2* o0 = reinterpret_cast<const float2*>(xs) + (2 * half) * (V2T * V2T);
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.mask && p.scale) { sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch)); sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch)); }
+#pragma unroll 1
+        for (int base = 0; base < V2T * V2T; base += 4 * (V2P * 16)) {
+            float4 xo[4], rv[4], ov[4];
+            long off[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pix = base + u * (V2P * 16) + (tid >> 1);
+                const int gh = h0 + (pix >> 5), gw = w0 + (pix & 31);
+                ok[u] = gh < p.H && gw < p.Wd;
+                off[u] = (img + (long)gh * p.Wd + gw) * p.C + ch;
+                if (ok[u]) {
+                    if (p.mask) xo[u] = __ldg(reinterpret_cast<const float4*>(p.Xorig + off[u]));
+                    if (p.res) rv[u] = __ldg(reinterpret_cast<const float4*>(p.res + off[u]));
+                    if (p.accum) ov[u] = *reinterpret_cast<const float4*>(p.Y + off[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                const int pix = base + u * (V2P * 16) + (tid >> 1);
+                const float2 a = o0[pix], bq = o0[V2T * V2T + pix];
+                float4 v = make_float4(a.x + bv.x, a.y + bv.y, bq.x + bv.z, bq.y + bv.w);
+                if (p.mask) {
+                    v.x = fmaf(sc.x, xo[u].x, sh.x) > 0.f ? v.x * sc.x : 0.f;
+                    v.y = fmaf(sc.y, xo[u].y, sh.y) > 0.f ? v.y * sc.y : 0.f;
+                    v.z = fmaf(sc.z, xo[u].z, sh.z) > 0.f ? v.z * sc.z : 0.f;
+                    v.w = fmaf(sc.w, xo[u].w, sh.w) > 0.f ? v.w * sc.w : 0.f;
+                }
+                if (p.res) { v.x += rv[u].x; v.y += rv[u].y; v.z += rv[u].z; v.w += rv[u].w; }
+                if (p.accum) { v.x += ov[u].x; v.y += ov[u].y; v.z += ov[u].z; v.w += ov[u].w; }
+                *reinterpret_cast<float4*>(p.Y + off[u]) = v;
+            }
+        }
+    }
+}
+
+template <int KW>
+static int launch_dw2_v2(DwParams& p, int B, cudaStream_t st) {
+    constexpr int ROWS = V2T + KW - 1, PITCH = ROWS * 8 + 16;
+    const size_t smem = (size_t)V2P * ROWS * PITCH + (size_t)V2P * KW * (KW + 1) * sizeof(float2);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(dwconv2d_v2_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024); attr = true; }
+    p.tiles_w = (int)cdiv(p.Wd, V2T);
+    dim3 grid((unsigned)(p.tiles_w * cdiv(p.H, V2T)), (unsigned)(p.C / (2 * V2P)), (unsigned)B);
+    dwconv2d_v2_kernel<KW><<<grid, V2P * 32, smem, st>>>(p);
+    count_launch();
+    return check_launch("dwconv2d_v2_kernel");
+}
+static bool dw2_v2_on() { static const bool on = [] { const char* e = getenv("NPF_DWCONV2D_V2"); return !(e && e[0] == '0'); }(); return on; }
+
 static bool dw2_ok(int H, int C, int kh, int kw) { return H > 1 && C % T2C == 0 && kh == kw && kh <= 11; }
 
 template <int KW>
 static int launch_dw2(DwParams& p, int B, cudaStream_t st) {
+    if (dw2_v2_on() && p.C % (2 * V2P) == 0 && p.kh == p.kw) return launch_dw2_v2<KW>(p, B, st);
     p.tiles_w = (int)cdiv(p.Wd, T2W);
     const size_t smem = ((size_t)(T2H + p.kh - 1) * (T2W + KW - 1) * T2C + (size_t)p.kh * KW * T2C) * sizeof(float);
     static bool attr = false;
