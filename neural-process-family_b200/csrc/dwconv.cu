@@ -975,6 +975,179 @@ static int launch_dw2_v2(DwParams& p, int B, cudaStream_t st) {
 }
 static bool dw2_v2_on() { static const bool on = [] { const char* e = getenv("NPF_DWCONV2D_V2"); return !(e && e[0] == '0'); }(); return on; }
 
+// ----------------------------------------------------------------------------------------------------------------
+// 2-D filter gradient, second arrangement: dW[c,i,j] = sum_{b,h,w} dY[b,h,w,c] act(X)[b,h+i-p,w+j-p,c].
+// A persistent CTA = 8 channels (4 pairs) x 3 groups of 4 filter rows = 12 warps; it walks a share of the images and keeps its
+// 4 x KW packed accumulators per lane IN REGISTERS for all of them: the cross-lane reduction (shuffles) and the atomics happen once per
+// CTA, not once per image.  Per image the act(X) halo tile and the dY tile are staged as channel-pair planes (the layout of
+// dwconv2d_v2_kernel, shifted every 4 rows); a lane owns 4 rows x 4 columns of a 16-row half of the tile: the 4 x 4 dY values sit in
+// registers, every act(X) row segment (4 + KW - 1 pixels, 7 LDS.128) it loads feeds up to 4 filter rows x KW taps x 4 columns = 176 FFMA2.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int WGI = 4;           // filter rows per warp group
+constexpr int WGG = 3;           // warp groups (3 x 4 >= KW)
+
+template <int KW>
+__global__ void __launch_bounds__(V2P * WGG * 32, 1) dwconv2d_wgrad_v2_kernel(DwParams p, const float* __restrict__ dY, float* __restrict__ dWt, int B, int ipc) {
+    constexpr int ROWS = V2T + KW - 1, COLS = V2T + KW - 1;
+    constexpr int PITCH = COLS * 8 + 16, PLANE = ROWS * PITCH;
+    constexpr int GPITCH = V2T * 8 + 16, GPLANE = V2T * GPITCH;
+    constexpr int XC = 4 + KW - 1;
+    constexpr int NT = V2P * WGG * 32;
+    static_assert(KW <= WGI * WGG && XC % 2 == 0, "filter rows per group");
+    extern __shared__ __align__(16) uint8_t smem_v2[];
+    uint8_t* xs = smem_v2;                                // act(X): [V2P][ROWS][PITCH]
+    uint8_t* gs = smem_v2 + V2P * PLANE;                  // dY:     [V2P][32][GPITCH]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pair = warp & (V2P - 1), grp = warp / V2P;
+    const int i0 = WGI * grp, IC = min(WGI, KW - i0);    // this warp's filter rows [i0, i0 + IC)
+    const int tile = blockIdx.x;
+    const int h0 = (tile / p.tiles_w) * V2T, w0 = (tile % p.tiles_w) * V2T;
+    const int c0 = blockIdx.y * (2 * V2P);
+    const int ph = KW / 2, joff = (KW - p.kw) / 2;
+    const int cq = lane & 7, rb = lane >> 3;
+
+    float2 acc[WGI][KW];
+#pragma unroll
+    for (int ii = 0; ii < WGI; ++ii)
+#pragma unroll
+        for (int j = 0; j < KW; ++j) acc[ii][j] = make_float2(0.f, 0.f);
+
+    const bool affine = p.relu_in && p.scale != nullptr;
+    const int half = tid & 1;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (affine) { sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4 * half)); sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4 * half)); }
+
+    const int b_begin = blockIdx.z * ipc, b_end = min(B, b_begin + ipc);
+    for (int b = b_begin; b < b_end; ++b) {
+        const long img = (long)b * p.H * p.Wd;
+        // ---- stage act(X) with halo and dY: thread = (pixel, half of the 8 channels)
+        for (int base = 0; base < ROWS * COLS; base += 4 * (NT / 2)) {
+            float4 v[4];
+            int pix[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pix[u] = base + u * (NT / 2) + (tid >> 1);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pix[u] < ROWS * COLS) {
+                    const int rr = pix[u] / COLS, cc = pix[u] - rr * COLS;
+                    const int gh = h0 + rr - ph, gw = w0 + cc - ph;
+                    if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.Wd) {
+                        v[u] = __ldg(reinterpret_cast<const float4*>(p.X + (img + (long)gh * p.Wd + gw) * p.C + c0 + 4 * half));
+                        if (p.relu_in) v[u] = act4(v[u], affine, sc, sh);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pix[u] >= ROWS * COLS) continue;
+                const int rr = pix[u] / COLS, cc = pix[u] - rr * COLS;
+                uint8_t* d = xs + (2 * half) * PLANE + rr * PITCH + ((rr >> 2) & 1) * 16 + cc * 8;
+                *reinterpret_cast<float2*>(d) = make_float2(v[u].x, v[u].y);
+                *reinterpret_cast<float2*>(d + PLANE) = make_float2(v[u].z, v[u].w);
+            }
+        }
+        for (int base = 0; base < V2T * V2T; base += 4 * (NT / 2)) {
+            float4 v[4];
+            int pix[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pix[u] = base + u * (NT / 2) + (tid >> 1);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pix[u] < V2T * V2T) {
+                    const int gh = h0 + (pix[u] >> 5), gw = w0 + (pix[u] & 31);
+                    if (gh < p.H && gw < p.Wd) v[u] = __ldg(reinterpret_cast<const float4*>(dY + (img + (long)gh * p.Wd + gw) * p.C + c0 + 4 * half));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pix[u] >= V2T * V2T) continue;
+                const int rr = pix[u] >> 5, cc = pix[u] & 31;
+                uint8_t* d = gs + (2 * half) * GPLANE + rr * GPITCH + ((rr >> 2) & 1) * 16 + cc * 8;
+                *reinterpret_cast<float2*>(d) = make_float2(v[u].x, v[u].y);
+                *reinterpret_cast<float2*>(d + GPLANE) = make_float2(v[u].z, v[u].w);
+            }
+        }
+        __syncthreads();
+        // ---- two 16-row halves of the tile; lane = (column quad cq, 4-row block rb)
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+            const int r0 = 16 * hh + 4 * rb;                       // first output row of this lane
+            float2 dy[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint8_t* gp = gs + pair * GPLANE + (r0 + r) * GPITCH + (((r0 + r) >> 2) & 1) * 16 + (4 * cq) * 8;
+                const float4 t0 = *reinterpret_cast<const float4*>(gp), t1 = *reinterpret_cast<const float4*>(gp + 16);
+                dy[r][0] = make_float2(t0.x, t0.y); dy[r][1] = make_float2(t0.z, t0.w);
+                dy[r][2] = make_float2(t1.x, t1.y); dy[r][3] = make_float2(t1.z, t1.w);
+            }
+            const uint8_t* plane = xs + pair * PLANE + (4 * cq) * 8;
+#pragma unroll
+            for (int rr = 0; rr < 4 + WGI - 1; ++rr) {             // act(X) tile row r0 + i0 + rr meets output row r through filter row i0 + (rr - r)
+                if (rr >= 4 + IC - 1) continue;                    // uniform over the warp
+                const int trow = r0 + i0 + rr;
+                const uint8_t* rowp = plane + trow * PITCH + ((trow >> 2) & 1) * 16;
+                float2 x[XC];
+#pragma unroll
+                for (int k = 0; k < XC / 2; ++k) {
+                    const float4 t = *reinterpret_cast<const float4*>(rowp + 16 * k);
+                    x[2 * k] = make_float2(t.x, t.y);
+                    x[2 * k + 1] = make_float2(t.z, t.w);
+                }
+#pragma unroll
+                for (int ii = 0; ii < WGI; ++ii) {
+                    const int r = rr - ii;
+                    if (r < 0 || r >= 4 || ii >= IC) continue;
+#pragma unroll
+                    for (int j = 0; j < KW; ++j)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[ii][j] = __ffma2_rn(dy[r][c], x[c + j], acc[ii][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- one reduction over the warp's lanes and one atomic per tap and channel for the whole share of images
+#pragma unroll
+    for (int ii = 0; ii < WGI; ++ii) {
+        if (ii >= IC) continue;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            float2 v = acc[ii][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+            }
+            const int ir = i0 + ii - joff, jr = j - joff;
+            if (lane == 0 && ir >= 0 && ir < p.kh && jr >= 0 && jr < p.kw) {
+                float* d = dWt + ((long)(c0 + 2 * pair) * p.kh + ir) * p.kw + jr;
+                atomicAdd(d, v.x);
+                atomicAdd(d + (long)p.kh * p.kw, v.y);
+            }
+        }
+    }
+}
+
+template <int KW>
+static int launch_dw2_wgrad_v2(DwParams& p, const float* dY, float* dWt, int B, cudaStream_t st) {
+    constexpr int ROWS = V2T + KW - 1, PITCH = ROWS * 8 + 16;
+    const size_t smem = (size_t)V2P * ROWS * PITCH + (size_t)V2P * V2T * (V2T * 8 + 16);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(dwconv2d_wgrad_v2_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); attr = true; }
+    p.tiles_w = (int)cdiv(p.Wd, V2T);
+    const int tiles = p.tiles_w * (int)cdiv(p.H, V2T), groups = p.C / (2 * V2P);
+    int nz = kNumSMs / (tiles * groups);                              // image shares: at most one CTA per SM (one resident CTA each: no second wave)
+    if (nz < 1) nz = 1;
+    if (nz > B) nz = B;
+    const int ipc = (int)cdiv(B, nz);
+    nz = (int)cdiv(B, ipc);
+    dim3 grid((unsigned)tiles, (unsigned)groups, (unsigned)nz);
+    dwconv2d_wgrad_v2_kernel<KW><<<grid, V2P * WGG * 32, smem, st>>>(p, dY, dWt, B, ipc);
+    count_launch();
+    return check_launch("dwconv2d_wgrad_v2_kernel");
+}
+
 static bool dw2_ok(int H, int C, int kh, int kw) { return H > 1 && C % T2C == 0 && kh == kw && kh <= 11; }
 
 template <int KW>
@@ -992,6 +1165,7 @@ static int launch_dw2(DwParams& p, int B, cudaStream_t st) {
 
 template <int KW>
 static int launch_dw2_wgrad(DwParams& p, const float* dY, float* dWt, int B, cudaStream_t st) {
+    if (dw2_v2_on() && p.C % (2 * V2P) == 0 && p.kh == p.kw) return launch_dw2_wgrad_v2<KW>(p, dY, dWt, B, st);
     p.tiles_w = (int)cdiv(p.Wd, T2W);
     const size_t smem = ((size_t)(T2H + p.kh - 1) * (T2W + KW - 1) * T2C + (size_t)T2H * T2W * T2C + (size_t)p.kh * KW * T2C) * sizeof(float);
     static bool attr = false;
