@@ -832,15 +832,16 @@ __global__ void __launch_bounds__(V2P * 32, 3) dwconv2d_v2_kernel(DwParams p) {
     }
     // ---- input tile with halo: thread = (pixel, half of the 8 channels); activation only on real pixels (the padding stays exactly 0)
     {
+        constexpr int SB = 14;                              // loads in flight per thread: the accumulators are not live yet, two round trips stage the tile
         const bool affine = p.relu_in && p.scale != nullptr;
         const int half = tid & 1;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (affine) { sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4 * half)); sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4 * half)); }
-        for (int base = 0; base < ROWS * COLS; base += 4 * (V2P * 16)) {
-            float4 v[4];
-            int pix[4];
+        for (int base = 0; base < ROWS * COLS; base += SB * (V2P * 16)) {
+            float4 v[SB];
+            int pix[SB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < SB; ++u) {
                 pix[u] = base + u * (V2P * 16) + (tid >> 1);
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pix[u] < ROWS * COLS) {
@@ -853,7 +854,7 @@ __global__ void __launch_bounds__(V2P * 32, 3) dwconv2d_v2_kernel(DwParams p) {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < SB; ++u) {
                 if (pix[u] >= ROWS * COLS) continue;
                 const int rr = pix[u] / COLS, cc = pix[u] - rr * COLS;
                 uint8_t* d = xs + (2 * half) * PLANE + rr * PITCH + ((rr >> 3) & 1) * 16 + cc * 8;
@@ -925,12 +926,13 @@ __global__ void __launch_bounds__(V2P * 32, 3) dwconv2d_v2_kernel(DwParams p) {
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.mask && p.scale) { sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch)); sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch)); }
 #pragma unroll 1
-        for (int base = 0; base < V2T * V2T; base += 4 * (V2P * 16)) {
-            float4 xo[4], rv[4], ov[4];
-            long off[4];
-            bool ok[4];
+        constexpr int EB = 8;
+        for (int base = 0; base < V2T * V2T; base += EB * (V2P * 16)) {
+            float4 xo[EB], rv[EB], ov[EB];
+            long off[EB];
+            bool ok[EB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < EB; ++u) {
                 const int pix = base + u * (V2P * 16) + (tid >> 1);
                 const int gh = h0 + (pix >> 5), gw = w0 + (pix & 31);
                 ok[u] = gh < p.H && gw < p.Wd;
@@ -942,7 +944,7 @@ __global__ void __launch_bounds__(V2P * 32, 3) dwconv2d_v2_kernel(DwParams p) {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < EB; ++u) {
                 if (!ok[u]) continue;
                 const int pix = base + u * (V2P * 16) + (tid >> 1);
                 const float2 a = o0[pix], bq = o0[V2T * V2T + pix];
