@@ -3,10 +3,11 @@
 // 3 MMAs per product (fp32-level logits and P.V).
 //
 // Forward, one CTA per (task, head, 128-query block), 128 threads = 128 TMEM lanes = 128 query rows:
-//   per 128-key chunk:  S = Q K^T          tcgen05.mma  M=128 N=128 K=D        (accumulator: TMEM cols [0,128))
+//   per chunk of KC = 128 or 64 keys (64: four CTAs per SM; chosen when the grid is large enough):
+//                       S = Q K^T          tcgen05.mma  M=128 N=KC K=D         (accumulator: TMEM cols [0,KC))
 //                       thread r reads row r of S from TMEM (tcgen05.ld), online softmax (running max / sum, exp2),
 //                       writes P (bf16 hi/lo) straight into the UMMA K-major operand layout in shared memory
-//                       O_c = P V          tcgen05.mma  M=128 N=Dv  K=128      (accumulator: TMEM cols [128,128+Dv))
+//                       O_c = P V          tcgen05.mma  M=128 N=Dv  K=KC       (accumulator: TMEM cols [KC,KC+Dv))
 //                       thread r: O_r = O_r * alpha + O_c[r, :]   (registers)
 //   The [Tq, Tk] logits / probabilities never leave the SM.
 //

@@ -5,14 +5,18 @@
 //     Y[l, :] = Wpw . O[l, :] + bpw                                               pointwise 128 -> 128
 //
 // The unfused path runs this as npf_dwconv_fwd + npf_linear_fwd: O makes a round trip through HBM (write 50 MB, read 50 MB
-// at config 2) between two launches.  Here a persistent CTA walks 128-row tiles of one task at a time:
+// at config 2) between two launches.  Here a persistent CTA walks 128- or 96-row tiles of one task at a time:
 //   * ONE thread issues a TMA bulk copy (cp.async.bulk, 1-D: the tile's rows and their +-p halo are contiguous in the
 //     channel-last layout) of the raw fp32 rows into shared memory; rows outside the task are zero-filled (padding);
 //   * 16 producer warps run the depthwise conv out of that raw tile (thread = 2 channels x 16 rows, the k taps of its two
 //     channels in registers for the whole kernel), add bias + residual, and write O split into bf16 hi / lo straight into the
 //     SWIZZLE_128B K-major A-operand image (optionally also as fp32 rows to HBM when the caller wants O saved);
 //   * 1 MMA warp multiplies by the once-staged pointwise weights (tcgen05, hi.hi + hi.lo + lo.hi, accumulator double-
-//     buffered in TMEM), 8 epilogue warps add the bias and store coalesced rows.
+//     buffered in TMEM).  The product is issued TRANSPOSED, Y^T = Wpw . O^T (both images are 128-column K-major, so they just swap
+//     roles): TMEM lane = output channel, column = tile row, and the 8 epilogue warps store 32 consecutive channels of a row straight
+//     from their tcgen05.ld registers -- no shared-memory transpose.  With the rows as the N extent of the MMA the tile may be 96 rows
+//     high (chosen when it leaves fewer rows on the busiest CTA).  NPF_RB_FWD_T = 0 keeps the row-major product (+ transpose),
+//     = 2 reads Wpw from TMEM (tcgen05.mma with a TMEM A operand; measured slower).
 // HBM sees X once (+ 2p / 128 halo re-reads out of L2) and Y once.
 #include <cstdlib>
 #include <type_traits>
@@ -351,8 +355,10 @@ static int launch_rb_fwd(RbFwdParams& p, cudaStream_t st) {
 // axis with X read from the raw tile in shared memory -- no exchange between threads.  dWpw accumulates in TMEM over the CTA's
 // tiles (A = dY^T, B = O: MN-major views; O rows outside the interior are zero so that every row counts once).
 // Roles: loader warp (TMA bulk copies of the raw dY / X tiles, zero fill outside the task), 16 producer warps (dY raw -> image;
-// O recomputed from raw X -> image), 1 MMA warp, 8 epilogue warps.  Raw X is double-buffered (the epilogue of tile i still reads
-// it while tile i + 1 is prepared).
+// O recomputed from raw X for the 48 interior rows -> image, whose halo rows are zeroed once), 1 MMA warp, 8 epilogue warps.
+// Wpw^T is the TMEM-resident A operand of the data-gradient product (written once per CTA with tcgen05.st): the 64 KB its
+// shared-memory images would take hold a third raw X and a second raw dY buffer (the epilogue of tile i still reads X(i) while
+// tiles i + 1, i + 2 are prepared).  NPF_RB_BWD_TW = 0 keeps the weights in shared memory (two X buffers, one dY buffer).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kRwRows = 64;
 constexpr int kRwInt = 48;                                      // interior rows per tile (k = 11: 48 + 2 * 5 = 58 <= 64)
